@@ -1,0 +1,229 @@
+/*
+ * mvae_b200.h — C ABI of libmvae_b200.so: the B200-native (sm_100a) hot path of the mixed-curvature VAE.
+ *
+ * The reference (oskopek/mvae) is pure Python/PyTorch and has no FFI of its own; its extension points are
+ * Python classes.  Each entry point below replaces a group of reference Python functions and
+ * cites them (paths relative to the reference root).  The Python host layer (mvae_b200/*.py) mirrors the
+ * reference classes and calls these through ctypes; INTEGRATION.md shows the stub a reference maintainer adds.
+ *
+ * Conventions
+ *   - all matrices are row-major, contiguous, fp32 unless the name says `bf16` (uint16 storage);
+ *   - every pointer is a DEVICE pointer unless the name ends in `_host`;
+ *   - all work is enqueued on the caller's `stream` (a cudaStream_t passed as void*); no entry point
+ *     synchronises the host, allocates, or keeps global state (the only cached state is per-device
+ *     attributes such as the SM count and func attributes set once);
+ *   - return value: 0 on success, negative mvae_status on error (never throws / aborts);
+ *     mvae_strerror() maps it to text;
+ *   - numerical faults (non-finite outputs) are reported through an optional device flag word, never by a sync.
+ */
+#ifndef MVAE_B200_H_
+#define MVAE_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MVAE_ABI_VERSION 1
+#define MVAE_MAX_COMPONENTS 96
+
+/* ------------------------------------------------------------------------------------------------ status */
+typedef enum mvae_status {
+  MVAE_OK = 0,
+  MVAE_ERR_INVALID_ARGUMENT = -1,  /* null pointer, bad shape, unknown component type            */
+  MVAE_ERR_UNSUPPORTED = -2,       /* valid request this build cannot serve (e.g. dim too large) */
+  MVAE_ERR_CUDA = -3,              /* a CUDA runtime / driver call failed (see mvae_last_cuda_error) */
+  MVAE_ERR_ALIGNMENT = -4,         /* pointer / leading dimension violates the documented alignment */
+  MVAE_ERR_NOT_SM100 = -5          /* device is not compute capability 10.x                       */
+} mvae_status;
+
+const char* mvae_strerror(int status);
+int mvae_abi_version(void);
+/* Last cudaError_t seen by this library on the calling thread (0 if none); does not clear sticky errors. */
+int mvae_last_cuda_error(void);
+
+/* ------------------------------------------------------------------------------------ product manifold */
+/* Component kinds, reference grammar letters (mt/mvae/utils.py:30-38). */
+typedef enum mvae_manifold {
+  MVAE_EUCLIDEAN = 0,   /* 'e'  mt/mvae/ops/euclidean.py  + EuclideanNormalProcedure (sampling_procedures.py:145-155) */
+  MVAE_HYPERBOLOID = 1, /* 'h'  mt/mvae/ops/hyperbolics.py + WrappedNormalProcedure (:91-116)   */
+  MVAE_SPHERE = 2,      /* 's'  mt/mvae/ops/spherical.py   + WrappedNormalProcedure             */
+  MVAE_POINCARE = 3,    /* 'p'  mt/mvae/ops/poincare.py (+geoopt 0.1.0) + WrappedNormalProcedure */
+  MVAE_PROJ_SPHERE = 4  /* 'd'  mt/mvae/ops/spherical_projected.py + WrappedNormalProcedure     */
+} mvae_manifold;
+
+/* One latent component.  n = true (tangent) dimension; d = ambient dimension of loc/z
+ * (n+1 for h,s — component.py:122,159 — and n for e,p,d). */
+typedef struct mvae_component {
+  int32_t type;    /* mvae_manifold                                                      */
+  int32_t n;       /* true dimension                                                      */
+  int32_t d;       /* ambient dimension                                                   */
+  int32_t m_off;   /* column of fc_mean's n outputs inside a row of `ml`                  */
+  int32_t l_off;   /* column of fc_logvar's l_n outputs inside a row of `ml`              */
+  int32_t l_n;     /* n (elliptic) or 1 (scalar_parametrization, component.py:47-50)       */
+  int32_t eps_off; /* column of this component's n noise values inside a row of `eps` / `sigma` */
+  int32_t z_off;   /* column of this component's d coordinates inside a row of `z` / `mu` */
+} mvae_component;
+
+typedef struct mvae_pm_desc {
+  int32_t C;       /* number of components (1..MVAE_MAX_COMPONENTS)                      */
+  int32_t ld_ml;   /* row stride (floats) of ml   — sum of n + sum of l_n when packed     */
+  int32_t ld_eps;  /* row stride (floats) of eps, sigma — sum of n when packed            */
+  int32_t ld_z;    /* row stride (floats) of z, mu, gz  — sum of d when packed            */
+  mvae_component comp[MVAE_MAX_COMPONENTS];
+} mvae_pm_desc;
+
+/* Fill offsets of a packed descriptor: ml = [m_0|l_0|m_1|l_1|...], eps/sigma and z/mu concatenated in
+ * component order (concat order of mt/mvae/models/vae.py:78).  types[i] in mvae_manifold, dims[i] = true dim. */
+int mvae_pm_desc_init(mvae_pm_desc* desc, int32_t C, const int32_t* types, const int32_t* dims,
+                      int32_t scalar_parametrization);
+
+/*
+ * Fused per-sample manifold + Wrapped-Normal forward for one product manifold, B samples.
+ * Replaces, per component: Component.encode (component.py:63-75: exp_map_mu0 + softplus+1e-5),
+ * SamplingProcedure.reparametrize (sampling_procedures.py:93-99,147-151), q_z.rsample_with_parts
+ * (wrapped_normal.py:70-78 -> sample_projection_mu0: hyperbolics.py:138-142, spherical.py:119-123,
+ * poincare.py:152-157), kl_loss (sampling_procedures.py:101-116,153-155: log_prob_from_parts
+ * wrapped_normal.py:84-97, logdet hyperbolics.py:58-65 / spherical.py:58-67 / poincare.py:55-89,
+ * prior log_prob wrapped_normal.py:99-103) and the concat of vae.py:78.
+ *
+ *   ml     [B, ld_ml]   head pre-activations (fc_mean | fc_logvar outputs)
+ *   eps    [B, ld_eps]  standard-normal noise (one draw per tangent coordinate)
+ *   radius [C]          raw radius parameters (_nradius/_pradius); R = clamp(relu(.),1e-8,1e8) (manifold.py:73-75);
+ *                       ignored for Euclidean components
+ *   z      [B, ld_z]    out: concat_z
+ *   kl     [B, C]       out: per-sample, per-component KL term
+ *   mu     [B, ld_z]    out, optional (NULL): q_z.loc
+ *   sigma  [B, ld_eps]  out, optional (NULL): q_z.scale (expanded to n columns)
+ *   nonfinite_flag      optional (NULL) device word, OR-ed with 1 if any output is not finite
+ */
+int mvae_pm_forward(const mvae_pm_desc* desc, int64_t B, const float* ml, const float* eps, const float* radius,
+                    float* z, float* kl, float* mu, float* sigma, uint32_t* nonfinite_flag, void* stream);
+
+/*
+ * Backward of mvae_pm_forward by recomputation from its inputs (autograd replay of the functions above,
+ * including the custom backward rules of ops/common.py:28-39 LeakyClamp, :46-63 Atanh, :76-94 Acosh).
+ *   gz      [B, ld_z]  upstream gradient of z
+ *   gkl     [B, C]     upstream gradient of kl, or NULL meaning the constant `gkl_scalar` (beta) for every entry
+ *   gml     [B, ld_ml] out: gradient of ml
+ *   gradius [C]        out: ACCUMULATED (+=) gradient of the raw radius parameters (zero it first)
+ */
+int mvae_pm_backward(const mvae_pm_desc* desc, int64_t B, const float* ml, const float* eps, const float* radius,
+                     const float* gz, const float* gkl, float gkl_scalar, float* gml, float* gradius, void* stream);
+
+/* --------------------------------------------------------------------------- standalone manifold ops */
+/* Per-sample vector ops of the Manifold interface (ops/manifold.py:22-60) for a single component.
+ * x/y are [B, d] or [B, n] as the op requires; out likewise.  `radius` is a device pointer to the raw radius. */
+typedef enum mvae_op {
+  MVAE_OP_EXP_MAP_MU0 = 0,         /* x [B,n] -> out [B,d]       (hyperbolics.py:114, spherical.py:94, poincare.py:132, euclidean.py:78) */
+  MVAE_OP_INV_EXP_MAP_MU0 = 1,     /* x [B,d] -> out [B,d]       (hyperbolics.py:131, spherical.py:112, poincare.py:148, euclidean.py:86) */
+  MVAE_OP_EXP_MAP = 2,             /* x tangent [B,d], y at_point [B,d] -> out [B,d] (hyperbolics.py:106, spherical.py:86, poincare.py:124, euclidean.py:74) */
+  MVAE_OP_INV_EXP_MAP = 3,         /* x point, y at_point -> tangent (hyperbolics.py:124, spherical.py:104, poincare.py:140, euclidean.py:82) */
+  MVAE_OP_PT_MU0 = 4,              /* x tangent at mu0, y dst -> tangent at dst (hyperbolics.py:87, spherical.py:74, poincare.py:116) */
+  MVAE_OP_INV_PT_MU0 = 5,          /* x tangent at src, y src -> tangent at mu0 (hyperbolics.py:96, spherical.py:80, poincare.py:120) */
+  MVAE_OP_DISTANCE = 6,            /* x, y points -> out [B,1] geodesic distance (poincare.py:96-105; tests/mvae/ops/test_hyperbolics.py:46, test_spherical.py:45, test_euclidean.py:41) */
+  MVAE_OP_MOBIUS_ADD = 7,          /* Poincare / projected sphere only: x (+) y (poincare.py:100, spherical_projected.py:107-113) */
+  MVAE_OP_MOBIUS_SCALAR_MUL = 8,   /* Poincare only: x[B,d], y[B,1] scalar r -> r (x) x. No reference call site: parity unpinned. */
+  MVAE_OP_LOGDET = 9,              /* x = u (h,s: [B,d]) -> out [B,1] (hyperbolics.py:58, spherical.py:58) */
+  MVAE_OP_TO_POINCARE = 10,        /* h: lorentz_to_poincare (hyperbolics.py:151); s: spherical_to_projected (spherical.py:132) */
+  MVAE_OP_FROM_POINCARE = 11       /* p: poincare_to_lorentz (poincare.py:167); d: projected_to_spherical (spherical_projected.py:191) */
+} mvae_op;
+
+int mvae_manifold_op(int32_t op, int32_t manifold, int32_t n, int64_t B, const float* x, const float* y,
+                     const float* radius, float* out, void* stream);
+
+/* Wrapped-Normal pieces for one component (distributions/wrapped_normal.py:70-103).
+ * rsample_with_parts: loc [B,d], scale [B,n], eps [B,n] -> z [B,d], u [B,d] (data[0]), v [B,n] (data[1]).
+ * log_prob_from_parts: scale [B,n], u [B,d], v [B,n] (+loc,z for Poincare) -> logp [B].
+ * log_prob: loc [B,d], scale [B,n], z [B,d] -> logp [B] (inverse_sample_projection_mu0 then from_parts). */
+int mvae_wn_rsample(int32_t manifold, int32_t n, int64_t B, const float* loc, const float* scale, const float* eps,
+                    const float* radius, float* z, float* u, float* v, void* stream);
+int mvae_wn_log_prob_from_parts(int32_t manifold, int32_t n, int64_t B, const float* loc, const float* scale,
+                                const float* z, const float* u, const float* v, const float* radius, float* logp,
+                                void* stream);
+int mvae_wn_log_prob(int32_t manifold, int32_t n, int64_t B, const float* loc, const float* scale, const float* z,
+                     const float* radius, float* logp, void* stream);
+
+/* ----------------------------------------------------------------------------------- dense layers (MLP) */
+/* Split-bf16 operand planes: an fp32 matrix X [R, K] is carried as `planes` bf16 matrices
+ * X_0 + X_1 (+ X_2) ~= X (X_0 = bf16(X), X_1 = bf16(X - X_0), ...), each [R, ldp] row-major with
+ * ldp a multiple of 8 elements (16 B) so that TMA can address it.  plane p starts at base + p*plane_stride. */
+typedef struct mvae_planes {
+  uint16_t* base;        /* device pointer to plane 0                               */
+  int64_t plane_stride;  /* elements between consecutive planes                     */
+  int32_t rows;          /* R                                                       */
+  int32_t cols;          /* K (logical)                                             */
+  int32_t ld;            /* row stride in elements, multiple of 8                   */
+  int32_t planes;        /* 1, 2 or 3                                               */
+} mvae_planes;
+
+/* fp32 [R,K] (row stride ld_src) -> planes, and optionally the transposed planes [K,R]. */
+int mvae_split_planes(const float* src, int64_t ld_src, int32_t R, int32_t K, const mvae_planes* dst,
+                      const mvae_planes* dst_transposed /* may be NULL */, void* stream);
+
+/* Epilogues of the tcgen05 GEMM  D[M,N] = A[M,K] . B[N,K]^T  (both operands K-major planes). */
+typedef enum mvae_epilogue {
+  MVAE_EPI_STORE = 0,        /* out_f32[M,N] = acc (+bias[n])                                                   */
+  MVAE_EPI_BIAS_RELU = 1,    /* y = relu(acc + bias[n]) -> planes (and transposed planes) — ffnn_vae.py:48,56    */
+  MVAE_EPI_HEADS_PM = 2,     /* acc + bias = ml row -> mvae_pm_forward per row — component.py:64,69 + K3         */
+  MVAE_EPI_BCE_ROWSUM = 3,   /* logits = acc + bias; bce[m] += sum_n BCEWithLogits(logit, x); g = sigmoid - x    */
+  MVAE_EPI_NLL_ROWSUM = 4,   /* logits = acc + bias; nll[m] += sum_n .5(x-l)^2 + .5 ln 2pi;     g = l - x        */
+  MVAE_EPI_RELU_MASK = 5,    /* y = acc * (mask > 0) -> planes (and transposed planes) — relu backward            */
+  MVAE_EPI_ACCUM = 6,        /* out_f32[M,N] += acc  (split-K weight gradients, red.global.add.f32)              */
+  MVAE_EPI_PM_BACKWARD = 7   /* acc = gz row -> mvae_pm_backward per row                                         */
+} mvae_epilogue;
+
+typedef struct mvae_gemm_args {
+  mvae_planes a;             /* [M, K]                                                   */
+  mvae_planes b;             /* [N, K]                                                   */
+  int32_t M, N, K;
+  int32_t epilogue;          /* mvae_epilogue                                            */
+  int32_t split_k;           /* >=1; >1 only with MVAE_EPI_ACCUM                         */
+  const float* bias;         /* [N] or NULL                                              */
+  float* out_f32;            /* [M, ld_out] or NULL                                      */
+  int64_t ld_out;
+  float* out_col;            /* ACCUM: column `col_split` of acc goes to out_col[m] (bias-gradient trick) or NULL */
+  int32_t col_split;
+  mvae_planes out_planes;    /* base==NULL if unused                                     */
+  mvae_planes out_planes_t;  /* transposed planes, base==NULL if unused                  */
+  const float* aux;          /* BCE/NLL: targets x [M, ld_aux]; RELU_MASK: forward activation [M, ld_aux] */
+  int64_t ld_aux;
+  float* rowsum;             /* BCE/NLL: [M] accumulated (+=) row sums                   */
+  /* HEADS_PM / PM_BACKWARD */
+  const mvae_pm_desc* pm;    /* HOST pointer                                             */
+  const float* eps;
+  const float* radius;
+  const float* ml;           /* PM_BACKWARD: saved head pre-activations                  */
+  float* z;
+  float* kl;
+  float* gradius;
+  float gkl_scalar;
+} mvae_gemm_args;
+
+int mvae_gemm(const mvae_gemm_args* args, void* stream);
+
+/* ------------------------------------------------------------------------------- reconstruction + ELBO */
+/* Standalone reconstruction losses (VaeDataset.reconstruction_loss + .sum(-1), vae.py:131):
+ * kind 0 = BCE-with-logits (data/image_reconstruction.py:81-82), 1 = unit-variance Gaussian NLL (data/synthetic.py:161-162).
+ * rowsum [B] = sum over D; glogits (optional) = d(sum)/dlogits. */
+int mvae_recon_loss(int32_t kind, int64_t B, int32_t D, const float* logits, const float* x, float* rowsum,
+                    float* glogits, void* stream);
+
+/* ELBO reduction (stats.py:144-202): out = [bce_sum, kl_sum, elbo, kl_c sums (C)] with
+ * elbo = sum_b(-bce_b - beta * sum_c kl_bc).  Warp-shuffle + block reduce; `out` [3+C] is overwritten. */
+int mvae_elbo_reduce(int64_t B, int32_t C, const float* bce, const float* kl, float beta, float* out, void* stream);
+
+/* Fused Adam (torch.optim.Adam defaults: betas .9/.999, eps 1e-8, no weight decay — train.py:343) over a flat
+ * fp32 parameter bucket.  step is 1-based.  grad_scale multiplies the gradient first. */
+int mvae_adam_step(int64_t n, float* param, const float* grad, float* exp_avg, float* exp_avg_sq, float lr,
+                   float beta1, float beta2, float eps, int32_t step, float grad_scale, void* stream);
+
+/* Device attributes the host layer needs for grid sizing / reporting. */
+int mvae_device_info(int32_t* sm_count, int32_t* cc_major, int32_t* cc_minor);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MVAE_B200_H_ */

@@ -1,0 +1,260 @@
+"""ctypes front end of the CPU oracle (oracle/liboracle.so) — TEST INFRASTRUCTURE ONLY.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs import this.
+The product (mvae_b200/) never does.  See oracle/mvae_oracle_impl.h for what each function restates.
+"""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "liboracle.so")
+
+MAX_COMPONENTS = 96
+TYPE_OF_LETTER = {"e": 0, "h": 1, "s": 2, "p": 3, "d": 4}
+
+
+class Component(ctypes.Structure):
+    _fields_ = [(k, ctypes.c_int32) for k in ("type", "n", "d", "m_off", "l_off", "l_n", "eps_off", "z_off")]
+
+
+class PmDesc(ctypes.Structure):
+    _fields_ = [("C", ctypes.c_int32), ("ld_ml", ctypes.c_int32), ("ld_eps", ctypes.c_int32),
+                ("ld_z", ctypes.c_int32), ("comp", Component * MAX_COMPONENTS)]
+
+
+def build(force: bool = False) -> str:
+    src = [os.path.join(_HERE, f) for f in ("mvae_oracle.c", "mvae_oracle_impl.h")]
+    src.append(os.path.join(_HERE, "..", "include", "mvae_b200.h"))
+    stale = (not os.path.exists(_LIB_PATH)) or any(
+        os.path.exists(s) and os.path.getmtime(s) > os.path.getmtime(_LIB_PATH) for s in src)
+    if force or stale:
+        subprocess.run(["make", "-C", _HERE, "-B" if force else "-s"], check=True, capture_output=True)
+    return _LIB_PATH
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_LIB_PATH):
+            build()
+        _lib = ctypes.CDLL(_LIB_PATH)
+        assert _lib.oracle_sizeof_pm_desc() == ctypes.sizeof(PmDesc)
+    return _lib
+
+
+def parse_signature(sig: str):
+    """'2h3,s2,e2' -> ([types], [dims]) following the reference grammar (mt/mvae/utils.py:78-140)."""
+    types, dims = [], []
+    for tok in sig.lower().strip().split(","):
+        tok = tok.strip().split("-")[0]
+        i = 0
+        while i < len(tok) and tok[i].isdigit():
+            i += 1
+        mult = int(tok[:i]) if i else 1
+        j = i
+        while j < len(tok) and tok[j].isalpha():
+            j += 1
+        letter, dim = tok[i:j], int(tok[j:])
+        for _ in range(mult):
+            types.append(TYPE_OF_LETTER[letter])
+            dims.append(dim)
+    return types, dims
+
+
+def make_desc(sig_or_types, dims=None, scalar_parametrization=False) -> PmDesc:
+    if isinstance(sig_or_types, str):
+        types, dims = parse_signature(sig_or_types)
+    else:
+        types = list(sig_or_types)
+    C = len(types)
+    d = PmDesc()
+    rc = lib().oracle_pm_desc_init(ctypes.byref(d), C, (ctypes.c_int32 * C)(*types), (ctypes.c_int32 * C)(*dims),
+                                   int(scalar_parametrization))
+    if rc != 0:
+        raise ValueError("bad product-manifold signature")
+    return d
+
+
+def _sfx(dtype):
+    dtype = np.dtype(dtype)
+    if dtype == np.float64:
+        return "_f64", ctypes.c_double
+    if dtype == np.float32:
+        return "_f32", ctypes.c_float
+    raise TypeError(dtype)
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(ctypes.c_void_p)
+
+
+def pm_forward(desc: PmDesc, ml, eps, radius, want=("z", "kl")):
+    """Returns dict with any of z, kl, mu, sigma, u, logq, logp."""
+    ml = np.ascontiguousarray(ml)
+    dt = ml.dtype
+    sfx, _ = _sfx(dt)
+    eps = np.ascontiguousarray(eps, dtype=dt)
+    radius = np.ascontiguousarray(radius, dtype=dt)
+    B = ml.shape[0]
+    assert ml.shape[1] == desc.ld_ml and eps.shape[1] == desc.ld_eps and radius.shape[0] == desc.C
+    shapes = {"z": desc.ld_z, "kl": desc.C, "mu": desc.ld_z, "sigma": desc.ld_eps, "u": desc.ld_z,
+              "logq": desc.C, "logp": desc.C}
+    out = {k: (np.zeros((B, shapes[k]), dtype=dt) if k in want else None) for k in shapes}
+    fn = getattr(lib(), "oracle_pm_forward" + sfx)
+    fn.restype = None
+    fn(ctypes.byref(desc), ctypes.c_int64(B), _p(ml), _p(eps), _p(radius), _p(out["z"]), _p(out["kl"]),
+       _p(out["mu"]), _p(out["sigma"]), _p(out["u"]), _p(out["logq"]), _p(out["logp"]))
+    return {k: v for k, v in out.items() if v is not None}
+
+
+def pm_backward(desc: PmDesc, ml, eps, radius, gz, gkl=None, gkl_scalar=1.0):
+    """Returns (gml [B, ld_ml], gradius [C] float64)."""
+    ml = np.ascontiguousarray(ml)
+    dt = ml.dtype
+    sfx, creal = _sfx(dt)
+    eps = np.ascontiguousarray(eps, dtype=dt)
+    radius = np.ascontiguousarray(radius, dtype=dt)
+    gz = np.ascontiguousarray(gz, dtype=dt)
+    gkl = None if gkl is None else np.ascontiguousarray(gkl, dtype=dt)
+    B = ml.shape[0]
+    gml = np.zeros_like(ml)
+    gR = np.zeros(desc.C, dtype=np.float64)
+    fn = getattr(lib(), "oracle_pm_backward" + sfx)
+    fn.restype = None
+    fn(ctypes.byref(desc), ctypes.c_int64(B), _p(ml), _p(eps), _p(radius), _p(gz), _p(gkl), creal(gkl_scalar),
+       _p(gml), _p(gR))
+    return gml, gR
+
+
+def recon(kind, logits, x, want_grad=False, gscale=1.0):
+    """kind 'bce' | 'nll' -> (rowsum [B], glogits or None)."""
+    logits = np.ascontiguousarray(logits)
+    dt = logits.dtype
+    sfx, creal = _sfx(dt)
+    x = np.ascontiguousarray(x, dtype=dt)
+    B, D = logits.shape
+    rs = np.zeros(B, dtype=dt)
+    g = np.zeros_like(logits) if want_grad else None
+    fn = getattr(lib(), "oracle_recon" + sfx)
+    fn.restype = None
+    fn(0 if kind == "bce" else 1, ctypes.c_int64(B), D, _p(logits), _p(x), _p(rs), _p(g), creal(gscale))
+    return rs, g
+
+
+def elbo(bce, kl, beta):
+    """-> float64 array [bce_sum, kl_sum, elbo, kl_c...] (stats.py:144-202)."""
+    bce = np.ascontiguousarray(bce)
+    dt = bce.dtype
+    sfx, creal = _sfx(dt)
+    kl = np.ascontiguousarray(kl, dtype=dt)
+    B, C = kl.shape
+    out = np.zeros(3 + C, dtype=np.float64)
+    fn = getattr(lib(), "oracle_elbo" + sfx)
+    fn.restype = None
+    fn(ctypes.c_int64(B), C, _p(bce), _p(kl), creal(beta), _p(out))
+    return out
+
+
+def linear(x, W, b, relu=False, use_blas=True):
+    """y = x W^T + b (optionally relu).  use_blas routes the contraction through numpy (threaded BLAS) — same
+    arithmetic, used by the timed CPU baseline; the plain-C loop is kept for cross-checking."""
+    if use_blas:
+        y = x @ W.T
+        if b is not None:
+            y += b
+        if relu:
+            np.maximum(y, 0, out=y)
+        return y
+    x = np.ascontiguousarray(x)
+    dt = x.dtype
+    sfx, _ = _sfx(dt)
+    W = np.ascontiguousarray(W, dtype=dt)
+    b = None if b is None else np.ascontiguousarray(b, dtype=dt)
+    B, K = x.shape
+    N = W.shape[0]
+    y = np.zeros((B, N), dtype=dt)
+    fn = getattr(lib(), "oracle_linear" + sfx)
+    fn.restype = None
+    fn(ctypes.c_int64(B), K, N, _p(x), _p(W), _p(b), _p(y), int(relu))
+    return y
+
+
+class OracleVAE:
+    """Whole hot path (ModelVAE.forward + compute_batch_stats + backward, vae.py:69-80,125-160) on the CPU:
+    numpy/BLAS for the three dense layers (ffnn_vae.py:42-60) + the C oracle for everything per-sample.
+    Parameters are a dict with the reference's state_dict names."""
+
+    def __init__(self, sig, in_dim, h_dim, recon_kind="bce", scalar_parametrization=False):
+        self.types, self.dims = parse_signature(sig)
+        self.desc = make_desc(self.types, self.dims, scalar_parametrization)
+        self.in_dim, self.h_dim, self.recon_kind = in_dim, h_dim, recon_kind
+        self.C = len(self.types)
+
+    def heads_matrix(self, params):
+        """Stack fc_mean / fc_logvar of every component in packed-ml order -> (W [P,H], b [P])."""
+        Ws, bs = [], []
+        for i in range(self.C):
+            Ws += [params[f"components.{i}.fc_mean.weight"], params[f"components.{i}.fc_logvar.weight"]]
+            bs += [params[f"components.{i}.fc_mean.bias"], params[f"components.{i}.fc_logvar.bias"]]
+        return np.concatenate(Ws, 0), np.concatenate(bs, 0)
+
+    def radii(self, params, dtype):
+        r = np.ones(self.C, dtype=dtype)
+        for i in range(self.C):
+            for nm in ("_nradius", "_pradius"):
+                k = f"components.{i}.{nm}"
+                if k in params:
+                    r[i] = params[k]
+        return r
+
+    def step(self, params, x, eps, beta=1.0, backward=True):
+        dt = x.dtype
+        Wh, bh = self.heads_matrix(params)
+        R = self.radii(params, dt)
+        h = linear(x, params["fc_e0.weight"], params["fc_e0.bias"], relu=True)
+        ml = linear(h, Wh, bh)
+        f = pm_forward(self.desc, ml, eps, R, want=("z", "kl", "mu", "sigma"))
+        dd = linear(f["z"], params["fc_d0.weight"], params["fc_d0.bias"], relu=True)
+        logits = linear(dd, params["fc_logits.weight"], params["fc_logits.bias"])
+        bce, glogits = recon(self.recon_kind, logits, x, want_grad=backward)
+        stats = elbo(bce, f["kl"], beta)
+        out = {"h": h, "ml": ml, "z": f["z"], "kl": f["kl"], "mu": f["mu"], "sigma": f["sigma"], "logits": logits,
+               "bce": bce, "bce_sum": stats[0], "kl_sum": stats[1], "elbo": stats[2], "kl_comp": stats[3:]}
+        if not backward:
+            return out
+        g = {}
+        # loss = -elbo = sum bce + beta * sum kl
+        g["fc_logits.weight"] = glogits.T @ dd
+        g["fc_logits.bias"] = glogits.sum(0)
+        gdd = (glogits @ params["fc_logits.weight"]) * (dd > 0)
+        g["fc_d0.weight"] = gdd.T @ f["z"]
+        g["fc_d0.bias"] = gdd.sum(0)
+        gz = gdd @ params["fc_d0.weight"]
+        gml, gR = pm_backward(self.desc, ml, eps, R, gz, None, beta)
+        gWh = gml.T @ h
+        gbh = gml.sum(0)
+        row = 0
+        for i in range(self.C):
+            c = self.desc.comp[i]
+            g[f"components.{i}.fc_mean.weight"] = gWh[row:row + c.n]
+            g[f"components.{i}.fc_mean.bias"] = gbh[row:row + c.n]
+            row += c.n
+            g[f"components.{i}.fc_logvar.weight"] = gWh[row:row + c.l_n]
+            g[f"components.{i}.fc_logvar.bias"] = gbh[row:row + c.l_n]
+            row += c.l_n
+            for nm in ("_nradius", "_pradius"):
+                if f"components.{i}.{nm}" in params:
+                    g[f"components.{i}.{nm}"] = np.asarray(gR[i])
+        gh = (gml @ Wh) * (h > 0)
+        g["fc_e0.weight"] = gh.T @ x
+        g["fc_e0.bias"] = gh.sum(0)
+        out["grads"] = g
+        out["gz"] = gz
+        out["gml"] = gml
+        return out
