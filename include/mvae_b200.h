@@ -147,14 +147,18 @@ int mvae_wn_log_prob(int32_t manifold, int32_t n, int64_t B, const float* loc, c
                      const float* radius, float* logp, void* stream);
 
 /* ----------------------------------------------------------------------------------- dense layers (MLP) */
-/* Split-bf16 operand planes: an fp32 matrix X [R, K] is carried as `planes` bf16 matrices
- * X_0 + X_1 (+ X_2) ~= X (X_0 = bf16(X), X_1 = bf16(X - X_0), ...), each [R, ldp] row-major with
- * ldp a multiple of 8 elements (16 B) so that TMA can address it.  plane p starts at base + p*plane_stride. */
+/* The dense layers of the reference (mt/mvae/models/ffnn_vae.py:42-60 fc_e0 / fc_d0 / fc_logits and the
+ * fc_mean / fc_logvar heads of mt/mvae/components/component.py:64,69), forward, dgrad and wgrad, all run through
+ * ONE tcgen05 GEMM kernel.  fp32 accuracy on bf16 tensor cores comes from split-bf16 operand planes:
+ * an fp32 matrix X [R, C] is carried as `planes` bf16 matrices X_0 + X_1 (+ X_2) ~= X
+ * (X_0 = bf16(X), X_1 = bf16(X - X_0), ...), each [R, ld] row-major with ld a multiple of 8 elements (16 B)
+ * so that TMA can address it; plane p starts at base + p*plane_stride.  The kernel accumulates the products
+ * X_i * Y_j with i + j < max(planes) in fp32 (2 planes: 3 MMAs per k-step, ~2^-16 relative error). */
 typedef struct mvae_planes {
   uint16_t* base;        /* device pointer to plane 0                               */
-  int64_t plane_stride;  /* elements between consecutive planes                     */
+  int64_t plane_stride;  /* elements between consecutive planes (multiple of 8)     */
   int32_t rows;          /* R                                                       */
-  int32_t cols;          /* K (logical)                                             */
+  int32_t cols;          /* C (logical)                                             */
   int32_t ld;            /* row stride in elements, multiple of 8                   */
   int32_t planes;        /* 1, 2 or 3                                               */
 } mvae_planes;
@@ -163,43 +167,45 @@ typedef struct mvae_planes {
 int mvae_split_planes(const float* src, int64_t ld_src, int32_t R, int32_t K, const mvae_planes* dst,
                       const mvae_planes* dst_transposed /* may be NULL */, void* stream);
 
-/* Epilogues of the tcgen05 GEMM  D[M,N] = A[M,K] . B[N,K]^T  (both operands K-major planes). */
+/* Epilogues of the tcgen05 GEMM  D[M,N] = sum_k A[m,k] * B[n,k]. */
 typedef enum mvae_epilogue {
-  MVAE_EPI_STORE = 0,        /* out_f32[M,N] = acc (+bias[n])                                                   */
-  MVAE_EPI_BIAS_RELU = 1,    /* y = relu(acc + bias[n]) -> planes (and transposed planes) — ffnn_vae.py:48,56    */
-  MVAE_EPI_HEADS_PM = 2,     /* acc + bias = ml row -> mvae_pm_forward per row — component.py:64,69 + K3         */
-  MVAE_EPI_BCE_ROWSUM = 3,   /* logits = acc + bias; bce[m] += sum_n BCEWithLogits(logit, x); g = sigmoid - x    */
-  MVAE_EPI_NLL_ROWSUM = 4,   /* logits = acc + bias; nll[m] += sum_n .5(x-l)^2 + .5 ln 2pi;     g = l - x        */
-  MVAE_EPI_RELU_MASK = 5,    /* y = acc * (mask > 0) -> planes (and transposed planes) — relu backward            */
-  MVAE_EPI_ACCUM = 6,        /* out_f32[M,N] += acc  (split-K weight gradients, red.global.add.f32)              */
-  MVAE_EPI_PM_BACKWARD = 7   /* acc = gz row -> mvae_pm_backward per row                                         */
+  MVAE_EPI_STORE = 0,       /* v = acc (+bias[n]); out_f32[m*ld_out+n] = v, or += v (atomic) when split_k > 1;
+                               column `col_split` (if >= 0) is diverted to out_col[m] (bias gradients)          */
+  MVAE_EPI_BIAS_RELU = 1,   /* y = relu(acc + bias[n]) -> out_planes (and out_f32 if given) — ffnn_vae.py:48,56   */
+  MVAE_EPI_RELU_MASK = 2,   /* y = acc * (mask[m,n] > 0) -> out_planes (and out_f32) — backward of the relu;
+                               mask = plane 0 of the forward activation                                         */
+  MVAE_EPI_BCE_ROWSUM = 3,  /* logit = acc + bias[n]; rowsum[m] += sum_n BCEWithLogits(logit, x[m,n]);
+                               g = sigmoid(logit) - x -> out_planes; logits -> out_f32 if given
+                               (image_reconstruction.py:81-82 + vae.py:131)                                     */
+  MVAE_EPI_NLL_ROWSUM = 4   /* logit = acc + bias[n]; rowsum[m] += sum_n .5(x-logit)^2 + .5 ln 2pi; g = logit - x
+                               (synthetic.py:161-162)                                                           */
 } mvae_epilogue;
 
+/* Operand layouts.  K_MAJOR: `planes` describes the matrix [rows = M or N, cols = K] (nn.Linear weight for the
+ * forward pass, activations as A).  MN_MAJOR: `planes` describes [rows = K, cols = M or N] — the same row-major
+ * buffer read "transposed" by TMA + an MN-major UMMA descriptor, which is how dgrad reads W and wgrad reads the
+ * activations without any transposed copy in HBM. */
+typedef enum mvae_operand_major { MVAE_K_MAJOR = 0, MVAE_MN_MAJOR = 1 } mvae_operand_major;
+
 typedef struct mvae_gemm_args {
-  mvae_planes a;             /* [M, K]                                                   */
-  mvae_planes b;             /* [N, K]                                                   */
+  mvae_planes a;           /* K_MAJOR: [M, K]   MN_MAJOR: [K, M]                       */
+  mvae_planes b;           /* K_MAJOR: [N, K]   MN_MAJOR: [K, N]                       */
+  int32_t a_major;         /* mvae_operand_major                                       */
+  int32_t b_major;
   int32_t M, N, K;
-  int32_t epilogue;          /* mvae_epilogue                                            */
-  int32_t split_k;           /* >=1; >1 only with MVAE_EPI_ACCUM                         */
-  const float* bias;         /* [N] or NULL                                              */
-  float* out_f32;            /* [M, ld_out] or NULL                                      */
+  int32_t epilogue;        /* mvae_epilogue                                            */
+  int32_t split_k;         /* >= 1; > 1 only with MVAE_EPI_STORE (atomic accumulate into zeroed out_f32/out_col) */
+  const float* bias;       /* [N] or NULL                                              */
+  float* out_f32;          /* [M, ld_out] or NULL                                      */
   int64_t ld_out;
-  float* out_col;            /* ACCUM: column `col_split` of acc goes to out_col[m] (bias-gradient trick) or NULL */
-  int32_t col_split;
-  mvae_planes out_planes;    /* base==NULL if unused                                     */
-  mvae_planes out_planes_t;  /* transposed planes, base==NULL if unused                  */
-  const float* aux;          /* BCE/NLL: targets x [M, ld_aux]; RELU_MASK: forward activation [M, ld_aux] */
+  float* out_col;          /* STORE: [M] receives column col_split, or NULL            */
+  int32_t col_split;       /* -1 if unused                                             */
+  mvae_planes out_planes;  /* base == NULL if unused; [M, N] planes                    */
+  const float* aux;        /* BCE/NLL: targets x [M, ld_aux]                           */
   int64_t ld_aux;
-  float* rowsum;             /* BCE/NLL: [M] accumulated (+=) row sums                   */
-  /* HEADS_PM / PM_BACKWARD */
-  const mvae_pm_desc* pm;    /* HOST pointer                                             */
-  const float* eps;
-  const float* radius;
-  const float* ml;           /* PM_BACKWARD: saved head pre-activations                  */
-  float* z;
-  float* kl;
-  float* gradius;
-  float gkl_scalar;
+  const uint16_t* mask;    /* RELU_MASK: bf16 [M, ld_mask] (plane 0 of the activation) */
+  int64_t ld_mask;
+  float* rowsum;           /* BCE/NLL: [M] accumulated (+=) row sums                   */
 } mvae_gemm_args;
 
 int mvae_gemm(const mvae_gemm_args* args, void* stream);
@@ -219,6 +225,9 @@ int mvae_elbo_reduce(int64_t B, int32_t C, const float* bce, const float* kl, fl
  * fp32 parameter bucket.  step is 1-based.  grad_scale multiplies the gradient first. */
 int mvae_adam_step(int64_t n, float* param, const float* grad, float* exp_avg, float* exp_avg_sq, float lr,
                    float beta1, float beta2, float eps, int32_t step, float grad_scale, void* stream);
+
+/* Plain SGD step p -= lr * grad_scale * g (torch.optim.SGD defaults — the curvature optimizers of train.py:346-355). */
+int mvae_sgd_step(int64_t n, float* param, const float* grad, float lr, float grad_scale, void* stream);
 
 /* Device attributes the host layer needs for grid sizing / reporting. */
 int mvae_device_info(int32_t* sm_count, int32_t* cc_major, int32_t* cc_minor);

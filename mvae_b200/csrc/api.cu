@@ -1,0 +1,60 @@
+// api.cu — status strings, ABI version, cached device attributes of libmvae_b200.so.
+#include <mutex>
+
+#include "mvae_common.cuh"
+
+namespace mvae {
+
+static thread_local int g_last_cuda_error = 0;
+void note_cuda_error(cudaError_t e) { g_last_cuda_error = (int)e; }
+
+int get_device_info(DeviceInfo* out) {
+  constexpr int kMaxDev = 64;
+  static DeviceInfo cache[kMaxDev];
+  static bool have[kMaxDev] = {};
+  static std::mutex mu;
+  int dev = 0;
+  MVAE_CUDA_TRY(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= kMaxDev) return MVAE_ERR_UNSUPPORTED;
+  std::lock_guard<std::mutex> lock(mu);
+  if (!have[dev]) {
+    DeviceInfo d;
+    MVAE_CUDA_TRY(cudaDeviceGetAttribute(&d.sm_count, cudaDevAttrMultiProcessorCount, dev));
+    MVAE_CUDA_TRY(cudaDeviceGetAttribute(&d.cc_major, cudaDevAttrComputeCapabilityMajor, dev));
+    MVAE_CUDA_TRY(cudaDeviceGetAttribute(&d.cc_minor, cudaDevAttrComputeCapabilityMinor, dev));
+    MVAE_CUDA_TRY(cudaDeviceGetAttribute(&d.max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    cache[dev] = d;
+    have[dev] = true;
+  }
+  *out = cache[dev];
+  if (out->cc_major != 10) return MVAE_ERR_NOT_SM100;
+  return MVAE_OK;
+}
+
+}  // namespace mvae
+
+extern "C" const char* mvae_strerror(int status) {
+  switch (status) {
+    case MVAE_OK: return "ok";
+    case MVAE_ERR_INVALID_ARGUMENT: return "invalid argument";
+    case MVAE_ERR_UNSUPPORTED: return "unsupported request";
+    case MVAE_ERR_CUDA: return "CUDA runtime error (see mvae_last_cuda_error)";
+    case MVAE_ERR_ALIGNMENT: return "pointer or leading dimension violates the documented alignment";
+    case MVAE_ERR_NOT_SM100: return "device is not compute capability 10.x (this library is sm_100a only)";
+    default: return "unknown mvae status";
+  }
+}
+
+extern "C" int mvae_abi_version(void) { return MVAE_ABI_VERSION; }
+
+extern "C" int mvae_last_cuda_error(void) { return mvae::g_last_cuda_error; }
+
+extern "C" int mvae_device_info(int32_t* sm_count, int32_t* cc_major, int32_t* cc_minor) {
+  mvae::DeviceInfo d;
+  int rc = mvae::get_device_info(&d);
+  if (rc != MVAE_OK && rc != MVAE_ERR_NOT_SM100) return rc;
+  if (sm_count) *sm_count = d.sm_count;
+  if (cc_major) *cc_major = d.cc_major;
+  if (cc_minor) *cc_minor = d.cc_minor;
+  return rc;
+}

@@ -1,0 +1,573 @@
+// gemm_sm100.cu — the dense layers of the VAE as ONE warp-specialised tcgen05 GEMM kernel (sm_100a).
+//
+//   D[M,N] = sum_k A[m,k] * B[n,k]      A, B: split-bf16 operand planes (include/mvae_b200.h), fp32 accumulate
+//
+// Per CTA: one 128 x BLOCK_N output tile (BLOCK_N a multiple of 16, <= 256), optionally one split-K slice.
+//   warp 0      TMA producer: cp.async.bulk.tensor (3-D maps: [plane][row][col], 128B swizzle) into an
+//               mbarrier-guarded ring of shared-memory stages; one k-block = 64 bf16 of K per operand plane.
+//   warp 1      allocates TMEM, then one elected lane issues tcgen05.mma (kind::f16, M=128, N=BLOCK_N, K=16) for
+//               every plane pair (i,j) with i+j < max(planes); tcgen05.commit releases stages / signals the epilogue.
+//   warps 2..5  epilogue: tcgen05.ld the fp32 accumulator (lane = row, column = n) and apply the fused epilogue
+//               (bias, relu, relu-mask, BCE / Gaussian-NLL row sums + dloss/dlogits, split planes for the next GEMM).
+// Operands may be K-major (row-major [rows, K]) or MN-major (row-major [K, rows], read through an MN-major UMMA
+// descriptor) so that dgrad and wgrad read the very same buffers as the forward pass — no transposes in HBM.
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <math.h>
+#include <string.h>
+
+#include <mutex>
+
+#include "mvae_common.cuh"
+
+namespace mvae {
+
+constexpr int kBlockM = 128;
+constexpr int kBlockK = 64;             // bf16 elements per k-block = one 128-byte swizzle row
+constexpr int kUmmaK = 16;              // K of one tcgen05.mma kind::f16
+constexpr int kGemmThreads = 192;       // 6 warps
+constexpr int kATileBytes = kBlockM * kBlockK * 2;  // 16 KiB per plane per stage
+constexpr int kMaxStages = 8;
+constexpr float kHalfLn2PiG = 0.9189385332046727f;
+
+struct GemmParams {
+  int M, N, K;
+  int block_n;       // multiple of 16
+  int a_major, b_major;
+  int a_planes, b_planes;
+  int stages;
+  int b_tile_bytes;  // per plane per stage
+  int kb_total;      // ceil(K / 64)
+  int kb_per_split;
+  int epilogue;
+  int atomic_out;    // split_k > 1
+  uint32_t tmem_cols;
+  uint32_t idesc;
+  const float* bias;
+  float* out_f32;
+  int64_t ld_out;
+  float* out_col;
+  int col_split;
+  uint16_t* op_base;  // out planes
+  int64_t op_stride;
+  int op_ld;
+  int op_planes;
+  const float* aux;
+  int64_t ld_aux;
+  const uint16_t* mask;
+  int64_t ld_mask;
+  float* rowsum;
+};
+
+// ------------------------------------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok = 0;
+  do {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  } while (!ok);
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1,
+                                            int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// UMMA shared-memory descriptor, 128-byte swizzle (cute::UMMA::SmemDescriptor: start>>4 @0, LBO>>4 @16, SBO>>4 @32,
+// version=1 @46, layout SWIZZLE_128B=2 @61).
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+
+// writes 16 consecutive values of row `m`, columns [n, n+16) as split-bf16 planes
+__device__ __forceinline__ void store_planes16(const GemmParams& p, int m, int n, const float (&y)[16]) {
+  float rem[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) rem[j] = y[j];
+  for (int pl = 0; pl < p.op_planes; ++pl) {
+    uint16_t* dst = p.op_base + (int64_t)pl * p.op_stride + (int64_t)m * p.op_ld + n;
+    float q[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      q[j] = __bfloat162float(__float2bfloat16_rn(rem[j]));
+      rem[j] -= q[j];
+    }
+    if (n + 16 <= p.N) {
+      uint4 v0 = make_uint4(pack_bf16x2(q[0], q[1]), pack_bf16x2(q[2], q[3]), pack_bf16x2(q[4], q[5]),
+                            pack_bf16x2(q[6], q[7]));
+      uint4 v1 = make_uint4(pack_bf16x2(q[8], q[9]), pack_bf16x2(q[10], q[11]), pack_bf16x2(q[12], q[13]),
+                            pack_bf16x2(q[14], q[15]));
+      *reinterpret_cast<uint4*>(dst) = v0;
+      *reinterpret_cast<uint4*>(dst + 8) = v1;
+    } else {
+#pragma unroll
+      for (int j = 0; j < 16; ++j)
+        if (n + j < p.N) {
+          __nv_bfloat16 h = __float2bfloat16_rn(q[j]);
+          dst[j] = *reinterpret_cast<uint16_t*>(&h);
+        }
+    }
+  }
+}
+
+__device__ __forceinline__ void store_f32_16(float* out, int64_t ld, int m, int n, int N, const float (&y)[16],
+                                             bool vec) {
+  float* dst = out + (int64_t)m * ld + n;
+  if (vec && n + 16 <= N) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      *reinterpret_cast<float4*>(dst + 4 * j) = make_float4(y[4 * j], y[4 * j + 1], y[4 * j + 2], y[4 * j + 3]);
+  } else {
+#pragma unroll
+    for (int j = 0; j < 16; ++j)
+      if (n + j < N) dst[j] = y[j];
+  }
+}
+
+__global__ void __launch_bounds__(kGemmThreads, 1)
+    gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                        const __grid_constant__ GemmParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int m0 = blockIdx.x * kBlockM;
+  const int n0 = blockIdx.y * p.block_n;
+  const int kb0 = blockIdx.z * p.kb_per_split;
+  const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
+  if (kb0 >= kb1) return;  // empty split-K slice (uniform over the CTA)
+  const int nkb = kb1 - kb0;
+
+  // ---- shared memory carve-up: [stages x (A planes | B planes)] | barriers | tmem slot ----
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  const uint32_t stage_bytes = p.a_planes * kATileBytes + p.b_planes * p.b_tile_bytes;
+  const uint32_t bar_base = base + p.stages * stage_bytes;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (kMaxStages + s); };
+  const uint32_t tmem_full_bar = bar_base + 8u * (2 * kMaxStages);
+  const uint32_t tmem_slot = bar_base + 8u * (2 * kMaxStages + 1);
+  volatile uint32_t* tmem_slot_ptr =
+      reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - raw));
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    mbar_init(tmem_full_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot),
+                 "r"(p.tmem_cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp == 0) {
+    // ===================================== TMA producer =====================================
+    if (lane == 0) {
+      const uint32_t tx_bytes = stage_bytes;
+      for (int i = 0; i < nkb; ++i) {
+        const int s = i % p.stages;
+        const uint32_t ph = (uint32_t)(i / p.stages) & 1u;
+        mbar_wait(empty_bar(s), ph ^ 1u);
+        mbar_expect_tx(full_bar(s), tx_bytes);
+        const int k = (kb0 + i) * kBlockK;
+        const uint32_t sa = base + s * stage_bytes;
+        const uint32_t sb = sa + p.a_planes * kATileBytes;
+        for (int pl = 0; pl < p.a_planes; ++pl) {
+          const uint32_t dst = sa + pl * kATileBytes;
+          if (p.a_major == MVAE_K_MAJOR) {
+            tma_load_3d(dst, &map_a, full_bar(s), k, m0, pl);
+          } else {
+            tma_load_3d(dst, &map_a, full_bar(s), m0, k, pl);
+            tma_load_3d(dst + 8192, &map_a, full_bar(s), m0 + 64, k, pl);
+          }
+        }
+        for (int pl = 0; pl < p.b_planes; ++pl) {
+          const uint32_t dst = sb + pl * p.b_tile_bytes;
+          if (p.b_major == MVAE_K_MAJOR) {
+            tma_load_3d(dst, &map_b, full_bar(s), k, n0, pl);
+          } else {
+            for (int c = 0; c * 8192 < p.b_tile_bytes; ++c) tma_load_3d(dst + c * 8192, &map_b, full_bar(s), n0 + c * 64, k, pl);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================== MMA issuer =====================================
+    if (lane == 0) {
+      const int pmax = max(p.a_planes, p.b_planes);
+      // K-major: rows of 128 B, 8-row groups 1024 B apart (SBO); k-step = 32 B inside the swizzle row.
+      // MN-major: 64-element column chunks 8192 B apart (LBO), 8-k-row groups 1024 B apart (SBO); k-step = 16 rows = 2048 B.
+      const uint32_t a_lbo = p.a_major == MVAE_K_MAJOR ? 16u : 8192u;
+      const uint32_t b_lbo = p.b_major == MVAE_K_MAJOR ? 16u : 8192u;
+      const uint32_t a_kstep = p.a_major == MVAE_K_MAJOR ? 32u : 2048u;
+      const uint32_t b_kstep = p.b_major == MVAE_K_MAJOR ? 32u : 2048u;
+      uint32_t accumulate = 0;
+      for (int i = 0; i < nkb; ++i) {
+        const int s = i % p.stages;
+        const uint32_t ph = (uint32_t)(i / p.stages) & 1u;
+        mbar_wait(full_bar(s), ph);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t sa = base + s * stage_bytes;
+        const uint32_t sb = sa + p.a_planes * kATileBytes;
+        const int k_left = p.K - (kb0 + i) * kBlockK;
+        const int nks = k_left >= kBlockK ? kBlockK / kUmmaK : (k_left + kUmmaK - 1) / kUmmaK;
+        for (int pa = 0; pa < p.a_planes; ++pa)
+          for (int pb = 0; pb < p.b_planes; ++pb) {
+            if (pa + pb >= pmax) continue;
+            const uint32_t ta = sa + pa * kATileBytes;
+            const uint32_t tb = sb + pb * p.b_tile_bytes;
+            for (int ks = 0; ks < nks; ++ks) {
+              const uint64_t da = make_desc(ta + ks * a_kstep, a_lbo, 1024u);
+              const uint64_t db = make_desc(tb + ks * b_kstep, b_lbo, 1024u);
+              umma_bf16(tmem_base, da, db, p.idesc, accumulate);
+              accumulate = 1;
+            }
+          }
+        umma_commit(empty_bar(s));  // stage reusable once these MMAs retire
+      }
+      umma_commit(tmem_full_bar);   // accumulator complete
+    }
+    __syncwarp();
+  } else {
+    // ===================================== epilogue =====================================
+    const int q = warp & 3;  // TMEM lane quadrant this warp may access
+    const int m = m0 + q * 32 + lane;
+    const bool row_ok = m < p.M;
+    mbar_wait(tmem_full_bar, 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const bool vec_out = p.out_f32 && ((p.ld_out & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.out_f32) & 15) == 0);
+    const bool vec_aux = p.aux && ((p.ld_aux & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.aux) & 15) == 0);
+    float row_acc = 0.f;
+    const float* bias = blockIdx.z == 0 ? p.bias : nullptr;  // split-K: only the first slice adds the bias
+    for (int c = 0; c < p.block_n; c += 16) {
+      const int n = n0 + c;
+      if (n >= p.N) break;  // warp-uniform
+      uint32_t r[16];
+      tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, r);
+      if (!row_ok) continue;
+      float y[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        y[j] = __uint_as_float(r[j]);
+        if (bias && n + j < p.N) y[j] += __ldg(bias + n + j);
+      }
+      switch (p.epilogue) {
+        case MVAE_EPI_STORE: {
+          if (p.atomic_out) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+              if (n + j < p.N) {
+                if (n + j == p.col_split) {
+                  if (p.out_col) atomicAdd(p.out_col + m, y[j]);
+                } else if (p.out_f32) {
+                  atomicAdd(p.out_f32 + (int64_t)m * p.ld_out + n + j, y[j]);
+                }
+              }
+          } else if (p.col_split >= n && p.col_split < n + 16) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+              if (n + j < p.N) {
+                if (n + j == p.col_split) {
+                  if (p.out_col) p.out_col[m] = y[j];
+                } else if (p.out_f32) {
+                  p.out_f32[(int64_t)m * p.ld_out + n + j] = y[j];
+                }
+              }
+          } else if (p.out_f32) {
+            store_f32_16(p.out_f32, p.ld_out, m, n, p.N, y, vec_out);
+          }
+        } break;
+        case MVAE_EPI_BIAS_RELU: {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) y[j] = fmaxf(y[j], 0.f);
+          if (p.op_base) store_planes16(p, m, n, y);
+          if (p.out_f32) store_f32_16(p.out_f32, p.ld_out, m, n, p.N, y, vec_out);
+        } break;
+        case MVAE_EPI_RELU_MASK: {
+          const uint16_t* mk = p.mask + (int64_t)m * p.ld_mask + n;
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            // bf16 > 0  <=>  sign bit clear and magnitude non-zero
+            uint16_t b = (n + j < p.N) ? __ldg(mk + j) : (uint16_t)0;
+            bool pos = ((b & 0x8000u) == 0) && ((b & 0x7FFFu) != 0);
+            y[j] = pos ? y[j] : 0.f;
+          }
+          if (p.op_base) store_planes16(p, m, n, y);
+          if (p.out_f32) store_f32_16(p.out_f32, p.ld_out, m, n, p.N, y, vec_out);
+        } break;
+        default: {  // BCE_ROWSUM / NLL_ROWSUM
+          float t[16];
+          const float* xr = p.aux + (int64_t)m * p.ld_aux + n;
+          if (vec_aux && n + 16 <= p.N) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              float4 v = __ldg(reinterpret_cast<const float4*>(xr) + j);
+              t[4 * j] = v.x;
+              t[4 * j + 1] = v.y;
+              t[4 * j + 2] = v.z;
+              t[4 * j + 3] = v.w;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) t[j] = (n + j < p.N) ? __ldg(xr + j) : 0.f;
+          }
+          if (p.out_f32) store_f32_16(p.out_f32, p.ld_out, m, n, p.N, y, vec_out);
+          float g[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const float lg = y[j];
+            float loss;
+            if (p.epilogue == MVAE_EPI_BCE_ROWSUM) {
+              const float ex = expf(-fabsf(lg));
+              loss = (1.f - t[j]) * lg - (fminf(lg, 0.f) - log1pf(ex));
+              g[j] = 1.f / (1.f + expf(-lg)) - t[j];
+            } else {
+              const float dlt = t[j] - lg;
+              loss = (dlt * dlt) / 2.f + kHalfLn2PiG;
+              g[j] = lg - t[j];
+            }
+            if (n + j < p.N) row_acc += loss;
+          }
+          if (p.op_base) store_planes16(p, m, n, g);
+        } break;
+      }
+    }
+    if ((p.epilogue == MVAE_EPI_BCE_ROWSUM || p.epilogue == MVAE_EPI_NLL_ROWSUM) && row_ok && p.rowsum)
+      atomicAdd(p.rowsum + m, row_acc);
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  }
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols)
+                 : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(f);
+  });
+  return fn;
+}
+
+// 3-D map over split planes: dims {cols, rows, planes}; box {64, box_rows, 1}; 128-byte swizzle, zero OOB fill.
+static int encode_planes(CUtensorMap* map, const mvae_planes& pl, int cols_bound, int box_rows) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return MVAE_ERR_CUDA;
+  cuuint64_t dims[3] = {(cuuint64_t)cols_bound, (cuuint64_t)pl.rows, (cuuint64_t)pl.planes};
+  cuuint64_t strides[2] = {(cuuint64_t)pl.ld * 2, (cuuint64_t)(pl.planes > 1 ? pl.plane_stride : (int64_t)pl.rows * pl.ld) * 2};
+  cuuint32_t box[3] = {64, (cuuint32_t)box_rows, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, pl.base, dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? MVAE_OK : MVAE_ERR_CUDA;
+}
+
+static int check_planes(const mvae_planes& p) {
+  if (!p.base || p.planes < 1 || p.planes > 3 || p.rows < 1 || p.cols < 1 || p.ld < p.cols)
+    return MVAE_ERR_INVALID_ARGUMENT;
+  if ((p.ld & 7) || (reinterpret_cast<uintptr_t>(p.base) & 15)) return MVAE_ERR_ALIGNMENT;
+  if (p.planes > 1 && ((p.plane_stride & 7) || p.plane_stride < (int64_t)p.rows * p.ld)) return MVAE_ERR_ALIGNMENT;
+  return MVAE_OK;
+}
+
+static int round_up(int x, int m) { return (x + m - 1) / m * m; }
+
+// BLOCK_N: split N into t tiles of equal width (multiple of 16, <= cap) minimising padded columns.
+static int pick_block_n(int N, int cap) {
+  int best_bn = 0, best_waste = 1 << 30;
+  const int t0 = (N + cap - 1) / cap;
+  for (int t = t0; t <= t0 + 3; ++t) {
+    int bn = round_up((N + t - 1) / t, 16);
+    if (bn > cap) continue;
+    int waste = ((N + bn - 1) / bn) * bn - N;
+    if (waste < best_waste) {
+      best_waste = waste;
+      best_bn = bn;
+    }
+  }
+  return best_bn;
+}
+
+}  // namespace mvae
+
+using namespace mvae;
+
+extern "C" int mvae_gemm(const mvae_gemm_args* a, void* stream) {
+  if (!a) return MVAE_ERR_INVALID_ARGUMENT;
+  if (a->M < 1 || a->N < 1 || a->K < 1 || a->split_k < 1) return MVAE_ERR_INVALID_ARGUMENT;
+  if (a->epilogue < MVAE_EPI_STORE || a->epilogue > MVAE_EPI_NLL_ROWSUM) return MVAE_ERR_INVALID_ARGUMENT;
+  if (a->split_k > 1 && a->epilogue != MVAE_EPI_STORE) return MVAE_ERR_INVALID_ARGUMENT;
+  if ((a->a_major != MVAE_K_MAJOR && a->a_major != MVAE_MN_MAJOR) ||
+      (a->b_major != MVAE_K_MAJOR && a->b_major != MVAE_MN_MAJOR))
+    return MVAE_ERR_INVALID_ARGUMENT;
+  int rc = check_planes(a->a);
+  if (rc != MVAE_OK) return rc;
+  rc = check_planes(a->b);
+  if (rc != MVAE_OK) return rc;
+  // logical shapes
+  const int a_rows = a->a_major == MVAE_K_MAJOR ? a->M : a->K, a_cols = a->a_major == MVAE_K_MAJOR ? a->K : a->M;
+  const int b_rows = a->b_major == MVAE_K_MAJOR ? a->N : a->K, b_cols = a->b_major == MVAE_K_MAJOR ? a->K : a->N;
+  if (a->a.rows != a_rows || a->a.ld < a_cols || a->b.rows != b_rows || a->b.ld < b_cols)
+    return MVAE_ERR_INVALID_ARGUMENT;
+  if (a->epilogue == MVAE_EPI_STORE && !a->out_f32 && !a->out_col) return MVAE_ERR_INVALID_ARGUMENT;
+  if ((a->epilogue == MVAE_EPI_BCE_ROWSUM || a->epilogue == MVAE_EPI_NLL_ROWSUM) && (!a->aux || a->ld_aux < a->N))
+    return MVAE_ERR_INVALID_ARGUMENT;
+  if (a->epilogue == MVAE_EPI_RELU_MASK && (!a->mask || a->ld_mask < a->N)) return MVAE_ERR_INVALID_ARGUMENT;
+  if (a->out_f32 && a->ld_out < (a->col_split == a->N - 1 ? a->N - 1 : a->N)) return MVAE_ERR_INVALID_ARGUMENT;
+  if (a->out_planes.base) {
+    rc = check_planes(a->out_planes);
+    if (rc != MVAE_OK) return rc;
+    if (a->out_planes.rows < a->M || a->out_planes.ld < a->N) return MVAE_ERR_INVALID_ARGUMENT;
+  }
+  DeviceInfo di;
+  rc = get_device_info(&di);
+  if (rc != MVAE_OK) return rc;
+
+  GemmParams p;
+  memset(&p, 0, sizeof(p));
+  p.M = a->M;
+  p.N = a->N;
+  p.K = a->K;
+  p.a_major = a->a_major;
+  p.b_major = a->b_major;
+  p.a_planes = a->a.planes;
+  p.b_planes = a->b.planes;
+  // stage budget: keep >= 3 stages
+  const int smem_budget = di.max_smem_optin - 1024 /*align*/ - 256 /*barriers*/;
+  int cap = 256;
+  for (;;) {
+    const int bt = p.b_major == MVAE_K_MAJOR ? cap * 128 : round_up(cap, 64) * 128;
+    if (3 * (p.a_planes * kATileBytes + p.b_planes * bt) <= smem_budget || cap <= 32) break;
+    cap -= 16;
+  }
+  p.block_n = pick_block_n(a->N, cap);
+  if (p.block_n <= 0) return MVAE_ERR_UNSUPPORTED;
+  p.b_tile_bytes = p.b_major == MVAE_K_MAJOR ? p.block_n * 128 : round_up(p.block_n, 64) * 128;
+  const int stage_bytes = p.a_planes * kATileBytes + p.b_planes * p.b_tile_bytes;
+  p.kb_total = (a->K + kBlockK - 1) / kBlockK;
+  int split = a->split_k < p.kb_total ? a->split_k : p.kb_total;
+  p.kb_per_split = (p.kb_total + split - 1) / split;
+  split = (p.kb_total + p.kb_per_split - 1) / p.kb_per_split;
+  p.atomic_out = a->split_k > 1;
+  int stages = smem_budget / stage_bytes;
+  if (stages > kMaxStages) stages = kMaxStages;
+  if (stages > p.kb_per_split) stages = p.kb_per_split;
+  if (stages < 1) return MVAE_ERR_UNSUPPORTED;
+  p.stages = stages;
+  p.epilogue = a->epilogue;
+  p.tmem_cols = p.block_n <= 32 ? 32 : p.block_n <= 64 ? 64 : p.block_n <= 128 ? 128 : 256;
+  p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)p.a_major << 15) | ((uint32_t)p.b_major << 16) |
+            ((uint32_t)(p.block_n >> 3) << 17) | ((uint32_t)(kBlockM >> 4) << 24);
+  p.bias = a->bias;
+  p.out_f32 = a->out_f32;
+  p.ld_out = a->ld_out;
+  p.out_col = a->out_col;
+  p.col_split = a->col_split;
+  p.op_base = a->out_planes.base;
+  p.op_stride = a->out_planes.planes > 1 ? a->out_planes.plane_stride : 0;
+  p.op_ld = a->out_planes.ld;
+  p.op_planes = a->out_planes.base ? a->out_planes.planes : 0;
+  p.aux = a->aux;
+  p.ld_aux = a->ld_aux;
+  p.mask = a->mask;
+  p.ld_mask = a->ld_mask;
+  p.rowsum = a->rowsum;
+
+  CUtensorMap map_a, map_b;
+  // K-major: inner dim = K (logical), box rows = tile rows.  MN-major: inner dim = M or N (logical), box = 64 x 64.
+  rc = encode_planes(&map_a, a->a, a_cols, a->a_major == MVAE_K_MAJOR ? kBlockM : kBlockK);
+  if (rc != MVAE_OK) return rc;
+  rc = encode_planes(&map_b, a->b, b_cols, a->b_major == MVAE_K_MAJOR ? p.block_n : kBlockK);
+  if (rc != MVAE_OK) return rc;
+
+  const size_t smem = (size_t)stages * stage_bytes + 1024 + 256;
+  static std::once_flag attr_once[64];
+  int dev = 0;
+  MVAE_CUDA_TRY(cudaGetDevice(&dev));
+  cudaError_t attr_err = cudaSuccess;
+  std::call_once(attr_once[dev & 63], [&] {
+    attr_err = cudaFuncSetAttribute(gemm_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    di.max_smem_optin);
+  });
+  MVAE_CUDA_TRY(attr_err);
+  dim3 grid((a->M + kBlockM - 1) / kBlockM, (a->N + p.block_n - 1) / p.block_n, split);
+  gemm_tcgen05_kernel<<<grid, kGemmThreads, smem, as_stream(stream)>>>(map_a, map_b, p);
+  MVAE_LAUNCH_CHECK();
+  return MVAE_OK;
+}

@@ -1,0 +1,243 @@
+"""Tensor-level wrappers over the C ABI (include/mvae_b200.h).  torch is used for device memory and streams only:
+every function enqueues hand-written sm_100a kernels from libmvae_b200.so on torch's current CUDA stream.
+All tensors must be contiguous CUDA tensors (float32 unless stated).  No fallbacks."""
+import ctypes
+from typing import Optional, Sequence
+
+import torch
+
+from . import _lib as L
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _f32(t: torch.Tensor, name: str) -> torch.Tensor:
+    if not t.is_cuda:
+        raise L.MvaeError(f"{name}: expected a CUDA tensor (the mvae_b200 path has no CPU fallback)")
+    if t.dtype != torch.float32:
+        raise L.MvaeError(f"{name}: expected float32, got {t.dtype}")
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def parse_signature(sig: str):
+    """'2h3,s2,e2' -> ([types], [dims]); grammar of mt/mvae/utils.py:78-140 (letters e,h,s,p; 'd','u' unsupported)."""
+    types, dims = [], []
+    for tok in sig.lower().strip().split(","):
+        tok = tok.strip().split("-")[0]
+        i = 0
+        while i < len(tok) and tok[i].isdigit():
+            i += 1
+        mult = int(tok[:i]) if i else 1
+        j = i
+        while j < len(tok) and tok[j].isalpha():
+            j += 1
+        letter, dim = tok[i:j], int(tok[j:])
+        if letter not in L.TYPE_OF_LETTER:
+            raise ValueError(f"unsupported component letter {letter!r} in {sig!r}")
+        for _ in range(mult):
+            types.append(L.TYPE_OF_LETTER[letter])
+            dims.append(dim)
+    return types, dims
+
+
+def make_desc(sig_or_types, dims: Optional[Sequence[int]] = None, scalar_parametrization: bool = False) -> L.PmDesc:
+    if isinstance(sig_or_types, str):
+        types, dims = parse_signature(sig_or_types)
+    else:
+        types = list(sig_or_types)
+    return L.make_desc(types, list(dims), scalar_parametrization)
+
+
+# ------------------------------------------------------------------------------------------ product manifold
+def pm_forward(desc: L.PmDesc, ml, eps, radius, want_mu_sigma: bool = False, flag: Optional[torch.Tensor] = None,
+               out: Optional[dict] = None):
+    """Fused manifold + Wrapped-Normal forward (mvae_pm_forward).  Returns dict(z, kl[, mu, sigma])."""
+    ml, eps, radius = _f32(ml, "ml"), _f32(eps, "eps"), _f32(radius, "radius")
+    B = ml.shape[0]
+    assert ml.shape[1] == desc.ld_ml and eps.shape == (B, desc.ld_eps) and radius.numel() == desc.C
+    out = out or {}
+    dev = ml.device
+    z = out.get("z") if out.get("z") is not None else torch.empty(B, desc.ld_z, device=dev)
+    kl = out.get("kl") if out.get("kl") is not None else torch.empty(B, desc.C, device=dev)
+    mu = sigma = None
+    if want_mu_sigma:
+        mu = out.get("mu") if out.get("mu") is not None else torch.empty(B, desc.ld_z, device=dev)
+        sigma = out.get("sigma") if out.get("sigma") is not None else torch.empty(B, desc.ld_eps, device=dev)
+    rc = L.lib().mvae_pm_forward(ctypes.byref(desc), B, _ptr(ml), _ptr(eps), _ptr(radius), _ptr(z), _ptr(kl), _ptr(mu),
+                                 _ptr(sigma), _ptr(flag), _stream())
+    L.check(rc, "mvae_pm_forward")
+    res = {"z": z, "kl": kl}
+    if want_mu_sigma:
+        res.update(mu=mu, sigma=sigma)
+    return res
+
+
+def pm_backward(desc: L.PmDesc, ml, eps, radius, gz, gkl: Optional[torch.Tensor] = None, gkl_scalar: float = 1.0,
+                gml: Optional[torch.Tensor] = None, gradius: Optional[torch.Tensor] = None):
+    """Backward of pm_forward by recomputation (mvae_pm_backward).  gradius is ACCUMULATED (zeroed here if created)."""
+    ml, eps, radius, gz = _f32(ml, "ml"), _f32(eps, "eps"), _f32(radius, "radius"), _f32(gz, "gz")
+    gkl = None if gkl is None else _f32(gkl, "gkl")
+    B = ml.shape[0]
+    if gml is None:
+        gml = torch.empty_like(ml)
+    if gradius is None:
+        gradius = torch.zeros(desc.C, device=ml.device)
+    rc = L.lib().mvae_pm_backward(ctypes.byref(desc), B, _ptr(ml), _ptr(eps), _ptr(radius), _ptr(gz), _ptr(gkl),
+                                  float(gkl_scalar), _ptr(gml), _ptr(gradius), _stream())
+    L.check(rc, "mvae_pm_backward")
+    return gml, gradius
+
+
+# ------------------------------------------------------------------------------------------ standalone ops
+def manifold_op(op: int, manifold: int, n: int, x, y=None, radius=None):
+    x = _f32(x, "x")
+    lead = x.shape[:-1]
+    x2 = x.reshape(-1, x.shape[-1])
+    B = x2.shape[0]
+    d = n + 1 if manifold in (L.HYPERBOLOID, L.SPHERE) else n
+    out_w = {L.OP_EXP_MAP_MU0: d, L.OP_DISTANCE: 1, L.OP_LOGDET: 1, L.OP_TO_POINCARE: n,
+             L.OP_FROM_POINCARE: n + 1}.get(op, d)
+    y2 = None
+    if y is not None:
+        y2 = _f32(y, "y").reshape(B, -1)
+    out = torch.empty(B, out_w, device=x.device)
+    rc = L.lib().mvae_manifold_op(op, manifold, n, B, _ptr(x2), _ptr(y2), _ptr(radius), _ptr(out), _stream())
+    L.check(rc, "mvae_manifold_op")
+    return out.reshape(*lead, out_w)
+
+
+def wn_rsample(manifold: int, n: int, loc, scale, eps, radius):
+    loc, scale, eps = _f32(loc, "loc"), _f32(scale, "scale"), _f32(eps, "eps")
+    B = loc.shape[0]
+    z, u, v = torch.empty_like(loc), torch.empty_like(loc), torch.empty_like(scale)
+    rc = L.lib().mvae_wn_rsample(manifold, n, B, _ptr(loc), _ptr(scale), _ptr(eps), _ptr(radius), _ptr(z), _ptr(u),
+                                 _ptr(v), _stream())
+    L.check(rc, "mvae_wn_rsample")
+    return z, u, v
+
+
+def wn_log_prob_from_parts(manifold: int, n: int, loc, scale, z, u, v, radius):
+    args = [_f32(t, "arg") for t in (loc, scale, z, u, v)]
+    B = args[0].shape[0]
+    logp = torch.empty(B, device=args[0].device)
+    rc = L.lib().mvae_wn_log_prob_from_parts(manifold, n, B, *[_ptr(t) for t in args], _ptr(radius), _ptr(logp),
+                                             _stream())
+    L.check(rc, "mvae_wn_log_prob_from_parts")
+    return logp
+
+
+def wn_log_prob(manifold: int, n: int, loc, scale, z, radius):
+    args = [_f32(t, "arg") for t in (loc, scale, z)]
+    B = args[0].shape[0]
+    logp = torch.empty(B, device=args[0].device)
+    rc = L.lib().mvae_wn_log_prob(manifold, n, B, *[_ptr(t) for t in args], _ptr(radius), _ptr(logp), _stream())
+    L.check(rc, "mvae_wn_log_prob")
+    return logp
+
+
+# ------------------------------------------------------------------------------------------ losses / optimizer
+def recon_loss(kind: str, logits, x, want_grad: bool = False):
+    """kind 'bce' | 'nll' -> (rowsum [B], glogits | None)  (mvae_recon_loss)."""
+    logits, x = _f32(logits, "logits"), _f32(x, "x")
+    B, D = logits.shape
+    rs = torch.empty(B, device=logits.device)
+    g = torch.empty_like(logits) if want_grad else None
+    rc = L.lib().mvae_recon_loss(0 if kind == "bce" else 1, B, D, _ptr(logits), _ptr(x), _ptr(rs), _ptr(g), _stream())
+    L.check(rc, "mvae_recon_loss")
+    return rs, g
+
+
+def elbo_reduce(bce, kl, beta: float, out: Optional[torch.Tensor] = None):
+    """-> float32 [3 + C] = [bce_sum, kl_sum, elbo, kl_c sums]  (mvae_elbo_reduce)."""
+    bce, kl = _f32(bce, "bce"), _f32(kl, "kl")
+    B, C = kl.shape
+    if out is None:
+        out = torch.empty(3 + C, device=kl.device)
+    rc = L.lib().mvae_elbo_reduce(B, C, _ptr(bce), _ptr(kl), float(beta), _ptr(out), _stream())
+    L.check(rc, "mvae_elbo_reduce")
+    return out
+
+
+def adam_step(param, grad, exp_avg, exp_avg_sq, lr, step, beta1=0.9, beta2=0.999, eps=1e-8, grad_scale=1.0):
+    rc = L.lib().mvae_adam_step(param.numel(), _ptr(param), _ptr(grad), _ptr(exp_avg), _ptr(exp_avg_sq), float(lr),
+                                float(beta1), float(beta2), float(eps), int(step), float(grad_scale), _stream())
+    L.check(rc, "mvae_adam_step")
+
+
+def sgd_step(param, grad, lr, grad_scale=1.0):
+    rc = L.lib().mvae_sgd_step(param.numel(), _ptr(param), _ptr(grad), float(lr), float(grad_scale), _stream())
+    L.check(rc, "mvae_sgd_step")
+
+
+# ------------------------------------------------------------------------------------------ planes + GEMM
+def _round_up(x, m):
+    return (x + m - 1) // m * m
+
+
+class PlaneBuf:
+    """Split-bf16 operand planes [planes, rows, ld] of an fp32 matrix [rows, cols] (mvae_planes).
+    `ones_col=True` reserves column `cols` and fills it with 1.0: read as part of an MN-major wgrad operand it
+    yields the bias gradient (column sums of the other operand) for free."""
+
+    def __init__(self, rows: int, cols: int, planes: int = 2, device="cuda", ones_col: bool = False):
+        self.rows, self.cols, self.planes, self.ones_col = rows, cols, planes, ones_col
+        self.ld = _round_up(cols + (1 if ones_col else 0), 8)
+        self.t = torch.zeros(planes, rows, self.ld, dtype=torch.bfloat16, device=device)
+        if ones_col:
+            self.t[0, :, cols] = 1.0
+
+    def struct(self, rows: Optional[int] = None, cols: Optional[int] = None) -> L.Planes:
+        return L.Planes(self.t.data_ptr(), self.rows * self.ld, rows if rows is not None else self.rows,
+                        cols if cols is not None else self.cols, self.ld, self.planes)
+
+    def to_float(self) -> torch.Tensor:
+        return self.t.float().sum(0)[:, :self.cols]
+
+    def plane0(self) -> torch.Tensor:
+        return self.t[0]
+
+
+def split_planes(src: torch.Tensor, dst: Optional[PlaneBuf] = None, dst_t: Optional[PlaneBuf] = None):
+    src = _f32(src, "src")
+    R, K = src.shape
+    ds = dst.struct() if dst is not None else None
+    dt = dst_t.struct() if dst_t is not None else None
+    rc = L.lib().mvae_split_planes(_ptr(src), src.stride(0), R, K, ctypes.byref(ds) if ds is not None else None,
+                                   ctypes.byref(dt) if dt is not None else None, _stream())
+    L.check(rc, "mvae_split_planes")
+
+
+def gemm(a: PlaneBuf, b: PlaneBuf, M: int, N: int, K: int, a_major: int = L.K_MAJOR, b_major: int = L.K_MAJOR,
+         epilogue: int = L.EPI_STORE, split_k: int = 1, bias=None, out_f32=None, ld_out: Optional[int] = None,
+         out_col=None, col_split: int = -1, out_planes: Optional[PlaneBuf] = None, aux=None, mask: Optional[PlaneBuf] = None,
+         rowsum=None):
+    """D[M,N] = sum_k A[m,k] B[n,k] on tcgen05 tensor cores with a fused epilogue (mvae_gemm)."""
+    g = L.GemmArgs()
+    g.a = a.struct(rows=M if a_major == L.K_MAJOR else K, cols=K if a_major == L.K_MAJOR else M)
+    g.b = b.struct(rows=N if b_major == L.K_MAJOR else K, cols=K if b_major == L.K_MAJOR else N)
+    g.a_major, g.b_major = a_major, b_major
+    g.M, g.N, g.K = M, N, K
+    g.epilogue, g.split_k = epilogue, split_k
+    g.bias = bias.data_ptr() if bias is not None else None
+    if out_f32 is not None:
+        g.out_f32 = out_f32.data_ptr()
+        g.ld_out = ld_out if ld_out is not None else out_f32.stride(0)
+    g.out_col = out_col.data_ptr() if out_col is not None else None
+    g.col_split = col_split
+    if out_planes is not None:
+        g.out_planes = out_planes.struct()
+    if aux is not None:
+        g.aux = aux.data_ptr()
+        g.ld_aux = aux.stride(0)
+    if mask is not None:
+        g.mask = mask.t.data_ptr()
+        g.ld_mask = mask.ld
+    g.rowsum = rowsum.data_ptr() if rowsum is not None else None
+    rc = L.lib().mvae_gemm(ctypes.byref(g), _stream())
+    L.check(rc, "mvae_gemm")
