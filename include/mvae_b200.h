@@ -194,7 +194,8 @@ typedef struct mvae_gemm_args {
   int32_t b_major;
   int32_t M, N, K;
   int32_t epilogue;        /* mvae_epilogue                                            */
-  int32_t split_k;         /* >= 1; > 1 only with MVAE_EPI_STORE (atomic accumulate into zeroed out_f32/out_col) */
+  int32_t split_k;         /* 1 = none; k > 1 = k slices of K, 0 = as many as fill the SMs — both only with
+                              MVAE_EPI_STORE and atomically ACCUMULATING into out_f32/out_col (zero them first) */
   const float* bias;       /* [N] or NULL                                              */
   float* out_f32;          /* [M, ld_out] or NULL                                      */
   int64_t ld_out;

@@ -470,9 +470,9 @@ using namespace mvae;
 
 extern "C" int mvae_gemm(const mvae_gemm_args* a, void* stream) {
   if (!a) return MVAE_ERR_INVALID_ARGUMENT;
-  if (a->M < 1 || a->N < 1 || a->K < 1 || a->split_k < 1) return MVAE_ERR_INVALID_ARGUMENT;
+  if (a->M < 1 || a->N < 1 || a->K < 1 || a->split_k < 0) return MVAE_ERR_INVALID_ARGUMENT;
   if (a->epilogue < MVAE_EPI_STORE || a->epilogue > MVAE_EPI_NLL_ROWSUM) return MVAE_ERR_INVALID_ARGUMENT;
-  if (a->split_k > 1 && a->epilogue != MVAE_EPI_STORE) return MVAE_ERR_INVALID_ARGUMENT;
+  if (a->split_k != 1 && a->epilogue != MVAE_EPI_STORE) return MVAE_ERR_INVALID_ARGUMENT;
   if ((a->a_major != MVAE_K_MAJOR && a->a_major != MVAE_MN_MAJOR) ||
       (a->b_major != MVAE_K_MAJOR && a->b_major != MVAE_MN_MAJOR))
     return MVAE_ERR_INVALID_ARGUMENT;
@@ -521,10 +521,18 @@ extern "C" int mvae_gemm(const mvae_gemm_args* a, void* stream) {
   p.b_tile_bytes = p.b_major == MVAE_K_MAJOR ? p.block_n * 128 : round_up(p.block_n, 64) * 128;
   const int stage_bytes = p.a_planes * kATileBytes + p.b_planes * p.b_tile_bytes;
   p.kb_total = (a->K + kBlockK - 1) / kBlockK;
-  int split = a->split_k < p.kb_total ? a->split_k : p.kb_total;
+  int split = a->split_k;
+  if (split == 0) {
+    // auto: enough K slices to put one CTA on every SM, each slice keeping >= 4 k-blocks
+    const int tiles = ((a->M + kBlockM - 1) / kBlockM) * ((a->N + p.block_n - 1) / p.block_n);
+    split = di.sm_count / tiles;
+    if (split > p.kb_total / 4) split = p.kb_total / 4;
+    if (split < 1) split = 1;
+  }
+  if (split > p.kb_total) split = p.kb_total;
   p.kb_per_split = (p.kb_total + split - 1) / split;
   split = (p.kb_total + p.kb_per_split - 1) / p.kb_per_split;
-  p.atomic_out = a->split_k > 1;
+  p.atomic_out = split > 1;
   int stages = smem_budget / stage_bytes;
   if (stages > kMaxStages) stages = kMaxStages;
   if (stages > p.kb_per_split) stages = p.kb_per_split;

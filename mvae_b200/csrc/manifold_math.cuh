@@ -7,9 +7,17 @@
 //   mt/mvae/distributions/wrapped_normal.py:70-103, mt/mvae/ops/{hyperbolics,spherical,euclidean,poincare}.py,
 //   guarded scalar math mt/mvae/ops/common.py:28-147 (LeakyClamp / Atanh / Acosh custom backward rules),
 //   geoopt==0.1.0 poincare math for the Poincare ball (un-vendored third party; constants as in DESIGN.md).
-// With BWD the function also runs the reverse sweep of that chain by recomputation (hand-derived; the
-// autograd conventions of the reference — leaky clamps pass 1e-8*g outside, plain clamps pass 0,
-// Acosh.backward = g / sqrt(x'^2-1) — are reproduced, not "fixed").
+// With BWD the function also runs the reverse sweep of that chain by recomputation (hand-derived).
+//
+// Formulation.  The reference evaluates the chain through ambient-space vector algebra (Lorentz products,
+// z - alpha*mu0, 1 - alpha^2, Poincare->Lorentz conversions) that cancels catastrophically in float32; its own
+// float32 run is only 1e-3 accurate on these terms.  The kernels evaluate the SAME functions
+// in the closed forms those expressions reduce to on the manifold (parallel transport is an isometry:
+// |u| = |v|; the prior's tangent vector has norm dist(mu0, z); Poincare and hyperboloid log-dets coincide), which
+// are well conditioned, so the float32 kernels track the reference's default float64 path to ~1e-6.  Guards of
+// the reference are kept where they act on these closed forms: +-85 clamp of cosh/sinh arguments, sqrt clamp at
+// 1e-9 with its leaky (1e-8) gradient, plain clamps (zero gradient) in the sphere log-det, geoopt's tanh (+-15)
+// and artanh (1-1e-5) clamps and MIN_NORM.  Derivations: DESIGN.md section 4.
 //
 // N > 0: true dimension known at compile time (everything lives in registers); N == 0: runtime n <= kDynMaxN
 // (arrays spill to local memory — slow path for unusually wide components).
@@ -98,9 +106,35 @@ struct CompOut {
   float mu[Cap<N>::d];
   float sigma[Cap<N>::n];
   float z[Cap<N>::d];
-  float u[Cap<N>::d];
-  float kl, logq, logp;
+  float kl;
 };
+
+// F(x) = log(sinh(x) / x) = logsinh(x) - log(x)  (hyperbolics.py:58-65 with common.py:122-128), x > 0.
+// 1 - e^{-2x} is taken from expm1 so that small x does not cancel.
+MVAE_DEV float log_sinhc(float x) {
+  float em = -expm1f(-2.f * x);
+  return x + logf(em / (2.f * x));
+}
+// F'(x) = coth(x) - 1/x
+MVAE_DEV float log_sinhc_d(float x) {
+  if (x < 0.25f) {
+    float x2 = x * x;
+    return x * (1.f / 3.f - x2 * (1.f / 45.f - x2 * (2.f / 945.f - x2 * (1.f / 4725.f))));
+  }
+  float E = expf(-2.f * x);
+  return (1.f + E) / (1.f - E) - 1.f / x;
+}
+// G(x) = log clamp(|sin x|, 1e-5) - log clamp(x, 1e-5)  (spherical.py:58-67, plain clamps: zero gradient outside)
+MVAE_DEV float log_sinc_abs(float x, float sn) {
+  return logf(fmaxf(fabsf(sn), 1e-5f)) - logf(fmaxf(x, 1e-5f));
+}
+MVAE_DEV float log_sinc_abs_d(float x, float sn, float cs) {
+  float as = fabsf(sn);
+  float d = 0.f;
+  if (as >= 1e-5f) d += (sn > 0.f ? cs : -cs) / as;
+  if (x >= 1e-5f) d -= 1.f / x;
+  return d;
+}
 
 // sigma_j = softplus(l_j) + 1e-5 (component.py:69-72; scalar parametrization repeats one value, wrapped_normal.py:46-49)
 template <int N>
@@ -144,24 +178,18 @@ MVAE_DEV void comp_e(int n, int l_n, const float* m, const float* l, const float
   MVAE_UN(N);
   constexpr int CN = Cap<N>::n;
   load_sigma<N>(n, l_n, l, o.sigma);
-  float kl = 0.f, lq = 0.f, lpz = 0.f;
+  float kl = 0.f;
   MVAE_UNROLL
   for (int j = 0; j < CN; ++j)
     if (j < n) {
       float mu = m[j] / 2.f;
       float s = o.sigma[j];
-      float z = mu + e[j] * s;
       o.mu[j] = mu;
-      o.z[j] = z;
-      o.u[j] = 0.f;
+      o.z[j] = mu + e[j] * s;
       float var_ratio = s * s;
       kl += 0.5f * (var_ratio + mu * mu - 1.f - logf(var_ratio));
-      lq += -((z - mu) * (z - mu)) / (2.f * s * s) - logf(s) - kHalfLn2Pi;
-      lpz += -(z * z) / 2.f - kHalfLn2Pi;
     }
   o.kl = kl;
-  o.logq = lq;
-  o.logp = lpz;
   if (!BWD) return;
   float g_s[CN];
   MVAE_UNROLL
@@ -174,873 +202,306 @@ MVAE_DEV void comp_e(int n, int l_n, const float* m, const float* l, const float
   store_gl<N>(n, l_n, l, g_s, gl);
 }
 
-// =============================================== HYPERBOLOID ===============================================
-// H._logdet (hyperbolics.py:58-65) on the Lorentz squared norm `pr` of u:
-// (n-1)(log R + logsinh(r) - log r), r = sqrt_g(pr)/R.  With BWD: *g_pr = g * d(ld)/d(pr), *gR += g * d(ld)/dR.
-template <bool BWD>
-MVAE_DEV float h_logdet_pr(int n, float pr, float R, float g, float* g_pr, float* gR) {
-  float s = sqrt_g(pr);
-  float r = s / R;
-  float dls = 0.f;
-  float ld = (float)(n - 1) * (logf(R) + logsinh_g<BWD>(r, &dls) - logf(r));
-  if (BWD) {
-    float g_r = g * (float)(n - 1) * (dls - 1.f / r);
-    *gR += g * (float)(n - 1) / R - g_r * r / R;
-    *g_pr = (g_r / R) * sqrt_g_d(pr, s);
-  }
-  return ld;
-}
-
-// Forward: component.py:63-75, hyperbolics.py:114-121 (exp_map_mu0), :87-93 (PT mu0->mu), :106-111 (exp_map),
-// wrapped_normal.py:84-103, hyperbolics.py:58-65 (logdet), :124-128 (inverse_exp_map), :96-103,145-148 (inverse PT).
-template <int N, bool BWD>
-MVAE_DEV void comp_h(int n, int l_n, const float* m, const float* l, const float* e, float R, CompOut<N>& o,
-                     const float* gz, float gkl, float* gm, float* gl, float* gR_out) {
-  MVAE_UN(N);
-  constexpr int CN = Cap<N>::n;
-  constexpr int CD = Cap<N>::d;
-  const int d = n + 1;
-  // ---- encode ----
-  float nm2 = 0.f;
-  MVAE_UNROLL
-  for (int j = 0; j < CN; ++j)
-    if (j < n) nm2 += m[j] * m[j];
-  float nm = sqrtf(nm2);
-  float a = nm / R;
-  float dn = fmaxf(nm, 1e-12f);
-  float ch, sh;
-  coshsinh_g(a, &ch, &sh);
-  float* mu = o.mu;
-  float xn[CN];
-  mu[0] = ch * R;
-  MVAE_UNROLL
-  for (int j = 0; j < CN; ++j)
-    if (j < n) {
-      xn[j] = (m[j] / dn) * R;
-      mu[j + 1] = sh * xn[j];
-    }
-  float* sg = o.sigma;
-  load_sigma<N>(n, l_n, l, sg);
-  // ---- sample: v = eps*sigma; u = PT_{mu0->mu}([0,v]); z = exp_mu(u) ----
-  float v[CN];
-  float lp = 0.f;
-  MVAE_UNROLL
-  for (int j = 0; j < CN; ++j)
-    if (j < n) {
-      v[j] = e[j] * sg[j];
-      lp += mu[j + 1] * v[j];
-    }
-  float denom = R * (R + mu[0]);
-  float coef = lp / denom;
-  float* u = o.u;
-  u[0] = coef * (mu[0] + R);
-  float pr = u[0] * u[0];
-  MVAE_UNROLL
-  for (int j = 0; j < CN; ++j)
-    if (j < n) {
-      u[j + 1] = v[j] + coef * mu[j + 1];
-      pr += u[j + 1] * u[j + 1];
-    }
-  pr = pr - 2.f * (u[0] * u[0]);
-  float ln = sqrt_g(pr);
-  float t = ln / R;
-  float cht, sht;
-  coshsinh_g(t, &cht, &sht);
-  float* z = o.z;
-  float un[CD];
-  MVAE_UNROLL
-  for (int k = 0; k < CD; ++k)
-    if (k < d) {
-      un[k] = u[k] / t;
-      z[k] = cht * mu[k] + sht * un[k];
-    }
-  // ---- log q ----
-  float nlp = 0.f;
-  MVAE_UNROLL
-  for (int j = 0; j < CN; ++j)
-    if (j < n) nlp += -(v[j] * v[j]) / (2.f * (sg[j] * sg[j])) - logf(sg[j]) - kHalfLn2Pi;
-  float ld = h_logdet_pr<false>(n, pr, R, 0.f, nullptr, nullptr);
-  o.logq = nlp - ld;
-  // ---- log p: at_point mu0 = [R,0..]; alpha = -<mu0,z>_L / R^2 ----
-  float lpz = R * z[0] - 2.f * (R * z[0]);
-  float alpha = -lpz / (R * R);
-  float zz;
-  float ach = acosh_g(alpha, &zz);
-  float sq = sqrt_g(alpha * alpha - 1.f);
-  float coefp = ach / sq;
-  float w[CD];
-  w[0] = coefp * (z[0] - alpha * R);
-  float pr0 = w[0] * w[0];
-  float nlp0 = 0.f;
-  MVAE_UNROLL
-  for (int j = 0; j < CN; ++j)
-    if (j < n) {
-      w[j + 1] = coefp * z[j + 1];
-      pr0 += w[j + 1] * w[j + 1];
-      nlp0 += -(w[j + 1] * w[j + 1]) / 2.f - kHalfLn2Pi;  // v0 = w[1:] (inverse PT to mu0 leaves the tail unchanged)
-    }
-  pr0 = pr0 - 2.f * (w[0] * w[0]);
-  float ld0 = h_logdet_pr<false>(n, pr0, R, 0.f, nullptr, nullptr);
-  o.logp = nlp0 - ld0;
-  o.kl = o.logq - o.logp;
-  if (!BWD) return;
-
-  // ================================ reverse sweep ================================
-  float gR = 0.f;
-  const float g_logq = gkl, g_logp = -gkl;
-  // logp = nlp0 - ld0
-  float g_pr0;
-  (void)h_logdet_pr<true>(n, pr0, R, -g_logp, &g_pr0, &gR);
-  float gw[CD];
-  gw[0] = g_pr0 * (-2.f * w[0]);
-  MVAE_UNROLL
-  for (int j = 0; j < CN; ++j)
-    if (j < n) gw[j + 1] = g_pr0 * 2.f * w[j + 1] + g_logp * (-w[j + 1]);
-  // inverse PT: c2 = -w0/(R+R) multiplies [2R, 0...]; only its (discarded) 0-th output depends on it -> no gradient.
-  // w = coefp (z - alpha mu0)
-  float gzt[CD];
-  float g_coefp = gw[0] * (z[0] - alpha * R);
-  float g_alpha = -gw[0] * coefp * R;
-  float g_mu0p0 = -gw[0] * coefp * alpha;
-  gzt[0] = gz[0] + gw[0] * coefp;
-  MVAE_UNROLL
-  for (int j = 0; j < CN; ++j)
-    if (j < n) {
-      g_coefp += gw[j + 1] * z[j + 1];
-      gzt[j + 1] = gz[j + 1] + gw[j + 1] * coefp;
-    }
-  float g_ach = g_coefp / sq;
-  float g_sq = -g_coefp * ach / (sq * sq);
-  g_alpha += g_sq * sqrt_g_d(alpha * alpha - 1.f, sq) * 2.f * alpha;
-  g_alpha += g_ach / zz;
-  // alpha = -lpz / R^2 ; lpz = mu0p0*z0 - 2 mu0p0*z0
-  float g_lpz = -g_alpha / (R * R);
-  gR += g_alpha * (-2.f * alpha / R);
-  gzt[0] += -g_lpz * R;
-  g_mu0p0 += -g_lpz * z[0];
-  gR += g_mu0p0;  // mu_0 = e_0 * radius (hyperbolics.py:68-69)
-  // logq = nlp - ld
-  float g_pr;
-  (void)h_logdet_pr<true>(n, pr, R, -g_logq, &g_pr, &gR);
-  const float g_nlp = g_logq;
-  // z = cht*mu + sht*un ; un = u/t
-  float g_cht = 0.f, g_sht = 0.f, g_t = 0.f;
-  float g_mu[CD], gu[CD];
-  MVAE_UNROLL
-  for (int k = 0; k < CD; ++k)
-    if (k < d) {
-      g_cht += gzt[k] * mu[k];
-      g_sht += gzt[k] * un[k];
-      g_mu[k] = gzt[k] * cht;
-      float g_un = gzt[k] * sht;
-      gu[k] = g_un / t;
-      g_t += -g_un * u[k] / (t * t);
-    }
-  g_t += (g_cht * sht + g_sht * cht) * lclamp_d(t, -kMaxHyp, kMaxHyp);
-  float g_ln = g_t / R;
-  gR += -g_t * t / R;
-  g_pr += g_ln * sqrt_g_d(pr, ln);
-  gu[0] += g_pr * -2.f * u[0];
-  MVAE_UNROLL
-  for (int j = 0; j < CN; ++j)
-    if (j < n) gu[j + 1] += g_pr * 2.f * u[j + 1];
-  // u0 = coef (mu0 + R); u_j = v_j + coef mu_j
-  float g_coef = gu[0] * (mu[0] + R);
-  g_mu[0] += gu[0] * coef;
-  gR += gu[0] * coef;
-  float g_v[CN];
-  MVAE_UNROLL
-  for (int j = 0; j < CN; ++j)
-    if (j < n) {
-      g_coef += gu[j + 1] * mu[j + 1];
-      g_v[j] = gu[j + 1];
-      g_mu[j + 1] += gu[j + 1] * coef;
-    }
-  float g_lp = g_coef / denom;
-  float g_denom = -g_coef * coef / denom;
-  MVAE_UNROLL
-  for (int j = 0; j < CN; ++j)
-    if (j < n) {
-      g_mu[j + 1] += g_lp * v[j];
-      g_v[j] += g_lp * mu[j + 1];
-    }
-  gR += g_denom * (2.f * R + mu[0]);
-  g_mu[0] += g_denom * R;
-  // nlp, v = e*sigma
-  float g_s[CN];
-  MVAE_UNROLL
-  for (int j = 0; j < CN; ++j)
-    if (j < n) {
-      float s = sg[j];
-      g_v[j] += g_nlp * (-v[j] / (s * s));
-      g_s[j] = g_nlp * (v[j] * v[j] / (s * s * s) - 1.f / s) + g_v[j] * e[j];
-    }
-  store_gl<N>(n, l_n, l, g_s, gl);
-  // mu0 = ch R ; mu_j = sh xn_j ; xn = m/dn*R
-  float g_ch = g_mu[0] * R;
-  gR += g_mu[0] * ch;
-  float g_sh = 0.f, g_dn = 0.f;
-  MVAE_UNROLL
-  for (int j = 0; j < CN; ++j)
-    if (j < n) {
-      g_sh += g_mu[j + 1] * xn[j];
-      float g_xn = g_mu[j + 1] * sh;
-      gR += g_xn * m[j] / dn;
-      gm[j] = g_xn * R / dn;
-      g_dn += -g_xn * R * m[j] / (dn * dn);
-    }
-  float g_a = (g_ch * sh + g_sh * ch) * lclamp_d(a, -kMaxHyp, kMaxHyp);
-  float g_nm = (nm >= 1e-12f) ? g_dn : 0.f;
-  g_nm += g_a / R;
-  gR += -g_a * a / R;
-  if (nm > 0.f) {
-    float k = g_nm / nm;
-    MVAE_UNROLL
-    for (int j = 0; j < CN; ++j)
-      if (j < n) gm[j] += k * m[j];
-  }
-  *gR_out = gR;
-}
-
-// ================================================== SPHERE ==================================================
-// S._logdet (spherical.py:58-67) on nu = ||u||_2: (n-1)(log R + log clamp(|sin r|, 1e-5) - log clamp(r, 1e-5)), plain clamps.
-template <bool BWD>
-MVAE_DEV float s_logdet_nu(int n, float nu, float R, float g, float* g_nu, float* gR) {
-  float r = nu / R;
-  float sn = sinf(r);
-  float as = fabsf(sn);
-  float asc = fmaxf(as, 1e-5f);
-  float rc = fmaxf(r, 1e-5f);
-  float ld = (float)(n - 1) * (logf(R) + logf(asc) - logf(rc));
-  if (BWD) {
-    float k1 = g * (float)(n - 1);
-    *gR += k1 / R;
-    float g_r = 0.f;
-    if (as >= 1e-5f) g_r += k1 / asc * (sn > 0.f ? 1.f : (sn < 0.f ? -1.f : 0.f)) * cosf(r);
-    if (r >= 1e-5f) g_r += -k1 / rc;
-    *gR += -g_r * r / R;
-    *g_nu = g_r / R;
-  }
-  return ld;
-}
-
-// spherical.py:94-101 (exp_map_mu0), :74-77 (PT), :86-91 (exp_map), :104-109 (inverse_exp_map), :80-83 (inverse PT).
-template <int N, bool BWD>
-MVAE_DEV void comp_s(int n, int l_n, const float* m, const float* l, const float* e, float R, CompOut<N>& o,
-                     const float* gz, float gkl, float* gm, float* gl, float* gR_out) {
-  MVAE_UN(N);
-  constexpr int CN = Cap<N>::n;
-  constexpr int CD = Cap<N>::d;
-  const int d = n + 1;
-  float nm2 = 0.f;
-  MVAE_UNROLL
-  for (int j = 0; j < CN; ++j)
-    if (j < n) nm2 += m[j] * m[j];
-  float nm = sqrtf(nm2);
-  float a = nm / R;
-  float dn = fmaxf(nm, 1e-12f);
-  float ca = cosf(a), sa = sinf(a);
-  float* mu = o.mu;
-  float xn[CN];
-  mu[0] = ca * R;
-  MVAE_UNROLL
-  for (int j = 0; j < CN; ++j)
-    if (j < n) {
-      xn[j] = (m[j] / dn) * R;
-      mu[j + 1] = sa * xn[j];
-    }
-  float* sg = o.sigma;
-  load_sigma<N>(n, l_n, l, sg);
-  float v[CN];
-  float dp = 0.f;
-  MVAE_UNROLL
-  for (int j = 0; j < CN; ++j)
-    if (j < n) {
-      v[j] = e[j] * sg[j];
-      dp += mu[j + 1] * v[j];
-    }
-  float denom = R * (R + mu[0]);
-  float coef = dp / denom;
-  float* u = o.u;
-  u[0] = 0.f - coef * (mu[0] + R);
-  float nu2 = u[0] * u[0];
-  MVAE_UNROLL
-  for (int j = 0; j < CN; ++j)
-    if (j < n) {
-      u[j + 1] = v[j] - coef * mu[j + 1];
-      nu2 += u[j + 1] * u[j + 1];
-    }
-  float nu = sqrtf(nu2);
-  float t = nu / R;
-  float ct = cosf(t), st = sinf(t);
-  float* z = o.z;
-  float un[CD];
-  MVAE_UNROLL
-  for (int k = 0; k < CD; ++k)
-    if (k < d) {
-      un[k] = u[k] / t;
-      z[k] = ct * mu[k] + st * un[k];
-    }
-  float nlp = 0.f;
-  MVAE_UNROLL
-  for (int j = 0; j < CN; ++j)
-    if (j < n) nlp += -(v[j] * v[j]) / (2.f * (sg[j] * sg[j])) - logf(sg[j]) - kHalfLn2Pi;
-  float ld = s_logdet_nu<false>(n, nu, R, 0.f, nullptr, nullptr);
-  o.logq = nlp - ld;
-  // prior: at_point = mu0 = [R, 0..]
-  float alpha = (R * z[0]) / (R * R);
-  float alc = fminf(fmaxf(alpha, -1.f), 1.f);
-  float ac_ = acosf(alc);
-  float om = 1.f - alpha * alpha;
-  float sq = sqrt_g(om);
-  float coefp = ac_ / sq;
-  float w[CD];
-  w[0] = coefp * (z[0] - alpha * R);
-  float nw2 = w[0] * w[0];
-  float nlp0 = 0.f;
-  MVAE_UNROLL
-  for (int j = 0; j < CN; ++j)
-    if (j < n) {
-      w[j + 1] = coefp * z[j + 1];
-      nw2 += w[j + 1] * w[j + 1];
-      nlp0 += -(w[j + 1] * w[j + 1]) / 2.f - kHalfLn2Pi;
-    }
-  float nw = sqrtf(nw2);
-  float ld0 = s_logdet_nu<false>(n, nw, R, 0.f, nullptr, nullptr);
-  o.logp = nlp0 - ld0;
-  o.kl = o.logq - o.logp;
-  if (!BWD) return;
-
-  float gR = 0.f;
-  const float g_logq = gkl, g_logp = -gkl;
-  float g_nw;
-  (void)s_logdet_nu<true>(n, nw, R, -g_logp, &g_nw, &gR);
-  float kw = nw > 0.f ? g_nw / nw : 0.f;
-  float gw[CD];
-  gw[0] = kw * w[0];
-  MVAE_UNROLL
-  for (int j = 0; j < CN; ++j)
-    if (j < n) gw[j + 1] = kw * w[j + 1] + g_logp * (-w[j + 1]);
-  // w0 = coefp (z0 - alpha R); w_k = coefp z_k
-  float gzt[CD];
-  float g_coefp = gw[0] * (z[0] - alpha * R);
-  gzt[0] = gz[0] + gw[0] * coefp;
-  float g_alpha = -gw[0] * coefp * R;
-  gR += -gw[0] * coefp * alpha;  // via mu0[0] = R
-  MVAE_UNROLL
-  for (int j = 0; j < CN; ++j)
-    if (j < n) {
-      g_coefp += gw[j + 1] * z[j + 1];
-      gzt[j + 1] = gz[j + 1] + gw[j + 1] * coefp;
-    }
-  float g_ac = g_coefp / sq;
-  float g_sq = -g_coefp * ac_ / (sq * sq);
-  g_alpha += g_sq * sqrt_g_d(om, sq) * (-2.f * alpha);
-  if (alpha >= -1.f && alpha <= 1.f) g_alpha += g_ac * (-1.f / sqrtf(1.f - alc * alc));
-  // alpha = (mu0 . z)/R^2, mu0 = [R,0..]
-  gzt[0] += g_alpha * R / (R * R);
-  gR += g_alpha * z[0] / (R * R);
-  gR += g_alpha * (-2.f * alpha / R);
-  // logq
-  float g_nu;
-  (void)s_logdet_nu<true>(n, nu, R, -g_logq, &g_nu, &gR);
-  const float g_nlp = g_logq;
-  float g_ct = 0.f, g_st = 0.f, g_t = 0.f;
-  float g_mu[CD], gu[CD];
-  MVAE_UNROLL
-  for (int k = 0; k < CD; ++k)
-    if (k < d) {
-      g_ct += gzt[k] * mu[k];
-      g_st += gzt[k] * un[k];
-      g_mu[k] = gzt[k] * ct;
-      float g_un = gzt[k] * st;
-      gu[k] = g_un / t;
-      g_t += -g_un * u[k] / (t * t);
-    }
-  g_t += -g_ct * st + g_st * ct;
-  g_nu += g_t / R;
-  gR += -g_t * t / R;
-  if (nu > 0.f) {
-    float k = g_nu / nu;
-    MVAE_UNROLL
-    for (int k2 = 0; k2 < CD; ++k2)
-      if (k2 < d) gu[k2] += k * u[k2];
-  }
-  // u0 = -coef (mu0+R); u_j = v_j - coef mu_j
-  float g_coef = -gu[0] * (mu[0] + R);
-  g_mu[0] += -gu[0] * coef;
-  gR += -gu[0] * coef;
-  float g_v[CN];
-  MVAE_UNROLL
-  for (int j = 0; j < CN; ++j)
-    if (j < n) {
-      g_coef += -gu[j + 1] * mu[j + 1];
-      g_v[j] = gu[j + 1];
-      g_mu[j + 1] += -gu[j + 1] * coef;
-    }
-  float g_dp = g_coef / denom;
-  float g_denom = -g_coef * coef / denom;
-  MVAE_UNROLL
-  for (int j = 0; j < CN; ++j)
-    if (j < n) {
-      g_mu[j + 1] += g_dp * v[j];
-      g_v[j] += g_dp * mu[j + 1];
-    }
-  gR += g_denom * (2.f * R + mu[0]);
-  g_mu[0] += g_denom * R;
-  float g_s[CN];
-  MVAE_UNROLL
-  for (int j = 0; j < CN; ++j)
-    if (j < n) {
-      float s = sg[j];
-      g_v[j] += g_nlp * (-v[j] / (s * s));
-      g_s[j] = g_nlp * (v[j] * v[j] / (s * s * s) - 1.f / s) + g_v[j] * e[j];
-    }
-  store_gl<N>(n, l_n, l, g_s, gl);
-  float g_ca = g_mu[0] * R;
-  gR += g_mu[0] * ca;
-  float g_sa = 0.f, g_dn = 0.f;
-  MVAE_UNROLL
-  for (int j = 0; j < CN; ++j)
-    if (j < n) {
-      g_sa += g_mu[j + 1] * xn[j];
-      float g_xn = g_mu[j + 1] * sa;
-      gR += g_xn * m[j] / dn;
-      gm[j] = g_xn * R / dn;
-      g_dn += -g_xn * R * m[j] / (dn * dn);
-    }
-  float g_a = -g_ca * sa + g_sa * ca;
-  float g_nm = (nm >= 1e-12f) ? g_dn : 0.f;
-  g_nm += g_a / R;
-  gR += -g_a * a / R;
-  if (nm > 0.f) {
-    float k = g_nm / nm;
-    MVAE_UNROLL
-    for (int j = 0; j < CN; ++j)
-      if (j < n) gm[j] += k * m[j];
-  }
-  *gR_out = gR;
-}
-
-// ============================================== POINCARE BALL ==============================================
+// ---- geoopt 0.1.0 guards used by the Poincare ball (poincare.py) ----
 // poincare.py + geoopt 0.1.0 poincare math (MIN_NORM 1e-15, tanh clamp +-15, artanh clamp 1-1e-5).
 constexpr float kPMin = 1e-15f;
 MVAE_DEV float cmin_d(float x, float lo) { return x >= lo ? 1.f : 0.f; }
 MVAE_DEV float tanh_c(float x) { return tanhf(fminf(fmaxf(x, -15.f), 15.f)); }
-MVAE_DEV float tanh_c_d(float x, float y) { return (x >= -15.f && x <= 15.f) ? (1.f - y * y) : 0.f; }
+// sech^2 of the clamped argument = 1 - tanh_c(x)^2, from one exponential (exact to rounding for large |x|)
+MVAE_DEV float sech2_c(float x) {
+  float e = expf(-2.f * fminf(fabsf(x), 15.f));
+  float d = 1.f + e;
+  return 4.f * e / (d * d);
+}
+MVAE_DEV float tanh_c_d(float x, float) { return (x >= -15.f && x <= 15.f) ? sech2_c(x) : 0.f; }
 MVAE_DEV float artanh_go(float x, float* xc_out) {
   float xc = fminf(fmaxf(x, -1.0f + 1e-5f), 1.0f - 1e-5f);
   *xc_out = xc;
   return (log1pf(xc) - log1pf(-xc)) * 0.5f;
 }
 
-// mobius_add(x, y, c) over n coordinates; sv = {x2, y2, xy, den}
-template <int N>
-MVAE_DEV void mobius_add(int n, const float* x, const float* y, float c, float* out, float* sv) {
-  MVAE_UN(N);
-  constexpr int CN = Cap<N>::n;
-  constexpr int CD = Cap<N>::d;
-  (void)CN; (void)CD;
-  float x2 = 0.f, y2 = 0.f, xy = 0.f;
-  MVAE_UNROLL
-  for (int j = 0; j < CN; ++j)
-    if (j < n) {
-      x2 += x[j] * x[j];
-      y2 += y[j] * y[j];
-      xy += x[j] * y[j];
-    }
-  float A = 1.f + 2.f * c * xy + c * y2;
-  float Bc = 1.f - c * x2;
-  float den = 1.f + 2.f * c * xy + c * c * x2 * y2;
-  float dc = fmaxf(den, kPMin);
-  MVAE_UNROLL
-  for (int j = 0; j < CN; ++j)
-    if (j < n) out[j] = (A * x[j] + Bc * y[j]) / dc;
-  sv[0] = x2;
-  sv[1] = y2;
-  sv[2] = xy;
-  sv[3] = den;
-}
-// accumulates into gx, gy (either may be nullptr), *gc
-template <int N>
-MVAE_DEV void mobius_add_bwd(int n, const float* x, const float* y, float c, const float* sv, const float* gout,
-                             float* gx, float* gy, float* gc) {
-  MVAE_UN(N);
-  constexpr int CN = Cap<N>::n;
-  constexpr int CD = Cap<N>::d;
-  (void)CN; (void)CD;
-  float x2 = sv[0], y2 = sv[1], xy = sv[2], den = sv[3];
-  float A = 1.f + 2.f * c * xy + c * y2;
-  float Bc = 1.f - c * x2;
-  float dc = fmaxf(den, kPMin);
-  float g_A = 0.f, g_B = 0.f, g_dc = 0.f;
-  MVAE_UNROLL
-  for (int j = 0; j < CN; ++j)
-    if (j < n) {
-      float num = A * x[j] + Bc * y[j];
-      float gn = gout[j] / dc;
-      g_dc += -gout[j] * num / (dc * dc);
-      g_A += gn * x[j];
-      g_B += gn * y[j];
-      if (gx) gx[j] += gn * A;
-      if (gy) gy[j] += gn * Bc;
-    }
-  float g_den = g_dc * cmin_d(den, kPMin);
-  float g_xy = g_A * 2.f * c + g_den * 2.f * c;
-  float g_y2 = g_A * c + g_den * c * c * x2;
-  float g_x2 = -g_B * c + g_den * c * c * y2;
-  *gc += g_A * (2.f * xy + y2) - g_B * x2 + g_den * (2.f * xy + 2.f * c * x2 * y2);
-  MVAE_UNROLL
-  for (int j = 0; j < CN; ++j)
-    if (j < n) {
-      if (gx) gx[j] += g_xy * y[j] + g_x2 * 2.f * x[j];
-      if (gy) gy[j] += g_xy * x[j] + g_y2 * 2.f * y[j];
-    }
-}
+// ============================= HYPERBOLOID, SPHERE and POINCARE BALL: one geodesic triangle =============================
+// Reference chain (H: hyperbolics.py, S: spherical.py), with a = |m|/R, mh = m/max(|m|,1e-12), v = eps*sigma,
+// p = <mh, v>, t = |v|/R:
+//   exp_map_mu0 (:114-121 / :94-101)      mu = [R C(a), R S(a) mh]                       C,S = cosh,sinh | cos,sin
+//   parallel_transport_mu0 (:87-93 / :74-77)
+//                                         u = [sg S(a) p,  v + (C(a) - 1) p mh]          sg = +1 (H) | -1 (S);  |u| = |v|
+//   exp_map (:106-111 / :86-91)           z = C(t) mu + S(t)/t u
+//     => z0 = R C(t) C(a) + sg A S(a) p,  z_tail = A v + Bc mh,  A = S(t)/t,  Bc = R C(t) S(a) + A (C(a)-1) p
+//   log q (wrapped_normal.py:84-97)       sum_j logN(v_j; 0, sigma_j) - (n-1)(log R + Fq(t))
+//   log p (wrapped_normal.py:99-103, inverse_exp_map :124-128 / :104-109, inverse PT :96-103 / :80-83)
+//                                         -r^2 R^2/2 - n ln sqrt(2pi) - (n-1)(log R + Fq(r)),  r = dist(mu0, z)/R
+//     H: r = acosh(z0/R) = asinh(|z_tail|/R), Fq = log(sinh x / x)       (logdet :58-65)
+//     S: r = acos(z0/R)  = atan2(|z_tail|/R, z0/R), Fq = log clamp|sin x| - log clamp x   (logdet :58-67)
+//   KL = log q - log p = -sum eps^2/2 - sum log sigma + R^2 r^2/2 - (n-1)(Fq(t) - Fq(r))
+// Poincare ball (poincare.py + geoopt 0.1.0; d = n): the ball of radius R is the hyperboloid seen through
+// lorentz_to_poincare (hyperbolics.py:151-152).  exp_map_mu0 (:132-137) gives mu = R tanh(a) mh, i.e. the hyperboloid
+// point at distance 2|m|; sample_projection_mu0 (:152-157: v_ = v/lambda_mu, expmap_mu(v_)) is the point at geodesic
+// distance lambda_mu |v_| = |v| from mu in the (conformal) direction of v.  So z_P = R Z_tail / (R + Z_0) with Z the
+// hyperboloid sample above evaluated at a -> 2a.  log q: PoincareBall.logdet (:84-89) maps to the Lorentz model and
+// takes H._logdet of the log map, whose norm is dist(mu, z) = |v|: the same Fq(t).  log p (:160-164): |logmap_0(z)|
+// lambda_0 = 2R artanh(|z|/R) = R r with geoopt's artanh clamp (|z|/R <= 1 - 1e-5, i.e. r <= 12.206), while the
+// log-det sees the unclamped r.  geoopt's tanh clamp (+-15) bounds a and t/2.
+enum { kHyp = 0, kSph = 1, kPoi = 2 };
 
-// poincare_to_lorentz (poincare.py:167-170): [R(R^2+|y|^2), 2R^2 y] / (R^2 - |y|^2), |y|^2 = norm(y)**2
-template <int N>
-MVAE_DEV void p2l(int n, const float* y, float R, float* out) {
+template <int N, bool BWD, int KIND>
+MVAE_DEV void comp_hsp(int n, int l_n, const float* m, const float* l, const float* e, float R, CompOut<N>& o,
+                       const float* gz, float gkl, float* gm, float* gl, float* gR_out) {
   MVAE_UN(N);
   constexpr int CN = Cap<N>::n;
-  constexpr int CD = Cap<N>::d;
-  (void)CN; (void)CD;
-  float s = 0.f;
-  MVAE_UNROLL
-  for (int j = 0; j < CN; ++j)
-    if (j < n) s += y[j] * y[j];
-  float nrm = sqrtf(s);
-  float nn = nrm * nrm;
-  float den = R * R - nn;
-  out[0] = R * (R * R + nn) / den;
-  MVAE_UNROLL
-  for (int j = 0; j < CN; ++j)
-    if (j < n) out[j + 1] = 2.f * (R * R) * y[j] / den;
-}
-template <int N>
-MVAE_DEV void p2l_bwd(int n, const float* y, float R, const float* gout, float* gy, float* gR) {
-  MVAE_UN(N);
-  constexpr int CN = Cap<N>::n;
-  constexpr int CD = Cap<N>::d;
-  (void)CN; (void)CD;
-  float s = 0.f;
-  MVAE_UNROLL
-  for (int j = 0; j < CN; ++j)
-    if (j < n) s += y[j] * y[j];
-  float nrm = sqrtf(s);
-  float nn = nrm * nrm;
-  float den = R * R - nn;
-  float num0 = R * (R * R + nn);
-  float g_den = -gout[0] * num0 / (den * den);
-  float g_nn = gout[0] * R / den;
-  *gR += gout[0] * (3.f * R * R + nn) / den;
-  MVAE_UNROLL
-  for (int j = 0; j < CN; ++j)
-    if (j < n) {
-      float numj = 2.f * (R * R) * y[j];
-      g_den += -gout[j + 1] * numj / (den * den);
-      if (gy) gy[j] += gout[j + 1] * 2.f * (R * R) / den;
-      *gR += gout[j + 1] * 4.f * R * y[j] / den;
-    }
-  *gR += g_den * 2.f * R;
-  g_nn += -g_den;
-  if (gy && nrm > 0.f) {
-    MVAE_UNROLL
-    for (int j = 0; j < CN; ++j)
-      if (j < n) gy[j] += g_nn * 2.f * nrm * (y[j] / nrm);
-  }
-}
-
-// H.inverse_exp_map (hyperbolics.py:124-128) on explicit ambient vectors; sv = {alpha, coef, acosh_z, sq}
-template <int N>
-MVAE_DEV void h_inv_exp(int d, const float* x, const float* at, float R, float* w, float* sv) {
-  MVAE_UN(N);
-  constexpr int CN = Cap<N>::n;
-  constexpr int CD = Cap<N>::d;
-  (void)CN; (void)CD;
-  float lpz = 0.f;
-  MVAE_UNROLL
-  for (int k = 0; k < CD; ++k)
-    if (k < d) lpz += at[k] * x[k];
-  lpz = lpz - 2.f * (at[0] * x[0]);
-  float alpha = -lpz / (R * R);
-  float zz;
-  float ach = acosh_g(alpha, &zz);
-  float sq = sqrt_g(alpha * alpha - 1.f);
-  float coef = ach / sq;
-  MVAE_UNROLL
-  for (int k = 0; k < CD; ++k)
-    if (k < d) w[k] = coef * (x[k] - alpha * at[k]);
-  sv[0] = alpha;
-  sv[1] = coef;
-  sv[2] = zz;
-  sv[3] = sq;
-}
-template <int N>
-MVAE_DEV void h_inv_exp_bwd(int d, const float* x, const float* at, float R, const float* sv, const float* gw,
-                            float* gx, float* gat, float* gR) {
-  MVAE_UN(N);
-  constexpr int CN = Cap<N>::n;
-  constexpr int CD = Cap<N>::d;
-  (void)CN; (void)CD;
-  float alpha = sv[0], coef = sv[1], zz = sv[2], sq = sv[3];
-  float ach = coef * sq;
-  float g_coef = 0.f, g_alpha = 0.f;
-  MVAE_UNROLL
-  for (int k = 0; k < CD; ++k)
-    if (k < d) {
-      g_coef += gw[k] * (x[k] - alpha * at[k]);
-      gx[k] += gw[k] * coef;
-      g_alpha += -gw[k] * coef * at[k];
-      gat[k] += -gw[k] * coef * alpha;
-    }
-  float g_ach = g_coef / sq;
-  float g_sq = -g_coef * ach / (sq * sq);
-  g_alpha += g_sq * sqrt_g_d(alpha * alpha - 1.f, sq) * 2.f * alpha;
-  g_alpha += g_ach / zz;
-  float g_lp = -g_alpha / (R * R);
-  *gR += g_alpha * (-2.f * alpha / R);
-  MVAE_UNROLL
-  for (int k = 0; k < CD; ++k)
-    if (k < d) {
-      float sgn = (k == 0) ? -1.f : 1.f;
-      gx[k] += g_lp * sgn * at[k];
-      gat[k] += g_lp * sgn * x[k];
-    }
-}
-
-// PoincareBall.logdet (poincare.py:84-89): H._logdet(H.inverse_exp_map(p2l(z), p2l(mu))).
-// With BWD accumulates g * d(logdet) into gzp, gmu (gmu may be nullptr) and *gR.
-template <int N, bool BWD>
-MVAE_DEV float p_logdet(int n, const float* z, const float* mu, float R, float g, float* gzp, float* gmu, float* gR) {
-  MVAE_UN(N);
-  constexpr int CN = Cap<N>::n;
-  constexpr int CD = Cap<N>::d;
-  const int d = n + 1;
-  float zs[CD], ms[CD], uu[CD], sv[4];
-  p2l<N>(n, z, R, zs);
-  p2l<N>(n, mu, R, ms);
-  h_inv_exp<N>(d, zs, ms, R, uu, sv);
-  float pr = 0.f;
-  MVAE_UNROLL
-  for (int k = 0; k < CD; ++k)
-    if (k < d) pr += uu[k] * uu[k];
-  pr = pr - 2.f * (uu[0] * uu[0]);
-  if (!BWD) return h_logdet_pr<false>(n, pr, R, 0.f, nullptr, nullptr);
-  float g_pr;
-  float ld = h_logdet_pr<true>(n, pr, R, g, &g_pr, gR);
-  float guu[CD], gzs[CD], gms[CD];
-  MVAE_UNROLL
-  for (int k = 0; k < CD; ++k)
-    if (k < d) {
-      guu[k] = g_pr * (k == 0 ? -2.f : 2.f) * uu[k];
-      gzs[k] = 0.f;
-      gms[k] = 0.f;
-    }
-  h_inv_exp_bwd<N>(d, zs, ms, R, sv, guu, gzs, gms, gR);
-  p2l_bwd<N>(n, z, R, gzs, gzp, gR);
-  p2l_bwd<N>(n, mu, R, gms, gmu, gR);
-  return ld;
-}
-
-template <int N, bool BWD>
-MVAE_DEV void comp_p(int n, int l_n, const float* m, const float* l, const float* e, float R, CompOut<N>& o,
-                     const float* gz, float gkl, float* gm, float* gl, float* gR_out) {
-  MVAE_UN(N);
-  constexpr int CN = Cap<N>::n;
-  float c = 1.f / (R * R);     // _c(radius) = 1 / radius**2 (poincare.py:108-109)
-  float sc = powf(c, 0.5f);    // c ** 0.5
-  // ---- encode: expmap0 ----
+  constexpr bool HYP = KIND != kSph;  // hyperbolic trigonometry
+  constexpr bool POI = KIND == kPoi;
+  const float sgn = HYP ? 1.f : -1.f;
+  // ---- encode ----
   float nm2 = 0.f;
   MVAE_UNROLL
   for (int j = 0; j < CN; ++j)
     if (j < n) nm2 += m[j] * m[j];
-  float nm = sqrtf(nm2);
-  float un_ = fmaxf(nm, kPMin);
-  float ta = sc * un_;
-  float th = tanh_c(ta);
-  float* mu = o.mu;
-  float mu2 = 0.f;
-  MVAE_UNROLL
-  for (int j = 0; j < CN; ++j)
-    if (j < n) {
-      mu[j] = th * m[j] / (sc * un_);
-      mu2 += mu[j] * mu[j];
-    }
+  const float nm = sqrtf(nm2);
+  const float nmin = POI ? kPMin : 1e-12f;  // geoopt MIN_NORM | F.normalize eps
+  const float dn = fmaxf(nm, nmin);
+  const float a = (POI ? dn : nm) / R;
+  const bool a_sat = POI && a > 15.f;       // geoopt tanh clamp (plain: zero gradient beyond)
+  const float aa = POI ? 2.f * fminf(a, 15.f) : a;
+  float ca, sa;
+  if (HYP) {
+    coshsinh_g(aa, &ca, &sa);
+  } else {
+    ca = cosf(aa);
+    sa = sinf(aa);
+  }
+  // C(a) - 1 without cancellation: H: S^2/(C+1);  S: -S^2/(1+C) (falls back to C-1 near a = pi)
+  const float cam1 = HYP ? sa * sa / (ca + 1.f) : (ca > -0.5f ? -(sa * sa) / (1.f + ca) : ca - 1.f);
   float* sg = o.sigma;
   load_sigma<N>(n, l_n, l, sg);
-  float v[CN];
-  // ---- sample_projection_mu0 (poincare.py:152-157): v_ = v / lambda_mu ; z = expmap_mu(v_) ----
-  float lden = 1.f - c * mu2;
-  float ldc = fmaxf(lden, kPMin);
-  float lam = 2.f / ldc;
-  float* vv = o.u;  // data[0] = v_
-  float vn2 = 0.f;
+  float mh[CN], v[CN];
+  float Sv = 0.f, p = 0.f, se2 = 0.f, slog = 0.f;
   MVAE_UNROLL
   for (int j = 0; j < CN; ++j)
     if (j < n) {
+      mh[j] = m[j] / dn;
       v[j] = e[j] * sg[j];
-      vv[j] = v[j] / lam;
-      vn2 += vv[j] * vv[j];
+      Sv += v[j] * v[j];
+      p += mh[j] * v[j];
+      se2 += e[j] * e[j];
+      slog += logf(sg[j]);
     }
-  float vn = sqrtf(vn2);
-  float vnc = fmaxf(vn, kPMin);
-  float tb = sc / 2.f * lam * vnc;
-  float thb = tanh_c(tb);
-  float sec[CN];
-  MVAE_UNROLL
-  for (int j = 0; j < CN; ++j)
-    if (j < n) sec[j] = thb * vv[j] / (sc * vnc);
-  float svm[4];
+  // ---- sample ----
+  float ln, t, ct, st;
+  bool t_sat = false;
+  if (HYP) {
+    ln = sqrt_g(Sv);
+    t = ln / R;
+    t_sat = POI && t > 30.f;
+    coshsinh_g(POI ? fminf(t, 30.f) : t, &ct, &st);
+  } else {
+    ln = sqrtf(Sv);
+    t = ln / R;
+    ct = cosf(t);
+    st = sinf(t);
+  }
+  const float A = t > 0.f ? st / t : 1.f;
+  const float z0 = R * ct * ca + sgn * A * sa * p;
+  const float Bc = R * ct * sa + A * cam1 * p;
   float* z = o.z;
-  mobius_add<N>(n, mu, sec, c, z, svm);
-  // ---- log q ----
-  float nlp = 0.f;
-  MVAE_UNROLL
-  for (int j = 0; j < CN; ++j)
-    if (j < n) nlp += -(v[j] * v[j]) / (2.f * (sg[j] * sg[j])) - logf(sg[j]) - kHalfLn2Pi;
-  float ld = p_logdet<N, false>(n, z, mu, R, 0.f, nullptr, nullptr, nullptr);
-  o.logq = nlp - ld;
-  // ---- log p: loc = 0, scale = 1 (poincare.py:160-164: logmap(0, z) * lambda_0) ----
-  float zero[CN], sub[CN];
-  MVAE_UNROLL
-  for (int j = 0; j < CN; ++j) zero[j] = 0.f;
-  float svs[4];
-  mobius_add<N>(n, zero, z, c, sub, svs);
-  float sn2 = 0.f;
-  MVAE_UNROLL
-  for (int j = 0; j < CN; ++j)
-    if (j < n) sn2 += sub[j] * sub[j];
-  float sn = sqrtf(sn2);
-  float snc = fmaxf(sn, kPMin);
-  const float lam0 = 2.f;
-  float atx;
-  float at = artanh_go(sc * snc, &atx);
-  float k0 = 2.f / sc / lam0 * at;
-  float x0[CN];
-  float nlp0 = 0.f;
+  float* mu = o.mu;
+  float zt[CN];
+  float zt2 = 0.f;
   MVAE_UNROLL
   for (int j = 0; j < CN; ++j)
     if (j < n) {
-      x0[j] = (k0 * sub[j] / snc) * lam0;
-      nlp0 += -(x0[j] * x0[j]) / 2.f - kHalfLn2Pi;
+      zt[j] = A * v[j] + Bc * mh[j];
+      zt2 += zt[j] * zt[j];
     }
-  float ld0 = p_logdet<N, false>(n, z, zero, R, 0.f, nullptr, nullptr, nullptr);
-  o.logp = nlp0 - ld0;
-  o.kl = o.logq - o.logp;
+  const float pj = POI ? R / (R + z0) : 1.f;  // lorentz_to_poincare
+  if (POI) {
+    const float Ta = sa / (ca + 1.f);  // tanh(a) = sinh(2a) / (cosh(2a) + 1)
+    MVAE_UNROLL
+    for (int j = 0; j < CN; ++j)
+      if (j < n) {
+        z[j] = pj * zt[j];
+        mu[j] = R * Ta * mh[j];
+      }
+  } else {
+    z[0] = z0;
+    mu[0] = R * ca;
+    MVAE_UNROLL
+    for (int j = 0; j < CN; ++j)
+      if (j < n) {
+        z[j + 1] = zt[j];
+        mu[j + 1] = R * sa * mh[j];
+      }
+  }
+  // ---- prior distance r = dist(mu0, z)/R from the tail norm (well conditioned everywhere) ----
+  const float s2 = zt2 / (R * R);
+  const float s = sqrtf(s2);
+  float r, Fr, Ft, alpha = 0.f, as_ = 0.f, snr = 0.f, csr = 0.f;
+  bool r_clamped = false, at_clamped = false;
+  const float kAtMax = 12.206062f;  // 2 artanh(1 - 1e-5)
+  float rq;                         // distance entering the Gaussian term of log p
+  if (HYP) {
+    as_ = sqrtf(1.f + s2);
+    r = log1pf(s + s2 / (1.f + as_));  // asinh(s)
+    // H._logdet applies sqrt() (clamp 1e-9) to the squared Lorentz norm R^2 r^2 of the prior's tangent vector
+    r_clamped = (R * R) * (r * r) < 1e-9f;
+    const float rl = r_clamped ? sqrtf(1e-9f) / R : r;
+    Fr = log_sinhc(rl);
+    Ft = log_sinhc(t);
+    at_clamped = POI && r > kAtMax;
+    rq = at_clamped ? kAtMax : r;
+  } else {
+    alpha = z0 / R;
+    r = atan2f(s, alpha);
+    const float inv_q = rsqrtf(alpha * alpha + s2);  // (alpha, s) is a unit vector up to rounding
+    snr = s * inv_q;                                  // sin r and cos r without going through r
+    csr = alpha * inv_q;
+    Fr = log_sinc_abs(r, snr);
+    Ft = log_sinc_abs(t, st);
+    rq = r;
+  }
+  const float nm1 = (float)(n - 1);
+  o.kl = -0.5f * se2 - slog + 0.5f * (R * R) * (rq * rq) - nm1 * (Ft - Fr);
   if (!BWD) return;
 
   // ================================ reverse sweep ================================
-  float gR = 0.f, g_c = 0.f, g_sc = 0.f;
-  const float g_logq = gkl, g_logp = -gkl;
-  float gzt[CN], g_mu[CN];
-  MVAE_UNROLL
-  for (int j = 0; j < CN; ++j) {
-    gzt[j] = (j < n) ? gz[j] : 0.f;
-    g_mu[j] = 0.f;
+  float gR = 0.f;
+  // KL -> r
+  float g_r = gkl * (R * R) * rq;
+  gR += gkl * R * (rq * rq);
+  if (at_clamped) {
+    // geoopt Artanh.backward = g / (1 - x'^2) on the clamped argument x' = 1 - 1e-5; d(rho)/d(r) = sech^2(r/2) / 2
+    g_r *= sech2_c(0.5f * r) / (1e-5f * (2.f - 1e-5f));
   }
-  // logp = nlp0 - ld0
-  (void)p_logdet<N, true>(n, z, zero, R, -g_logp, gzt, nullptr, &gR);
-  float g_sub[CN];
-  float g_k0 = 0.f, g_snc = 0.f;
-  MVAE_UNROLL
-  for (int j = 0; j < CN; ++j)
-    if (j < n) {
-      float g_x0 = g_logp * (-x0[j]);
-      g_k0 += g_x0 * lam0 * sub[j] / snc;
-      g_sub[j] = g_x0 * lam0 * k0 / snc;
-      g_snc += -g_x0 * lam0 * k0 * sub[j] / (snc * snc);
+  float g_s, g_alpha = 0.f;
+  if (HYP) {
+    if (!r_clamped) {
+      g_r += gkl * nm1 * log_sinhc_d(r);
+    } else {
+      const float rl = sqrtf(1e-9f) / R;
+      gR += -(gkl * nm1 * log_sinhc_d(rl)) * rl / R;  // leaky clamp: the 1e-8 * g path into r is dropped
     }
-  float g_at = g_k0 * 2.f / sc / lam0;
-  g_sc += -g_k0 * k0 / sc;
-  float g_arg = g_at / (1.f - atx * atx);
-  g_sc += g_arg * snc;
-  g_snc += g_arg * sc;
-  float g_sn = g_snc * cmin_d(sn, kPMin);
-  if (sn > 0.f) {
-    float k = g_sn / sn;
+    g_s = g_r / as_;
+  } else {
+    g_r += gkl * nm1 * log_sinc_abs_d(r, snr, csr);
+    // r = atan2(s, alpha): any smooth extension off the constraint alpha^2 + s^2 = 1 has the same total derivative
+    const float q2 = alpha * alpha + s2;
+    g_s = g_r * alpha / q2;
+    g_alpha = -g_r * s / q2;
+  }
+  // s = |z_tail| / R ; alpha = z0 / R
+  const float k_zt = s > 0.f ? g_s / (R * R * s) : 0.f;
+  gR += -g_s * s / R;
+  float g_z0 = 0.f;
+  if (POI) {
+    // z_j = R Z_j / (R + Z_0)
     MVAE_UNROLL
     for (int j = 0; j < CN; ++j)
-      if (j < n) g_sub[j] += k * sub[j];
+      if (j < n) {
+        g_z0 += -gz[j] * z[j] / (R + z0);
+        gR += gz[j] * (z[j] / R - z[j] / (R + z0));
+      }
+  } else {
+    g_z0 = gz[0];
+    if (!HYP) {
+      g_z0 += g_alpha / R;
+      gR += -g_alpha * alpha / R;
+    }
   }
-  mobius_add_bwd<N>(n, zero, z, c, svs, g_sub, nullptr, gzt, &g_c);
-  // logq = nlp - ld
-  (void)p_logdet<N, true>(n, z, mu, R, -g_logq, gzt, g_mu, &gR);
-  const float g_nlp = g_logq;
-  // z = mobius_add(mu, sec)
-  float g_sec[CN];
-  MVAE_UNROLL
-  for (int j = 0; j < CN; ++j) g_sec[j] = 0.f;
-  mobius_add_bwd<N>(n, mu, sec, c, svm, gzt, g_mu, g_sec, &g_c);
-  // sec = thb * vv / (sc*vnc)
-  float g_thb = 0.f, g_q = 0.f;
-  float g_vv[CN];
-  float q = sc * vnc;
+  // z0 = R ct ca + sgn A sa p ;  Bc = R ct sa + A cam1 p ; z_tail = A v + Bc mh
+  float g_A = 0.f, g_Bc = 0.f;
+  float g_v[CN], g_mh[CN];
   MVAE_UNROLL
   for (int j = 0; j < CN; ++j)
     if (j < n) {
-      g_thb += g_sec[j] * vv[j] / q;
-      g_vv[j] = g_sec[j] * thb / q;
-      g_q += -g_sec[j] * thb * vv[j] / (q * q);
+      const float G = (POI ? pj * gz[j] : gz[j + 1]) + k_zt * zt[j];
+      g_A += G * v[j];
+      g_Bc += G * mh[j];
+      g_v[j] = A * G;
+      g_mh[j] = Bc * G;
     }
-  g_sc += g_q * vnc;
-  float g_vnc = g_q * sc;
-  float g_tb = g_thb * tanh_c_d(tb, thb);
-  g_sc += g_tb * lam * vnc / 2.f;
-  float g_lam = g_tb * sc / 2.f * vnc;
-  g_vnc += g_tb * sc / 2.f * lam;
-  float g_vn = g_vnc * cmin_d(vn, kPMin);
-  if (vn > 0.f) {
-    float k = g_vn / vn;
-    MVAE_UNROLL
-    for (int j = 0; j < CN; ++j)
-      if (j < n) g_vv[j] += k * vv[j];
+  float g_ct = g_z0 * R * ca + g_Bc * R * sa;
+  float g_ca = g_z0 * R * ct + g_Bc * A * p;  // d(cam1)/d(ca) = 1
+  float g_sa = g_z0 * sgn * A * p + g_Bc * R * ct;
+  float g_p = g_z0 * sgn * A * sa + g_Bc * A * cam1;
+  gR += g_z0 * ct * ca + g_Bc * ct * sa;
+  g_A += g_z0 * sgn * sa * p + g_Bc * cam1 * p;
+  // A = st / t ; ct, st functions of t ; KL has -(n-1) Fq(t)
+  float g_t = 0.f;
+  if (t > 0.f) {
+    const float g_st = g_A / t;
+    g_t += -g_A * A / t;
+    if (HYP) {
+      const float dclamp = POI ? (t_sat ? 0.f : 1.f) : lclamp_d(t, -kMaxHyp, kMaxHyp);
+      g_t += (g_ct * st + g_st * ct) * dclamp;
+      g_t += -gkl * nm1 * log_sinhc_d(t);
+    } else {
+      g_t += -g_ct * st + g_st * ct;
+      g_t += -gkl * nm1 * log_sinc_abs_d(t, st, ct);
+    }
   }
-  float g_v[CN];
+  // t = ln / R ; ln = sqrt(Sv) ; Sv = <v, v>
+  gR += -g_t * t / R;
+  const float g_ln = g_t / R;
+  const float g_Sv = HYP ? g_ln * sqrt_g_d(Sv, ln) : (ln > 0.f ? g_ln * 0.5f / ln : 0.f);
+  // a : ca, sa
+  float g_a;
+  if (POI) g_a = a_sat ? 0.f : 2.f * (g_ca * sa + g_sa * ca);
+  else if (HYP) g_a = (g_ca * sa + g_sa * ca) * lclamp_d(a, -kMaxHyp, kMaxHyp);
+  else g_a = -g_ca * sa + g_sa * ca;
+  gR += -g_a * a / R;
+  float g_nm = POI ? 0.f : g_a / R;   // P: a = max(|m|, MIN_NORM) / R
+  float g_dn = POI ? g_a / R : 0.f;
+  // v = eps * sigma ; p = <mh, v> ; mh = m / dn
+  float g_s_[CN];
   MVAE_UNROLL
   for (int j = 0; j < CN; ++j)
     if (j < n) {
-      g_v[j] = g_vv[j] / lam;
-      g_lam += -g_vv[j] * v[j] / (lam * lam);
+      const float gv = g_v[j] + 2.f * g_Sv * v[j] + g_p * mh[j];
+      g_s_[j] = gv * e[j] - gkl / sg[j];
+      const float gmh = g_mh[j] + g_p * v[j];
+      gm[j] = gmh / dn;
+      g_dn += -gmh * mh[j] / dn;
     }
-  float g_lden = (-g_lam * 2.f / (ldc * ldc)) * cmin_d(lden, kPMin);
-  g_c += -g_lden * mu2;
-  float g_mu2 = -g_lden * c;
-  float g_s[CN];
-  MVAE_UNROLL
-  for (int j = 0; j < CN; ++j)
-    if (j < n) {
-      g_mu[j] += g_mu2 * 2.f * mu[j];
-      float s = sg[j];
-      g_v[j] += g_nlp * (-v[j] / (s * s));
-      g_s[j] = g_nlp * (v[j] * v[j] / (s * s * s) - 1.f / s) + g_v[j] * e[j];
-    }
-  store_gl<N>(n, l_n, l, g_s, gl);
-  // mu = th * m / (sc*un_)
-  float p_ = sc * un_;
-  float g_th = 0.f, g_p = 0.f;
-  MVAE_UNROLL
-  for (int j = 0; j < CN; ++j)
-    if (j < n) {
-      g_th += g_mu[j] * m[j] / p_;
-      gm[j] = g_mu[j] * th / p_;
-      g_p += -g_mu[j] * th * m[j] / (p_ * p_);
-    }
-  g_sc += g_p * un_;
-  float g_un = g_p * sc;
-  float g_ta = g_th * tanh_c_d(ta, th);
-  g_sc += g_ta * un_;
-  g_un += g_ta * sc;
-  float g_nm = g_un * cmin_d(nm, kPMin);
+  store_gl<N>(n, l_n, l, g_s_, gl);
+  if (nm >= nmin) g_nm += g_dn;
   if (nm > 0.f) {
-    float k = g_nm / nm;
+    const float k = g_nm / nm;
     MVAE_UNROLL
     for (int j = 0; j < CN; ++j)
       if (j < n) gm[j] += k * m[j];
   }
-  g_c += g_sc * 0.5f / sc;
-  gR += g_c * (-2.f / (R * R * R));
   *gR_out = gR;
 }
+
+template <int N, bool BWD>
+MVAE_DEV void comp_h(int n, int l_n, const float* m, const float* l, const float* e, float R, CompOut<N>& o,
+                     const float* gz, float gkl, float* gm, float* gl, float* gR_out) {
+  comp_hsp<N, BWD, kHyp>(n, l_n, m, l, e, R, o, gz, gkl, gm, gl, gR_out);
+}
+template <int N, bool BWD>
+MVAE_DEV void comp_s(int n, int l_n, const float* m, const float* l, const float* e, float R, CompOut<N>& o,
+                     const float* gz, float gkl, float* gm, float* gl, float* gR_out) {
+  comp_hsp<N, BWD, kSph>(n, l_n, m, l, e, R, o, gz, gkl, gm, gl, gR_out);
+}
+template <int N, bool BWD>
+MVAE_DEV void comp_p(int n, int l_n, const float* m, const float* l, const float* e, float R, CompOut<N>& o,
+                     const float* gz, float gkl, float* gm, float* gl, float* gR_out) {
+  comp_hsp<N, BWD, kPoi>(n, l_n, m, l, e, R, o, gz, gkl, gm, gl, gR_out);
+}
+
+// H._logdet (hyperbolics.py:58-65) on the Lorentz squared norm `pr` of u (standalone ops)
+template <bool BWD>
+MVAE_DEV float h_logdet_pr(int n, float pr, float R, float g, float* g_pr, float* gR) {
+  float s = sqrt_g(pr);
+  float r = s / R;
+  return (float)(n - 1) * (logf(R) + log_sinhc(r));
+}
+// S._logdet (spherical.py:58-67) on nu = ||u||_2 (standalone ops)
+template <bool BWD>
+MVAE_DEV float s_logdet_nu(int n, float nu, float R, float g, float* g_nu, float* gR) {
+  float r = nu / R;
+  return (float)(n - 1) * (logf(R) + log_sinc_abs(r, sinf(r)));
+}
+
 
 }  // namespace mvae

@@ -1,0 +1,474 @@
+"""FusedFeedForwardVAE — drop-in for the reference's `FeedForwardVAE` / `ModelVAE`
+(mt/mvae/models/ffnn_vae.py:27-60, mt/mvae/models/vae.py:41-166) whose whole train_step runs in hand-written
+sm_100a kernels (libmvae_b200.so):
+
+  encode   fc_e0 + relu                      tcgen05 GEMM, BIAS_RELU epilogue -> split-bf16 planes of h
+  heads    all fc_mean / fc_logvar at once   tcgen05 GEMM (one concatenated weight [sum(n)+sum(l_n), H])
+  latent   Component.encode + reparametrize + rsample_with_parts + kl_loss for every component
+                                             ONE fused product-manifold kernel (mvae_pm_forward)
+  decode   fc_d0 + relu, fc_logits           tcgen05 GEMMs; the BCE / Gaussian-NLL row sums and dloss/dlogits are
+                                             fused into the logits GEMM epilogue (logits never reach HBM in training)
+  ELBO     BatchStats (stats.py:144-202)     warp-shuffle reduction (mvae_elbo_reduce)
+  backward dgrad / wgrad                     the same GEMM kernel reading the forward buffers MN-major; bias gradients
+                                             ride along as an extra "ones" column; relu masks in the epilogue;
+                                             the latent backward is mvae_pm_backward (recompute from inputs)
+  update   Adam on one flat bucket + SGD on the radii (train.py:327-360)   mvae_adam_step / mvae_sgd_step
+
+Parameters keep the reference's names and shapes (state_dict round-trips) but live as views
+into one flat fp32 buffer; gradients are views into one flat bucket [net grads | radius grads | ELBO stats] so that
+data-parallel training needs a single SUM all-reduce per step (mvae_b200/parallel.py).
+"""
+from typing import List, Optional, Tuple
+
+import torch
+import torch.nn as nn
+from torch import Tensor
+
+from . import _lib as L
+from . import ops
+from .components import Component
+from .distributions import EuclideanNormal, WrappedNormal
+
+
+class Reparametrized:
+    """mt/mvae/models/vae.py:29-35.  `data` (= (u, v) of rsample_with_parts) is recomputed on demand."""
+
+    def __init__(self, q_z, p_z, z: Tensor, kl: Tensor, eps: Optional[Tensor]) -> None:
+        self.q_z = q_z
+        self.p_z = p_z
+        self.z = z
+        self.kl = kl
+        self._eps = eps
+        self._data = None
+
+    @property
+    def data(self):
+        if isinstance(self.q_z, EuclideanNormal):
+            return None
+        if self._data is None:
+            v = self._eps * self.q_z.scale
+            _, (u, _) = self.q_z.manifold.sample_projection_mu0(v.contiguous(), self.q_z.loc)
+            self._data = (u, v)
+        return self._data
+
+
+class BatchStatsFloat:
+    """mt/mvae/stats.py:115-142: the per-step scalars, read back with ONE device->host copy."""
+
+    def __init__(self, bce: float, kl: float, elbo: float, component_kl: List[float], beta: float,
+                 log_likelihood=None, mutual_info=None, cov_norm=None) -> None:
+        self.bce, self.kl, self.elbo = bce, kl, elbo
+        self.log_likelihood, self.mutual_info, self.cov_norm = log_likelihood, mutual_info, cov_norm
+        self.component_kl = component_kl
+        self.beta = beta
+
+    def to_print(self):
+        return {"bce": self.bce, "kl": self.kl, "elbo": self.elbo,
+                "ll": 0.0 if self.log_likelihood is None else self.log_likelihood,
+                "mi": 0.0 if self.mutual_info is None else self.mutual_info,
+                "cov_norm": 0.0 if self.cov_norm is None else self.cov_norm, "beta": self.beta}
+
+    def summaries(self, stats, prefix: str = "train/batch") -> None:
+        stats.add_scalar(prefix + "/bce", self.bce)
+        stats.add_scalar(prefix + "/kl", self.kl)
+        stats.add_scalar(prefix + "/elbo", self.elbo)
+
+
+class BatchStats:
+    """mt/mvae/stats.py:144-212 over the device vector [bce_sum, kl_sum, elbo, kl_c...] of mvae_elbo_reduce."""
+
+    def __init__(self, stats_vec: Tensor, beta: float, bce_rows: Optional[Tensor] = None,
+                 kl_rows: Optional[Tensor] = None) -> None:
+        self._vec = stats_vec
+        self._beta = beta
+        self._bce = bce_rows
+        self._component_kl = None if kl_rows is None else [kl_rows[:, i] for i in range(kl_rows.shape[1])]
+
+    bce = property(lambda self: self._vec[0])
+    kl = property(lambda self: self._vec[1])
+    elbo = property(lambda self: self._vec[2])
+    beta = property(lambda self: self._beta)
+    log_likelihood = mutual_info = cov_norm = None
+
+    @property
+    def component_kl(self) -> List[Tensor]:
+        return [self._vec[3 + i] for i in range(self._vec.numel() - 3)]
+
+    def convert_to_float(self) -> BatchStatsFloat:
+        h = self._vec.detach().cpu().tolist()  # one D2H copy (the reference does 3 + C .item() syncs)
+        return BatchStatsFloat(h[0], h[1], h[2], h[3:], self._beta)
+
+
+def _recon_kind_of(dataset) -> str:
+    kind = getattr(dataset, "recon_kind", None)
+    if kind in ("bce", "nll"):
+        return kind
+    name = type(dataset).__name__.lower()
+    if "bdp" in name:
+        return "nll"  # mt/data/synthetic.py:161-162
+    return "bce"      # mt/data/image_reconstruction.py:81-82, :142-143 (MNIST / Omniglot / CIFAR)
+
+
+class _Workspace:
+    """Per-batch-size activation buffers (allocated once, reused every step; addresses stay fixed for CUDA graphs)."""
+
+    def __init__(self, m: "FusedFeedForwardVAE", B: int) -> None:
+        dev, D, H, P, Sn, Sd, C = m.device, m.in_dim, m.h_dim, m.desc.ld_ml, m.desc.ld_eps, m.desc.ld_z, m.desc.C
+        f = dict(device=dev, dtype=torch.float32)
+        self.B = B
+        self.x = torch.zeros(B, D, **f)
+        self.eps = torch.zeros(B, Sn, **f)
+        self.xp = ops.PlaneBuf(B, D, m.input_planes, dev, ones_col=True)
+        self.hp = ops.PlaneBuf(B, H, 2, dev, ones_col=True)
+        self.ml = torch.zeros(B, P, **f)
+        self.z = torch.zeros(B, Sd, **f)
+        self.kl = torch.zeros(B, C, **f)
+        self.mu = torch.zeros(B, Sd, **f)
+        self.sigma = torch.zeros(B, Sn, **f)
+        self.zp = ops.PlaneBuf(B, Sd, 2, dev, ones_col=True)
+        self.ddp = ops.PlaneBuf(B, H, 2, dev, ones_col=True)
+        self.bce = torch.zeros(B, **f)
+        self.logits = None  # allocated on first forward() that needs them
+        self.gLp = ops.PlaneBuf(B, D, 2, dev)
+        self.gddp = ops.PlaneBuf(B, H, 2, dev)
+        self.gz = torch.zeros(B, Sd, **f)
+        self.gml = torch.zeros(B, P, **f)
+        self.gmlp = ops.PlaneBuf(B, P, 2, dev)
+        self.ghp = ops.PlaneBuf(B, H, 2, dev)
+        self.flag = torch.zeros(1, device=dev, dtype=torch.int32)
+
+
+class FusedFeedForwardVAE(nn.Module):
+
+    def __init__(self, h_dim: int, components: List[Component], dataset, scalar_parametrization: bool,
+                 device="cuda", input_planes: int = 2) -> None:
+        """Same signature as FeedForwardVAE (ffnn_vae.py:29-30) plus the device.  `input_planes=1` may be used when the
+        inputs are exactly representable in bf16 (binarised images); 2 is always safe."""
+        super().__init__()
+        self.device = torch.device(device)
+        self.h_dim = h_dim
+        self.in_dim = dataset.in_dim
+        self.recon_kind = _recon_kind_of(dataset)
+        self.scalar_parametrization = scalar_parametrization
+        self.input_planes = input_planes
+        self.components = nn.ModuleList(components)
+        self.total_z_dim = sum(c.dim for c in components)
+        # construction order of the reference (vae.py:55-57 then ffnn_vae.py:35-40) => identical default init per seed
+        for c in components:
+            c.init_layers(h_dim, scalar_parametrization=scalar_parametrization)
+        self.fc_e0 = nn.Linear(self.in_dim, h_dim)
+        self.fc_d0 = nn.Linear(self.total_z_dim, h_dim)
+        self.fc_logits = nn.Linear(h_dim, self.in_dim)
+        self.desc = L.make_desc([c.kind for c in components], [c.true_dim for c in components],
+                                scalar_parametrization)
+        assert self.desc.ld_z == self.total_z_dim
+        self._ws = {}
+        self._eps_override: Optional[Tensor] = None
+        self._flat = None
+        self.check_finite = False
+        if self.device.type == "cuda":
+            self._flatten()
+
+    # ------------------------------------------------------------------------------------------ parameter storage
+    def _net_params(self) -> List[Tuple[str, nn.Parameter]]:
+        heads_w, heads_b = [], []
+        for i, c in enumerate(self.components):
+            heads_w += [(f"components.{i}.fc_mean.weight", c.fc_mean.weight),
+                        (f"components.{i}.fc_logvar.weight", c.fc_logvar.weight)]
+            heads_b += [(f"components.{i}.fc_mean.bias", c.fc_mean.bias),
+                        (f"components.{i}.fc_logvar.bias", c.fc_logvar.bias)]
+        rest = [("fc_e0.weight", self.fc_e0.weight), ("fc_e0.bias", self.fc_e0.bias),
+                ("fc_d0.weight", self.fc_d0.weight), ("fc_d0.bias", self.fc_d0.bias),
+                ("fc_logits.weight", self.fc_logits.weight), ("fc_logits.bias", self.fc_logits.bias)]
+        return heads_w + heads_b + rest
+
+    def _flatten(self) -> None:
+        """Re-home every parameter as a view into one flat fp32 buffer (and its gradient into one flat bucket)."""
+        dev = self.device
+        net = self._net_params()
+        n_net = sum(p.numel() for _, p in net)
+        C = self.desc.C
+        flat = torch.empty(n_net, device=dev, dtype=torch.float32)
+        rflat = torch.ones(C, device=dev, dtype=torch.float32)
+        bucket = torch.zeros(n_net + C + 3 + C, device=dev, dtype=torch.float32)
+        off = 0
+        self._slices = {}
+        for name, p in net:
+            n = p.numel()
+            flat[off:off + n].copy_(p.data.reshape(-1).to(dev, torch.float32))
+            p.data = flat[off:off + n].view(p.shape)
+            p.grad = bucket[off:off + n].view(p.shape)
+            self._slices[name] = (off, n)
+            off += n
+        self._radius_mask = torch.zeros(C, device=dev, dtype=torch.float32)
+        for i, c in enumerate(self.components):
+            _, rp = c.radius_parameter()
+            if rp is not None:
+                rflat[i] = rp.data.to(dev, torch.float32)
+                rp.data = rflat[i]
+                if rp.requires_grad:
+                    rp.grad = bucket[n_net + i]
+                    self._radius_mask[i] = 1.0
+        self._flat, self._rflat, self._bucket, self._n_net = flat, rflat, bucket, n_net
+        self._gnet = bucket[:n_net]
+        self._gradius = bucket[n_net:n_net + C]
+        self._stats = bucket[n_net + C:]
+        H, D, P, Sd = self.h_dim, self.in_dim, self.desc.ld_ml, self.desc.ld_z
+
+        def view(buf, name, shape):
+            o, n = self._slices[name]
+            return buf[o:o + n].view(shape)
+
+        o0, _ = self._slices["components.0.fc_mean.weight"]
+        self.Wh, self.gWh = flat[o0:o0 + P * H].view(P, H), bucket[o0:o0 + P * H].view(P, H)
+        b0, _ = self._slices["components.0.fc_mean.bias"]
+        self.bh, self.gbh = flat[b0:b0 + P], bucket[b0:b0 + P]
+        self.gWe0, self.gbe0 = view(bucket, "fc_e0.weight", (H, D)), view(bucket, "fc_e0.bias", (H,))
+        self.gWd0, self.gbd0 = view(bucket, "fc_d0.weight", (H, Sd)), view(bucket, "fc_d0.bias", (H,))
+        self.gWl, self.gbl = view(bucket, "fc_logits.weight", (D, H)), view(bucket, "fc_logits.bias", (D,))
+        # split-bf16 planes of the four weight matrices (refreshed after every optimizer step)
+        self.We0p = ops.PlaneBuf(H, D, 2, dev)
+        self.Whp = ops.PlaneBuf(P, H, 2, dev)
+        self.Wd0p = ops.PlaneBuf(H, Sd, 2, dev)
+        self.Wlp = ops.PlaneBuf(D, H, 2, dev)
+        self._planes_stale = True
+        self._ws = {}
+
+    def _apply(self, fn, *args, **kwargs):
+        out = super()._apply(fn, *args, **kwargs)
+        p = self.fc_e0.weight
+        if p.device.type == "cuda" and (self._flat is None or p.data.untyped_storage().data_ptr() !=
+                                        self._flat.untyped_storage().data_ptr()):
+            self.device = p.device
+            self._flatten()
+        return out
+
+    def to(self, *args, **kwargs):
+        out = super().to(*args, **kwargs)
+        return out
+
+    def load_state_dict(self, state_dict, strict: bool = True):
+        res = super().load_state_dict(state_dict, strict=strict)  # copies in place into the flat views
+        self._planes_stale = True
+        return res
+
+    def refresh_weight_planes(self) -> None:
+        ops.split_planes(self.fc_e0.weight.data, self.We0p)
+        ops.split_planes(self.Wh, self.Whp)
+        ops.split_planes(self.fc_d0.weight.data, self.Wd0p)
+        ops.split_planes(self.fc_logits.weight.data, self.Wlp)
+        self._planes_stale = False
+
+    def mark_parameters_changed(self) -> None:
+        """Call after modifying parameters outside of train_step (external optimizers are handled automatically)."""
+        self._planes_stale = True
+
+    def _workspace(self, B: int) -> _Workspace:
+        ws = self._ws.get(B)
+        if ws is None:
+            ws = self._ws[B] = _Workspace(self, B)
+        return ws
+
+    # ------------------------------------------------------------------------------------------ kernel sequences
+    def _forward_kernels(self, ws: _Workspace, beta: float, train: bool, want_mu_sigma: bool, logits: Optional[Tensor]):
+        B, D, H, P, Sd = ws.B, self.in_dim, self.h_dim, self.desc.ld_ml, self.desc.ld_z
+        if self._planes_stale:
+            self.refresh_weight_planes()
+        ops.split_planes(ws.x, ws.xp)
+        ops.gemm(ws.xp, self.We0p, B, H, D, epilogue=L.EPI_BIAS_RELU, bias=self.fc_e0.bias.data, out_planes=ws.hp)
+        ops.gemm(ws.hp, self.Whp, B, P, H, bias=self.bh, out_f32=ws.ml)
+        out = {"z": ws.z, "kl": ws.kl, "mu": ws.mu, "sigma": ws.sigma}
+        ops.pm_forward(self.desc, ws.ml, ws.eps, self._rflat, want_mu_sigma=want_mu_sigma,
+                       flag=ws.flag if self.check_finite else None, out=out)
+        ops.split_planes(ws.z, ws.zp)
+        ops.gemm(ws.zp, self.Wd0p, B, H, Sd, epilogue=L.EPI_BIAS_RELU, bias=self.fc_d0.bias.data, out_planes=ws.ddp)
+        ws.bce.zero_()
+        epi = L.EPI_BCE_ROWSUM if self.recon_kind == "bce" else L.EPI_NLL_ROWSUM
+        ops.gemm(ws.ddp, self.Wlp, B, D, H, epilogue=epi, bias=self.fc_logits.bias.data, aux=ws.x, rowsum=ws.bce,
+                 out_planes=ws.gLp if train else None, out_f32=logits)
+        ops.elbo_reduce(ws.bce, ws.kl, beta, out=self._stats)
+
+    def _backward_kernels(self, ws: _Workspace, beta: float):
+        B, D, H, P, Sd, C = ws.B, self.in_dim, self.h_dim, self.desc.ld_ml, self.desc.ld_z, self.desc.C
+        self._bucket[:self._n_net + C].zero_()
+        MN = L.MN_MAJOR
+        # fc_logits: gW = gL^T dd (+ bias from the ones column of dd), then gdd = (gL W) * 1[dd > 0]
+        ops.gemm(ws.gLp, ws.ddp, D, H + 1, B, a_major=MN, b_major=MN, split_k=0, out_f32=self.gWl, out_col=self.gbl,
+                 col_split=H)
+        ops.gemm(ws.gLp, self.Wlp, B, H, D, b_major=MN, epilogue=L.EPI_RELU_MASK, mask=ws.ddp, out_planes=ws.gddp)
+        # fc_d0
+        ops.gemm(ws.gddp, ws.zp, H, Sd + 1, B, a_major=MN, b_major=MN, split_k=0, out_f32=self.gWd0,
+                 out_col=self.gbd0, col_split=Sd)
+        ops.gemm(ws.gddp, self.Wd0p, B, Sd, H, b_major=MN, out_f32=ws.gz)
+        # latent: d(-ELBO)/d kl = beta
+        ops.pm_backward(self.desc, ws.ml, ws.eps, self._rflat, ws.gz, None, beta, gml=ws.gml, gradius=self._gradius)
+        ops.split_planes(ws.gml, ws.gmlp)
+        # heads
+        ops.gemm(ws.gmlp, ws.hp, P, H + 1, B, a_major=MN, b_major=MN, split_k=0, out_f32=self.gWh, out_col=self.gbh,
+                 col_split=H)
+        ops.gemm(ws.gmlp, self.Whp, B, H, P, b_major=MN, epilogue=L.EPI_RELU_MASK, mask=ws.hp, out_planes=ws.ghp)
+        # fc_e0 (no dgrad into x)
+        ops.gemm(ws.ghp, ws.xp, H, D + 1, B, a_major=MN, b_major=MN, split_k=0, out_f32=self.gWe0,
+                 out_col=self.gbe0, col_split=D)
+
+    def _stage(self, ws: _Workspace, x: Tensor, eps: Optional[Tensor]) -> None:
+        ws.x.copy_(x.reshape(ws.B, self.in_dim), non_blocking=True)  # H2D if x lives on the host
+        if eps is None:
+            eps = self._eps_override
+        if eps is None:
+            ws.eps.normal_()
+        else:
+            ws.eps.copy_(eps, non_blocking=True)
+
+    # ------------------------------------------------------------------------------------------ reference API
+    def encode(self, x: Tensor) -> Tensor:
+        """ffnn_vae.py:42-50 -> relu(fc_e0(x)) as fp32."""
+        ws = self._workspace(x.shape[0])
+        ws.x.copy_(x)
+        if self._planes_stale:
+            self.refresh_weight_planes()
+        ops.split_planes(ws.x, ws.xp)
+        h = torch.empty(ws.B, self.h_dim, device=self.device)
+        ops.gemm(ws.xp, self.We0p, ws.B, self.h_dim, self.in_dim, epilogue=L.EPI_BIAS_RELU,
+                 bias=self.fc_e0.bias.data, out_planes=ws.hp, out_f32=h)
+        return h
+
+    def decode(self, concat_z: Tensor) -> Tensor:
+        """ffnn_vae.py:52-60 for [B, total_z_dim] or [n, B, total_z_dim]."""
+        lead = concat_z.shape[:-1]
+        z2 = concat_z.reshape(-1, self.total_z_dim).float().contiguous()
+        Bz = z2.shape[0]
+        if self._planes_stale:
+            self.refresh_weight_planes()
+        zp = ops.PlaneBuf(Bz, self.total_z_dim, 2, self.device)
+        ddp = ops.PlaneBuf(Bz, self.h_dim, 2, self.device)
+        ops.split_planes(z2, zp)
+        ops.gemm(zp, self.Wd0p, Bz, self.h_dim, self.total_z_dim, epilogue=L.EPI_BIAS_RELU, bias=self.fc_d0.bias.data,
+                 out_planes=ddp)
+        out = torch.empty(Bz, self.in_dim, device=self.device)
+        ops.gemm(ddp, self.Wlp, Bz, self.in_dim, self.h_dim, bias=self.fc_logits.bias.data, out_f32=out)
+        return out.reshape(*lead, self.in_dim)
+
+    def _reparametrized(self, ws: _Workspace) -> List[Reparametrized]:
+        res = []
+        for i, c in enumerate(self.components):
+            d = self.desc.comp[i]
+            loc = ws.mu[:, d.z_off:d.z_off + d.d]
+            scale = ws.sigma[:, d.eps_off:d.eps_off + d.n]
+            z = ws.z[:, d.z_off:d.z_off + d.d]
+            if c.kind == L.EUCLIDEAN:
+                q_z = EuclideanNormal(loc, scale)
+                p_z = EuclideanNormal(torch.zeros_like(loc), torch.ones_like(scale))
+            else:
+                q_z = WrappedNormal(loc, scale, c.manifold)
+                p_z = WrappedNormal(c.manifold.mu_0(loc.shape, device=loc.device, dtype=loc.dtype),
+                                    torch.ones_like(scale), c.manifold)
+            res.append(Reparametrized(q_z, p_z, z, ws.kl[:, i], ws.eps[:, d.eps_off:d.eps_off + d.n]))
+        return res
+
+    @torch.no_grad()
+    def forward(self, x: Tensor, eps: Optional[Tensor] = None, beta: float = 1.0):
+        """vae.py:69-80 -> (List[Reparametrized], concat_z, x_).  Also leaves the ELBO statistics of this batch in
+        the stats vector (see compute_batch_stats)."""
+        x = x.to(self.device, non_blocking=True)
+        ws = self._workspace(x.shape[0])
+        self._stage(ws, x, eps)
+        if ws.logits is None:
+            ws.logits = torch.empty(ws.B, self.in_dim, device=self.device)
+        self._forward_kernels(ws, beta, train=False, want_mu_sigma=True, logits=ws.logits)
+        self._last_ws = ws
+        return self._reparametrized(ws), ws.z, ws.logits
+
+    @torch.no_grad()
+    def compute_batch_stats(self, x_mb: Tensor, x_mb_: Tensor, reparametrized: List[Reparametrized], beta: float,
+                            likelihood_n: int = 0) -> BatchStats:
+        """vae.py:125-147: bce row sums of the given logits + the per-component KL of `reparametrized` -> BatchStats."""
+        if likelihood_n:
+            raise NotImplementedError("log_likelihood (IWAE, vae.py:82-123) is outside the round-1 hot path")
+        x_mb = x_mb.to(self.device).float().contiguous()
+        bce, _ = ops.recon_loss(self.recon_kind, x_mb_.float().contiguous(), x_mb)
+        kl = torch.stack([r.kl for r in reparametrized], dim=-1).contiguous()
+        vec = ops.elbo_reduce(bce, kl, beta)
+        return BatchStats(vec, beta, bce, kl)
+
+    @torch.no_grad()
+    def train_step(self, optimizer, x_mb: Tensor, beta: float, eps: Optional[Tensor] = None,
+                   sync_stats: bool = True):
+        """vae.py:149-166: zero_grad, forward, ELBO, backward, (clip: no 'curvature'-named params here), optimizer
+        step, stats to floats.  Returns (BatchStatsFloat | BatchStats, (reparametrized, concat_z, x_mb_)); x_mb_
+        (the logits) is not materialised in training — call forward() when it is needed."""
+        ws = self._workspace(x_mb.shape[0])
+        self._stage(ws, x_mb, eps)
+        fused = isinstance(optimizer, FusedCurvatureOptimizer)
+        if not fused:
+            optimizer.zero_grad()
+        self._forward_kernels(ws, beta, train=True, want_mu_sigma=False, logits=None)
+        self._backward_kernels(ws, beta)
+        if self._grad_hook is not None:
+            self._grad_hook(self._bucket)  # data-parallel: one SUM all-reduce over [grads | radius grads | stats]
+        if not fused:
+            self._attach_grads()
+        optimizer.step()
+        self._planes_stale = True
+        stats = BatchStats(self._stats.clone() if not sync_stats else self._stats, beta)
+        self._last_ws = ws
+        out = (None, ws.z, None)
+        if sync_stats:
+            if self.check_finite and int(ws.flag.item()) != 0:
+                raise FloatingPointError("non-finite latent sample or KL term (device flag set by mvae_pm_forward)")
+            return stats.convert_to_float(), out
+        return stats, out
+
+    _grad_hook = None
+
+    def _attach_grads(self) -> None:
+        """torch optimizers' zero_grad(set_to_none=True) drops .grad; re-attach the bucket views."""
+        for name, p in self._net_params():
+            o, n = self._slices[name]
+            p.grad = self._bucket[o:o + n].view(p.shape)
+        for i, c in enumerate(self.components):
+            _, rp = c.radius_parameter()
+            if rp is not None and rp.requires_grad:
+                rp.grad = self._bucket[self._n_net + i]
+
+    def reparametrized_of_last_step(self) -> List[Reparametrized]:
+        return self._reparametrized(self._last_ws)
+
+
+class FusedCurvatureOptimizer:
+    """Kernel counterpart of Trainer.build_optimizer (train.py:327-360) + CurvatureOptimizer (utils.py:148-180):
+    Adam(lr) over every network parameter (one launch over the flat bucket) and SGD(lr=1e-4) over the radii,
+    stepped only when `should_do_curvature_step()` (reference: not fixed_curvature and epoch >= 10)."""
+
+    def __init__(self, model: FusedFeedForwardVAE, learning_rate: float = 1e-3, fixed_curvature: bool = True,
+                 should_do_curvature_step=lambda: False, curvature_lr: float = 1e-4, betas=(0.9, 0.999),
+                 eps: float = 1e-8) -> None:
+        self.model = model
+        self.lr, self.betas, self.eps = learning_rate, betas, eps
+        self.fixed_curvature = fixed_curvature
+        self.curv_condition = should_do_curvature_step
+        self.curvature_lr = curvature_lr
+        self.exp_avg = torch.zeros_like(model._flat)
+        self.exp_avg_sq = torch.zeros_like(model._flat)
+        self.step_count = 0
+        self.param_groups = [{"params": [p for _, p in model._net_params()], "lr": learning_rate}]
+
+    def zero_grad(self) -> None:
+        pass  # the backward kernels overwrite / zero the bucket themselves
+
+    def step(self, closure=None) -> None:
+        m = self.model
+        self.step_count += 1
+        ops.adam_step(m._flat, m._gnet, self.exp_avg, self.exp_avg_sq, self.lr, self.step_count, self.betas[0],
+                      self.betas[1], self.eps)
+        if (not self.fixed_curvature) and self.curv_condition():
+            g = m._gradius * m._radius_mask
+            ops.sgd_step(m._rflat, g, self.curvature_lr)
+
+    def state_dict(self):
+        return {"exp_avg": self.exp_avg, "exp_avg_sq": self.exp_avg_sq, "step": self.step_count}
+
+    def load_state_dict(self, sd) -> None:
+        self.exp_avg.copy_(sd["exp_avg"])
+        self.exp_avg_sq.copy_(sd["exp_avg_sq"])
+        self.step_count = int(sd["step"])
