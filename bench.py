@@ -1,0 +1,368 @@
+#!/usr/bin/env python
+"""bench.py — ELBO training throughput of the mvae hot path on B200 (see BASELINE.json / DESIGN.md §6).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg2|cfg3|cfg4a|cfg4b|cfg1]
+
+A step = one full ModelVAE.train_step (vae.py:149-166) on one synthetic MNIST-shaped batch: forward, ELBO, backward,
+optimizer update (+ the single gradient all-reduce when N > 1).  N=1 workload = BASELINE.json configs[1]
+(MNIST h2,s2,e2, learnable curvature, batch 4096); N>1 keeps 4096 samples per GPU (weak scaling).
+
+  value   whole-job samples/s (steps/s x global batch), inputs resident in HBM, CUDA-event timed, L2 flushed between steps
+  e2e     the same through the public API model.train_step(optimizer, x_host, beta): pinned-host -> device copy of the
+          batch and device -> host read of the ELBO statistics inside the timed region
+  roofline  the fused product-manifold kernel (the kernel BASELINE names): algorithmic bytes / CUDA-event time vs
+            the measured HBM copy bandwidth; `roofline_gemm` does the same for the tcgen05 GEMM against measured bf16
+  cpu_baseline / --impl reference   the oracle port of the reference's algorithm (oracle/, numpy BLAS + C/OpenMP) on the
+          host cores; the reference itself is pure Python and is not present on the GPU box
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (signature, per-GPU batch, in_dim, h_dim, recon, fixed_curvature, description)
+    "cfg1": ("e2", 128, 784, 400, "bce", True, "MNIST e2 fixed curvature batch 128"),
+    "cfg2": ("h2,s2,e2", 4096, 784, 400, "bce", False, "MNIST h2,s2,e2 learnable curvature batch 4096"),
+    "cfg3": ("h6,h6,s6,s6,e6", 8192, 784, 400, "bce", False, "MNIST h6,h6,s6,s6,e6 batch 8192 per GPU"),
+    "cfg4a": ("h2", 16384, 50, 400, "nll", False, "BDP-shaped h2 (hyperboloid) batch 16384"),
+    "cfg4b": ("p2", 16384, 50, 400, "nll", False, "BDP-shaped p2 (Poincare ball) batch 16384"),
+}
+METRIC = "ELBO train throughput (steps/sec x global batch)"
+UNIT = "samples/s"
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as fh:
+            d = json.load(fh)
+        return {"hbm_gbs": d["hbm_gbs"], "bf16_tflops": d["bf16_tflops"], "source": "measured (MEASURED_PEAKS.json)"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "source": "fallback (B200_PROFILING.md)"}
+
+
+def synthetic_x(recon, B, D, seed):
+    import torch
+    g = torch.Generator().manual_seed(seed)
+    if recon == "bce":
+        return (torch.rand(B, D, generator=g) < 0.1307).float()
+    return torch.randn(B, D, generator=g)
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+                for n, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except (ValueError, IndexError):
+                pass
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------ CPU arm
+def cpu_step_fn(workload, B, seed=0):
+    """One train step of the oracle port (forward + ELBO + backward + Adam) in float32 on the host cores."""
+    import numpy as np
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import oracle as orc
+    sig, _, D, H, recon, fixed, _ = WORKLOADS[workload]
+    from mvae_b200 import components
+    torch.manual_seed(seed)
+    comps = components.parse_components(sig, fixed)
+    types, dims = orc.parse_signature(sig)
+    ov = orc.OracleVAE(sig, D, H, recon, False)
+    # reference-shaped parameters with nn.Linear default init (CPU only; no kernels involved)
+    params = {}
+    for i, c in enumerate(comps):
+        c.init_layers(H, False)
+        params[f"components.{i}.fc_mean.weight"] = c.fc_mean.weight.detach().numpy().copy()
+        params[f"components.{i}.fc_mean.bias"] = c.fc_mean.bias.detach().numpy().copy()
+        params[f"components.{i}.fc_logvar.weight"] = c.fc_logvar.weight.detach().numpy().copy()
+        params[f"components.{i}.fc_logvar.bias"] = c.fc_logvar.bias.detach().numpy().copy()
+        name, rp = c.radius_parameter()
+        if rp is not None:
+            params[f"components.{i}.{name}"] = np.asarray(1.0, dtype=np.float32)
+    tz = sum(c.dim for c in comps)
+    for nm, (o, i_) in (("fc_e0", (H, D)), ("fc_d0", (H, tz)), ("fc_logits", (D, H))):
+        lin = torch.nn.Linear(i_, o)
+        params[nm + ".weight"] = lin.weight.detach().numpy().copy()
+        params[nm + ".bias"] = lin.bias.detach().numpy().copy()
+    x = synthetic_x(recon, B, D, seed).numpy()
+    rng = np.random.default_rng(seed)
+    m = {k: np.zeros_like(v) for k, v in params.items()}
+    v = {k: np.zeros_like(v) for k, v in params.items()}
+    state = {"t": 0}
+
+    def step():
+        eps = rng.standard_normal((B, ov.desc.ld_eps), dtype=np.float32)
+        out = ov.step(params, x, eps, beta=1.0)
+        state["t"] += 1
+        t = state["t"]
+        for k, g in out["grads"].items():
+            if "radius" in k:
+                continue
+            g = g.astype(np.float32)
+            m[k] = 0.9 * m[k] + 0.1 * g
+            v[k] = 0.999 * v[k] + 0.001 * g * g
+            params[k] = params[k] - (1e-3 / (1 - 0.9**t)) * m[k] / (np.sqrt(v[k]) / np.sqrt(1 - 0.999**t) + 1e-8)
+        return out["elbo"]
+
+    return step
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    os.environ.setdefault("OMP_NUM_THREADS", str(cores))
+    sig, B, D, H, recon, fixed, desc = WORKLOADS[args.workload]
+    step = cpu_step_fn(args.workload, B)
+    for _ in range(max(args.warmup, 1)):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = time.perf_counter() - t0
+    ms = dt / args.steps * 1e3
+    value = B / (ms / 1e3)
+    sample = f"{args.steps} full steps of batch {B} ({desc}), float32"
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms, "steps_per_sec": 1e3 / ms, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": desc, "signature": sig, "batch_per_gpu": B, "global_batch": B, "in_dim": D,
+                       "h_dim": H, "note": "CPU arm runs one replica of the per-GPU workload on the host cores"},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------ GPU arm
+def time_kernel(fn, iters, flush):
+    import torch
+    s = [torch.cuda.Event(enable_timing=True) for _ in range(iters)]
+    e = [torch.cuda.Event(enable_timing=True) for _ in range(iters)]
+    for _ in range(3):
+        fn()
+    for i in range(iters):
+        flush()
+        s[i].record()
+        fn()
+        e[i].record()
+    torch.cuda.synchronize()
+    return sum(a.elapsed_time(b) for a, b in zip(s, e)) / iters  # ms
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from mvae_b200 import components, data, ops, parallel, vae
+    rank, world, local = parallel.init_from_env("nccl")
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (the mvae_b200 path has no CPU fallback)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    sig, B, D, H, recon, fixed, desc = WORKLOADS[args.workload]
+    peaks = measured_peaks()
+    torch.manual_seed(0)
+    comps = components.parse_components(sig, fixed)
+    model = vae.FusedFeedForwardVAE(H, comps, data.GenericDataset(B, D, recon), False, device=dev)
+    model.use_cuda_graph = not args.no_graph
+    opt = vae.FusedCurvatureOptimizer(model, 1e-3, fixed_curvature=fixed, should_do_curvature_step=lambda: True)
+    if world > 1:
+        parallel.broadcast_parameters(model)
+        parallel.attach(model)
+    C, Sn, Sd, P = model.desc.C, model.desc.ld_eps, model.desc.ld_z, model.desc.ld_ml
+    # distinct batches per rank, rotated so that consecutive steps never see the same input
+    n_rot = 4
+    xs_host = [synthetic_x(recon, B, D, 1000 * rank + i).pin_memory() for i in range(n_rot)]
+    xs_dev = [x.to(dev) for x in xs_host]
+    flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+
+    def flush():
+        flush_buf.zero_()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---------------- value: device-resident inputs, no host sync inside the timed region ----------------
+    for i in range(max(args.warmup, 3)):
+        model.train_step(opt, xs_dev[i % n_rot], 1.0, sync_stats=False)
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    n0 = ops.launch_count()
+    starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    ends = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    barrier()
+    for i in range(args.steps):
+        flush()
+        starts[i].record()
+        model.train_step(opt, xs_dev[i % n_rot], 1.0, sync_stats=False)
+        ends[i].record()
+    barrier()
+    launches = ops.launch_count() - n0
+    total_ms = sum(a.elapsed_time(b) for a, b in zip(starts, ends))
+    if world > 1:
+        t = torch.tensor([total_ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms = float(t.item())
+    ms = total_ms / args.steps
+    clocks = sampler.stop() if rank == 0 else None
+    stats_vec = model._stats.clone()
+
+    # ---------------- e2e: public API with host buffers (H2D of x, D2H of the statistics, every step) ----------------
+    for i in range(3):
+        model.train_step(opt, xs_host[i % n_rot], 1.0)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        bs, _ = model.train_step(opt, xs_host[i % n_rot], 1.0)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([e2e_s], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    e2e_ms = e2e_s / args.steps * 1e3
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    gb = B * world
+    line = {"metric": METRIC, "value": gb / (ms / 1e3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms, "steps_per_sec": 1e3 / ms, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32 (split-bf16 tensor-core GEMMs, fp32 accumulate)",
+            "data": "synthetic",
+            "config": {"workload": desc, "signature": sig, "batch_per_gpu": B, "global_batch": gb, "in_dim": D,
+                       "h_dim": H, "parallelism": f"dp{world}", "l2": "flushed between timed steps (256 MiB memset)",
+                       "cuda_graph": bool(model.use_cuda_graph), "optimizer": "Adam(1e-3) + SGD(1e-4) on radii"},
+            "e2e": {"value": gb / (e2e_ms / 1e3), "unit": UNIT, "ms_per_step": e2e_ms,
+                    "h2d_bytes_per_step": B * D * 4, "d2h_bytes_per_step": (3 + C) * 4},
+            "gpu_launches": int(launches), "clocks": clocks, "elbo_per_sample": float(bs.elbo) / gb,
+            "peaks": peaks["source"]}
+
+    # ---------------- roofline of the fused product-manifold kernel (HBM bound) ----------------
+    if not args.skip_roofline:
+        bytes_fwd = 4 * (3 * Sn + Sd + C)   # read ml (2 Sn = m|l), eps (Sn); write z (Sd), kl (C)   [SURVEY §8d]
+        bytes_bwd = 4 * (5 * Sn + Sd)       # read ml, eps, gz; write gml
+        Bbig = 1 << 22
+        g = torch.Generator(device=dev).manual_seed(0)
+        ml = torch.randn(Bbig, P, device=dev, generator=g) * 0.5
+        eps = torch.randn(Bbig, Sn, device=dev, generator=g)
+        z = torch.empty(Bbig, Sd, device=dev)
+        kl = torch.empty(Bbig, C, device=dev)
+        out = {"z": z, "kl": kl}
+        ms_f = time_kernel(lambda: ops.pm_forward(model.desc, ml, eps, model._rflat, out=out), 20, flush)
+        gz = torch.randn(Bbig, Sd, device=dev, generator=g)
+        gml = torch.empty_like(ml)
+        gR = torch.zeros(C, device=dev)
+        ms_b = time_kernel(lambda: ops.pm_backward(model.desc, ml, eps, model._rflat, gz, None, 1.0, gml=gml, gradius=gR),
+                           20, flush)
+        ws = model._workspace(B)
+        ms_f_cfg = time_kernel(lambda: ops.pm_forward(model.desc, ws.ml, ws.eps, model._rflat,
+                                                      out={"z": ws.z, "kl": ws.kl}), 20, flush)
+        ach = Bbig * bytes_fwd / (ms_f * 1e-3) / 1e9
+        line["roofline"] = {"kernel": "pm_forward_kernel", "bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"],
+                            "unit": "GB/s", "frac": ach / peaks["hbm_gbs"], "traffic": None,
+                            "bytes_per_sample": bytes_fwd, "samples_per_launch": Bbig, "us_per_launch": ms_f * 1e3,
+                            "us_at_config_batch": ms_f_cfg * 1e3, "peak_source": peaks["source"]}
+        achb = Bbig * bytes_bwd / (ms_b * 1e-3) / 1e9
+        line["roofline_backward"] = {"kernel": "pm_backward_kernel", "bound": "hbm", "achieved": achb,
+                                     "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achb / peaks["hbm_gbs"],
+                                     "bytes_per_sample": bytes_bwd, "samples_per_launch": Bbig,
+                                     "us_per_launch": ms_b * 1e3}
+        del ml, eps, z, kl, gz, gml
+        # tcgen05 GEMM (tensor bound): encoder layer of the workload, algorithmic flops 2*B*D*H
+        ms_g = time_kernel(lambda: ops.gemm(ws.xp, model.We0p, B, H, D, epilogue=1, bias=model.fc_e0.bias.data,
+                                            out_planes=ws.hp), 20, flush)
+        tf = 2.0 * B * D * H / (ms_g * 1e-3) / 1e12
+        line["roofline_gemm"] = {"kernel": "gemm_tcgen05_kernel (fc_e0 forward)", "bound": "tensor", "achieved": tf,
+                                 "peak": peaks["bf16_tflops"], "unit": "TFLOP/s", "frac": tf / peaks["bf16_tflops"],
+                                 "us_per_launch": ms_g * 1e3,
+                                 "note": "algorithmic fp32 flops; the kernel issues 3 bf16 MMAs per product (split planes)"}
+
+    # ---------------- CPU baseline (oracle port on the host cores), bounded sample ----------------
+    if world == 1 and not args.skip_cpu:
+        cores = os.cpu_count() or 1
+        torch.set_num_threads(cores)
+        step = cpu_step_fn(args.workload, B)
+        step()
+        n_cpu = 5
+        t0 = time.perf_counter()
+        for _ in range(n_cpu):
+            step()
+        dt = (time.perf_counter() - t0) / n_cpu
+        line["cpu_baseline"] = {"value": B / dt, "unit": UNIT, "cores": cores, "kind": "port",
+                                "sample": f"{n_cpu} full steps of batch {B}, float32, numpy BLAS + C/OpenMP oracle",
+                                "ms_per_step": dt * 1e3}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly instead of replaying CUDA graphs")
+    ap.add_argument("--skip-roofline", action="store_true")
+    ap.add_argument("--skip-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

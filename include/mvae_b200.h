@@ -227,6 +227,12 @@ int mvae_elbo_reduce(int64_t B, int32_t C, const float* bce, const float* kl, fl
 int mvae_adam_step(int64_t n, float* param, const float* grad, float* exp_avg, float* exp_avg_sq, float lr,
                    float beta1, float beta2, float eps, int32_t step, float grad_scale, void* stream);
 
+/* Same update with the 1-based step counter on the device: *step_dev is incremented first (in stream order), then
+ * used for the bias corrections — nothing step-dependent is baked into launch parameters, so the call can be
+ * captured once in a CUDA graph and replayed. */
+int mvae_adam_step_dev(int64_t n, float* param, const float* grad, float* exp_avg, float* exp_avg_sq, float lr,
+                       float beta1, float beta2, float eps, int32_t* step_dev, float grad_scale, void* stream);
+
 /* Plain SGD step p -= lr * grad_scale * g (torch.optim.SGD defaults — the curvature optimizers of train.py:346-355). */
 int mvae_sgd_step(int64_t n, float* param, const float* grad, float lr, float grad_scale, void* stream);
 

@@ -66,6 +66,7 @@ PROTOTYPES = {
     "mvae_recon_loss": (ctypes.c_int, [_i32, _i64, _i32, _vp, _vp, _vp, _vp, _vp]),
     "mvae_elbo_reduce": (ctypes.c_int, [_i64, _i32, _vp, _vp, _f32, _vp, _vp]),
     "mvae_adam_step": (ctypes.c_int, [_i64, _vp, _vp, _vp, _vp, _f32, _f32, _f32, _f32, _i32, _f32, _vp]),
+    "mvae_adam_step_dev": (ctypes.c_int, [_i64, _vp, _vp, _vp, _vp, _f32, _f32, _f32, _f32, _vp, _f32, _vp]),
     "mvae_sgd_step": (ctypes.c_int, [_i64, _vp, _vp, _f32, _f32, _vp]),
     "mvae_device_info": (ctypes.c_int, [ctypes.POINTER(_i32), ctypes.POINTER(_i32), ctypes.POINTER(_i32)]),
 }

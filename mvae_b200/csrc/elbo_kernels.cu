@@ -133,6 +133,29 @@ __global__ void __launch_bounds__(256) adam_kernel(int64_t n, float* __restrict_
   }
 }
 
+// Same update with the step counter living on the device (CUDA-graph replay: nothing step-dependent is baked into
+// the launch parameters).  bump_step_kernel runs first in stream order.
+__global__ void bump_step_kernel(int32_t* step) { *step += 1; }
+__global__ void __launch_bounds__(256) adam_dev_kernel(int64_t n, float* __restrict__ p, const float* __restrict__ g,
+                                                       float* __restrict__ m, float* __restrict__ v, float lr,
+                                                       float b1, float b2, float eps, const int32_t* __restrict__ step,
+                                                       float gscale) {
+  const double st = (double)(*step);
+  const float step_size = (float)((double)lr / (1.0 - pow((double)b1, st)));
+  const float inv_bc2_sqrt = (float)(1.0 / sqrt(1.0 - pow((double)b2, st)));
+  const float w1 = 1.f - b1, w2 = 1.f - b2;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    float gi = g[i] * gscale;
+    float mi = m[i];
+    mi = mi + (gi - mi) * w1;
+    float vi = v[i] * b2 + w2 * (gi * gi);
+    m[i] = mi;
+    v[i] = vi;
+    float denom = sqrtf(vi) * inv_bc2_sqrt + eps;
+    p[i] = p[i] - step_size * (mi / denom);
+  }
+}
+
 __global__ void __launch_bounds__(256) sgd_kernel(int64_t n, float* __restrict__ p, const float* __restrict__ g,
                                                   float lr, float gscale) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
@@ -247,6 +270,25 @@ extern "C" int mvae_adam_step(int64_t n, float* param, const float* grad, float*
   const int grid = (int)(want < (int64_t)di.sm_count * 8 ? want : (int64_t)di.sm_count * 8);
   adam_kernel<<<grid, 256, 0, as_stream(stream)>>>(n, param, grad, exp_avg, exp_avg_sq, 1.f - beta1, beta2,
                                                    1.f - beta2, step_size, inv_bc2_sqrt, eps, grad_scale);
+  MVAE_LAUNCH_CHECK();
+  return MVAE_OK;
+}
+
+extern "C" int mvae_adam_step_dev(int64_t n, float* param, const float* grad, float* exp_avg, float* exp_avg_sq,
+                                  float lr, float beta1, float beta2, float eps, int32_t* step_dev, float grad_scale,
+                                  void* stream) {
+  if (n < 0 || !step_dev) return MVAE_ERR_INVALID_ARGUMENT;
+  if (n > 0 && (!param || !grad || !exp_avg || !exp_avg_sq)) return MVAE_ERR_INVALID_ARGUMENT;
+  DeviceInfo di;
+  int rc = get_device_info(&di);
+  if (rc != MVAE_OK) return rc;
+  bump_step_kernel<<<1, 1, 0, as_stream(stream)>>>(step_dev);
+  MVAE_LAUNCH_CHECK();
+  if (n == 0) return MVAE_OK;
+  const int64_t want = (n + 255) / 256;
+  const int grid = (int)(want < (int64_t)di.sm_count * 8 ? want : (int64_t)di.sm_count * 8);
+  adam_dev_kernel<<<grid, 256, 0, as_stream(stream)>>>(n, param, grad, exp_avg, exp_avg_sq, lr, beta1, beta2, eps,
+                                                       step_dev, grad_scale);
   MVAE_LAUNCH_CHECK();
   return MVAE_OK;
 }

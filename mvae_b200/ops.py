@@ -9,6 +9,19 @@ import torch
 from . import _lib as L
 
 
+_LAUNCHES = [0]
+
+
+def launch_count() -> int:
+    """Number of kernel launches issued through this module (each C entry point = its kernels; graph replays are
+    added by the caller through add_launches)."""
+    return _LAUNCHES[0]
+
+
+def add_launches(n: int) -> None:
+    _LAUNCHES[0] += n
+
+
 def _ptr(t: Optional[torch.Tensor]):
     return None if t is None else ctypes.c_void_p(t.data_ptr())
 
@@ -72,6 +85,7 @@ def pm_forward(desc: L.PmDesc, ml, eps, radius, want_mu_sigma: bool = False, fla
     rc = L.lib().mvae_pm_forward(ctypes.byref(desc), B, _ptr(ml), _ptr(eps), _ptr(radius), _ptr(z), _ptr(kl), _ptr(mu),
                                  _ptr(sigma), _ptr(flag), _stream())
     L.check(rc, "mvae_pm_forward")
+    _LAUNCHES[0] += 1
     res = {"z": z, "kl": kl}
     if want_mu_sigma:
         res.update(mu=mu, sigma=sigma)
@@ -91,6 +105,7 @@ def pm_backward(desc: L.PmDesc, ml, eps, radius, gz, gkl: Optional[torch.Tensor]
     rc = L.lib().mvae_pm_backward(ctypes.byref(desc), B, _ptr(ml), _ptr(eps), _ptr(radius), _ptr(gz), _ptr(gkl),
                                   float(gkl_scalar), _ptr(gml), _ptr(gradius), _stream())
     L.check(rc, "mvae_pm_backward")
+    _LAUNCHES[0] += 1
     return gml, gradius
 
 
@@ -109,6 +124,7 @@ def manifold_op(op: int, manifold: int, n: int, x, y=None, radius=None):
     out = torch.empty(B, out_w, device=x.device)
     rc = L.lib().mvae_manifold_op(op, manifold, n, B, _ptr(x2), _ptr(y2), _ptr(radius), _ptr(out), _stream())
     L.check(rc, "mvae_manifold_op")
+    _LAUNCHES[0] += 1
     return out.reshape(*lead, out_w)
 
 
@@ -119,6 +135,7 @@ def wn_rsample(manifold: int, n: int, loc, scale, eps, radius):
     rc = L.lib().mvae_wn_rsample(manifold, n, B, _ptr(loc), _ptr(scale), _ptr(eps), _ptr(radius), _ptr(z), _ptr(u),
                                  _ptr(v), _stream())
     L.check(rc, "mvae_wn_rsample")
+    _LAUNCHES[0] += 1
     return z, u, v
 
 
@@ -129,6 +146,7 @@ def wn_log_prob_from_parts(manifold: int, n: int, loc, scale, z, u, v, radius):
     rc = L.lib().mvae_wn_log_prob_from_parts(manifold, n, B, *[_ptr(t) for t in args], _ptr(radius), _ptr(logp),
                                              _stream())
     L.check(rc, "mvae_wn_log_prob_from_parts")
+    _LAUNCHES[0] += 1
     return logp
 
 
@@ -138,6 +156,7 @@ def wn_log_prob(manifold: int, n: int, loc, scale, z, radius):
     logp = torch.empty(B, device=args[0].device)
     rc = L.lib().mvae_wn_log_prob(manifold, n, B, *[_ptr(t) for t in args], _ptr(radius), _ptr(logp), _stream())
     L.check(rc, "mvae_wn_log_prob")
+    _LAUNCHES[0] += 1
     return logp
 
 
@@ -150,6 +169,7 @@ def recon_loss(kind: str, logits, x, want_grad: bool = False):
     g = torch.empty_like(logits) if want_grad else None
     rc = L.lib().mvae_recon_loss(0 if kind == "bce" else 1, B, D, _ptr(logits), _ptr(x), _ptr(rs), _ptr(g), _stream())
     L.check(rc, "mvae_recon_loss")
+    _LAUNCHES[0] += 1
     return rs, g
 
 
@@ -161,6 +181,7 @@ def elbo_reduce(bce, kl, beta: float, out: Optional[torch.Tensor] = None):
         out = torch.empty(3 + C, device=kl.device)
     rc = L.lib().mvae_elbo_reduce(B, C, _ptr(bce), _ptr(kl), float(beta), _ptr(out), _stream())
     L.check(rc, "mvae_elbo_reduce")
+    _LAUNCHES[0] += 1
     return out
 
 
@@ -168,11 +189,22 @@ def adam_step(param, grad, exp_avg, exp_avg_sq, lr, step, beta1=0.9, beta2=0.999
     rc = L.lib().mvae_adam_step(param.numel(), _ptr(param), _ptr(grad), _ptr(exp_avg), _ptr(exp_avg_sq), float(lr),
                                 float(beta1), float(beta2), float(eps), int(step), float(grad_scale), _stream())
     L.check(rc, "mvae_adam_step")
+    _LAUNCHES[0] += 1
+
+
+def adam_step_dev(param, grad, exp_avg, exp_avg_sq, lr, step_dev, beta1=0.9, beta2=0.999, eps=1e-8, grad_scale=1.0):
+    """Adam with the step counter on the device (int32 tensor, incremented by the call): CUDA-graph replayable."""
+    rc = L.lib().mvae_adam_step_dev(param.numel(), _ptr(param), _ptr(grad), _ptr(exp_avg), _ptr(exp_avg_sq), float(lr),
+                                    float(beta1), float(beta2), float(eps), _ptr(step_dev), float(grad_scale),
+                                    _stream())
+    L.check(rc, "mvae_adam_step_dev")
+    _LAUNCHES[0] += 2
 
 
 def sgd_step(param, grad, lr, grad_scale=1.0):
     rc = L.lib().mvae_sgd_step(param.numel(), _ptr(param), _ptr(grad), float(lr), float(grad_scale), _stream())
     L.check(rc, "mvae_sgd_step")
+    _LAUNCHES[0] += 1
 
 
 # ------------------------------------------------------------------------------------------ planes + GEMM
@@ -211,6 +243,7 @@ def split_planes(src: torch.Tensor, dst: Optional[PlaneBuf] = None, dst_t: Optio
     rc = L.lib().mvae_split_planes(_ptr(src), src.stride(0), R, K, ctypes.byref(ds) if ds is not None else None,
                                    ctypes.byref(dt) if dt is not None else None, _stream())
     L.check(rc, "mvae_split_planes")
+    _LAUNCHES[0] += 1
 
 
 def gemm(a: PlaneBuf, b: PlaneBuf, M: int, N: int, K: int, a_major: int = L.K_MAJOR, b_major: int = L.K_MAJOR,
@@ -241,3 +274,4 @@ def gemm(a: PlaneBuf, b: PlaneBuf, M: int, N: int, K: int, a_major: int = L.K_MA
     g.rowsum = rowsum.data_ptr() if rowsum is not None else None
     rc = L.lib().mvae_gemm(ctypes.byref(g), _stream())
     L.check(rc, "mvae_gemm")
+    _LAUNCHES[0] += 1

@@ -163,6 +163,7 @@ class FusedFeedForwardVAE(nn.Module):
                                 scalar_parametrization)
         assert self.desc.ld_z == self.total_z_dim
         self._ws = {}
+        self._graphs = {}
         self._eps_override: Optional[Tensor] = None
         self._flat = None
         self.check_finite = False
@@ -209,6 +210,8 @@ class FusedFeedForwardVAE(nn.Module):
                 if rp.requires_grad:
                     rp.grad = bucket[n_net + i]
                     self._radius_mask[i] = 1.0
+        self._any_fixed_radius = any((c.radius_parameter()[1] is not None) and (not c.radius_parameter()[1].requires_grad)
+                                     for c in self.components)
         self._flat, self._rflat, self._bucket, self._n_net = flat, rflat, bucket, n_net
         self._gnet = bucket[:n_net]
         self._gradius = bucket[n_net:n_net + C]
@@ -233,6 +236,7 @@ class FusedFeedForwardVAE(nn.Module):
         self.Wlp = ops.PlaneBuf(D, H, 2, dev)
         self._planes_stale = True
         self._ws = {}
+        self._graphs = {}
 
     def _apply(self, fn, *args, **kwargs):
         out = super()._apply(fn, *args, **kwargs)
@@ -302,6 +306,8 @@ class FusedFeedForwardVAE(nn.Module):
         ops.gemm(ws.gddp, self.Wd0p, B, Sd, H, b_major=MN, out_f32=ws.gz)
         # latent: d(-ELBO)/d kl = beta
         ops.pm_backward(self.desc, ws.ml, ws.eps, self._rflat, ws.gz, None, beta, gml=ws.gml, gradius=self._gradius)
+        if self._any_fixed_radius:
+            self._gradius.mul_(self._radius_mask)  # requires_grad=False radii (fixed curvature) get no gradient
         ops.split_planes(ws.gml, ws.gmlp)
         # heads
         ops.gemm(ws.gmlp, ws.hp, P, H + 1, B, a_major=MN, b_major=MN, split_k=0, out_f32=self.gWh, out_col=self.gbh,
@@ -400,16 +406,19 @@ class FusedFeedForwardVAE(nn.Module):
         ws = self._workspace(x_mb.shape[0])
         self._stage(ws, x_mb, eps)
         fused = isinstance(optimizer, FusedCurvatureOptimizer)
-        if not fused:
-            optimizer.zero_grad()
-        self._forward_kernels(ws, beta, train=True, want_mu_sigma=False, logits=None)
-        self._backward_kernels(ws, beta)
-        if self._grad_hook is not None:
-            self._grad_hook(self._bucket)  # data-parallel: one SUM all-reduce over [grads | radius grads | stats]
-        if not fused:
-            self._attach_grads()
-        optimizer.step()
-        self._planes_stale = True
+        if fused and self.use_cuda_graph:
+            self._graphed_step(optimizer, ws, beta)
+        else:
+            if not fused:
+                optimizer.zero_grad()
+            self._forward_kernels(ws, beta, train=True, want_mu_sigma=False, logits=None)
+            self._backward_kernels(ws, beta)
+            if self._grad_hook is not None:
+                self._grad_hook(self._bucket)  # data-parallel: one SUM all-reduce over [grads | radius grads | stats]
+            if not fused:
+                self._attach_grads()
+            optimizer.step()
+            self._planes_stale = True
         stats = BatchStats(self._stats.clone() if not sync_stats else self._stats, beta)
         self._last_ws = ws
         out = (None, ws.z, None)
@@ -420,6 +429,47 @@ class FusedFeedForwardVAE(nn.Module):
         return stats, out
 
     _grad_hook = None
+    use_cuda_graph = False
+
+    def _graphed_step(self, optimizer: "FusedCurvatureOptimizer", ws: _Workspace, beta: float) -> None:
+        """Replay the whole step from CUDA graphs (launch-bound otherwise: ~30 kernels of a few microseconds).
+        Graph A = forward + backward into the gradient bucket; [the data-parallel all-reduce runs between the two,
+        eagerly]; graph B = optimizer step + refresh of the weight planes.  Keyed by everything baked into launch
+        parameters: batch size, beta, and whether the curvature optimizers step."""
+        key = (ws.B, float(beta), optimizer.curvature_step_enabled(), id(optimizer))
+        entry = self._graphs.get(key)
+        if entry is None:
+            if self._planes_stale:
+                self.refresh_weight_planes()
+            # warm-up on a side stream (lazy func attributes / module loading must not happen during capture)
+            side = torch.cuda.Stream(device=self.device)
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                self._forward_kernels(ws, beta, train=True, want_mu_sigma=False, logits=None)
+                self._backward_kernels(ws, beta)
+            torch.cuda.current_stream().wait_stream(side)
+            n0 = ops.launch_count()
+            ga = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(ga):
+                self._forward_kernels(ws, beta, train=True, want_mu_sigma=False, logits=None)
+                self._backward_kernels(ws, beta)
+            n1 = ops.launch_count()
+            gb = torch.cuda.CUDAGraph()
+            saved = optimizer.step_count
+            with torch.cuda.graph(gb):
+                optimizer.step()
+                self.refresh_weight_planes()
+            optimizer.step_count = saved  # capture does not execute
+            n2 = ops.launch_count()
+            entry = self._graphs[key] = (ga, gb, n1 - n0, n2 - n1)
+        ga, gb, la, lb = entry
+        ga.replay()
+        if self._grad_hook is not None:
+            self._grad_hook(self._bucket)
+        gb.replay()
+        optimizer.step_count += 1
+        ops.add_launches(la + lb)
+        self._planes_stale = False
 
     def _attach_grads(self) -> None:
         """torch optimizers' zero_grad(set_to_none=True) drops .grad; re-attach the bucket views."""
@@ -451,24 +501,30 @@ class FusedCurvatureOptimizer:
         self.exp_avg = torch.zeros_like(model._flat)
         self.exp_avg_sq = torch.zeros_like(model._flat)
         self.step_count = 0
+        self.step_dev = torch.zeros(1, device=model._flat.device, dtype=torch.int32)  # 1-based after the first step
         self.param_groups = [{"params": [p for _, p in model._net_params()], "lr": learning_rate}]
 
     def zero_grad(self) -> None:
         pass  # the backward kernels overwrite / zero the bucket themselves
 
+    def curvature_step_enabled(self) -> bool:
+        return (not self.fixed_curvature) and bool(self.curv_condition())
+
     def step(self, closure=None) -> None:
+        """The Adam step counter lives on the device (mvae_adam_step_dev), so this call can be captured in a CUDA
+        graph and replayed."""
         m = self.model
         self.step_count += 1
-        ops.adam_step(m._flat, m._gnet, self.exp_avg, self.exp_avg_sq, self.lr, self.step_count, self.betas[0],
-                      self.betas[1], self.eps)
-        if (not self.fixed_curvature) and self.curv_condition():
-            g = m._gradius * m._radius_mask
-            ops.sgd_step(m._rflat, g, self.curvature_lr)
+        ops.adam_step_dev(m._flat, m._gnet, self.exp_avg, self.exp_avg_sq, self.lr, self.step_dev, self.betas[0],
+                          self.betas[1], self.eps)
+        if self.curvature_step_enabled():
+            ops.sgd_step(m._rflat, m._gradius, self.curvature_lr)  # fixed radii receive no gradient (masked below)
 
     def state_dict(self):
-        return {"exp_avg": self.exp_avg, "exp_avg_sq": self.exp_avg_sq, "step": self.step_count}
+        return {"exp_avg": self.exp_avg, "exp_avg_sq": self.exp_avg_sq, "step": int(self.step_dev.item())}
 
     def load_state_dict(self, sd) -> None:
         self.exp_avg.copy_(sd["exp_avg"])
         self.exp_avg_sq.copy_(sd["exp_avg_sq"])
         self.step_count = int(sd["step"])
+        self.step_dev.fill_(self.step_count)
