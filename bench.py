@@ -207,7 +207,8 @@ def run_ours(args):
     peaks = measured_peaks()
     torch.manual_seed(0)
     comps = components.parse_components(sig, fixed)
-    model = vae.FusedFeedForwardVAE(H, comps, data.GenericDataset(B, D, recon), False, device=dev)
+    model = vae.FusedFeedForwardVAE(H, comps, data.GenericDataset(B, D, recon, binary_inputs=(recon == "bce")), False,
+                                    device=dev)  # MNIST-shaped batches are binarised (0/1): one exact bf16 plane
     model.use_cuda_graph = not args.no_graph
     opt = vae.FusedCurvatureOptimizer(model, 1e-3, fixed_curvature=fixed, should_do_curvature_step=lambda: True)
     if world > 1:

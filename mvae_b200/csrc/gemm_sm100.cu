@@ -174,7 +174,7 @@ __device__ __forceinline__ void store_f32_16(float* out, int64_t ld, int m, int 
   }
 }
 
-__global__ void __launch_bounds__(kGemmThreads, 1)
+__global__ void __launch_bounds__(kGemmThreads, 2)
     gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                         const __grid_constant__ GemmParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -198,6 +198,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
   const uint32_t tmem_slot = bar_base + 8u * (2 * kMaxStages + 1);
   volatile uint32_t* tmem_slot_ptr =
       reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - raw));
+  float* s_bias = reinterpret_cast<float*>(smem_raw + (bar_base + 256u - raw));  // [block_n <= 256] bias slice
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.stages; ++s) {
@@ -295,24 +296,80 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
     const int q = warp & 3;  // TMEM lane quadrant this warp may access
     const int m = m0 + q * 32 + lane;
     const bool row_ok = m < p.M;
-    mbar_wait(tmem_full_bar, 0);
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const int te = threadIdx.x - 64;  // 0..127 within the epilogue warps
+    // stage the bias slice of this tile in shared memory while the main loop runs (split-K: first slice only)
+    {
+      const float* bias = blockIdx.z == 0 ? p.bias : nullptr;
+      for (int i = te; i < p.block_n; i += 128) s_bias[i] = (bias && n0 + i < p.N) ? __ldg(bias + n0 + i) : 0.f;
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+    }
     const bool vec_out = p.out_f32 && ((p.ld_out & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.out_f32) & 15) == 0);
     const bool vec_aux = p.aux && ((p.ld_aux & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.aux) & 15) == 0);
+    const bool is_loss = p.epilogue == MVAE_EPI_BCE_ROWSUM || p.epilogue == MVAE_EPI_NLL_ROWSUM;
+    const bool is_mask = p.epilogue == MVAE_EPI_RELU_MASK;
+    // operands of the epilogue that do not depend on the accumulator are fetched one chunk ahead
+    float t_nxt[16];
+    uint32_t mk_nxt = 0;
+    auto prefetch = [&](int c) {
+      const int n = n0 + c;
+      if (!row_ok || n >= p.N) return;
+      if (is_loss) {
+        const float* xr = p.aux + (int64_t)m * p.ld_aux + n;
+        if (vec_aux && n + 16 <= p.N) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            float4 v = __ldg(reinterpret_cast<const float4*>(xr) + j);
+            t_nxt[4 * j] = v.x;
+            t_nxt[4 * j + 1] = v.y;
+            t_nxt[4 * j + 2] = v.z;
+            t_nxt[4 * j + 3] = v.w;
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) t_nxt[j] = (n + j < p.N) ? __ldg(xr + j) : 0.f;
+        }
+      } else if (is_mask) {
+        const uint16_t* mk = p.mask + (int64_t)m * p.ld_mask + n;
+        uint32_t bits = 0;
+        if (n + 16 <= p.ld_mask && ((p.ld_mask & 7) == 0)) {
+          const uint4 a0 = __ldg(reinterpret_cast<const uint4*>(mk));
+          const uint4 a1 = __ldg(reinterpret_cast<const uint4*>(mk) + 1);
+          const uint32_t w[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            // bf16 > 0  <=>  sign bit clear and magnitude non-zero
+            const uint32_t lo = w[j] & 0xFFFFu, hi = w[j] >> 16;
+            bits |= (uint32_t)(((lo & 0x8000u) == 0) && ((lo & 0x7FFFu) != 0)) << (2 * j);
+            bits |= (uint32_t)(((hi & 0x8000u) == 0) && ((hi & 0x7FFFu) != 0)) << (2 * j + 1);
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const uint16_t bq = (n + j < p.N) ? __ldg(mk + j) : (uint16_t)0;
+            bits |= (uint32_t)(((bq & 0x8000u) == 0) && ((bq & 0x7FFFu) != 0)) << j;
+          }
+        }
+        mk_nxt = bits;
+      }
+    };
+    prefetch(0);
+    mbar_wait(tmem_full_bar, 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     float row_acc = 0.f;
-    const float* bias = blockIdx.z == 0 ? p.bias : nullptr;  // split-K: only the first slice adds the bias
     for (int c = 0; c < p.block_n; c += 16) {
       const int n = n0 + c;
       if (n >= p.N) break;  // warp-uniform
+      float t[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) t[j] = t_nxt[j];
+      const uint32_t mk_cur = mk_nxt;
+      if (c + 16 < p.block_n) prefetch(c + 16);
       uint32_t r[16];
       tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, r);
       if (!row_ok) continue;
       float y[16];
 #pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        y[j] = __uint_as_float(r[j]);
-        if (bias && n + j < p.N) y[j] += __ldg(bias + n + j);
-      }
+      for (int j = 0; j < 16; ++j) y[j] = __uint_as_float(r[j]) + s_bias[c + j];
       switch (p.epilogue) {
         case MVAE_EPI_STORE: {
           if (p.atomic_out) {
@@ -346,33 +403,12 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
           if (p.out_f32) store_f32_16(p.out_f32, p.ld_out, m, n, p.N, y, vec_out);
         } break;
         case MVAE_EPI_RELU_MASK: {
-          const uint16_t* mk = p.mask + (int64_t)m * p.ld_mask + n;
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            // bf16 > 0  <=>  sign bit clear and magnitude non-zero
-            uint16_t b = (n + j < p.N) ? __ldg(mk + j) : (uint16_t)0;
-            bool pos = ((b & 0x8000u) == 0) && ((b & 0x7FFFu) != 0);
-            y[j] = pos ? y[j] : 0.f;
-          }
+          for (int j = 0; j < 16; ++j) y[j] = ((mk_cur >> j) & 1u) ? y[j] : 0.f;
           if (p.op_base) store_planes16(p, m, n, y);
           if (p.out_f32) store_f32_16(p.out_f32, p.ld_out, m, n, p.N, y, vec_out);
         } break;
         default: {  // BCE_ROWSUM / NLL_ROWSUM
-          float t[16];
-          const float* xr = p.aux + (int64_t)m * p.ld_aux + n;
-          if (vec_aux && n + 16 <= p.N) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              float4 v = __ldg(reinterpret_cast<const float4*>(xr) + j);
-              t[4 * j] = v.x;
-              t[4 * j + 1] = v.y;
-              t[4 * j + 2] = v.z;
-              t[4 * j + 3] = v.w;
-            }
-          } else {
-#pragma unroll
-            for (int j = 0; j < 16; ++j) t[j] = (n + j < p.N) ? __ldg(xr + j) : 0.f;
-          }
           if (p.out_f32) store_f32_16(p.out_f32, p.ld_out, m, n, p.N, y, vec_out);
           float g[16];
 #pragma unroll
@@ -380,9 +416,13 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
             const float lg = y[j];
             float loss;
             if (p.epilogue == MVAE_EPI_BCE_ROWSUM) {
-              const float ex = expf(-fabsf(lg));
-              loss = (1.f - t[j]) * lg - (fminf(lg, 0.f) - log1pf(ex));
-              g[j] = 1.f / (1.f + expf(-lg)) - t[j];
+              // (1-t) x - log_sigmoid(x), log_sigmoid(x) = min(x,0) - log1p(e^-|x|); sigmoid from the same exponential
+              const float ex = __expf(-fabsf(lg));
+              const float u = 1.f + ex;
+              const float l1p = (u == 1.f) ? ex : __logf(u) * __fdividef(ex, u - 1.f);  // compensated log1p
+              loss = (1.f - t[j]) * lg - (fminf(lg, 0.f) - l1p);
+              const float inv = __fdividef(1.f, u);
+              g[j] = (lg >= 0.f ? inv : ex * inv) - t[j];
             } else {
               const float dlt = t[j] - lg;
               loss = (dlt * dlt) / 2.f + kHalfLn2PiG;
@@ -394,8 +434,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
         } break;
       }
     }
-    if ((p.epilogue == MVAE_EPI_BCE_ROWSUM || p.epilogue == MVAE_EPI_NLL_ROWSUM) && row_ok && p.rowsum)
-      atomicAdd(p.rowsum + m, row_acc);
+    if (is_loss && row_ok && p.rowsum) atomicAdd(p.rowsum + m, row_acc);
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   }
   __syncthreads();
@@ -508,16 +547,26 @@ extern "C" int mvae_gemm(const mvae_gemm_args* a, void* stream) {
   p.b_major = a->b_major;
   p.a_planes = a->a.planes;
   p.b_planes = a->b.planes;
-  // stage budget: keep >= 3 stages
-  const int smem_budget = di.max_smem_optin - 1024 /*align*/ - 256 /*barriers*/;
+  // Tile policy.  The shapes of this workload are small (M = batch of a few thousand rows), so one CTA per SM leaves
+  // the tensor pipe idle during every prologue / epilogue.  Prefer TWO co-resident CTAs per SM (each <= ~112 KiB of
+  // shared memory, >= 2 stages): one CTA's epilogue overlaps the other's main loop, and twice as many tiles fit in a
+  // wave.  BLOCK_N is capped accordingly; a single-CTA-per-SM deep pipeline is used only when the grid is small.
+  const int kExtra = 1024 /*align*/ + 256 /*barriers*/ + 1024 /*bias slice*/;
+  const int smem_one = di.max_smem_optin - kExtra;
+  const int smem_two = (di.max_smem_optin + 1024) / 2 - 1024 - kExtra;  // two CTAs + 1 KiB system reservation each
+  auto stage_bytes_of = [&](int bn) {
+    const int bt = p.b_major == MVAE_K_MAJOR ? bn * 128 : round_up(bn, 64) * 128;
+    return p.a_planes * kATileBytes + p.b_planes * bt;
+  };
   int cap = 256;
-  for (;;) {
-    const int bt = p.b_major == MVAE_K_MAJOR ? cap * 128 : round_up(cap, 64) * 128;
-    if (3 * (p.a_planes * kATileBytes + p.b_planes * bt) <= smem_budget || cap <= 32) break;
-    cap -= 16;
-  }
+  while (cap > 32 && 2 * stage_bytes_of(cap) > smem_two) cap -= 16;
+  int smem_budget = smem_two;
   p.block_n = pick_block_n(a->N, cap);
   if (p.block_n <= 0) return MVAE_ERR_UNSUPPORTED;
+  {
+    const int64_t tiles = (int64_t)((a->M + kBlockM - 1) / kBlockM) * ((a->N + p.block_n - 1) / p.block_n);
+    if (tiles * (a->split_k > 1 ? a->split_k : 1) <= di.sm_count && a->split_k != 0) smem_budget = smem_one;
+  }
   p.b_tile_bytes = p.b_major == MVAE_K_MAJOR ? p.block_n * 128 : round_up(p.block_n, 64) * 128;
   const int stage_bytes = p.a_planes * kATileBytes + p.b_planes * p.b_tile_bytes;
   p.kb_total = (a->K + kBlockK - 1) / kBlockK;
@@ -564,7 +613,7 @@ extern "C" int mvae_gemm(const mvae_gemm_args* a, void* stream) {
   rc = encode_planes(&map_b, a->b, b_cols, a->b_major == MVAE_K_MAJOR ? p.block_n : kBlockK);
   if (rc != MVAE_OK) return rc;
 
-  const size_t smem = (size_t)stages * stage_bytes + 1024 + 256;
+  const size_t smem = (size_t)stages * stage_bytes + kExtra;
   static std::once_flag attr_once[64];
   int dev = 0;
   MVAE_CUDA_TRY(cudaGetDevice(&dev));

@@ -45,19 +45,47 @@ constexpr float kHalfLn2Pi = 0.9189385332046727f;
 constexpr float kLn2 = 0.6931471805599453f;
 constexpr float kMaxHyp = 85.f;  // common.py:107-114 clamp of cosh/sinh arguments
 
+// ---- elementary functions ----------------------------------------------------------------------------------
+// The kernels are instruction-issue bound, so exp / log / division / sqrt go through the SFU
+// approximations (MUFU.EX2 / LG2 / RCP / RSQ, <= 2 ulp) wrapped so that the well-conditioned closed forms above keep
+// their accuracy: log1p is compensated, sinh switches to its series near 0, sin / cos stay on the accurate sincosf.
+#ifdef __CUDA_ARCH__
+MVAE_DEV float f_exp(float x) { return __expf(x); }
+MVAE_DEV float f_log(float x) { return __logf(x); }
+MVAE_DEV float f_div(float a, float b) { return __fdividef(a, b); }
+MVAE_DEV float f_sqrt(float x) { return x > 0.f ? x * rsqrtf(x) : 0.f; }
+MVAE_DEV float f_rsqrt(float x) { return rsqrtf(x); }
+#else
+MVAE_DEV float f_exp(float x) { return expf(x); }
+MVAE_DEV float f_log(float x) { return logf(x); }
+MVAE_DEV float f_div(float a, float b) { return a / b; }
+MVAE_DEV float f_sqrt(float x) { return sqrtf(x); }
+MVAE_DEV float f_rsqrt(float x) { return 1.f / sqrtf(x); }
+#endif
+// log(1 + t), t >= 0, accurate for tiny t: log(u) * t / (u - 1) with u = fl(1 + t) cancels the rounding of u
+MVAE_DEV float f_log1p(float t) {
+  const float u = 1.f + t;
+  return u == 1.f ? t : f_log(u) * f_div(t, u - 1.f);
+}
+
 // ---- guarded scalar math, ops/common.py --------------------------------------------------------------------
 MVAE_DEV float lclamp(float x, float lo, float hi) { return x < lo ? lo : (x > hi ? hi : x); }
 MVAE_DEV float lclamp_d(float x, float lo, float hi) { return (x >= lo && x <= hi) ? 1.f : 1e-8f; }
 MVAE_DEV float lclamp_lo(float x, float lo) { return x < lo ? lo : x; }
 MVAE_DEV float lclamp_lo_d(float x, float lo) { return x >= lo ? 1.f : 1e-8f; }
 // sqrt (common.py:117-119)
-MVAE_DEV float sqrt_g(float x) { return sqrtf(lclamp_lo(x, 1e-9f)); }
-MVAE_DEV float sqrt_g_d(float x, float y) { return lclamp_lo_d(x, 1e-9f) * 0.5f / y; }
+MVAE_DEV float sqrt_g(float x) { return f_sqrt(lclamp_lo(x, 1e-9f)); }
+MVAE_DEV float sqrt_g_d(float x, float y) { return lclamp_lo_d(x, 1e-9f) * f_div(0.5f, y); }
 // cosh & sinh of a clamped argument in one go: e = exp(|x|)
 MVAE_DEV void coshsinh_g(float x, float* ch, float* sh) {
-  float xc = lclamp(x, -kMaxHyp, kMaxHyp);
-  *ch = coshf(xc);
-  *sh = sinhf(xc);
+  const float xc = lclamp(x, -kMaxHyp, kMaxHyp);
+  const float ax = fabsf(xc);
+  const float E = f_exp(ax), Ei = f_div(1.f, E);
+  *ch = 0.5f * (E + Ei);
+  const float x2 = ax * ax;
+  const float s_small = ax * (1.f + x2 * (1.f / 6.f + x2 * (1.f / 120.f + x2 * (1.f / 5040.f))));  // |x| < 0.35: < 1e-9 rel
+  const float s = ax < 0.35f ? s_small : 0.5f * (E - Ei);
+  *sh = xc < 0.f ? -s : s;
 }
 // acosh (common.py:76-94)
 MVAE_DEV float acosh_g(float x, float* z_out) {
@@ -84,11 +112,12 @@ MVAE_DEV float logsinh_g(float x, float* d) {
   return y;
 }
 // F.softplus (beta 1, threshold 20)
-MVAE_DEV float softplus(float x) { return x > 20.f ? x : log1pf(expf(x)); }
+MVAE_DEV float softplus(float x) { return x > 20.f ? x : fmaxf(x, 0.f) + f_log1p(f_exp(-fabsf(x))); }
 MVAE_DEV float softplus_d(float x) {
   if (x > 20.f) return 1.f;
-  float z = expf(x);
-  return z / (z + 1.f);
+  const float e = f_exp(-fabsf(x));
+  const float inv = f_div(1.f, 1.f + e);
+  return x >= 0.f ? inv : e * inv;
 }
 // radius = clamp(relu(R_param), 1e-8, 1e8) (manifold.py:73-75), plain clamp
 MVAE_DEV float radius_of(float rp) {
@@ -112,8 +141,11 @@ struct CompOut {
 // F(x) = log(sinh(x) / x) = logsinh(x) - log(x)  (hyperbolics.py:58-65 with common.py:122-128), x > 0.
 // 1 - e^{-2x} is taken from expm1 so that small x does not cancel.
 MVAE_DEV float log_sinhc(float x) {
-  float em = -expm1f(-2.f * x);
-  return x + logf(em / (2.f * x));
+  if (x < 0.5f) {  // x^2/6 - x^4/180 + x^6/2835 - x^8/37800
+    const float x2 = x * x;
+    return x2 * (1.f / 6.f - x2 * (1.f / 180.f - x2 * (1.f / 2835.f - x2 * (1.f / 37800.f))));
+  }
+  return x + f_log(f_div(1.f - f_exp(-2.f * x), 2.f * x));
 }
 // F'(x) = coth(x) - 1/x
 MVAE_DEV float log_sinhc_d(float x) {
@@ -121,18 +153,18 @@ MVAE_DEV float log_sinhc_d(float x) {
     float x2 = x * x;
     return x * (1.f / 3.f - x2 * (1.f / 45.f - x2 * (2.f / 945.f - x2 * (1.f / 4725.f))));
   }
-  float E = expf(-2.f * x);
-  return (1.f + E) / (1.f - E) - 1.f / x;
+  const float E = f_exp(-2.f * x);
+  return f_div(1.f + E, 1.f - E) - f_div(1.f, x);
 }
 // G(x) = log clamp(|sin x|, 1e-5) - log clamp(x, 1e-5)  (spherical.py:58-67, plain clamps: zero gradient outside)
 MVAE_DEV float log_sinc_abs(float x, float sn) {
-  return logf(fmaxf(fabsf(sn), 1e-5f)) - logf(fmaxf(x, 1e-5f));
+  return f_log(f_div(fmaxf(fabsf(sn), 1e-5f), fmaxf(x, 1e-5f)));
 }
 MVAE_DEV float log_sinc_abs_d(float x, float sn, float cs) {
   float as = fabsf(sn);
   float d = 0.f;
-  if (as >= 1e-5f) d += (sn > 0.f ? cs : -cs) / as;
-  if (x >= 1e-5f) d -= 1.f / x;
+  if (as >= 1e-5f) d += f_div(sn > 0.f ? cs : -cs, as);
+  if (x >= 1e-5f) d -= f_div(1.f, x);
   return d;
 }
 
@@ -182,12 +214,12 @@ MVAE_DEV void comp_e(int n, int l_n, const float* m, const float* l, const float
   MVAE_UNROLL
   for (int j = 0; j < CN; ++j)
     if (j < n) {
-      float mu = m[j] / 2.f;
+      float mu = 0.5f * m[j];
       float s = o.sigma[j];
       o.mu[j] = mu;
       o.z[j] = mu + e[j] * s;
       float var_ratio = s * s;
-      kl += 0.5f * (var_ratio + mu * mu - 1.f - logf(var_ratio));
+      kl += 0.5f * (var_ratio + mu * mu - 1.f) - f_log(s);
     }
   o.kl = kl;
   if (!BWD) return;
@@ -196,8 +228,8 @@ MVAE_DEV void comp_e(int n, int l_n, const float* m, const float* l, const float
   for (int j = 0; j < CN; ++j)
     if (j < n) {
       float mu = o.mu[j], s = o.sigma[j];
-      gm[j] = (gz[j] + gkl * mu) / 2.f;
-      g_s[j] = gz[j] * e[j] + gkl * (s - 1.f / s);
+      gm[j] = 0.5f * (gz[j] + gkl * mu);
+      g_s[j] = gz[j] * e[j] + gkl * (s - f_div(1.f, s));
     }
   store_gl<N>(n, l_n, l, g_s, gl);
 }
@@ -209,9 +241,9 @@ MVAE_DEV float cmin_d(float x, float lo) { return x >= lo ? 1.f : 0.f; }
 MVAE_DEV float tanh_c(float x) { return tanhf(fminf(fmaxf(x, -15.f), 15.f)); }
 // sech^2 of the clamped argument = 1 - tanh_c(x)^2, from one exponential (exact to rounding for large |x|)
 MVAE_DEV float sech2_c(float x) {
-  float e = expf(-2.f * fminf(fabsf(x), 15.f));
+  float e = f_exp(-2.f * fminf(fabsf(x), 15.f));
   float d = 1.f + e;
-  return 4.f * e / (d * d);
+  return f_div(4.f * e, d * d);
 }
 MVAE_DEV float tanh_c_d(float x, float) { return (x >= -15.f && x <= 15.f) ? sech2_c(x) : 0.f; }
 MVAE_DEV float artanh_go(float x, float* xc_out) {
@@ -257,21 +289,23 @@ MVAE_DEV void comp_hsp(int n, int l_n, const float* m, const float* l, const flo
   MVAE_UNROLL
   for (int j = 0; j < CN; ++j)
     if (j < n) nm2 += m[j] * m[j];
-  const float nm = sqrtf(nm2);
+  // the sphere's log-det is singular at |v| = pi R: its angles keep correctly rounded sqrt / division
+  const float nm = HYP ? f_sqrt(nm2) : sqrtf(nm2);
   const float nmin = POI ? kPMin : 1e-12f;  // geoopt MIN_NORM | F.normalize eps
   const float dn = fmaxf(nm, nmin);
-  const float a = (POI ? dn : nm) / R;
+  const float iR = f_div(1.f, R);
+  const float idn = f_div(1.f, dn);
+  const float a = HYP ? (POI ? dn : nm) * iR : nm / R;
   const bool a_sat = POI && a > 15.f;       // geoopt tanh clamp (plain: zero gradient beyond)
   const float aa = POI ? 2.f * fminf(a, 15.f) : a;
   float ca, sa;
   if (HYP) {
     coshsinh_g(aa, &ca, &sa);
   } else {
-    ca = cosf(aa);
-    sa = sinf(aa);
+    sincosf(aa, &sa, &ca);
   }
   // C(a) - 1 without cancellation: H: S^2/(C+1);  S: -S^2/(1+C) (falls back to C-1 near a = pi)
-  const float cam1 = HYP ? sa * sa / (ca + 1.f) : (ca > -0.5f ? -(sa * sa) / (1.f + ca) : ca - 1.f);
+  const float cam1 = HYP ? f_div(sa * sa, ca + 1.f) : (ca > -0.5f ? -f_div(sa * sa, 1.f + ca) : ca - 1.f);
   float* sg = o.sigma;
   load_sigma<N>(n, l_n, l, sg);
   float mh[CN], v[CN];
@@ -279,28 +313,28 @@ MVAE_DEV void comp_hsp(int n, int l_n, const float* m, const float* l, const flo
   MVAE_UNROLL
   for (int j = 0; j < CN; ++j)
     if (j < n) {
-      mh[j] = m[j] / dn;
+      mh[j] = m[j] * idn;
       v[j] = e[j] * sg[j];
       Sv += v[j] * v[j];
       p += mh[j] * v[j];
       se2 += e[j] * e[j];
-      slog += logf(sg[j]);
+      slog += f_log(sg[j]);
     }
   // ---- sample ----
   float ln, t, ct, st;
   bool t_sat = false;
   if (HYP) {
     ln = sqrt_g(Sv);
-    t = ln / R;
+    t = ln * iR;
     t_sat = POI && t > 30.f;
     coshsinh_g(POI ? fminf(t, 30.f) : t, &ct, &st);
   } else {
     ln = sqrtf(Sv);
     t = ln / R;
-    ct = cosf(t);
-    st = sinf(t);
+    sincosf(t, &st, &ct);
   }
-  const float A = t > 0.f ? st / t : 1.f;
+  const float it = t > 0.f ? f_div(1.f, t) : 0.f;
+  const float A = t > 0.f ? st * it : 1.f;
   const float z0 = R * ct * ca + sgn * A * sa * p;
   const float Bc = R * ct * sa + A * cam1 * p;
   float* z = o.z;
@@ -313,9 +347,10 @@ MVAE_DEV void comp_hsp(int n, int l_n, const float* m, const float* l, const flo
       zt[j] = A * v[j] + Bc * mh[j];
       zt2 += zt[j] * zt[j];
     }
-  const float pj = POI ? R / (R + z0) : 1.f;  // lorentz_to_poincare
+  const float iRz = POI ? f_div(1.f, R + z0) : 0.f;
+  const float pj = POI ? R * iRz : 1.f;  // lorentz_to_poincare
   if (POI) {
-    const float Ta = sa / (ca + 1.f);  // tanh(a) = sinh(2a) / (cosh(2a) + 1)
+    const float Ta = f_div(sa, ca + 1.f);  // tanh(a) = sinh(2a) / (cosh(2a) + 1)
     MVAE_UNROLL
     for (int j = 0; j < CN; ++j)
       if (j < n) {
@@ -333,26 +368,26 @@ MVAE_DEV void comp_hsp(int n, int l_n, const float* m, const float* l, const flo
       }
   }
   // ---- prior distance r = dist(mu0, z)/R from the tail norm (well conditioned everywhere) ----
-  const float s2 = zt2 / (R * R);
-  const float s = sqrtf(s2);
+  const float s2 = zt2 * (iR * iR);
+  const float s = f_sqrt(s2);
   float r, Fr, Ft, alpha = 0.f, as_ = 0.f, snr = 0.f, csr = 0.f;
   bool r_clamped = false, at_clamped = false;
   const float kAtMax = 12.206062f;  // 2 artanh(1 - 1e-5)
   float rq;                         // distance entering the Gaussian term of log p
   if (HYP) {
-    as_ = sqrtf(1.f + s2);
-    r = log1pf(s + s2 / (1.f + as_));  // asinh(s)
+    as_ = f_sqrt(1.f + s2);
+    r = s > 0.5f ? f_log(s + as_) : f_log1p(s + f_div(s2, 1.f + as_));  // asinh(s)
     // H._logdet applies sqrt() (clamp 1e-9) to the squared Lorentz norm R^2 r^2 of the prior's tangent vector
     r_clamped = (R * R) * (r * r) < 1e-9f;
-    const float rl = r_clamped ? sqrtf(1e-9f) / R : r;
+    const float rl = r_clamped ? 3.1622776e-5f * iR : r;
     Fr = log_sinhc(rl);
     Ft = log_sinhc(t);
     at_clamped = POI && r > kAtMax;
     rq = at_clamped ? kAtMax : r;
   } else {
-    alpha = z0 / R;
+    alpha = z0 * iR;
     r = atan2f(s, alpha);
-    const float inv_q = rsqrtf(alpha * alpha + s2);  // (alpha, s) is a unit vector up to rounding
+    const float inv_q = f_rsqrt(alpha * alpha + s2);  // (alpha, s) is a unit vector up to rounding
     snr = s * inv_q;                                  // sin r and cos r without going through r
     csr = alpha * inv_q;
     Fr = log_sinc_abs(r, snr);
@@ -370,41 +405,41 @@ MVAE_DEV void comp_hsp(int n, int l_n, const float* m, const float* l, const flo
   gR += gkl * R * (rq * rq);
   if (at_clamped) {
     // geoopt Artanh.backward = g / (1 - x'^2) on the clamped argument x' = 1 - 1e-5; d(rho)/d(r) = sech^2(r/2) / 2
-    g_r *= sech2_c(0.5f * r) / (1e-5f * (2.f - 1e-5f));
+    g_r *= sech2_c(0.5f * r) * (1.f / (1e-5f * (2.f - 1e-5f)));
   }
   float g_s, g_alpha = 0.f;
   if (HYP) {
     if (!r_clamped) {
       g_r += gkl * nm1 * log_sinhc_d(r);
     } else {
-      const float rl = sqrtf(1e-9f) / R;
-      gR += -(gkl * nm1 * log_sinhc_d(rl)) * rl / R;  // leaky clamp: the 1e-8 * g path into r is dropped
+      const float rl = 3.1622776e-5f * iR;
+      gR += -(gkl * nm1 * log_sinhc_d(rl)) * rl * iR;  // leaky clamp: the 1e-8 * g path into r is dropped
     }
-    g_s = g_r / as_;
+    g_s = f_div(g_r, as_);
   } else {
     g_r += gkl * nm1 * log_sinc_abs_d(r, snr, csr);
     // r = atan2(s, alpha): any smooth extension off the constraint alpha^2 + s^2 = 1 has the same total derivative
-    const float q2 = alpha * alpha + s2;
-    g_s = g_r * alpha / q2;
-    g_alpha = -g_r * s / q2;
+    const float iq2 = f_div(1.f, alpha * alpha + s2);
+    g_s = g_r * alpha * iq2;
+    g_alpha = -g_r * s * iq2;
   }
   // s = |z_tail| / R ; alpha = z0 / R
-  const float k_zt = s > 0.f ? g_s / (R * R * s) : 0.f;
-  gR += -g_s * s / R;
+  const float k_zt = s > 0.f ? f_div(g_s * (iR * iR), s) : 0.f;
+  gR += -g_s * s * iR;
   float g_z0 = 0.f;
   if (POI) {
     // z_j = R Z_j / (R + Z_0)
     MVAE_UNROLL
     for (int j = 0; j < CN; ++j)
       if (j < n) {
-        g_z0 += -gz[j] * z[j] / (R + z0);
-        gR += gz[j] * (z[j] / R - z[j] / (R + z0));
+        g_z0 += -gz[j] * z[j] * iRz;
+        gR += gz[j] * z[j] * (iR - iRz);
       }
   } else {
     g_z0 = gz[0];
     if (!HYP) {
-      g_z0 += g_alpha / R;
-      gR += -g_alpha * alpha / R;
+      g_z0 += g_alpha * iR;
+      gR += -g_alpha * alpha * iR;
     }
   }
   // z0 = R ct ca + sgn A sa p ;  Bc = R ct sa + A cam1 p ; z_tail = A v + Bc mh
@@ -428,8 +463,8 @@ MVAE_DEV void comp_hsp(int n, int l_n, const float* m, const float* l, const flo
   // A = st / t ; ct, st functions of t ; KL has -(n-1) Fq(t)
   float g_t = 0.f;
   if (t > 0.f) {
-    const float g_st = g_A / t;
-    g_t += -g_A * A / t;
+    const float g_st = g_A * it;
+    g_t += -g_A * A * it;
     if (HYP) {
       const float dclamp = POI ? (t_sat ? 0.f : 1.f) : lclamp_d(t, -kMaxHyp, kMaxHyp);
       g_t += (g_ct * st + g_st * ct) * dclamp;
@@ -440,32 +475,32 @@ MVAE_DEV void comp_hsp(int n, int l_n, const float* m, const float* l, const flo
     }
   }
   // t = ln / R ; ln = sqrt(Sv) ; Sv = <v, v>
-  gR += -g_t * t / R;
-  const float g_ln = g_t / R;
-  const float g_Sv = HYP ? g_ln * sqrt_g_d(Sv, ln) : (ln > 0.f ? g_ln * 0.5f / ln : 0.f);
+  gR += -g_t * t * iR;
+  const float g_ln = g_t * iR;
+  const float g_Sv = HYP ? g_ln * sqrt_g_d(Sv, ln) : (ln > 0.f ? g_ln * f_div(0.5f, ln) : 0.f);
   // a : ca, sa
   float g_a;
   if (POI) g_a = a_sat ? 0.f : 2.f * (g_ca * sa + g_sa * ca);
   else if (HYP) g_a = (g_ca * sa + g_sa * ca) * lclamp_d(a, -kMaxHyp, kMaxHyp);
   else g_a = -g_ca * sa + g_sa * ca;
-  gR += -g_a * a / R;
-  float g_nm = POI ? 0.f : g_a / R;   // P: a = max(|m|, MIN_NORM) / R
-  float g_dn = POI ? g_a / R : 0.f;
+  gR += -g_a * a * iR;
+  float g_nm = POI ? 0.f : g_a * iR;   // P: a = max(|m|, MIN_NORM) / R
+  float g_dn = POI ? g_a * iR : 0.f;
   // v = eps * sigma ; p = <mh, v> ; mh = m / dn
   float g_s_[CN];
   MVAE_UNROLL
   for (int j = 0; j < CN; ++j)
     if (j < n) {
       const float gv = g_v[j] + 2.f * g_Sv * v[j] + g_p * mh[j];
-      g_s_[j] = gv * e[j] - gkl / sg[j];
+      g_s_[j] = gv * e[j] - f_div(gkl, sg[j]);
       const float gmh = g_mh[j] + g_p * v[j];
-      gm[j] = gmh / dn;
-      g_dn += -gmh * mh[j] / dn;
+      gm[j] = gmh * idn;
+      g_dn += -gmh * mh[j] * idn;
     }
   store_gl<N>(n, l_n, l, g_s_, gl);
   if (nm >= nmin) g_nm += g_dn;
   if (nm > 0.f) {
-    const float k = g_nm / nm;
+    const float k = f_div(g_nm, nm);
     MVAE_UNROLL
     for (int j = 0; j < CN; ++j)
       if (j < n) gm[j] += k * m[j];

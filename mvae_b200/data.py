@@ -13,6 +13,7 @@ from . import ops
 class VaeDataset:
 
     recon_kind = "bce"
+    binary_inputs = False  # True: every input value is 0 or 1 (exactly representable in one bf16 plane)
 
     def __init__(self, batch_size: int, in_dim: int, img_dims: Optional[Tuple[int, ...]]) -> None:
         self.batch_size = batch_size
@@ -41,6 +42,7 @@ class SyntheticMnistDataset(VaeDataset):
     """MNIST-shaped: binarised pixels with MNIST's mean density (the reference binarises with x > U(0,1),
     image_reconstruction.py:37-53)."""
     recon_kind = "bce"
+    binary_inputs = True
 
     def __init__(self, batch_size: int) -> None:
         super().__init__(batch_size, in_dim=784, img_dims=(-1, 1, 28, 28))
@@ -77,6 +79,7 @@ class SyntheticCifarDataset(VaeDataset):
 
 class GenericDataset(VaeDataset):
 
-    def __init__(self, batch_size: int, in_dim: int, recon_kind: str = "bce") -> None:
+    def __init__(self, batch_size: int, in_dim: int, recon_kind: str = "bce", binary_inputs: bool = False) -> None:
         super().__init__(batch_size, in_dim, None)
         self.recon_kind = recon_kind
+        self.binary_inputs = binary_inputs

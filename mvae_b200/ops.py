@@ -224,9 +224,11 @@ class PlaneBuf:
         if ones_col:
             self.t[0, :, cols] = 1.0
 
-    def struct(self, rows: Optional[int] = None, cols: Optional[int] = None) -> L.Planes:
+    def struct(self, rows: Optional[int] = None, cols: Optional[int] = None, planes: Optional[int] = None) -> L.Planes:
+        """`planes` < self.planes reads only the leading planes (a lower-precision view of the same buffer)."""
         return L.Planes(self.t.data_ptr(), self.rows * self.ld, rows if rows is not None else self.rows,
-                        cols if cols is not None else self.cols, self.ld, self.planes)
+                        cols if cols is not None else self.cols, self.ld,
+                        min(planes, self.planes) if planes is not None else self.planes)
 
     def to_float(self) -> torch.Tensor:
         return self.t.float().sum(0)[:, :self.cols]
@@ -249,11 +251,11 @@ def split_planes(src: torch.Tensor, dst: Optional[PlaneBuf] = None, dst_t: Optio
 def gemm(a: PlaneBuf, b: PlaneBuf, M: int, N: int, K: int, a_major: int = L.K_MAJOR, b_major: int = L.K_MAJOR,
          epilogue: int = L.EPI_STORE, split_k: int = 1, bias=None, out_f32=None, ld_out: Optional[int] = None,
          out_col=None, col_split: int = -1, out_planes: Optional[PlaneBuf] = None, aux=None, mask: Optional[PlaneBuf] = None,
-         rowsum=None):
+         rowsum=None, a_planes: Optional[int] = None, b_planes: Optional[int] = None):
     """D[M,N] = sum_k A[m,k] B[n,k] on tcgen05 tensor cores with a fused epilogue (mvae_gemm)."""
     g = L.GemmArgs()
-    g.a = a.struct(rows=M if a_major == L.K_MAJOR else K, cols=K if a_major == L.K_MAJOR else M)
-    g.b = b.struct(rows=N if b_major == L.K_MAJOR else K, cols=K if b_major == L.K_MAJOR else N)
+    g.a = a.struct(rows=M if a_major == L.K_MAJOR else K, cols=K if a_major == L.K_MAJOR else M, planes=a_planes)
+    g.b = b.struct(rows=N if b_major == L.K_MAJOR else K, cols=K if b_major == L.K_MAJOR else N, planes=b_planes)
     g.a_major, g.b_major = a_major, b_major
     g.M, g.N, g.K = M, N, K
     g.epilogue, g.split_k = epilogue, split_k

@@ -119,13 +119,13 @@ class _Workspace:
         self.x = torch.zeros(B, D, **f)
         self.eps = torch.zeros(B, Sn, **f)
         self.xp = ops.PlaneBuf(B, D, m.input_planes, dev, ones_col=True)
-        self.hp = ops.PlaneBuf(B, H, 2, dev, ones_col=True)
+        self.hp = ops.PlaneBuf(B, H, 3, dev, ones_col=True)   # 3 planes: feeds the heads at fp32 accuracy
         self.ml = torch.zeros(B, P, **f)
         self.z = torch.zeros(B, Sd, **f)
         self.kl = torch.zeros(B, C, **f)
         self.mu = torch.zeros(B, Sd, **f)
         self.sigma = torch.zeros(B, Sn, **f)
-        self.zp = ops.PlaneBuf(B, Sd, 2, dev, ones_col=True)
+        self.zp = ops.PlaneBuf(B, Sd, 3, dev, ones_col=True)  # 3 planes: pre-activation of the decoder relu
         self.ddp = ops.PlaneBuf(B, H, 2, dev, ones_col=True)
         self.bce = torch.zeros(B, **f)
         self.logits = None  # allocated on first forward() that needs them
@@ -141,16 +141,17 @@ class _Workspace:
 class FusedFeedForwardVAE(nn.Module):
 
     def __init__(self, h_dim: int, components: List[Component], dataset, scalar_parametrization: bool,
-                 device="cuda", input_planes: int = 2) -> None:
-        """Same signature as FeedForwardVAE (ffnn_vae.py:29-30) plus the device.  `input_planes=1` may be used when the
-        inputs are exactly representable in bf16 (binarised images); 2 is always safe."""
+                 device="cuda", input_planes: Optional[int] = None) -> None:
+        """Same signature as FeedForwardVAE (ffnn_vae.py:29-30) plus the device.  `input_planes`: bf16 planes carrying
+        the input batch — 1 when the dataset declares `binary_inputs` (dynamically binarised images are exact in
+        bf16), else 3 (fp32 accuracy for real-valued inputs)."""
         super().__init__()
         self.device = torch.device(device)
         self.h_dim = h_dim
         self.in_dim = dataset.in_dim
         self.recon_kind = _recon_kind_of(dataset)
         self.scalar_parametrization = scalar_parametrization
-        self.input_planes = input_planes
+        self.input_planes = input_planes or (1 if getattr(dataset, "binary_inputs", False) else 3)
         self.components = nn.ModuleList(components)
         self.total_z_dim = sum(c.dim for c in components)
         # construction order of the reference (vae.py:55-57 then ffnn_vae.py:35-40) => identical default init per seed
@@ -230,9 +231,13 @@ class FusedFeedForwardVAE(nn.Module):
         self.gWd0, self.gbd0 = view(bucket, "fc_d0.weight", (H, Sd)), view(bucket, "fc_d0.bias", (H,))
         self.gWl, self.gbl = view(bucket, "fc_logits.weight", (D, H)), view(bucket, "fc_logits.bias", (D,))
         # split-bf16 planes of the four weight matrices (refreshed after every optimizer step)
-        self.We0p = ops.PlaneBuf(H, D, 2, dev)
-        self.Whp = ops.PlaneBuf(P, H, 2, dev)
-        self.Wd0p = ops.PlaneBuf(H, Sd, 2, dev)
+        # Operands that produce the argument of a NON-SMOOTH function (the two relus, the manifold maps with their
+        # clamps and singular log-dets) carry 3 planes (~2^-24, fp32 accuracy): with 2 planes (~2^-16) relu decisions
+        # near zero flip ~30x more often than in a true fp32 run.  Smooth consumers (logits -> BCE, every dgrad / wgrad)
+        # read 2 planes.
+        self.We0p = ops.PlaneBuf(H, D, 3, dev)
+        self.Whp = ops.PlaneBuf(P, H, 3, dev)
+        self.Wd0p = ops.PlaneBuf(H, Sd, 3, dev)
         self.Wlp = ops.PlaneBuf(D, H, 2, dev)
         self._planes_stale = True
         self._ws = {}
@@ -302,8 +307,8 @@ class FusedFeedForwardVAE(nn.Module):
         ops.gemm(ws.gLp, self.Wlp, B, H, D, b_major=MN, epilogue=L.EPI_RELU_MASK, mask=ws.ddp, out_planes=ws.gddp)
         # fc_d0
         ops.gemm(ws.gddp, ws.zp, H, Sd + 1, B, a_major=MN, b_major=MN, split_k=0, out_f32=self.gWd0,
-                 out_col=self.gbd0, col_split=Sd)
-        ops.gemm(ws.gddp, self.Wd0p, B, Sd, H, b_major=MN, out_f32=ws.gz)
+                 out_col=self.gbd0, col_split=Sd, b_planes=2)
+        ops.gemm(ws.gddp, self.Wd0p, B, Sd, H, b_major=MN, out_f32=ws.gz, b_planes=2)
         # latent: d(-ELBO)/d kl = beta
         ops.pm_backward(self.desc, ws.ml, ws.eps, self._rflat, ws.gz, None, beta, gml=ws.gml, gradius=self._gradius)
         if self._any_fixed_radius:
@@ -311,11 +316,12 @@ class FusedFeedForwardVAE(nn.Module):
         ops.split_planes(ws.gml, ws.gmlp)
         # heads
         ops.gemm(ws.gmlp, ws.hp, P, H + 1, B, a_major=MN, b_major=MN, split_k=0, out_f32=self.gWh, out_col=self.gbh,
-                 col_split=H)
-        ops.gemm(ws.gmlp, self.Whp, B, H, P, b_major=MN, epilogue=L.EPI_RELU_MASK, mask=ws.hp, out_planes=ws.ghp)
+                 col_split=H, b_planes=2)
+        ops.gemm(ws.gmlp, self.Whp, B, H, P, b_major=MN, epilogue=L.EPI_RELU_MASK, mask=ws.hp, out_planes=ws.ghp,
+                 b_planes=2)
         # fc_e0 (no dgrad into x)
         ops.gemm(ws.ghp, ws.xp, H, D + 1, B, a_major=MN, b_major=MN, split_k=0, out_f32=self.gWe0,
-                 out_col=self.gbe0, col_split=D)
+                 out_col=self.gbe0, col_split=D, b_planes=2)
 
     def _stage(self, ws: _Workspace, x: Tensor, eps: Optional[Tensor]) -> None:
         ws.x.copy_(x.reshape(ws.B, self.in_dim), non_blocking=True)  # H2D if x lives on the host

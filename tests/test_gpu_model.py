@@ -107,11 +107,11 @@ def test_train_step_vs_oracle(dev, oracle, sig, B, D, H, recon, fixed):
     params = {k: v.detach().cpu().double().numpy() for k, v in model.state_dict().items()}
     ovae = oracle.OracleVAE(sig, D, H, recon, False)
     ref = ovae.step(params, x.double().numpy(), eps.double().numpy(), beta=0.8)
-    # conditioning yardstick: the same oracle run in float32.  The sphere log-det is singular at |v| = pi R and the
-    # Poincare maps near the boundary, so a few samples amplify ANY float32 rounding of the head pre-activations;
-    # where that happens the bar follows the float32 oracle's own deviation (capped), elsewhere it is 2e-4.
-    p32 = {k: v.astype(np.float32) for k, v in params.items()}
-    ref32 = ovae.step(p32, x.float().numpy(), eps.float().numpy(), beta=0.8)
+    # Gradient bars.  The two relus make the map parameters -> gradients discontinuous: a hidden unit whose
+    # pre-activation is within float32 rounding of zero may switch side relative to the float64 oracle (expected
+    # ~0.3 units per step at fp32 accuracy for these sizes; the reference's own float32 run has the same property).
+    # One switched unit moves isolated entries of a gradient by O(1e-3) of its largest entry but leaves its bulk
+    # untouched, so every tensor must match to 1e-4 in the Frobenius sense and to 2e-3 in the max norm.
 
     class NoOpt:
         def zero_grad(self):
@@ -129,13 +129,13 @@ def test_train_step_vs_oracle(dev, oracle, sig, B, D, H, recon, fixed):
         if k not in ref["grads"]:
             continue
         got = p.grad.detach().cpu().numpy()
+        r = np.asarray(ref["grads"][k], dtype=np.float64)
         if got.ndim:
-            err = normwise(got, ref["grads"][k])
-            cond = normwise(ref32["grads"][k], ref["grads"][k])
+            err_max = normwise(got, r)
+            err_fro = float(np.linalg.norm(got - r) / max(np.linalg.norm(r), 1e-30))
         else:
-            err = abs(got - ref["grads"][k]) / max(1.0, abs(ref["grads"][k]))
-            cond = abs(ref32["grads"][k] - ref["grads"][k]) / max(1.0, abs(ref["grads"][k]))
-        assert err < max(2e-4, min(3 * cond, 2e-3)), (k, err, cond)
+            err_max = err_fro = abs(got - r) / max(1.0, abs(r))
+        assert err_fro < 1e-4 and err_max < 2e-3, (k, err_fro, err_max)
 
 
 def test_optimizer_step_matches_torch(dev):
