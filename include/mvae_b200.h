@@ -211,6 +211,31 @@ typedef struct mvae_gemm_args {
 
 int mvae_gemm(const mvae_gemm_args* args, void* stream);
 
+/* ---------------------------------------------------------------------------------- skinny dense layers */
+/* Dense layers whose N or K is tiny — the latent heads (component.py:64,69: N = sum(n)+sum(l_n)) and the first decoder
+ * layer (ffnn_vae.py:56: K = sum(d)) and their backward passes — run on the CUDA cores in exact fp32 FMA arithmetic
+ * (they are far below a tensor-core tile).  W(n, k) = W[n*w_stride_n + k*w_stride_k], so a weight can be read as
+ * stored ([out, in]) or transposed without a copy.  Wide operands are given either as fp32 or as split planes. */
+
+/* out[b, n] = sum_k A[b, k] W(n, k) (+ bias[n]);  N <= 64, any K.   A: a_f32 [B, ld_a] or a_planes. */
+int mvae_skinny_rowdot(int64_t B, int32_t K, int32_t N, const float* a_f32, int64_t ld_a, const mvae_planes* a_planes,
+                       const float* W, int64_t w_stride_n, int64_t w_stride_k, const float* bias, float* out,
+                       int64_t ld_out, void* stream);
+
+/* out[b, n] = act(sum_k A[b, k] W(n, k) + bias[n]);  K <= 64, any N.  act: 0 none, 1 relu, 2 relu-mask (mask = bf16
+ * [B, ld_mask], plane 0 of the forward activation).  Result as planes and / or fp32. */
+int mvae_skinny_expand(int64_t B, int32_t K, int32_t N, const float* a, int64_t ld_a, const float* W,
+                       int64_t w_stride_n, int64_t w_stride_k, const float* bias, int32_t act, const uint16_t* mask,
+                       int64_t ld_mask, const mvae_planes* out_planes, float* out_f32, int64_t ld_out, void* stream);
+
+/* out[s*out_stride_s + w*out_stride_w] += sum_b small[b, s] wide[b, w]   (ACCUMULATES: zero the outputs first);
+ * S <= 64.  small_ones != 0: out_row[w] += sum_b wide[b, w] (bias gradient of the wide side);
+ * col_split >= 0: wide column col_split (a ones column) goes to out_col[s] += sum_b small[b, s]. */
+int mvae_skinny_wgrad(int64_t B, int32_t S, int32_t Wd, const float* small, int64_t ld_small, int32_t small_ones,
+                      const float* wide_f32, int64_t ld_wide, const mvae_planes* wide_planes, float* out,
+                      int64_t out_stride_s, int64_t out_stride_w, float* out_row, float* out_col, int32_t col_split,
+                      void* stream);
+
 /* ------------------------------------------------------------------------------- reconstruction + ELBO */
 /* Standalone reconstruction losses (VaeDataset.reconstruction_loss + .sum(-1), vae.py:131):
  * kind 0 = BCE-with-logits (data/image_reconstruction.py:81-82), 1 = unit-variance Gaussian NLL (data/synthetic.py:161-162).

@@ -277,3 +277,51 @@ def gemm(a: PlaneBuf, b: PlaneBuf, M: int, N: int, K: int, a_major: int = L.K_MA
     rc = L.lib().mvae_gemm(ctypes.byref(g), _stream())
     L.check(rc, "mvae_gemm")
     _LAUNCHES[0] += 1
+
+
+# ------------------------------------------------------------------------------------------ skinny dense layers
+ACT_NONE, ACT_RELU, ACT_MASK = 0, 1, 2
+
+
+def _wide(x):
+    """(f32 ptr, ld, planes struct ptr) of a wide operand given as fp32 tensor or PlaneBuf / (PlaneBuf, planes)."""
+    if isinstance(x, torch.Tensor):
+        return _ptr(x), x.stride(0), None
+    buf, planes = x if isinstance(x, tuple) else (x, None)
+    st = buf.struct(planes=planes)
+    return None, 0, st
+
+
+def skinny_rowdot(a, W, w_stride_n: int, w_stride_k: int, K: int, N: int, bias, out):
+    """out[b, n] = sum_k a[b, k] W(n, k) + bias[n]  (mvae_skinny_rowdot); a: fp32 [B, >=K] or planes."""
+    af, lda, ap = _wide(a)
+    B = out.shape[0]
+    rc = L.lib().mvae_skinny_rowdot(B, K, N, af, lda, ctypes.byref(ap) if ap is not None else None, _ptr(W), w_stride_n,
+                                    w_stride_k, _ptr(bias), _ptr(out), out.stride(0), _stream())
+    L.check(rc, "mvae_skinny_rowdot")
+    _LAUNCHES[0] += (N + 15) // 16
+
+
+def skinny_expand(a, W, w_stride_n: int, w_stride_k: int, K: int, N: int, bias=None, act: int = ACT_NONE,
+                  mask: Optional[PlaneBuf] = None, out_planes: Optional[PlaneBuf] = None, out_f32=None):
+    """out[b, n] = act(sum_k a[b, k] W(n, k) + bias[n])  (mvae_skinny_expand); a: fp32 [B, K]."""
+    B = a.shape[0]
+    op = out_planes.struct() if out_planes is not None else None
+    rc = L.lib().mvae_skinny_expand(B, K, N, _ptr(a), a.stride(0), _ptr(W), w_stride_n, w_stride_k, _ptr(bias), act,
+                                    ctypes.c_void_p(mask.t.data_ptr()) if mask is not None else None,
+                                    mask.ld if mask is not None else 0, ctypes.byref(op) if op is not None else None,
+                                    _ptr(out_f32), out_f32.stride(0) if out_f32 is not None else 0, _stream())
+    L.check(rc, "mvae_skinny_expand")
+    _LAUNCHES[0] += 1
+
+
+def skinny_wgrad(small, S: int, wide, Wd: int, out, out_stride_s: int, out_stride_w: int, small_ones: bool = False,
+                 out_row=None, out_col=None, col_split: int = -1):
+    """out(s, w) += sum_b small[b, s] wide[b, w]  (mvae_skinny_wgrad, accumulating)."""
+    wf, ldw, wp = _wide(wide)
+    B = small.shape[0]
+    rc = L.lib().mvae_skinny_wgrad(B, S, Wd, _ptr(small), small.stride(0), int(small_ones), wf, ldw,
+                                   ctypes.byref(wp) if wp is not None else None, _ptr(out), out_stride_s, out_stride_w,
+                                   _ptr(out_row), _ptr(out_col), col_split, _stream())
+    L.check(rc, "mvae_skinny_wgrad")
+    _LAUNCHES[0] += 1

@@ -125,7 +125,6 @@ class _Workspace:
         self.kl = torch.zeros(B, C, **f)
         self.mu = torch.zeros(B, Sd, **f)
         self.sigma = torch.zeros(B, Sn, **f)
-        self.zp = ops.PlaneBuf(B, Sd, 3, dev, ones_col=True)  # 3 planes: pre-activation of the decoder relu
         self.ddp = ops.PlaneBuf(B, H, 2, dev, ones_col=True)
         self.bce = torch.zeros(B, **f)
         self.logits = None  # allocated on first forward() that needs them
@@ -133,7 +132,6 @@ class _Workspace:
         self.gddp = ops.PlaneBuf(B, H, 2, dev)
         self.gz = torch.zeros(B, Sd, **f)
         self.gml = torch.zeros(B, P, **f)
-        self.gmlp = ops.PlaneBuf(B, P, 2, dev)
         self.ghp = ops.PlaneBuf(B, H, 2, dev)
         self.flag = torch.zeros(1, device=dev, dtype=torch.int32)
 
@@ -163,6 +161,8 @@ class FusedFeedForwardVAE(nn.Module):
         self.desc = L.make_desc([c.kind for c in components], [c.true_dim for c in components],
                                 scalar_parametrization)
         assert self.desc.ld_z == self.total_z_dim
+        if self.desc.ld_ml > 64 or self.desc.ld_z > 64:
+            raise NotImplementedError("product manifolds with more than 64 head outputs / latent coordinates")
         self._ws = {}
         self._graphs = {}
         self._eps_override: Optional[Tensor] = None
@@ -235,9 +235,8 @@ class FusedFeedForwardVAE(nn.Module):
         # clamps and singular log-dets) carry 3 planes (~2^-24, fp32 accuracy): with 2 planes (~2^-16) relu decisions
         # near zero flip ~30x more often than in a true fp32 run.  Smooth consumers (logits -> BCE, every dgrad / wgrad)
         # read 2 planes.
+        # The heads and fc_d0 are "skinny" layers computed in exact fp32 on the CUDA cores (no planes at all).
         self.We0p = ops.PlaneBuf(H, D, 3, dev)
-        self.Whp = ops.PlaneBuf(P, H, 3, dev)
-        self.Wd0p = ops.PlaneBuf(H, Sd, 3, dev)
         self.Wlp = ops.PlaneBuf(D, H, 2, dev)
         self._planes_stale = True
         self._ws = {}
@@ -263,8 +262,6 @@ class FusedFeedForwardVAE(nn.Module):
 
     def refresh_weight_planes(self) -> None:
         ops.split_planes(self.fc_e0.weight.data, self.We0p)
-        ops.split_planes(self.Wh, self.Whp)
-        ops.split_planes(self.fc_d0.weight.data, self.Wd0p)
         ops.split_planes(self.fc_logits.weight.data, self.Wlp)
         self._planes_stale = False
 
@@ -285,12 +282,14 @@ class FusedFeedForwardVAE(nn.Module):
             self.refresh_weight_planes()
         ops.split_planes(ws.x, ws.xp)
         ops.gemm(ws.xp, self.We0p, B, H, D, epilogue=L.EPI_BIAS_RELU, bias=self.fc_e0.bias.data, out_planes=ws.hp)
-        ops.gemm(ws.hp, self.Whp, B, P, H, bias=self.bh, out_f32=ws.ml)
+        # heads: N = P is tiny -> CUDA-core row dots in exact fp32 (h read from its 3 planes)
+        ops.skinny_rowdot((ws.hp, 3), self.Wh, H, 1, K=H, N=P, bias=self.bh, out=ws.ml)
         out = {"z": ws.z, "kl": ws.kl, "mu": ws.mu, "sigma": ws.sigma}
         ops.pm_forward(self.desc, ws.ml, ws.eps, self._rflat, want_mu_sigma=want_mu_sigma,
                        flag=ws.flag if self.check_finite else None, out=out)
-        ops.split_planes(ws.z, ws.zp)
-        ops.gemm(ws.zp, self.Wd0p, B, H, Sd, epilogue=L.EPI_BIAS_RELU, bias=self.fc_d0.bias.data, out_planes=ws.ddp)
+        # fc_d0: K = total_z_dim is tiny -> CUDA-core expansion in exact fp32, relu, planes of dd for the logits GEMM
+        ops.skinny_expand(ws.z, self.fc_d0.weight.data, Sd, 1, K=Sd, N=H, bias=self.fc_d0.bias.data, act=ops.ACT_RELU,
+                          out_planes=ws.ddp)
         ws.bce.zero_()
         epi = L.EPI_BCE_ROWSUM if self.recon_kind == "bce" else L.EPI_NLL_ROWSUM
         ops.gemm(ws.ddp, self.Wlp, B, D, H, epilogue=epi, bias=self.fc_logits.bias.data, aux=ws.x, rowsum=ws.bce,
@@ -305,20 +304,16 @@ class FusedFeedForwardVAE(nn.Module):
         ops.gemm(ws.gLp, ws.ddp, D, H + 1, B, a_major=MN, b_major=MN, split_k=0, out_f32=self.gWl, out_col=self.gbl,
                  col_split=H)
         ops.gemm(ws.gLp, self.Wlp, B, H, D, b_major=MN, epilogue=L.EPI_RELU_MASK, mask=ws.ddp, out_planes=ws.gddp)
-        # fc_d0
-        ops.gemm(ws.gddp, ws.zp, H, Sd + 1, B, a_major=MN, b_major=MN, split_k=0, out_f32=self.gWd0,
-                 out_col=self.gbd0, col_split=Sd, b_planes=2)
-        ops.gemm(ws.gddp, self.Wd0p, B, Sd, H, b_major=MN, out_f32=ws.gz, b_planes=2)
+        # fc_d0 (skinny): gW[h, j] = sum_b gdd[b, h] z[b, j], gb[h] = sum_b gdd[b, h];  gz = gdd W
+        ops.skinny_wgrad(ws.z, Sd, (ws.gddp, 2), H, self.gWd0, 1, Sd, small_ones=True, out_row=self.gbd0)
+        ops.skinny_rowdot((ws.gddp, 2), self.fc_d0.weight.data, 1, Sd, K=H, N=Sd, bias=None, out=ws.gz)
         # latent: d(-ELBO)/d kl = beta
         ops.pm_backward(self.desc, ws.ml, ws.eps, self._rflat, ws.gz, None, beta, gml=ws.gml, gradius=self._gradius)
         if self._any_fixed_radius:
             self._gradius.mul_(self._radius_mask)  # requires_grad=False radii (fixed curvature) get no gradient
-        ops.split_planes(ws.gml, ws.gmlp)
-        # heads
-        ops.gemm(ws.gmlp, ws.hp, P, H + 1, B, a_major=MN, b_major=MN, split_k=0, out_f32=self.gWh, out_col=self.gbh,
-                 col_split=H, b_planes=2)
-        ops.gemm(ws.gmlp, self.Whp, B, H, P, b_major=MN, epilogue=L.EPI_RELU_MASK, mask=ws.hp, out_planes=ws.ghp,
-                 b_planes=2)
+        # heads (skinny): gWh[p, k] = sum_b gml[b, p] h[b, k] (+ bias from h's ones column);  gh = (gml Wh) * 1[h > 0]
+        ops.skinny_wgrad(ws.gml, P, (ws.hp, 2), H + 1, self.gWh, H, 1, out_col=self.gbh, col_split=H)
+        ops.skinny_expand(ws.gml, self.Wh, 1, H, K=P, N=H, act=ops.ACT_MASK, mask=ws.hp, out_planes=ws.ghp)
         # fc_e0 (no dgrad into x)
         ops.gemm(ws.ghp, ws.xp, H, D + 1, B, a_major=MN, b_major=MN, split_k=0, out_f32=self.gWe0,
                  out_col=self.gbe0, col_split=D, b_planes=2)
@@ -352,11 +347,9 @@ class FusedFeedForwardVAE(nn.Module):
         Bz = z2.shape[0]
         if self._planes_stale:
             self.refresh_weight_planes()
-        zp = ops.PlaneBuf(Bz, self.total_z_dim, 2, self.device)
         ddp = ops.PlaneBuf(Bz, self.h_dim, 2, self.device)
-        ops.split_planes(z2, zp)
-        ops.gemm(zp, self.Wd0p, Bz, self.h_dim, self.total_z_dim, epilogue=L.EPI_BIAS_RELU, bias=self.fc_d0.bias.data,
-                 out_planes=ddp)
+        ops.skinny_expand(z2, self.fc_d0.weight.data, self.total_z_dim, 1, K=self.total_z_dim, N=self.h_dim,
+                          bias=self.fc_d0.bias.data, act=ops.ACT_RELU, out_planes=ddp)
         out = torch.empty(Bz, self.in_dim, device=self.device)
         ops.gemm(ddp, self.Wlp, Bz, self.in_dim, self.h_dim, bias=self.fc_logits.bias.data, out_f32=out)
         return out.reshape(*lead, self.in_dim)

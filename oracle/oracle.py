@@ -213,26 +213,35 @@ class OracleVAE:
                     r[i] = params[k]
         return r
 
-    def step(self, params, x, eps, beta=1.0, backward=True):
+    def step(self, params, x, eps, beta=1.0, backward=True, relu_decisions=None):
+        """relu_decisions = {"h": bool [B,H], "dd": bool [B,H]} (optional): the backward pass uses these relu masks
+        instead of its own (h > 0), (dd > 0).  relu'(0) is a convention and a pre-activation within float32 rounding
+        of zero may fall on either side in a float32 implementation; the parity tests pass the decisions the device
+        took, after checking that every differing unit really sits at the kink (|pre-activation| ~ 0).  The
+        pre-activations are returned as "h_pre" / "dd_pre" for that check.  Forward values are unaffected."""
         dt = x.dtype
         Wh, bh = self.heads_matrix(params)
         R = self.radii(params, dt)
-        h = linear(x, params["fc_e0.weight"], params["fc_e0.bias"], relu=True)
+        h_pre = linear(x, params["fc_e0.weight"], params["fc_e0.bias"])
+        h = np.maximum(h_pre, 0)
         ml = linear(h, Wh, bh)
         f = pm_forward(self.desc, ml, eps, R, want=("z", "kl", "mu", "sigma"))
-        dd = linear(f["z"], params["fc_d0.weight"], params["fc_d0.bias"], relu=True)
+        dd_pre = linear(f["z"], params["fc_d0.weight"], params["fc_d0.bias"])
+        dd = np.maximum(dd_pre, 0)
         logits = linear(dd, params["fc_logits.weight"], params["fc_logits.bias"])
         bce, glogits = recon(self.recon_kind, logits, x, want_grad=backward)
         stats = elbo(bce, f["kl"], beta)
         out = {"h": h, "ml": ml, "z": f["z"], "kl": f["kl"], "mu": f["mu"], "sigma": f["sigma"], "logits": logits,
-               "bce": bce, "bce_sum": stats[0], "kl_sum": stats[1], "elbo": stats[2], "kl_comp": stats[3:]}
+               "bce": bce, "h_pre": h_pre, "dd_pre": dd_pre, "bce_sum": stats[0], "kl_sum": stats[1], "elbo": stats[2], "kl_comp": stats[3:]}
         if not backward:
             return out
         g = {}
         # loss = -elbo = sum bce + beta * sum kl
         g["fc_logits.weight"] = glogits.T @ dd
         g["fc_logits.bias"] = glogits.sum(0)
-        gdd = (glogits @ params["fc_logits.weight"]) * (dd > 0)
+        h_on = (h > 0) if relu_decisions is None else np.asarray(relu_decisions["h"], dtype=bool)
+        dd_on = (dd > 0) if relu_decisions is None else np.asarray(relu_decisions["dd"], dtype=bool)
+        gdd = (glogits @ params["fc_logits.weight"]) * dd_on
         g["fc_d0.weight"] = gdd.T @ f["z"]
         g["fc_d0.bias"] = gdd.sum(0)
         gz = gdd @ params["fc_d0.weight"]
@@ -251,7 +260,7 @@ class OracleVAE:
             for nm in ("_nradius", "_pradius"):
                 if f"components.{i}.{nm}" in params:
                     g[f"components.{i}.{nm}"] = np.asarray(gR[i])
-        gh = (gml @ Wh) * (h > 0)
+        gh = (gml @ Wh) * h_on
         g["fc_e0.weight"] = gh.T @ x
         g["fc_e0.bias"] = gh.sum(0)
         out["grads"] = g

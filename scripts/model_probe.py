@@ -44,7 +44,6 @@ for sig, B, D, H, recon in [("p2", 2048, 50, 400, "nll"), ("h2,s2,e2", 4096, 784
     print("  gz  ", normwise(ws.gz.cpu().numpy(), ref["gz"]))
     gml = ws.gml.cpu().numpy()
     print("  gml ", normwise(gml, ref["gml"]), "cols", ["%.1e" % normwise(gml[:, j], ref["gml"][:, j]) for j in range(gml.shape[1])])
-    print("  gmlp", normwise(ws.gmlp.to_float().cpu().numpy(), ref["gml"]))
     e = np.abs(gml - ref["gml"])
     b = np.unravel_index(np.argmax(e), e.shape)
     print("  worst gml row", b, gml[b[0]], ref["gml"][b[0]], "ml", ref["ml"][b[0]], "eps", eps[b[0]].numpy())
@@ -57,3 +56,32 @@ for sig, B, D, H, recon in [("p2", 2048, 50, 400, "nll"), ("h2,s2,e2", 4096, 784
     gWh = ws.gml.double().t() @ ws.hp.to_float().double()
     print("  heads wgrad vs fp64 product of the kernel's own operands:",
           normwise(model.gWh.cpu().numpy(), gWh.cpu().numpy()))
+    # ---- fp32-inherent floor: the oracle itself in float32 vs float64, and relu decision flips ----
+    p32 = {k: v.astype(np.float32) for k, v in params.items()}
+    r32 = orc.OracleVAE(sig, D, H, recon, False).step(p32, x.float().numpy(), eps.float().numpy(), beta=np.float32(0.8))
+    print("  oracle32 vs oracle64: gz %.2e gml %.2e" % (normwise(r32["gz"], ref["gz"]), normwise(r32["gml"], ref["gml"])))
+    for k in ref["grads"]:
+        a, b = np.asarray(r32["grads"][k], dtype=np.float64), np.asarray(ref["grads"][k])
+        if a.ndim:
+            print("  oracle32 grad %-36s max %.2e fro %.2e" % (k, normwise(a, b), np.linalg.norm(a - b) / np.linalg.norm(b)))
+    dd64 = np.maximum(ref["z"] @ params["fc_d0.weight"].T + params["fc_d0.bias"], 0)
+    dd_k = ws.ddp.to_float().cpu().numpy()
+    flips_k = np.argwhere((dd_k > 0) != (dd64 > 0))
+    dd32 = np.maximum(r32["z"] @ p32["fc_d0.weight"].T + p32["fc_d0.bias"], 0)
+    flips_o = np.argwhere((dd32 > 0) != (dd64 > 0))
+    h_k = ws.hp.to_float().cpu().numpy()
+    print("  relu flips vs f64: fc_d0 kernel %d oracle32 %d | fc_e0 kernel %d oracle32 %d" % (
+        len(flips_k), len(flips_o), int(((h_k > 0) != (ref["h"] > 0)).sum()), int(((r32["h"] > 0) != (ref["h"] > 0)).sum())))
+    egz = np.abs(ws.gz.cpu().numpy() - ref["gz"]).max(1)
+    top = np.argsort(-egz)[:5]
+    print("  worst gz rows", top, egz[top], "flip rows kernel", sorted(set(flips_k[:, 0].tolist()))[:10])
+    egml = np.abs(gml - ref["gml"])
+    for j in range(min(gml.shape[1], 4)):
+        t5 = np.argsort(-egml[:, j])[:4]
+        print("  gml col", j, "worst rows", t5, egml[t5, j], "ref", ref["gml"][t5, j])
+    # wgrad of heads from kernel's gml & ORACLE h, and oracle gml & kernel h: which operand carries the error
+    hk = h_k.astype(np.float64)
+    for nm, A, Bm in (("kernel gml x oracle h", gml.astype(np.float64), ref["h"]), ("oracle gml x kernel h", ref["gml"], hk)):
+        W = A.T @ Bm
+        Wr = ref["gml"].T @ ref["h"]
+        print("   ", nm, "rows fro:", ["%.1e" % (np.linalg.norm(W[i] - Wr[i]) / np.linalg.norm(Wr[i])) for i in range(min(4, W.shape[0]))])

@@ -364,3 +364,79 @@ def test_gemm_rejects_bad_arguments(dev):
         ops.gemm(a, a, 64, 64, 64, epilogue=_lib.EPI_BIAS_RELU, split_k=2, out_f32=out)  # split-K needs STORE
     with pytest.raises(_lib.MvaeError):
         ops.gemm(a, a, 64, 64, 0, out_f32=out)
+
+
+# ------------------------------------------------------------------------------------------ skinny dense layers
+@pytest.mark.parametrize("B,K,N", [(4096, 400, 12), (8229, 400, 60), (1000, 37, 8), (5, 400, 1)])
+def test_skinny_rowdot(dev, B, K, N):
+    """Heads forward (component.py:64,69) and dgrad into z: exact fp32 row dots from fp32 or 3-plane operands."""
+    from mvae_b200 import ops
+    g = torch.Generator(device=dev).manual_seed(B + K + N)
+    a = torch.randn(B, K, device=dev, generator=g)
+    W = torch.randn(N, K, device=dev, generator=g) / K**0.5
+    b = torch.randn(N, device=dev, generator=g)
+    ref = a.double() @ W.double().t() + b.double()
+    out = torch.full((B, N), float("nan"), device=dev)
+    ops.skinny_rowdot(a, W, K, 1, K=K, N=N, bias=b, out=out)
+    assert ((out.double() - ref).abs().max() / ref.abs().max()).item() < 2e-6
+    ap = _planes_of(a, dev, planes=3, ones_col=True)
+    out2 = torch.full((B, N), float("nan"), device=dev)
+    ops.skinny_rowdot((ap, 3), W, K, 1, K=K, N=N, bias=b, out=out2)
+    assert ((out2.double() - ref).abs().max() / ref.abs().max()).item() < 2e-6
+    # transposed weight access: out = a Wt with Wt [K, N] stored row-major
+    Wt = W.t().contiguous()
+    out3 = torch.full((B, N), float("nan"), device=dev)
+    ops.skinny_rowdot(a, Wt, 1, N, K=K, N=N, bias=None, out=out3)
+    assert ((out3.double() - (ref - b.double())).abs().max() / ref.abs().max()).item() < 2e-6
+
+
+@pytest.mark.parametrize("B,K,N", [(4096, 8, 400), (1000, 34, 400), (77, 12, 130), (4096, 60, 400)])
+def test_skinny_expand(dev, B, K, N):
+    """fc_d0 forward (ffnn_vae.py:56) with relu -> planes, and the relu-masked dgrad into h."""
+    from mvae_b200 import ops
+    g = torch.Generator(device=dev).manual_seed(B * 3 + K + N)
+    a = torch.randn(B, K, device=dev, generator=g)
+    W = torch.randn(N, K, device=dev, generator=g)
+    b = torch.randn(N, device=dev, generator=g)
+    pre = a.double() @ W.double().t() + b.double()
+    outp = ops.PlaneBuf(B, N, 2, dev, ones_col=True)
+    out32 = torch.empty(B, N, device=dev)
+    ops.skinny_expand(a, W, K, 1, K=K, N=N, bias=b, act=ops.ACT_RELU, out_planes=outp, out_f32=out32)
+    ref = pre.clamp(min=0)
+    assert ((out32.double() - ref).abs().max() / ref.abs().max()).item() < 2e-6
+    assert ((outp.to_float().double() - ref).abs().max() / ref.abs().max()).item() < 2e-5
+    assert torch.equal(outp.t[0, :, N].float(), torch.ones(B, device=dev))  # ones column untouched
+    ga = torch.randn(B, K, device=dev, generator=g)
+    Wt = W.t().contiguous()  # [K, N]
+    gout = ops.PlaneBuf(B, N, 2, dev)
+    ops.skinny_expand(ga, Wt, 1, N, K=K, N=N, act=ops.ACT_MASK, mask=outp, out_planes=gout)
+    refm = (ga.double() @ Wt.double()) * (out32 > 0)
+    assert ((gout.to_float().double() - refm).abs().max() / refm.abs().max()).item() < 2e-5
+
+
+@pytest.mark.parametrize("B,S,Wd", [(4096, 8, 400), (4096, 12, 400), (8229, 60, 400), (333, 3, 50)])
+def test_skinny_wgrad(dev, B, S, Wd):
+    """Weight / bias gradients of the skinny layers: batch reductions with the bias riding along."""
+    from mvae_b200 import ops
+    g = torch.Generator(device=dev).manual_seed(B + S * 7 + Wd)
+    small = torch.randn(B, S, device=dev, generator=g)
+    wide = torch.randn(B, Wd, device=dev, generator=g)
+    # (a) fc_d0 style: out[w, s], bias of the wide side from the implicit ones
+    out = torch.zeros(Wd, S, device=dev)
+    brow = torch.zeros(Wd, device=dev)
+    ops.skinny_wgrad(small, S, (_planes_of(wide, dev), 2), Wd, out, 1, S, small_ones=True, out_row=brow)
+    ref = wide.double().t() @ small.double()
+    assert ((out.double() - ref).abs().max() / ref.abs().max()).item() < 3e-5
+    assert ((brow.double() - wide.double().sum(0)).abs().max() / wide.double().sum(0).abs().max()).item() < 3e-5
+    # (b) heads style: out[s, w], bias of the small side from the wide operand's ones column
+    wp = _planes_of(wide, dev, planes=3, ones_col=True)
+    out2 = torch.zeros(S, Wd, device=dev)
+    bcol = torch.zeros(S, device=dev)
+    ops.skinny_wgrad(small, S, (wp, 2), Wd + 1, out2, Wd, 1, out_col=bcol, col_split=Wd)
+    ref2 = small.double().t() @ wide.double()
+    assert ((out2.double() - ref2).abs().max() / ref2.abs().max()).item() < 3e-5
+    assert ((bcol.double() - small.double().sum(0)).abs().max() / small.double().sum(0).abs().max()).item() < 1e-5
+    # fp32 wide operand: exact fp32 accumulation
+    out3 = torch.zeros(S, Wd, device=dev)
+    ops.skinny_wgrad(small, S, wide, Wd, out3, Wd, 1)
+    assert ((out3.double() - ref2).abs().max() / ref2.abs().max()).item() < 2e-6

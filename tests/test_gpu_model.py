@@ -106,12 +106,6 @@ def test_train_step_vs_oracle(dev, oracle, sig, B, D, H, recon, fixed):
     eps = torch.randn(B, model.desc.ld_eps, generator=g)
     params = {k: v.detach().cpu().double().numpy() for k, v in model.state_dict().items()}
     ovae = oracle.OracleVAE(sig, D, H, recon, False)
-    ref = ovae.step(params, x.double().numpy(), eps.double().numpy(), beta=0.8)
-    # Gradient bars.  The two relus make the map parameters -> gradients discontinuous: a hidden unit whose
-    # pre-activation is within float32 rounding of zero may switch side relative to the float64 oracle (expected
-    # ~0.3 units per step at fp32 accuracy for these sizes; the reference's own float32 run has the same property).
-    # One switched unit moves isolated entries of a gradient by O(1e-3) of its largest entry but leaves its bulk
-    # untouched, so every tensor must match to 1e-4 in the Frobenius sense and to 2e-3 in the max norm.
 
     class NoOpt:
         def zero_grad(self):
@@ -121,10 +115,28 @@ def test_train_step_vs_oracle(dev, oracle, sig, B, D, H, recon, fixed):
             pass
 
     bs, _ = model.train_step(NoOpt(), x, 0.8, eps=eps.to(dev))
+    ws = model._last_ws
+    fwd = ovae.step(params, x.double().numpy(), eps.double().numpy(), beta=0.8, backward=False)
+    # The two relus make the map parameters -> gradients discontinuous: a hidden unit whose pre-activation is within
+    # float32 rounding of zero may fall on the other side than in the float64 oracle (expected ~1 of the 2*B*H units
+    # per step at these sizes for ANY float32 implementation; relu'(0) is a convention).  The device's decisions are
+    # therefore checked on their own — every unit that differs from the oracle must sit at the kink, and there may
+    # only be a handful — and the oracle's backward pass then takes the same decisions, so that every gradient is
+    # compared at the tight bar.
+    decisions = {}
+    for name, planes, pre in (("h", ws.hp, fwd["h_pre"]), ("dd", ws.ddp, fwd["dd_pre"])):
+        on = planes.to_float().cpu().numpy() > 0
+        diff = on != (pre > 0)
+        assert diff.sum() <= 4, (name, int(diff.sum()))
+        assert np.all(np.abs(pre[diff]) <= 2e-6 * np.abs(pre).max()), (name, np.abs(pre[diff]).max())
+        decisions[name] = on
+    ref = ovae.step(params, x.double().numpy(), eps.double().numpy(), beta=0.8, relu_decisions=decisions)
     assert abs(bs.elbo - ref["elbo"]) < TOL_SUM * abs(ref["elbo"])
     assert abs(bs.bce - ref["bce_sum"]) < TOL_SUM * abs(ref["bce_sum"])
     assert abs(bs.kl - ref["kl_sum"]) < TOL_SUM * abs(ref["kl_sum"]) + 1e-3
     np.testing.assert_allclose(bs.component_kl, ref["kl_comp"], rtol=2e-5, atol=1e-2)
+    assert normwise(ws.gz.cpu().numpy(), ref["gz"]) < TOL
+    assert normwise(ws.gml.cpu().numpy(), ref["gml"]) < TOL
     for k, p in model.named_parameters():
         if k not in ref["grads"]:
             continue
@@ -135,7 +147,7 @@ def test_train_step_vs_oracle(dev, oracle, sig, B, D, H, recon, fixed):
             err_fro = float(np.linalg.norm(got - r) / max(np.linalg.norm(r), 1e-30))
         else:
             err_max = err_fro = abs(got - r) / max(1.0, abs(r))
-        assert err_fro < 1e-4 and err_max < 2e-3, (k, err_fro, err_max)
+        assert err_fro < TOL and err_max < TOL, (k, err_fro, err_max)
 
 
 def test_optimizer_step_matches_torch(dev):
