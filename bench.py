@@ -56,14 +56,55 @@ def synthetic_x(recon, B, D, seed):
 
 
 class ClockSampler:
-    """nvidia-smi clocks/throttle reasons sampled DURING the timed region."""
+    """SM clock and clock-event (throttle) reasons sampled DURING the timed region.
+
+    NVML is polled from a thread every ~2 ms (a timed region of a few dozen 0.3 ms steps is far shorter than one
+    `nvidia-smi -lms` period); `nvidia-smi` is the fallback when the NVML binding is unavailable."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
     def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.rows, self.proc, self.thread = index, [], None, None
+        self.stop_flag = threading.Event()
+        self.nvml, self.handle, self.max_mhz = None, None, None
+
+    def _nvml_open(self):
+        try:
+            import pynvml
+            import torch
+            pynvml.nvmlInit()
+            h = None
+            try:
+                uuid = str(torch.cuda.get_device_properties(self.index).uuid)
+                h = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid).encode())
+            except Exception:
+                h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+            pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)
+            self.nvml, self.handle = pynvml, h
+            return True
+        except Exception:
+            return False
+
+    def _poll(self):
+        nv, h = self.nvml, self.handle
+        masks = [nv.nvmlClocksEventReasonHwSlowdown, nv.nvmlClocksEventReasonHwThermalSlowdown,
+                 nv.nvmlClocksEventReasonSwThermalSlowdown, nv.nvmlClocksEventReasonSwPowerCap]
+        while not self.stop_flag.is_set():
+            try:
+                mhz = float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                bits = int(nv.nvmlDeviceGetCurrentClocksEventReasons(h))
+                self.rows.append([mhz, self.max_mhz] + [bool(bits & m) for m in masks])
+            except Exception:
+                pass
+            time.sleep(0.002)
 
     def start(self):
+        if self._nvml_open():
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
+            return
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
                                           "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
@@ -74,26 +115,31 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
-
-    def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+            c = [x.strip() for x in line.split(",")]
             try:
-                sm.append(float(r[0]))
-                mx.append(float(r[1]))
-                for n, v in zip(names, r[3:7]):
-                    if v.lower().startswith("active"):
-                        reasons.add(n)
+                self.rows.append([float(c[0]), float(c[1])] + [v.lower().startswith("active") for v in c[3:7]])
             except (ValueError, IndexError):
                 pass
-        sm.sort()
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+
+    def mark(self):
+        """Samples taken before this call (warm-up, idle) are dropped."""
+        self.rows = []
+
+    def stop(self):
+        if self.thread is not None:
+            self.stop_flag.set()
+            self.thread.join(timeout=1.0)
+            how = "nvml"
+        elif self.proc is not None:
+            self.proc.terminate()
+            how = "nvidia-smi"
+        else:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml and nvidia-smi unavailable"], "samples": 0}
+        rows = list(self.rows)
+        sm = sorted(r[0] for r in rows)
+        reasons = sorted({n for r in rows for n, v in zip(self.NAMES, r[2:6]) if v})
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(r[1] for r in rows) if rows else self.max_mhz,
+                "reasons": reasons, "samples": len(sm), "source": how}
 
 
 # ------------------------------------------------------------------------------------------------ CPU arm
@@ -157,7 +203,20 @@ def run_reference(args):
     torch.set_num_threads(cores)
     os.environ.setdefault("OMP_NUM_THREADS", str(cores))
     sig, B, D, H, recon, fixed, desc = WORKLOADS[args.workload]
-    step = cpu_step_fn(args.workload, B)
+    # bounded sample: a step is a full train step on the first Bs rows of the workload's batch, Bs chosen so that the
+    # whole run (warm-up + K steps) stays near two minutes of CPU time
+    Bs = B
+    step = cpu_step_fn(args.workload, Bs)
+    step()
+    t0 = time.perf_counter()
+    step()
+    t1 = time.perf_counter() - t0
+    budget_s = 120.0
+    n_total = args.steps + max(args.warmup, 1)
+    if t1 * n_total > budget_s:
+        Bs = int(B * budget_s / (t1 * n_total)) // 128 * 128
+        Bs = min(B, max(128, Bs))
+        step = cpu_step_fn(args.workload, Bs)
     for _ in range(max(args.warmup, 1)):
         step()
     t0 = time.perf_counter()
@@ -165,8 +224,9 @@ def run_reference(args):
         step()
     dt = time.perf_counter() - t0
     ms = dt / args.steps * 1e3
-    value = B / (ms / 1e3)
-    sample = f"{args.steps} full steps of batch {B} ({desc}), float32"
+    value = Bs / (ms / 1e3)
+    sample = (f"{args.steps} full train steps on {Bs} of the {B} rows of the batch ({desc}), float32, "
+              f"numpy BLAS + C/OpenMP oracle port")
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms, "steps_per_sec": 1e3 / ms, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -230,16 +290,17 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     # ---------------- value: device-resident inputs, no host sync inside the timed region ----------------
-    for i in range(max(args.warmup, 3)):
-        model.train_step(opt, xs_dev[i % n_rot], 1.0, sync_stats=False)
-    barrier()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+    for i in range(max(args.warmup, 3)):
+        model.train_step(opt, xs_dev[i % n_rot], 1.0, sync_stats=False)
+    barrier()
     n0 = ops.launch_count()
     starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     ends = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     barrier()
+    sampler.mark()
     for i in range(args.steps):
         flush()
         starts[i].record()
@@ -351,8 +412,8 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=1000)
+    ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly instead of replaying CUDA graphs")

@@ -3,7 +3,7 @@
 // pm_kernels_impl.cuh and are instantiated in pm_fwd.cu / pm_bwd.cu.
 #include <string.h>
 
-#include "manifold_math.cuh"
+#include "pm_math.cuh"
 #include "pm_params.cuh"
 
 namespace mvae {
@@ -17,7 +17,7 @@ static int validate_desc(const mvae_pm_desc* d) {
     if (c.type < MVAE_EUCLIDEAN || c.type > MVAE_PROJ_SPHERE) return MVAE_ERR_INVALID_ARGUMENT;
     if (c.type == MVAE_PROJ_SPHERE) return MVAE_ERR_UNSUPPORTED;
     if (c.n < 1) return MVAE_ERR_INVALID_ARGUMENT;
-    if (c.n > kDynMaxN) return MVAE_ERR_UNSUPPORTED;
+    if (c.n > pm::kDynMaxN) return MVAE_ERR_UNSUPPORTED;
     const int d_expect = (c.type == MVAE_HYPERBOLOID || c.type == MVAE_SPHERE) ? c.n + 1 : c.n;
     if (c.d != d_expect) return MVAE_ERR_INVALID_ARGUMENT;
     if (c.l_n != c.n && c.l_n != 1) return MVAE_ERR_INVALID_ARGUMENT;

@@ -4,8 +4,7 @@
 
 namespace mvae {
 
-
-constexpr int kPmThreads = 128;
+constexpr int kPmMaxThreads = 512;  // register budget: 128 per thread
 
 struct PmParams {
   mvae_pm_desc desc;
@@ -26,12 +25,11 @@ struct PmParams {
   float* gml;
   float* gradius;
   // tiling
-  int S;  // samples per CTA tile (multiple of 32)
-  int ldp_ml, ldp_eps, ldp_z, ldp_c;
-  FastDiv fd_ml, fd_eps, fd_z, fd_c, fd_S;
-  int vec_ok;  // all global pointers 16-byte aligned
+  int S;          // samples per tile (multiple of 32)
+  int n_tiles;    // ceil(B / S)
+  int vec_ok;     // all global pointers 16-byte aligned: tiles move with bulk async copies (TMA)
+  int zero_gml;   // backward: some column of a gml row is owned by no component -> tiles are zero-filled first
 };
-
 
 int launch_pm_forward(PmParams& p, void* stream);
 int launch_pm_backward(PmParams& p, void* stream);

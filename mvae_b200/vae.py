@@ -116,7 +116,10 @@ class _Workspace:
         dev, D, H, P, Sn, Sd, C = m.device, m.in_dim, m.h_dim, m.desc.ld_ml, m.desc.ld_eps, m.desc.ld_z, m.desc.C
         f = dict(device=dev, dtype=torch.float32)
         self.B = B
-        self.x = torch.zeros(B, D, **f)
+        # two input slots: train_epoch() copies batch i+1 host->device into one while the kernels of step i read the
+        # other (the CUDA graphs are keyed by slot, the buffers never move)
+        self.xbuf = [torch.zeros(B, D, **f), torch.zeros(B, D, **f)]
+        self.slot = 0
         self.eps = torch.zeros(B, Sn, **f)
         self.xp = ops.PlaneBuf(B, D, m.input_planes, dev, ones_col=True)
         self.hp = ops.PlaneBuf(B, H, 3, dev, ones_col=True)   # 3 planes: feeds the heads at fp32 accuracy
@@ -134,6 +137,10 @@ class _Workspace:
         self.gml = torch.zeros(B, P, **f)
         self.ghp = ops.PlaneBuf(B, H, 2, dev)
         self.flag = torch.zeros(1, device=dev, dtype=torch.int32)
+
+    @property
+    def x(self) -> Tensor:
+        return self.xbuf[self.slot]
 
 
 class FusedFeedForwardVAE(nn.Module):
@@ -404,6 +411,17 @@ class FusedFeedForwardVAE(nn.Module):
         (the logits) is not materialised in training — call forward() when it is needed."""
         ws = self._workspace(x_mb.shape[0])
         self._stage(ws, x_mb, eps)
+        self._step_kernels(optimizer, ws, beta)
+        stats = BatchStats(self._stats.clone() if not sync_stats else self._stats, beta)
+        self._last_ws = ws
+        out = (None, ws.z, None)
+        if sync_stats:
+            if self.check_finite and int(ws.flag.item()) != 0:
+                raise FloatingPointError("non-finite latent sample or KL term (device flag set by mvae_pm_forward)")
+            return stats.convert_to_float(), out
+        return stats, out
+
+    def _step_kernels(self, optimizer, ws: _Workspace, beta: float) -> None:
         fused = isinstance(optimizer, FusedCurvatureOptimizer)
         if fused and self.use_cuda_graph:
             self._graphed_step(optimizer, ws, beta)
@@ -418,14 +436,93 @@ class FusedFeedForwardVAE(nn.Module):
                 self._attach_grads()
             optimizer.step()
             self._planes_stale = True
-        stats = BatchStats(self._stats.clone() if not sync_stats else self._stats, beta)
+
+    @torch.no_grad()
+    def train_epoch(self, optimizer, batches, beta: float, eps_batches=None) -> List[BatchStatsFloat]:
+        """The batch loop of Trainer._train_epoch (train.py:198-199, 209-210): `for x_mb, y_mb in train_data:
+        stats, _ = model.train_step(optimizer, x_mb, beta)` -> list of per-batch BatchStatsFloat, with the host<->device
+        traffic of that loop pipelined instead of serialised with the kernels:
+
+          * batch i+1 is copied host->device on a copy stream into the idle input slot while step i runs,
+          * the ELBO statistics of step i leave through an asynchronous device->host copy into a pinned ring and are
+            converted to floats when the ring wraps / at the end (the reference blocks on 3+C .item() calls per step).
+
+        `batches` yields x_mb or (x_mb, y_mb) like the reference's DataLoader; host tensors should be pinned for the
+        copies to overlap.  `eps_batches` optionally supplies the noise (tests)."""
+        main = torch.cuda.current_stream(self.device)
+        if getattr(self, "_copy_stream", None) is None:
+            self._copy_stream = torch.cuda.Stream(device=self.device)
+            self._slot_ready = [torch.cuda.Event(), torch.cuda.Event()]
+            self._slot_free = [torch.cuda.Event(), torch.cuda.Event()]
+        copy = self._copy_stream
+        ring_n, nst = 64, self._stats.numel()
+        if getattr(self, "_stats_ring", None) is None:
+            self._stats_ring = torch.zeros(ring_n, nst, dtype=torch.float32).pin_memory()
+            self._ring_ev = [torch.cuda.Event() for _ in range(ring_n)]
+        ring, ring_ev = self._stats_ring, self._ring_ev
+        results: List[BatchStatsFloat] = []
+
+        def take(item):
+            x = item[0] if isinstance(item, (tuple, list)) else item
+            return x
+
+        def prefetch(ws, slot, x, first):
+            if not first:
+                copy.wait_event(self._slot_free[slot])  # the step that last read this slot has finished
+            else:
+                copy.wait_stream(main)
+            with torch.cuda.stream(copy):
+                ws.xbuf[slot].copy_(x.reshape(ws.B, self.in_dim), non_blocking=True)
+                self._slot_ready[slot].record(copy)
+
+        def drain(i):
+            ring_ev[i % ring_n].synchronize()
+            h = ring[i % ring_n].tolist()
+            results.append(BatchStatsFloat(h[0], h[1], h[2], h[3:], beta))
+
+        it = iter(batches)
+        eps_it = iter(eps_batches) if eps_batches is not None else None
+        nxt = next(it, None)
+        if nxt is None:
+            return results
+        x = take(nxt)
+        ws = self._workspace(x.shape[0])
+        slot = ws.slot
+        prefetch(ws, slot, x, first=True)
+        i = 0
+        while x is not None:
+            B = x.shape[0]
+            nxt = next(it, None)
+            x_next = take(nxt) if nxt is not None else None
+            main.wait_event(self._slot_ready[slot])
+            ws.slot = slot
+            if x_next is not None and x_next.shape[0] == B:
+                prefetch(ws, 1 - slot, x_next, first=(i == 0))
+            eps = next(eps_it) if eps_it is not None else self._eps_override
+            if eps is None:
+                ws.eps.normal_()
+            else:
+                ws.eps.copy_(eps, non_blocking=True)
+            self._step_kernels(optimizer, ws, beta)
+            self._slot_free[slot].record(main)
+            if i >= ring_n:
+                drain(i - ring_n)
+            ring[i % ring_n].copy_(self._stats, non_blocking=True)
+            ring_ev[i % ring_n].record(main)
+            i += 1
+            if x_next is not None and x_next.shape[0] != B:  # ragged last batch: its own workspace, no overlap
+                ws = self._workspace(x_next.shape[0])
+                slot = ws.slot
+                prefetch(ws, slot, x_next, first=True)
+            else:
+                slot = 1 - slot
+            x = x_next
+        for j in range(max(0, i - ring_n), i):
+            drain(j)
         self._last_ws = ws
-        out = (None, ws.z, None)
-        if sync_stats:
-            if self.check_finite and int(ws.flag.item()) != 0:
-                raise FloatingPointError("non-finite latent sample or KL term (device flag set by mvae_pm_forward)")
-            return stats.convert_to_float(), out
-        return stats, out
+        if self.check_finite and int(ws.flag.item()) != 0:
+            raise FloatingPointError("non-finite latent sample or KL term (device flag set by mvae_pm_forward)")
+        return results
 
     _grad_hook = None
     use_cuda_graph = False
@@ -435,7 +532,7 @@ class FusedFeedForwardVAE(nn.Module):
         Graph A = forward + backward into the gradient bucket; [the data-parallel all-reduce runs between the two,
         eagerly]; graph B = optimizer step + refresh of the weight planes.  Keyed by everything baked into launch
         parameters: batch size, beta, and whether the curvature optimizers step."""
-        key = (ws.B, float(beta), optimizer.curvature_step_enabled(), id(optimizer))
+        key = (ws.B, ws.slot, float(beta), optimizer.curvature_step_enabled(), id(optimizer))
         entry = self._graphs.get(key)
         if entry is None:
             if self._planes_stale:
