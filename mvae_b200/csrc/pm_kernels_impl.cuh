@@ -14,6 +14,7 @@
 // Ragged last tiles and unaligned pointers take a cooperative load / store path through the same shared-memory tiles.
 #pragma once
 #include <math.h>
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -85,153 +86,384 @@ struct __align__(16) ItemInfo {
   int pad;
 };
 
-template <int N, bool BWD, bool WANT_MS>
-__device__ __forceinline__ bool run_item(const ItemInfo& c, const float* ml_row, const float* eps_row, float* z_row,
-                                         float* kl_slot, float* mu_row, float* sigma_row, const float* gz_row,
-                                         float gkl, float* gml_row, float* gR_acc) {
+// One (component, sample) item with every operand pointer final (component offsets applied): m, l, e [, gz] in the input
+// stage; z, kl [, mu, sigma] or gm, gl in the output staging tile.  Returns false if a produced value is non-finite
+// (only evaluated when `check`).
+template <int N, int TYPE, bool BWD, bool WANT_MS>
+__device__ __forceinline__ bool run_item(int n_rt, int l_n, const CompConst& K, const float* m, const float* l,
+                                         const float* e, float* z, float* kl, float* mu, float* sigma,
+                                         const float* gz, float gkl, float* gm_out, float* gl_out, float* gR_acc,
+                                         bool check) {
   CompOut<N> o;
-  const int n = N > 0 ? N : c.n;
+  const int n = N > 0 ? N : n_rt;
   constexpr int CN = Cap<N>::n;
-  // operands are read from the shared-memory tile where they are needed (keeps the register footprint small)
-  const float* m = ml_row + c.m_off;
-  const float* l = ml_row + c.l_off;
-  const float* e = eps_row + c.eps_off;
-  const float* gz = BWD ? gz_row + c.z_off : nullptr;
+  constexpr bool AMB = TYPE == MVAE_HYPERBOLOID || TYPE == MVAE_SPHERE;  // ambient dimension n + 1
   float gm[BWD ? CN : 1], gl[BWD ? CN : 1];
   float gR = 0.f;
-  switch (c.type) {
-    case MVAE_EUCLIDEAN: comp_e<N, BWD>(n, c.l_n, m, l, e, o, gz, gkl, gm, gl); break;
-    case MVAE_HYPERBOLOID: comp_hsp<N, BWD, kHyp, WANT_MS>(n, c.l_n, m, l, e, c.K, o, gz, gkl, gm, gl, &gR); break;
-    case MVAE_SPHERE: comp_hsp<N, BWD, kSph, WANT_MS>(n, c.l_n, m, l, e, c.K, o, gz, gkl, gm, gl, &gR); break;
-    default: comp_hsp<N, BWD, kPoi, WANT_MS>(n, c.l_n, m, l, e, c.K, o, gz, gkl, gm, gl, &gR); break;
-  }
+  if (TYPE == MVAE_EUCLIDEAN) comp_e<N, BWD>(n, l_n, m, l, e, o, gz, gkl, gm, gl);
+  else if (TYPE == MVAE_HYPERBOLOID) comp_hsp<N, BWD, kHyp, WANT_MS>(n, l_n, m, l, e, K, o, gz, gkl, gm, gl, &gR);
+  else if (TYPE == MVAE_SPHERE) comp_hsp<N, BWD, kSph, WANT_MS>(n, l_n, m, l, e, K, o, gz, gkl, gm, gl, &gR);
+  else comp_hsp<N, BWD, kPoi, WANT_MS>(n, l_n, m, l, e, K, o, gz, gkl, gm, gl, &gR);
   if (BWD) {
     *gR_acc += gR;
     if (N > 0) {
 #pragma unroll
       for (int j = 0; j < N; ++j) {
-        gml_row[c.m_off + j] = gm[j];
-        if (j < c.l_n) gml_row[c.l_off + j] = gl[j];
+        gm_out[j] = gm[j];
+        if (j < l_n) gl_out[j] = gl[j];
       }
     } else {
       for (int j = 0; j < n; ++j) {
-        gml_row[c.m_off + j] = gm[j];
-        if (j < c.l_n) gml_row[c.l_off + j] = gl[j];
+        gm_out[j] = gm[j];
+        if (j < l_n) gl_out[j] = gl[j];
       }
     }
     return true;
   }
-  // a sum is non-finite iff a term is (up to overflow of finite terms near FLT_MAX, which the flag may also report)
-  float chk = o.kl;
-  const int d = c.d;
+  const int d = AMB ? n + 1 : n;
   if (N > 0) {
 #pragma unroll
     for (int k = 0; k < N + 1; ++k)
       if (k < d) {
-        z_row[c.z_off + k] = o.z[k];
-        chk += o.z[k];
-        if (WANT_MS) mu_row[c.z_off + k] = o.mu[k];
+        z[k] = o.z[k];
+        if (WANT_MS) mu[k] = o.mu[k];
       }
     if (WANT_MS) {
 #pragma unroll
-      for (int j = 0; j < N; ++j) sigma_row[c.eps_off + j] = o.sigma[j];
+      for (int j = 0; j < N; ++j) sigma[j] = o.sigma[j];
     }
   } else {
     for (int k = 0; k < d; ++k) {
-      z_row[c.z_off + k] = o.z[k];
-      chk += o.z[k];
-      if (WANT_MS) mu_row[c.z_off + k] = o.mu[k];
+      z[k] = o.z[k];
+      if (WANT_MS) mu[k] = o.mu[k];
     }
     if (WANT_MS)
-      for (int j = 0; j < n; ++j) sigma_row[c.eps_off + j] = o.sigma[j];
+      for (int j = 0; j < n; ++j) sigma[j] = o.sigma[j];
   }
-  *kl_slot = o.kl;
+  *kl = o.kl;
+  if (!check) return true;
+  // KL is a function of every produced value except, for Euclidean components, of eps (z = mu + eps sigma): there
+  // the z coordinates join the sum.  A sum is non-finite iff a term is (up to overflow near FLT_MAX).
+  float chk = o.kl;
+  if (TYPE == MVAE_EUCLIDEAN) {
+    if (N > 0) {
+#pragma unroll
+      for (int k = 0; k < N; ++k) chk += o.z[k];
+    } else {
+      for (int k = 0; k < d; ++k) chk += o.z[k];
+    }
+  }
   return chk - chk == 0.f;
 }
 
+// Runtime (type, n) -> static instantiation.  MAXN > 0: only dimensions <= MAXN are compiled in (register budget =
+// that of the widest one); MAXN == 0: all static dimensions plus the runtime-dimension path.
+#define MVAE_PM_FOR_DIMS(MAXN, n, CALL)                                     \
+  switch (n) {                                                              \
+    case 1: CALL(1) break;                                                  \
+    case 2: CALL(2) break;                                                  \
+    case 3: if constexpr (MAXN == 0 || MAXN >= 3) { CALL(3) } break;        \
+    case 4: if constexpr (MAXN == 0 || MAXN >= 4) { CALL(4) } break;        \
+    case 5: if constexpr (MAXN == 0 || MAXN >= 5) { CALL(5) } break;        \
+    case 6: if constexpr (MAXN == 0 || MAXN >= 6) { CALL(6) } break;        \
+    case 8: if constexpr (MAXN == 0 || MAXN >= 8) { CALL(8) } break;        \
+    default: if constexpr (MAXN == 0) { CALL(0) } break;                    \
+  }
+
+// looping variant: dispatch per item
 template <bool BWD, int MAXN, bool WANT_MS>
 __device__ __forceinline__ bool dispatch_item(const ItemInfo& c, const float* ml_row, const float* eps_row,
                                               float* z_row, float* kl_slot, float* mu_row, float* sigma_row,
-                                              const float* gz_row, float gkl, float* gml_row, float* gR_acc) {
-  // MAXN > 0: only dimensions <= MAXN are compiled in (register budget = that of the widest one); MAXN == 0: all
-  // static dimensions plus the runtime-dimension path.
-#define MVAE_CASE(NN)                                                                                               \
-  case NN:                                                                                                          \
-    if constexpr (MAXN == 0 || NN <= MAXN)                                                                          \
-      return run_item<NN, BWD, WANT_MS>(c, ml_row, eps_row, z_row, kl_slot, mu_row, sigma_row, gz_row, gkl, gml_row, \
-                                        gR_acc);                                                                    \
-    else                                                                                                            \
-      return true;
-  switch (c.n) {
-    MVAE_CASE(1)
-    MVAE_CASE(2)
-    MVAE_CASE(3)
-    MVAE_CASE(4)
-    MVAE_CASE(5)
-    MVAE_CASE(6)
-    MVAE_CASE(8)
-    default:
-      if constexpr (MAXN == 0)
-        return run_item<0, BWD, WANT_MS>(c, ml_row, eps_row, z_row, kl_slot, mu_row, sigma_row, gz_row, gkl, gml_row,
-                                         gR_acc);
-      else
-        return true;  // unreachable: the host picks the kernel whose MAXN covers every component
+                                              const float* gz_row, float gkl, float* gml_row, float* gR_acc,
+                                              bool check) {
+  bool ok = true;
+#define MVAE_PM_ITEM(TT, NN)                                                                                          \
+  ok = run_item<NN, TT, BWD, WANT_MS>(c.n, c.l_n, c.K, ml_row + c.m_off, ml_row + c.l_off, eps_row + c.eps_off,       \
+                                      z_row + c.z_off, kl_slot, mu_row + c.z_off, sigma_row + c.eps_off,              \
+                                      gz_row + c.z_off, gkl, gml_row + c.m_off, gml_row + c.l_off, gR_acc, check);
+#define MVAE_PM_E(NN) MVAE_PM_ITEM(MVAE_EUCLIDEAN, NN)
+#define MVAE_PM_H(NN) MVAE_PM_ITEM(MVAE_HYPERBOLOID, NN)
+#define MVAE_PM_S(NN) MVAE_PM_ITEM(MVAE_SPHERE, NN)
+#define MVAE_PM_P(NN) MVAE_PM_ITEM(MVAE_POINCARE, NN)
+  switch (c.type) {
+    case MVAE_EUCLIDEAN: MVAE_PM_FOR_DIMS(MAXN, c.n, MVAE_PM_E) break;
+    case MVAE_HYPERBOLOID: MVAE_PM_FOR_DIMS(MAXN, c.n, MVAE_PM_H) break;
+    case MVAE_SPHERE: MVAE_PM_FOR_DIMS(MAXN, c.n, MVAE_PM_S) break;
+    default: MVAE_PM_FOR_DIMS(MAXN, c.n, MVAE_PM_P) break;
   }
-#undef MVAE_CASE
+#undef MVAE_PM_E
+#undef MVAE_PM_H
+#undef MVAE_PM_S
+#undef MVAE_PM_P
+#undef MVAE_PM_ITEM
+  return ok;
 }
 
 // ------------------------------------------------------------------------------------------------ tile layout
-// Shared memory (floats): [ItemInfo x C] | 2 x input stage | 2 x output stage | 2 mbarriers.  Every tile is a
-// multiple of 128 bytes (S is a multiple of 32) so all bulk copies are 16-byte aligned.
-struct PmLayout {
-  int info_floats;
-  int in_ml, in_eps, in_gz, in_gkl, in_stage;      // offsets inside an input stage, stage size
-  int out_a, out_b, out_c, out_d, out_stage;       // fwd: z, kl, mu, sigma    bwd: gml
-  int total_floats;
-};
-__host__ __device__ inline PmLayout pm_layout(int C, int ld_ml, int ld_eps, int ld_z, int S, bool bwd, bool want_ms,
-                                              bool has_gkl) {
-  PmLayout L;
-  L.info_floats = (C * (int)(sizeof(ItemInfo) / 4) + 31) & ~31;
+// Shared memory (floats): [ItemInfo x C] | nst x input stage | 2 x output stage | nst mbarriers.  Every tile is a
+// multiple of 128 bytes (S is a multiple of 32) so all bulk copies are 16-byte aligned.  The host computes every
+// offset (fill_layout) so that the kernel reads them as constant-bank operands.
+constexpr int kPmMaxStages = 8;
+
+static inline size_t fill_layout(PmParams& p, bool bwd, bool want_ms, bool has_gkl) {
+  const int C = p.desc.C, ld_ml = p.desc.ld_ml, ld_eps = p.desc.ld_eps, ld_z = p.desc.ld_z, S = p.S;
+  const int info_floats = (C * (int)(sizeof(ItemInfo) / 4) + 31) & ~31;
   int o = 0;
-  L.in_ml = o;
+  p.in_ml = o;
   o += S * ld_ml;
-  L.in_eps = o;
+  p.in_eps = o;
   o += S * ld_eps;
-  L.in_gz = o;
+  p.in_gz = o;
   if (bwd) o += S * ld_z;
-  L.in_gkl = o;
+  p.in_gkl = o;
   if (bwd && has_gkl) o += S * C;
-  L.in_stage = o;
+  p.in_stage = o;
   o = 0;
-  L.out_a = o;
+  p.out_a = o;
   o += bwd ? S * ld_ml : S * ld_z;
-  L.out_b = o;
+  p.out_b = o;
   if (!bwd) o += S * C;
-  L.out_c = o;
+  p.out_c = o;
   if (!bwd && want_ms) o += S * ld_z;
-  L.out_d = o;
+  p.out_d = o;
   if (!bwd && want_ms) o += S * ld_eps;
-  L.out_stage = o;
-  L.total_floats = L.info_floats + 2 * L.in_stage + 2 * L.out_stage + 8;
-  return L;
+  p.out_stage = o;
+  p.in_base = info_floats;
+  p.out_base = p.in_base + p.nst * p.in_stage;
+  p.bar_base = p.out_base + 2 * p.out_stage;
+  p.bytes_ml = 4u * (uint32_t)(S * ld_ml);
+  p.bytes_eps = 4u * (uint32_t)(S * ld_eps);
+  p.bytes_z = 4u * (uint32_t)(S * ld_z);
+  p.bytes_c = 4u * (uint32_t)(S * C);
+  p.bytes_in = 4u * (uint32_t)p.in_stage;
+  return (size_t)(p.bar_base + 2 * kPmMaxStages) * 4;
 }
 
-// SINGLE: blockDim = 32 x (warp-items per tile), every warp keeps ONE (component, 32-sample block) for the whole launch.
-// !SINGLE: more warp-items than warps (many components): warps loop over the items of a tile.
+// The persistent tile loop.  TYPE >= 0: this warp keeps ONE component of static (TYPE, N) for the whole launch
+// (blockDim = 32 x the warps of all components) — no dispatch, every shared-memory offset final.  TYPE < 0: looping variant (more
+// warp-items than warps: many components), items are dispatched one by one.
+template <bool BWD, int MAXN, bool WANT_MS, int TYPE, int N>
+__device__ __forceinline__ void pm_tile_loop(const PmParams& p, float* smem, const ItemInfo* info, int my_ci,
+                                             uint32_t smem0, uint32_t bar0) {
+  constexpr bool SINGLE = TYPE >= 0;
+  const int C = p.desc.C;
+  const int ld_ml = p.desc.ld_ml, ld_eps = p.desc.ld_eps, ld_z = p.desc.ld_z;
+  const bool has_gkl = BWD && p.gkl != nullptr;
+  const bool check = !BWD && p.flag != nullptr;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+  auto issue_loads = [&](int tile, int st) {  // one thread
+    const int64_t row0 = (int64_t)tile * p.S;
+    const uint32_t bar = bar0 + 8u * st;
+    const uint32_t dst = smem0 + 4u * (uint32_t)(p.in_base + st * p.in_stage);
+    pm_mbar_expect_tx(bar, p.bytes_in);
+    pm_bulk_g2s(dst + 4u * p.in_ml, p.ml + row0 * ld_ml, p.bytes_ml, bar);
+    pm_bulk_g2s(dst + 4u * p.in_eps, p.eps + row0 * ld_eps, p.bytes_eps, bar);
+    if (BWD) {
+      pm_bulk_g2s(dst + 4u * p.in_gz, p.gz + row0 * ld_z, p.bytes_z, bar);
+      if (has_gkl) pm_bulk_g2s(dst + 4u * p.in_gkl, p.gkl + row0 * C, p.bytes_c, bar);
+    }
+  };
+
+  // this thread's operand offsets (floats from smem[0]) inside stage 0 / staging buffer 0, block 0
+  ItemInfo mine;
+  int r0 = lane;
+  int o_m = 0, o_l = 0, o_e = 0, o_gz = 0, o_gkl = 0, o_z = 0, o_kl = 0, o_mu = 0, o_sg = 0, o_gm = 0, o_gl = 0;
+  if (SINGLE) {
+    mine = info[my_ci];
+    r0 = ((int)p.w_blk0[warp] << 5) + lane;
+    o_m = p.in_base + p.in_ml + r0 * ld_ml + mine.m_off;
+    o_l = p.in_base + p.in_ml + r0 * ld_ml + mine.l_off;
+    o_e = p.in_base + p.in_eps + r0 * ld_eps + mine.eps_off;
+    o_gz = p.in_base + p.in_gz + r0 * ld_z + mine.z_off;
+    o_gkl = p.in_base + p.in_gkl + r0 * C + my_ci;
+    o_z = p.out_base + p.out_a + r0 * ld_z + mine.z_off;
+    o_kl = p.out_base + p.out_b + r0 * C + my_ci;
+    o_mu = p.out_base + p.out_c + r0 * ld_z + mine.z_off;
+    o_sg = p.out_base + p.out_d + r0 * ld_eps + mine.eps_off;
+    o_gm = p.out_base + p.out_a + r0 * ld_ml + mine.m_off;
+    o_gl = p.out_base + p.out_a + r0 * ld_ml + mine.l_off;
+  }
+  // per-warp block walk: nblk blocks, srows rows apart
+  const int nblk = SINGLE ? (int)p.w_nblk[warp] : 0;
+  const int srows = SINGLE ? (int)p.w_bstride[warp] << 5 : 0;
+  const int rs_ml = srows * ld_ml, rs_eps = srows * ld_eps, rs_z = srows * ld_z, rs_c = srows * C;
+  float* const b_m = smem + o_m;
+  float* const b_l = smem + o_l;
+  float* const b_e = smem + o_e;
+  float* const b_gz = smem + o_gz;
+  float* const b_gkl = smem + o_gkl;
+  float* const b_z = smem + o_z;
+  float* const b_kl = smem + o_kl;
+  float* const b_mu = smem + o_mu;
+  float* const b_sg = smem + o_sg;
+  float* const b_gm = smem + o_gm;
+  float* const b_gl = smem + o_gl;
+  float gR_acc = 0.f;
+  bool finite = true;
+
+  int tile = blockIdx.x;
+  if (tid == 0) {  // prologue: nst - 1 tiles in flight
+    int t = tile;
+    for (int i = 0; i < p.nst - 1 && t < p.n_bulk_tiles; ++i, t += gridDim.x) issue_loads(t, i);
+  }
+  int st = 0;
+  int in_off = 0, out_off = 0;  // float offsets of the current input stage / output staging buffer
+  uint32_t parity = 0;
+  for (; tile < p.n_tiles; tile += gridDim.x) {
+    const bool bulk = tile < p.n_bulk_tiles;
+    int rows = p.S;
+    if (tid == 0) {
+      // the stage consumed in the previous iteration is free: refill it with the tile nst - 1 ahead
+      const int ahead = tile + (p.nst - 1) * (int)gridDim.x;  // n_tiles * 8 stays far below 2^31 (host check)
+      if (ahead < p.n_bulk_tiles) issue_loads(ahead, st == 0 ? p.nst - 1 : st - 1);
+    }
+    if (bulk) {
+      pm_mbar_wait(bar0 + 8u * st, parity);
+    } else {
+      const int64_t row0 = (int64_t)tile * p.S;
+      rows = (int)min((int64_t)p.S, p.B - row0);
+      float* sin_ = smem + p.in_base + in_off;
+      coop_load(sin_ + p.in_ml, p.ml + row0 * ld_ml, rows * ld_ml);
+      coop_load(sin_ + p.in_eps, p.eps + row0 * ld_eps, rows * ld_eps);
+      if (BWD) {
+        coop_load(sin_ + p.in_gz, p.gz + row0 * ld_z, rows * ld_z);
+        if (has_gkl) coop_load(sin_ + p.in_gkl, p.gkl + row0 * C, rows * C);
+      }
+      __syncthreads();
+    }
+    if (BWD && p.zero_gml) {
+      float* g0 = smem + p.out_base + out_off + p.out_a;
+      for (int i = tid; i < p.S * ld_ml; i += blockDim.x) g0[i] = 0.f;
+      __syncthreads();
+    }
+    // ---- compute ----
+    if constexpr (SINGLE) {
+      // operand pointers are loop-carried (one add per block) so that the shared-memory base is formed once
+      const float* pm = b_m + in_off;
+      const float* pl = b_l + in_off;
+      const float* pe = b_e + in_off;
+      const float* pgz = b_gz + in_off;
+      const float* pgkl = b_gkl + in_off;
+      float* pz = b_z + out_off;
+      float* pkl = b_kl + out_off;
+      float* pmu = b_mu + out_off;
+      float* psg = b_sg + out_off;
+      float* pgm = b_gm + out_off;
+      float* pgl = b_gl + out_off;
+      int row = r0;
+#pragma unroll 1
+      for (int r = 0; r < nblk; ++r) {
+        if (row < rows) {
+          const float gkl = BWD ? (has_gkl ? *pgkl : p.gkl_scalar) : 0.f;
+          finite &= run_item<N, TYPE, BWD, WANT_MS>(mine.n, mine.l_n, mine.K, pm, pl, pe, pz, pkl, pmu, psg, pgz, gkl,
+                                                    pgm, pgl, &gR_acc, check);
+        }
+        row += srows;
+        pm += rs_ml;
+        pl += rs_ml;
+        pe += rs_eps;
+        if (BWD) {
+          pgz += rs_z;
+          pgkl += rs_c;
+          pgm += rs_ml;
+          pgl += rs_ml;
+        } else {
+          pz += rs_z;
+          pkl += rs_c;
+          if (WANT_MS) {
+            pmu += rs_z;
+            psg += rs_eps;
+          }
+        }
+      }
+    } else {
+      const int nwarps = blockDim.x >> 5, blocks = p.nb;  // 32-sample blocks per tile
+      float* sin_ = smem + p.in_base + in_off;
+      float* sout = smem + p.out_base + out_off;
+      for (int w = warp; w < C * blocks; w += nwarps) {
+        const int ci = w / blocks;
+        const int sidx = ((w - ci * blocks) << 5) + lane;
+        float gR = 0.f;
+        if (sidx < rows) {
+          const ItemInfo c = info[ci];
+          const float gkl = BWD ? (has_gkl ? sin_[p.in_gkl + sidx * C + ci] : p.gkl_scalar) : 0.f;
+          finite &= dispatch_item<BWD, MAXN, WANT_MS>(
+              c, sin_ + p.in_ml + sidx * ld_ml, sin_ + p.in_eps + sidx * ld_eps, sout + p.out_a + sidx * ld_z,
+              sout + p.out_b + sidx * C + ci, sout + p.out_c + sidx * ld_z, sout + p.out_d + sidx * ld_eps,
+              sin_ + p.in_gz + sidx * ld_z, gkl, sout + p.out_a + sidx * ld_ml, &gR, check);
+          gR *= radius_d(c.rp);
+        }
+        if (BWD && p.gradius) {
+          gR = warp_sum(gR);
+          if (lane == 0 && gR != 0.f) atomicAdd(p.gradius + ci, gR);
+        }
+      }
+    }
+    // ---- store ----
+    if (bulk) {
+      pm_fence_async();
+      if (tid == 0) pm_bulk_wait_read0();  // the store of the previous tile (other staging buffer) has left shared memory
+      __syncthreads();
+      if (tid == 0) {
+        const int64_t row0 = (int64_t)tile * p.S;
+        const uint32_t src = smem0 + 4u * (uint32_t)(p.out_base + out_off);
+        if (BWD) {
+          pm_bulk_s2g(p.gml + row0 * ld_ml, src + 4u * p.out_a, p.bytes_ml);
+        } else {
+          pm_bulk_s2g(p.z + row0 * ld_z, src + 4u * p.out_a, p.bytes_z);
+          pm_bulk_s2g(p.kl + row0 * C, src + 4u * p.out_b, p.bytes_c);
+          if (WANT_MS) {
+            pm_bulk_s2g(p.mu + row0 * ld_z, src + 4u * p.out_c, p.bytes_z);
+            pm_bulk_s2g(p.sigma + row0 * ld_eps, src + 4u * p.out_d, p.bytes_eps);
+          }
+        }
+        pm_bulk_commit();
+      }
+    } else {
+      const int64_t row0 = (int64_t)tile * p.S;
+      const float* sout = smem + p.out_base + out_off;
+      __syncthreads();
+      if (BWD) {
+        coop_store(p.gml + row0 * ld_ml, sout + p.out_a, rows * ld_ml);
+      } else {
+        coop_store(p.z + row0 * ld_z, sout + p.out_a, rows * ld_z);
+        coop_store(p.kl + row0 * C, sout + p.out_b, rows * C);
+        if (WANT_MS) {
+          coop_store(p.mu + row0 * ld_z, sout + p.out_c, rows * ld_z);
+          coop_store(p.sigma + row0 * ld_eps, sout + p.out_d, rows * ld_eps);
+        }
+      }
+      __syncthreads();
+    }
+    in_off += p.in_stage;
+    if (++st == p.nst) {
+      st = 0;
+      in_off = 0;
+      parity ^= 1u;
+    }
+    out_off = out_off ? 0 : p.out_stage;
+  }
+  if (tid == 0) pm_bulk_wait_all0();  // shared memory must outlive the last bulk store
+  if (BWD) {
+    if (SINGLE && p.gradius) {
+      const float g = warp_sum(gR_acc * radius_d(mine.rp));
+      if (lane == 0 && g != 0.f) atomicAdd(p.gradius + my_ci, g);
+    }
+  } else if (p.flag) {
+    const unsigned bad = __ballot_sync(0xffffffffu, !finite);
+    if (bad && lane == 0) atomicOr(p.flag, 1u);
+  }
+}
+
 template <bool BWD, int MAXN, bool WANT_MS, bool SINGLE>
 __device__ __forceinline__ void pm_kernel_body(const PmParams& p) {
   extern __shared__ __align__(128) float smem[];
-  const int C = p.desc.C, S = p.S;
-  const int ld_ml = p.desc.ld_ml, ld_eps = p.desc.ld_eps, ld_z = p.desc.ld_z;
-  const bool has_gkl = BWD && p.gkl != nullptr;
-  const PmLayout L = pm_layout(C, ld_ml, ld_eps, ld_z, S, BWD, WANT_MS, has_gkl);
+  const int C = p.desc.C;
   ItemInfo* info = reinterpret_cast<ItemInfo*>(smem);
-  float* in_base = smem + L.info_floats;
-  float* out_base = in_base + 2 * L.in_stage;
-  const uint32_t bar0 = pm_smem_u32(out_base + 2 * L.out_stage);
-
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+  const uint32_t smem0 = pm_smem_u32(smem);
+  const uint32_t bar0 = smem0 + 4u * (uint32_t)p.bar_base;
+  const int tid = threadIdx.x;
   for (int i = tid; i < C; i += blockDim.x) {
     const mvae_component c = p.desc.comp[i];
     ItemInfo ii;
@@ -249,151 +481,49 @@ __device__ __forceinline__ void pm_kernel_body(const PmParams& p) {
     info[i] = ii;
   }
   if (tid == 0) {
-    pm_mbar_init(bar0, 1);
-    pm_mbar_init(bar0 + 8, 1);
+    for (int i = 0; i < p.nst; ++i) pm_mbar_init(bar0 + 8u * i, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
-
-  const int wpc = S >> 5;            // warps per component inside a tile
-  const int n_items = C * wpc;       // warp-items per tile
-  const uint32_t in_bytes = (uint32_t)L.in_stage * 4u;
-
-  auto use_bulk = [&](int tile) { return p.vec_ok && (int64_t)(tile + 1) * S <= p.B; };
-  auto issue_loads = [&](int tile, int st) {  // one thread
-    const int64_t row0 = (int64_t)tile * S;
-    const uint32_t bar = bar0 + 8u * st;
-    const uint32_t dst = pm_smem_u32(in_base + st * L.in_stage);
-    pm_mbar_expect_tx(bar, in_bytes);
-    pm_bulk_g2s(dst + 4u * L.in_ml, p.ml + row0 * ld_ml, (uint32_t)(S * ld_ml) * 4u, bar);
-    pm_bulk_g2s(dst + 4u * L.in_eps, p.eps + row0 * ld_eps, (uint32_t)(S * ld_eps) * 4u, bar);
-    if (BWD) {
-      pm_bulk_g2s(dst + 4u * L.in_gz, p.gz + row0 * ld_z, (uint32_t)(S * ld_z) * 4u, bar);
-      if (has_gkl) pm_bulk_g2s(dst + 4u * L.in_gkl, p.gkl + row0 * C, (uint32_t)(S * C) * 4u, bar);
+  if constexpr (SINGLE) {
+    // Every warp of the CTA runs the same number of tile iterations, so the __syncthreads inside the per-(type, n)
+    // copies of the loop pair up across warps that took different cases.
+    const int my_ci = p.w_ci[tid >> 5];
+    const int type = info[my_ci].type, n = info[my_ci].n;
+#define MVAE_PM_LOOP_E(NN) pm_tile_loop<BWD, MAXN, WANT_MS, MVAE_EUCLIDEAN, NN>(p, smem, info, my_ci, smem0, bar0);
+#define MVAE_PM_LOOP_H(NN) pm_tile_loop<BWD, MAXN, WANT_MS, MVAE_HYPERBOLOID, NN>(p, smem, info, my_ci, smem0, bar0);
+#define MVAE_PM_LOOP_S(NN) pm_tile_loop<BWD, MAXN, WANT_MS, MVAE_SPHERE, NN>(p, smem, info, my_ci, smem0, bar0);
+#define MVAE_PM_LOOP_P(NN) pm_tile_loop<BWD, MAXN, WANT_MS, MVAE_POINCARE, NN>(p, smem, info, my_ci, smem0, bar0);
+    switch (type) {
+      case MVAE_EUCLIDEAN: MVAE_PM_FOR_DIMS(MAXN, n, MVAE_PM_LOOP_E) break;
+      case MVAE_HYPERBOLOID: MVAE_PM_FOR_DIMS(MAXN, n, MVAE_PM_LOOP_H) break;
+      case MVAE_SPHERE: MVAE_PM_FOR_DIMS(MAXN, n, MVAE_PM_LOOP_S) break;
+      default: MVAE_PM_FOR_DIMS(MAXN, n, MVAE_PM_LOOP_P) break;
     }
-  };
-
-  // the component this warp keeps (single-item mode)
-  ItemInfo mine;
-  int my_ci = 0, my_sub = 0;
-  if (SINGLE) {
-    my_ci = warp / wpc;
-    mine = info[my_ci];
-    my_sub = (warp % wpc) << 5;
-  }
-  float gR_acc = 0.f;
-  bool finite = true;
-
-  int tile = blockIdx.x;
-  if (tid == 0 && tile < p.n_tiles && use_bulk(tile)) issue_loads(tile, 0);
-  for (int k = 0; tile < p.n_tiles; ++k, tile += gridDim.x) {
-    const int st = k & 1;
-    const int64_t row0 = (int64_t)tile * S;
-    const int rows = (int)min((int64_t)S, p.B - row0);
-    const bool bulk = use_bulk(tile);
-    float* sin_ = in_base + st * L.in_stage;
-    float* sout = out_base + st * L.out_stage;
-    const int next = tile + gridDim.x;
-    if (tid == 0 && next < p.n_tiles && use_bulk(next)) issue_loads(next, st ^ 1);
-    if (bulk) {
-      pm_mbar_wait(bar0 + 8u * st, (uint32_t)(k >> 1) & 1u);
-    } else {
-      coop_load(sin_ + L.in_ml, p.ml + row0 * ld_ml, rows * ld_ml);
-      coop_load(sin_ + L.in_eps, p.eps + row0 * ld_eps, rows * ld_eps);
-      if (BWD) {
-        coop_load(sin_ + L.in_gz, p.gz + row0 * ld_z, rows * ld_z);
-        if (has_gkl) coop_load(sin_ + L.in_gkl, p.gkl + row0 * C, rows * C);
-      }
-      __syncthreads();
-    }
-    if (BWD && p.zero_gml) {
-      for (int i = tid; i < S * ld_ml; i += blockDim.x) sout[L.out_a + i] = 0.f;
-      __syncthreads();
-    }
-    // ---- compute ----
-    if (SINGLE) {
-      const int sidx = my_sub + lane;
-      if (sidx < rows) {
-        const float gkl = BWD ? (has_gkl ? sin_[L.in_gkl + sidx * C + my_ci] : p.gkl_scalar) : 0.f;
-        finite &= dispatch_item<BWD, MAXN, WANT_MS>(
-            mine, sin_ + L.in_ml + sidx * ld_ml, sin_ + L.in_eps + sidx * ld_eps, sout + L.out_a + sidx * ld_z,
-            sout + L.out_b + sidx * C + my_ci, sout + L.out_c + sidx * ld_z, sout + L.out_d + sidx * ld_eps,
-            sin_ + L.in_gz + sidx * ld_z, gkl, sout + L.out_a + sidx * ld_ml, &gR_acc);
-      }
-    } else {
-      for (int w = warp; w < n_items; w += nwarps) {
-        const int ci = w / wpc;
-        const int sidx = ((w % wpc) << 5) + lane;
-        float gR = 0.f;
-        if (sidx < rows) {
-          const ItemInfo c = info[ci];
-          const float gkl = BWD ? (has_gkl ? sin_[L.in_gkl + sidx * C + ci] : p.gkl_scalar) : 0.f;
-          finite &= dispatch_item<BWD, MAXN, WANT_MS>(
-              c, sin_ + L.in_ml + sidx * ld_ml, sin_ + L.in_eps + sidx * ld_eps, sout + L.out_a + sidx * ld_z,
-              sout + L.out_b + sidx * C + ci, sout + L.out_c + sidx * ld_z, sout + L.out_d + sidx * ld_eps,
-              sin_ + L.in_gz + sidx * ld_z, gkl, sout + L.out_a + sidx * ld_ml, &gR);
-          gR *= radius_d(c.rp);
-        }
-        if (BWD && p.gradius) {
-          gR = warp_sum(gR);
-          if (lane == 0 && gR != 0.f) atomicAdd(p.gradius + ci, gR);
-        }
-      }
-    }
-    // ---- store ----
-    if (bulk) {
-      pm_fence_async();
-      if (tid == 0) pm_bulk_wait_read0();  // the store of tile k-1 (other staging buffer) has left shared memory
-      __syncthreads();
-      if (tid == 0) {
-        const uint32_t src = pm_smem_u32(sout);
-        if (BWD) {
-          pm_bulk_s2g(p.gml + row0 * ld_ml, src + 4u * L.out_a, (uint32_t)(S * ld_ml) * 4u);
-        } else {
-          pm_bulk_s2g(p.z + row0 * ld_z, src + 4u * L.out_a, (uint32_t)(S * ld_z) * 4u);
-          pm_bulk_s2g(p.kl + row0 * C, src + 4u * L.out_b, (uint32_t)(S * C) * 4u);
-          if (WANT_MS) {
-            pm_bulk_s2g(p.mu + row0 * ld_z, src + 4u * L.out_c, (uint32_t)(S * ld_z) * 4u);
-            pm_bulk_s2g(p.sigma + row0 * ld_eps, src + 4u * L.out_d, (uint32_t)(S * ld_eps) * 4u);
-          }
-        }
-        pm_bulk_commit();
-      }
-    } else {
-      __syncthreads();
-      if (BWD) {
-        coop_store(p.gml + row0 * ld_ml, sout + L.out_a, rows * ld_ml);
-      } else {
-        coop_store(p.z + row0 * ld_z, sout + L.out_a, rows * ld_z);
-        coop_store(p.kl + row0 * C, sout + L.out_b, rows * C);
-        if (WANT_MS) {
-          coop_store(p.mu + row0 * ld_z, sout + L.out_c, rows * ld_z);
-          coop_store(p.sigma + row0 * ld_eps, sout + L.out_d, rows * ld_eps);
-        }
-      }
-      __syncthreads();
-    }
-  }
-  if (tid == 0) pm_bulk_wait_all0();  // shared memory must outlive the last bulk store
-  if (BWD) {
-    if (SINGLE && p.gradius) {
-      const float g = warp_sum(gR_acc * radius_d(mine.rp));
-      if (lane == 0 && g != 0.f) atomicAdd(p.gradius + my_ci, g);
-    }
-  } else if (p.flag) {
-    const unsigned bad = __ballot_sync(0xffffffffu, !finite);
-    if (bad && lane == 0) atomicOr(p.flag, 1u);
+#undef MVAE_PM_LOOP_E
+#undef MVAE_PM_LOOP_H
+#undef MVAE_PM_LOOP_S
+#undef MVAE_PM_LOOP_P
+  } else {
+    pm_tile_loop<BWD, MAXN, WANT_MS, -1, 0>(p, smem, info, 0, smem0, bar0);
   }
 }
 
+// Register budgets (launch bounds): the kernels are latency-sensitive, so the narrow-dimension variants are held to
+// 48 / 64 / 80 registers to keep 32+ warps resident; the widest ones take what they need.
+#ifndef MVAE_PM_MINB
+#define MVAE_PM_MINB(MAXN, BWD) ((MAXN) == 2 ? ((BWD) ? 4 : 5) : (MAXN) == 4 ? ((BWD) ? 3 : 4) : (MAXN) == 8 ? ((BWD) ? 2 : 3) : 1)
+#endif
 #if !MVAE_PM_BWD
 template <int MAXN, bool WANT_MS, bool SINGLE>
-__global__ void __launch_bounds__(kPmMaxThreads, 1) pm_forward_kernel(const __grid_constant__ PmParams p) {
+__global__ void __launch_bounds__(kPmMaxThreads, MVAE_PM_MINB(MAXN, false))
+    pm_forward_kernel(const __grid_constant__ PmParams p) {
   pm_kernel_body<false, MAXN, WANT_MS, SINGLE>(p);
 }
 #else
 template <int MAXN, bool SINGLE>
-__global__ void __launch_bounds__(kPmMaxThreads, 1) pm_backward_kernel(const __grid_constant__ PmParams p) {
+__global__ void __launch_bounds__(kPmMaxThreads, MVAE_PM_MINB(MAXN, true))
+    pm_backward_kernel(const __grid_constant__ PmParams p) {
   pm_kernel_body<true, MAXN, false, SINGLE>(p);
 }
 #endif
@@ -421,13 +551,8 @@ static int launch_pm(PmParams& p, void* stream) {
     for (int i = 0; i < D.C; ++i) owned += D.comp[i].n + D.comp[i].l_n;
     p.zero_gml = owned != D.ld_ml;
   }
-  // one warp per (component, 32 samples) when that fits a CTA, else the looping variant with all dimensions compiled in
-  int S = 64;
-  if (p.B < (int64_t)64 * 8 * di.sm_count || D.C * 2 * 32 > kPmMaxThreads) S = 32;
-  {
-    static const char* s_env = getenv("MVAE_PM_TILE");  // tuning aid: force the tile height (32 | 64)
-    if (s_env && (atoi(s_env) == 32 || (atoi(s_env) == 64 && D.C * 2 * 32 <= kPmMaxThreads))) S = atoi(s_env);
-  }
+  // SINGLE variant: one warp per (component, 32-sample block column) when C warps fit a CTA; else the looping variant
+  // with all dimensions compiled in.
   const bool single = !dyn && D.C * 32 <= kPmMaxThreads;
   void (*kern)(PmParams);
 #if MVAE_PM_BWD
@@ -444,35 +569,147 @@ static int launch_pm(PmParams& p, void* stream) {
                                                       : maxn <= 4   ? pm_forward_kernel<4, false, true>
                                                                     : pm_forward_kernel<8, false, true>;
 #endif
-  // Tile height: 64 samples when the batch still yields several tiles per resident CTA, else 32 (small batches want
-  // as many CTAs as possible).
+  // Tile shape.  A tile is nb blocks of 32 samples.  One-component-per-warp variant: component c gets w_c warps
+  // (w_c divides nb), each walking nb / w_c blocks; the w_c are chosen so that the warps of a CTA finish a tile
+  // together (arithmetic cost model below) — warps that wait at the tile barrier for the slowest component are lost
+  // issue capacity.  More blocks per tile amortise the per-tile costs (barrier, mbarrier wait, the issuing thread's
+  // copies); the ring depth nst keeps enough bulk copies in flight to cover HBM latency.  Small batches want many small
+  // tiles instead (one per SM at least).
   cudaFuncAttributes fa;
   MVAE_CUDA_TRY(cudaFuncGetAttributes(&fa, kern));
-  int threads = 0, blocks_per_sm = 0;
-  size_t smem = 0;
-  for (;; S = 32) {
-    const PmLayout L = pm_layout(D.C, D.ld_ml, D.ld_eps, D.ld_z, S, bwd, want_ms, has_gkl);
-    smem = (size_t)L.total_floats * 4;
-    int warps = D.C * (S / 32);
-    if (!single) {
-      if (warps > 8) warps = 8;  // looping variant: 128-register kernels, keep several CTAs resident
+  auto cost_of = [&](const mvae_component& c) {  // issue slots per item, from the SASS of the static variants
+    const int base = c.type == MVAE_EUCLIDEAN ? 20 : c.type == MVAE_SPHERE ? 125 : c.type == MVAE_POINCARE ? 115 : 105;
+    return (bwd ? 3 : 2) * (base + (c.type == MVAE_EUCLIDEAN ? 15 : 25) * c.n) / 2;
+  };
+  int wc[MVAE_MAX_COMPONENTS];
+  // best split of <= kPmMaxWarps warps over the components for nb blocks per tile; returns efficiency in 1/1024
+  auto plan = [&](int nb, int* w_out) {
+    int w[MVAE_MAX_COMPONENTS], total = D.C;
+    for (int i = 0; i < D.C; ++i) w[i] = 1;
+    int best_eff = -1;
+    for (;;) {
+      int sum_cost = 0, max_load = 0, arg = 0;
+      for (int i = 0; i < D.C; ++i) {
+        const int load = cost_of(D.comp[i]) * (nb / w[i]);
+        sum_cost += cost_of(D.comp[i]) * nb;
+        if (load > max_load) {
+          max_load = load;
+          arg = i;
+        }
+      }
+      const int eff = (int)((int64_t)sum_cost * 1024 / ((int64_t)total * max_load));
+      if (eff > best_eff) {
+        best_eff = eff;
+        for (int i = 0; i < D.C; ++i) w_out[i] = w[i];
+      }
+      // give the most loaded component the next divisor of nb
+      int nw = w[arg] + 1;
+      while (nw <= nb && nb % nw) ++nw;
+      if (nw > nb || total - w[arg] + nw > kPmMaxWarps) break;
+      total += nw - w[arg];
+      w[arg] = nw;
     }
-    threads = warps * 32;
-    bool ok = smem <= (size_t)di.max_smem_optin && threads <= fa.maxThreadsPerBlock &&
-              threads * fa.numRegs <= 65536;
-    if (ok) {
-      if (smem > 48 * 1024)
-        MVAE_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      MVAE_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kern, threads, smem));
-      ok = blocks_per_sm >= 1;
+    return best_eff;
+  };
+  int nb = 1;
+  if (single) {
+    const int bytes_per_block = 32 * 4 * (D.ld_ml + D.ld_eps + D.ld_z + D.C + (bwd ? D.ld_ml : 0));
+    int best = -1;
+    for (int cand = 1; cand <= 8; ++cand) {
+      if (cand * bytes_per_block > 40 * 1024 && cand > 1) break;       // tiles of wide products are big already
+      if (p.B < (int64_t)32 * cand * 4 * di.sm_count && cand > 1) break;  // small batch: smallest tiles
+      int w_try[MVAE_MAX_COMPONENTS];
+      const int eff = plan(cand, w_try) + 16 * cand;  // ties (and near-ties) go to the bigger tile
+      if (eff > best) {
+        best = eff;
+        nb = cand;
+      }
     }
-    if (ok && (S == 32 || blocks_per_sm * threads >= 768)) break;  // S = 64 only if it keeps >= 24 warps per SM
-    if (S == 32) return MVAE_ERR_UNSUPPORTED;
   }
-  p.S = S;
+  // For the chosen nb (shrunk if shared memory would cap residency below ~24 warps per SM or below what the registers
+  // allow): the shallowest ring whose copies in flight on one SM reach 64 KiB (HBM latency x bandwidth per SM).
+  int S = 32 * nb, threads = 0, blocks_per_sm = 0;
+  size_t smem = 0;
+  auto configure = [&](int nb_, int nst_, int* blocks, size_t* bytes) -> int {  // fills p for (nb_, nst_)
+    p.S = 32 * nb_;
+    p.nb = nb_;
+    p.nst = nst_;
+    *bytes = fill_layout(p, bwd, want_ms, has_gkl);
+    int warps = 0;
+    if (single) {
+      plan(nb_, wc);
+      for (int i = 0; i < D.C; ++i)
+        for (int j = 0; j < wc[i]; ++j, ++warps) {
+          p.w_ci[warps] = (uint8_t)i;
+          p.w_blk0[warps] = (uint8_t)j;
+          p.w_bstride[warps] = (uint8_t)wc[i];
+          p.w_nblk[warps] = (uint8_t)(nb_ / wc[i]);
+        }
+    } else {
+      warps = D.C * nb_;
+      if (warps > kPmMaxWarps) warps = kPmMaxWarps;  // looping variant: 128-register kernels, several CTAs resident
+    }
+    p.n_warps = warps;
+    const int th = warps * 32;
+    *blocks = 0;
+    if (*bytes > (size_t)di.max_smem_optin || th > fa.maxThreadsPerBlock || th * fa.numRegs > 65536) return MVAE_OK;
+    if (*bytes > 48 * 1024)
+      MVAE_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)*bytes));
+    MVAE_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks, kern, th, *bytes));
+    return MVAE_OK;
+  };
+  int forced_nst = 0;
+  {
+    static const char* tune = getenv("MVAE_PM_TUNE");  // tuning aid: "nb,nst"
+    int a = 0, b = 0;
+    if (tune && sscanf(tune, "%d,%d", &a, &b) == 2 && a >= 1 && a <= 8 && b >= 2 && b <= kPmMaxStages) {
+      nb = a;
+      forced_nst = b;
+    }
+  }
+  int nst = 2;
+  for (;; --nb) {
+    int blocks = 0, reg_blocks = 0, pick = 0;
+    size_t bytes = 0;
+    rc = configure(nb, 2, &blocks, &bytes);
+    if (rc != MVAE_OK) return rc;
+    if (blocks >= 1) {
+      const int th = p.n_warps * 32;
+      MVAE_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&reg_blocks, kern, th, 0));
+      int want = (768 + th - 1) / th;
+      if (want > reg_blocks) want = reg_blocks;
+      for (int cand = 2; cand <= (forced_nst ? forced_nst : 4); ++cand) {
+        rc = configure(nb, cand, &blocks, &bytes);
+        if (rc != MVAE_OK) return rc;
+        if (blocks < want && !(nb == 1 && cand == 2 && blocks >= 1)) break;
+        pick = cand;
+        if (!forced_nst && (int64_t)(cand - 1) * p.bytes_in * blocks >= 64 * 1024) break;
+      }
+    }
+    if (pick) {
+      nst = pick;
+      break;
+    }
+    if (nb == 1) return MVAE_ERR_UNSUPPORTED;
+  }
+  rc = configure(nb, nst, &blocks_per_sm, &smem);
+  if (rc != MVAE_OK) return rc;
+  S = 32 * nb;
+  threads = p.n_warps * 32;
+  {
+    static const bool dbg = getenv("MVAE_PM_DEBUG") != nullptr;
+    if (dbg) {
+      fprintf(stderr, "[mvae pm %s] B=%lld C=%d single=%d nb=%d nst=%d warps=%d regs=%d smem=%zu blocks/SM=%d w=", bwd ? "bwd" : "fwd",
+              (long long)p.B, D.C, (int)single, nb, nst, p.n_warps, fa.numRegs, smem, blocks_per_sm);
+      if (single)
+        for (int i = 0; i < D.C; ++i) fprintf(stderr, "%d%s", wc[i], i + 1 < D.C ? "," : "");
+      fprintf(stderr, "\n");
+    }
+  }
   const int64_t tiles = (p.B + S - 1) / S;
-  if (tiles > 0x7fffffff) return MVAE_ERR_UNSUPPORTED;
+  if (tiles > (0x7fffffff >> 4)) return MVAE_ERR_UNSUPPORTED;
   p.n_tiles = (int)tiles;
+  p.n_bulk_tiles = p.vec_ok ? (int)(p.B / S) : 0;
   int64_t grid = (int64_t)blocks_per_sm * di.sm_count;
   if (grid > tiles) grid = tiles;
   kern<<<(unsigned)grid, threads, smem, as_stream(stream)>>>(p);

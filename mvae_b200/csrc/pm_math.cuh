@@ -226,7 +226,7 @@ struct CompOut {
 template <int N>
 PM_DEV void load_sigma(int n, int l_n, const float* l, float* sg) {
   PM_UN(N);
-  if (l_n == 1) {
+  if (N != 1 && l_n == 1) {  // (for n = 1 the two parametrizations coincide)
     const float s = softplus(l[0]) + 1e-5f;
     PM_UNROLL
     for (int j = 0; j < Cap<N>::n; ++j)
@@ -257,7 +257,7 @@ PM_DEV float sum_log(int n, const float* sg) {
 template <int N>
 PM_DEV void store_gl(int n, int l_n, const float* l, const float* g_s, float* gl) {
   PM_UN(N);
-  if (l_n == 1) {
+  if (N != 1 && l_n == 1) {
     float acc = 0.f;
     PM_UNROLL
     for (int j = 0; j < Cap<N>::n; ++j)
