@@ -236,6 +236,31 @@ int mvae_skinny_wgrad(int64_t B, int32_t S, int32_t Wd, const float* small, int6
                       int64_t out_stride_s, int64_t out_stride_w, float* out_row, float* out_col, int32_t col_split,
                       void* stream);
 
+/* -------------------------------------------------------------------------------- fused latent block */
+/* The whole latent block of FeedForwardVAE in one launch per direction.  The per-sample intermediates (head
+ * pre-activations on the way back, gz, gml) never leave shared memory and h / gdd are read exactly once.
+ *
+ * forward (ModelVAE.forward vae.py:69-80 between fc_e0 and fc_logits):
+ *   ml = h Wh^T + bh            all fc_mean / fc_logvar heads (component.py:64,69), Wh [P, H], P = desc->ld_ml
+ *   z, kl = mvae_pm_forward(ml, eps, radius)
+ *   dd = relu(z Wd0^T + bd0)    fc_d0 (ffnn_vae.py:56), Wd0 [H, Sd], Sd = desc->ld_z, written as split planes
+ * h: split planes of relu(fc_e0(x)) [B, H] (all of its planes are read).  Requirements: H % 8 == 0, P <= 64, Sd <= 64,
+ * Wh 16-byte aligned.  Outputs ml [B, P], z [B, Sd], kl [B, C] are kept for the backward pass / the statistics. */
+int mvae_latent_forward(const mvae_pm_desc* desc, int64_t B, int32_t H, const mvae_planes* h, const float* Wh,
+                        const float* bh, const float* eps, const float* radius, const float* Wd0, const float* bd0,
+                        float* ml, float* z, float* kl, const mvae_planes* dd_out, uint32_t* nonfinite_flag,
+                        void* stream);
+
+/* backward of the block for d(loss)/d(dd) = gdd (already masked by relu'(dd)) and d(loss)/d(kl) = gkl_scalar:
+ *   gz = gdd Wd0;  gml = mvae_pm_backward(ml, eps, radius, gz, gkl_scalar);  gh = (gml Wh) * 1[h > 0]  -> planes
+ *   gWd0 [H, Sd] += gdd^T z;  gbd0 [H] += colsum(gdd);  gWh [P, H] += gml^T h;  gbh [P] += colsum(gml);
+ *   gradius [C] += dR          (all ACCUMULATED: zero them first)
+ * Requirements as above plus Wd0 / gWd0 16-byte and Wh / gWh / gbd0 8-byte aligned. */
+int mvae_latent_backward(const mvae_pm_desc* desc, int64_t B, int32_t H, const mvae_planes* gdd, const mvae_planes* h,
+                         const float* Wh, const float* Wd0, const float* ml, const float* eps, const float* radius,
+                         const float* z, float gkl_scalar, const mvae_planes* gh_out, float* gWd0, float* gbd0,
+                         float* gWh, float* gbh, float* gradius, void* stream);
+
 /* ------------------------------------------------------------------------------- reconstruction + ELBO */
 /* Standalone reconstruction losses (VaeDataset.reconstruction_loss + .sum(-1), vae.py:131):
  * kind 0 = BCE-with-logits (data/image_reconstruction.py:81-82), 1 = unit-variance Gaussian NLL (data/synthetic.py:161-162).

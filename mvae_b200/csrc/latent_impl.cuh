@@ -1,0 +1,495 @@
+// latent_impl.cuh — the whole latent block of the VAE in ONE kernel per direction (mvae_latent_forward /
+// mvae_latent_backward, include/mvae_b200.h):
+//
+//   forward   h --fc_mean/fc_logvar--> ml --Component.encode, reparametrize, rsample, kl_loss--> z, kl --fc_d0, relu--> dd
+//             (component.py:63-75, sampling_procedures.py:91-116,145-155, vae.py:69-80, ffnn_vae.py:56)
+//   backward  gdd --fc_d0 dgrad--> gz --reverse sweep of the manifold chain--> gml --heads dgrad, relu mask--> gh
+//             plus the weight / bias gradients of fc_d0 and of the heads, and dR
+//
+// The dense layers here are "skinny" (N = sum(n)+sum(l_n) ~ 12..60 outputs, K = sum(d) ~ 8..34 inputs): far below a
+// tcgen05 tile, a few MB of traffic.  Done as separate launches they cost six kernels and five round trips of
+// [B, P] / [B, Sd] / [B, H] intermediates through L2; fused, the per-sample intermediates (ml on the way back, gz, gml)
+// never leave shared memory and the activations h / gdd are read exactly once.
+//
+// A CTA owns R = 16 consecutive rows.  Their rows of the split-bf16 planes of h (or gdd and h) are contiguous per
+// plane: one bulk asynchronous copy (TMA) per plane lands them in shared memory, where they serve both access
+// patterns — warp-per-row dot products (lanes along the hidden dimension, shuffle reduction) and thread-per-column
+// outer products (rows unrolled in registers).  The manifold arithmetic is pm_math.cuh through dispatch_item, one warp
+// per component, lane = row.  Weight gradients are accumulated per CTA in registers over its 16 rows and leave as
+// vector reductions (red.global.add.v2/.v4.f32).  All arithmetic is exact fp32 FMA on values reconstructed from the
+// planes (the sum of the bf16 planes is the fp32 value the producing GEMM computed, to 2^-24 with three planes).
+#pragma once
+#include <cuda_bf16.h>
+
+#include "pm_item.cuh"
+
+#ifndef MVAE_LAT_BWD
+#error "define MVAE_LAT_BWD to 0 (forward) or 1 (backward) before including latent_impl.cuh"
+#endif
+
+namespace mvae {
+
+constexpr int kLatRows = 16;      // rows per CTA
+constexpr int kLatThreads = 256;  // 8 warps
+
+struct LatParams {
+  mvae_pm_desc desc;
+  int64_t B;
+  int H;                       // hidden width (multiple of 8)
+  // h planes (forward: 3 read for the heads; backward: planes 0,1 for the weight gradient, plane 0 for the relu mask)
+  const uint16_t* h;
+  int64_t h_stride;
+  int h_ld, h_planes;
+  const float* Wh;             // [P, H]
+  const float* bh;             // [P]
+  const float* Wd0;            // [H, Sd]
+  const float* bd0;            // [H]
+  const float* eps;
+  const float* radius;
+  // forward outputs
+  float* ml;
+  float* z;
+  float* kl;
+  uint16_t* dd;
+  int64_t dd_stride;
+  int dd_ld, dd_planes;
+  uint32_t* flag;
+  // backward
+  const uint16_t* gdd;
+  int64_t gdd_stride;
+  int gdd_ld, gdd_planes;
+  const float* ml_in;
+  const float* z_in;
+  float gkl;
+  uint16_t* gh;
+  int64_t gh_stride;
+  int gh_ld, gh_planes;
+  float* gWd0;
+  float* gbd0;
+  float* gWh;
+  float* gbh;
+  float* gradius;
+  int zero_gml;
+  // shared-memory layout (bytes from the start of dynamic shared memory), host-computed
+  int off_a, off_b, off_ml, off_eps, off_z, off_kl, off_gz, off_gml, off_bar;
+};
+
+__device__ __forceinline__ float bf16lo(uint32_t w) { return __uint_as_float(w << 16); }
+__device__ __forceinline__ float bf16hi(uint32_t w) { return __uint_as_float(w & 0xFFFF0000u); }
+
+// sum of `planes` bf16 planes for 8 consecutive columns of one row held in shared memory
+__device__ __forceinline__ void planes_load8(const uint16_t* s, int plane_elems, int planes, float (&v)[8]) {
+#pragma unroll
+  for (int j = 0; j < 8; ++j) v[j] = 0.f;
+#pragma unroll
+  for (int p = 0; p < 3; ++p)
+    if (p < planes) {
+      const uint4 q = *reinterpret_cast<const uint4*>(s + p * plane_elems);
+      const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        v[2 * j] += bf16lo(w[j]);
+        v[2 * j + 1] += bf16hi(w[j]);
+      }
+    }
+}
+// sum of `planes` planes for a column pair
+__device__ __forceinline__ float2 planes_load2(const uint16_t* s, int plane_elems, int planes) {
+  float2 r = make_float2(0.f, 0.f);
+#pragma unroll
+  for (int p = 0; p < 3; ++p)
+    if (p < planes) {
+      const uint32_t w = *reinterpret_cast<const uint32_t*>(s + p * plane_elems);
+      r.x += bf16lo(w);
+      r.y += bf16hi(w);
+    }
+  return r;
+}
+// split a column pair into bf16 planes and store it (32-bit stores, coalesced across the warp)
+__device__ __forceinline__ void planes_store2(uint16_t* dst, int64_t stride, int planes, float a, float b) {
+  for (int p = 0; p < planes; ++p) {
+    const __nv_bfloat16 ha = __float2bfloat16_rn(a), hb = __float2bfloat16_rn(b);
+    const uint32_t ua = *reinterpret_cast<const uint16_t*>(&ha), ub = *reinterpret_cast<const uint16_t*>(&hb);
+    *reinterpret_cast<uint32_t*>(dst + p * stride) = ua | (ub << 16);
+    a -= __bfloat162float(ha);
+    b -= __bfloat162float(hb);
+  }
+}
+__device__ __forceinline__ void red_add2(float* p, float a, float b) {
+  asm volatile("red.global.add.v2.f32 [%0], {%1,%2};" ::"l"(p), "f"(a), "f"(b) : "memory");
+}
+__device__ __forceinline__ void red_add4(float* p, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+// out[r][n] = sum_k rowvec[k] * W[n][k] for ONE row held as planes in shared memory; lanes stride the K = H columns in
+// chunks of 8, W rows are read with 128-bit loads through L1 (every warp of every CTA reads the same few KB).
+template <int NMAX>
+__device__ __forceinline__ void row_dot_WnK(const uint16_t* srow, int plane_elems, int planes, int H,
+                                            const float* __restrict__ W, int N, float (&acc)[NMAX]) {
+  const int lane = threadIdx.x & 31;
+#pragma unroll
+  for (int n = 0; n < NMAX; ++n) acc[n] = 0.f;
+  for (int c = lane; 8 * c < H; c += 32) {
+    float v[8];
+    planes_load8(srow + 8 * c, plane_elems, planes, v);
+#pragma unroll
+    for (int n = 0; n < NMAX; ++n)
+      if (n < N) {
+        const float4 w0 = __ldg(reinterpret_cast<const float4*>(W + (int64_t)n * H + 8 * c));
+        const float4 w1 = __ldg(reinterpret_cast<const float4*>(W + (int64_t)n * H + 8 * c) + 1);
+        float t = acc[n];
+        t = fmaf(v[0], w0.x, t); t = fmaf(v[1], w0.y, t); t = fmaf(v[2], w0.z, t); t = fmaf(v[3], w0.w, t);
+        t = fmaf(v[4], w1.x, t); t = fmaf(v[5], w1.y, t); t = fmaf(v[6], w1.z, t); t = fmaf(v[7], w1.w, t);
+        acc[n] = t;
+      }
+  }
+#pragma unroll
+  for (int n = 0; n < NMAX; ++n)
+    if (n < N) acc[n] = warp_sum(acc[n]);
+}
+
+// out[r][j] = sum_h rowvec[h] * W[h][j] (W row-major [H, J], J small): the dgrad of fc_d0 into z
+template <int JMAX>
+__device__ __forceinline__ void row_dot_WKn(const uint16_t* srow, int plane_elems, int planes, int H,
+                                            const float* __restrict__ W, int J, float (&acc)[JMAX]) {
+  const int lane = threadIdx.x & 31;
+#pragma unroll
+  for (int j = 0; j < JMAX; ++j) acc[j] = 0.f;
+  const bool vec = (J & 3) == 0;
+  for (int c = lane; 8 * c < H; c += 32) {
+    float v[8];
+    planes_load8(srow + 8 * c, plane_elems, planes, v);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float* wr = W + (int64_t)(8 * c + i) * J;
+      if (vec) {
+#pragma unroll
+        for (int j = 0; j < JMAX; j += 4)
+          if (j < J) {
+            const float4 w = __ldg(reinterpret_cast<const float4*>(wr + j));
+            acc[j] = fmaf(v[i], w.x, acc[j]);
+            acc[j + 1] = fmaf(v[i], w.y, acc[j + 1]);
+            acc[j + 2] = fmaf(v[i], w.z, acc[j + 2]);
+            acc[j + 3] = fmaf(v[i], w.w, acc[j + 3]);
+          }
+      } else {
+#pragma unroll
+        for (int j = 0; j < JMAX; ++j)
+          if (j < J) acc[j] = fmaf(v[i], __ldg(wr + j), acc[j]);
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < JMAX; ++j)
+    if (j < J) acc[j] = warp_sum(acc[j]);
+}
+
+#if !MVAE_LAT_BWD
+// ================================================= forward =================================================
+template <int MAXN, int SMAX>
+__global__ void __launch_bounds__(kLatThreads) latent_forward_kernel(const __grid_constant__ LatParams p) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  constexpr int R = kLatRows;
+  const int C = p.desc.C, P = p.desc.ld_ml, Sn = p.desc.ld_eps, Sd = p.desc.ld_z, H = p.H;
+  ItemInfo* info = reinterpret_cast<ItemInfo*>(smem);
+  uint16_t* sH = reinterpret_cast<uint16_t*>(smem + p.off_a);
+  float* sML = reinterpret_cast<float*>(smem + p.off_ml);
+  float* sEPS = reinterpret_cast<float*>(smem + p.off_eps);
+  float* sZ = reinterpret_cast<float*>(smem + p.off_z);
+  float* sKL = reinterpret_cast<float*>(smem + p.off_kl);
+  const uint32_t bar = pm_smem_u32(smem + p.off_bar);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int64_t row0 = (int64_t)blockIdx.x * R;
+  const int rows = (int)min((int64_t)R, p.B - row0);
+  const int plane_elems = R * p.h_ld;
+
+  stage_items(info, p.desc, p.radius);
+  if (tid == 0) {
+    pm_mbar_init(bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    const uint32_t bytes = (uint32_t)(rows * p.h_ld) * 2u;
+    pm_mbar_expect_tx(bar, bytes * (uint32_t)p.h_planes);
+    for (int pl = 0; pl < p.h_planes; ++pl)
+      pm_bulk_g2s(pm_smem_u32(sH + pl * plane_elems), p.h + pl * p.h_stride + row0 * p.h_ld, bytes, bar);
+  }
+  for (int i = tid; i < rows * Sn; i += blockDim.x) sEPS[i] = __ldg(p.eps + row0 * Sn + i);
+  __syncthreads();
+  pm_mbar_wait(bar, 0);
+
+  // ---- heads: ml[r][p] = <h[r], Wh[p]> + bh[p]; one warp per row ----
+  for (int r = warp; r < rows; r += kLatThreads / 32) {
+    float acc[SMAX];
+    row_dot_WnK<SMAX>(sH + r * p.h_ld, plane_elems, p.h_planes, H, p.Wh, P, acc);
+    if (lane == 0) {
+#pragma unroll
+      for (int n = 0; n < SMAX; ++n)
+        if (n < P) sML[r * P + n] = acc[n] + __ldg(p.bh + n);
+    }
+  }
+  __syncthreads();
+
+  // ---- manifold chain: one warp per component, lane = row ----
+  bool finite = true;
+  const bool check = p.flag != nullptr;
+  for (int ci = warp; ci < C; ci += kLatThreads / 32) {
+    if (lane < rows) {
+      const ItemInfo c = info[ci];
+      float unused = 0.f;
+      finite &= dispatch_item<false, MAXN, false>(c, sML + lane * P, sEPS + lane * Sn, sZ + lane * Sd,
+                                                  sKL + lane * C + ci, nullptr, nullptr, nullptr, 0.f, nullptr,
+                                                  &unused, check);
+    }
+  }
+  if (check) {
+    const unsigned bad = __ballot_sync(0xffffffffu, !finite);
+    if (bad && lane == 0) atomicOr(p.flag, 1u);
+  }
+  __syncthreads();
+  for (int i = tid; i < rows * P; i += blockDim.x) p.ml[row0 * P + i] = sML[i];
+  for (int i = tid; i < rows * Sd; i += blockDim.x) p.z[row0 * Sd + i] = sZ[i];
+  for (int i = tid; i < rows * C; i += blockDim.x) p.kl[row0 * C + i] = sKL[i];
+
+  // ---- fc_d0 + relu -> planes: thread per column pair, the 16 rows unrolled in registers ----
+  for (int n = 2 * tid; n < H; n += 2 * kLatThreads) {
+    float a0[R], a1[R];
+    const float b0 = __ldg(p.bd0 + n), b1 = __ldg(p.bd0 + n + 1);
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      a0[r] = b0;
+      a1[r] = b1;
+    }
+    for (int k = 0; k < Sd; ++k) {
+      const float w0 = __ldg(p.Wd0 + (int64_t)n * Sd + k), w1 = __ldg(p.Wd0 + (int64_t)(n + 1) * Sd + k);
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        const float zz = sZ[r * Sd + k];
+        a0[r] = fmaf(zz, w0, a0[r]);
+        a1[r] = fmaf(zz, w1, a1[r]);
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+      if (r < rows)
+        planes_store2(p.dd + (row0 + r) * p.dd_ld + n, p.dd_stride, p.dd_planes, fmaxf(a0[r], 0.f), fmaxf(a1[r], 0.f));
+  }
+}
+
+#else
+// ================================================= backward =================================================
+template <int MAXN, int SMAX>
+__global__ void __launch_bounds__(kLatThreads) latent_backward_kernel(const __grid_constant__ LatParams p) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  constexpr int R = kLatRows;
+  const int C = p.desc.C, P = p.desc.ld_ml, Sn = p.desc.ld_eps, Sd = p.desc.ld_z, H = p.H;
+  ItemInfo* info = reinterpret_cast<ItemInfo*>(smem);
+  uint16_t* sG = reinterpret_cast<uint16_t*>(smem + p.off_a);
+  uint16_t* sH = reinterpret_cast<uint16_t*>(smem + p.off_b);
+  float* sML = reinterpret_cast<float*>(smem + p.off_ml);
+  float* sEPS = reinterpret_cast<float*>(smem + p.off_eps);
+  float* sZ = reinterpret_cast<float*>(smem + p.off_z);
+  float* sGZ = reinterpret_cast<float*>(smem + p.off_gz);
+  float* sGML = reinterpret_cast<float*>(smem + p.off_gml);
+  const uint32_t bar = pm_smem_u32(smem + p.off_bar);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int64_t row0 = (int64_t)blockIdx.x * R;
+  const int rows = (int)min((int64_t)R, p.B - row0);
+  const int g_elems = R * p.gdd_ld, h_elems = R * p.h_ld;
+  const int hpl = p.h_planes < 2 ? p.h_planes : 2;
+
+  stage_items(info, p.desc, p.radius);
+  if (tid == 0) {
+    pm_mbar_init(bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    const uint32_t gb = (uint32_t)(rows * p.gdd_ld) * 2u, hb = (uint32_t)(rows * p.h_ld) * 2u;
+    pm_mbar_expect_tx(bar, gb * (uint32_t)p.gdd_planes + hb * (uint32_t)hpl);
+    for (int pl = 0; pl < p.gdd_planes; ++pl)
+      pm_bulk_g2s(pm_smem_u32(sG + pl * g_elems), p.gdd + pl * p.gdd_stride + row0 * p.gdd_ld, gb, bar);
+    for (int pl = 0; pl < hpl; ++pl)
+      pm_bulk_g2s(pm_smem_u32(sH + pl * h_elems), p.h + pl * p.h_stride + row0 * p.h_ld, hb, bar);
+  }
+  for (int i = tid; i < R * P; i += blockDim.x) {
+    sML[i] = i < rows * P ? __ldg(p.ml_in + row0 * P + i) : 0.f;
+    sGML[i] = 0.f;  // rows past the end and columns no component owns contribute nothing below
+  }
+  for (int i = tid; i < rows * Sn; i += blockDim.x) sEPS[i] = __ldg(p.eps + row0 * Sn + i);
+  for (int i = tid; i < R * Sd; i += blockDim.x) sZ[i] = i < rows * Sd ? __ldg(p.z_in + row0 * Sd + i) : 0.f;
+  __syncthreads();
+  pm_mbar_wait(bar, 0);
+
+  // ---- gz[r][j] = sum_h gdd[r][h] Wd0[h][j]; one warp per row ----
+  for (int r = warp; r < rows; r += kLatThreads / 32) {
+    float acc[SMAX];
+    row_dot_WKn<SMAX>(sG + r * p.gdd_ld, g_elems, p.gdd_planes, H, p.Wd0, Sd, acc);
+    if (lane == 0) {
+#pragma unroll
+      for (int j = 0; j < SMAX; ++j)
+        if (j < Sd) sGZ[r * Sd + j] = acc[j];
+    }
+  }
+  // ---- fc_d0 weight / bias gradient: gWd0[n][j] += sum_r gdd[r][n] z[r][j]; thread per column pair ----
+  for (int n = 2 * tid; n < H; n += 2 * kLatThreads) {
+    float g0[R], g1[R];
+    float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      float2 g = make_float2(0.f, 0.f);
+      if (r < rows) g = planes_load2(sG + r * p.gdd_ld + n, g_elems, p.gdd_planes);
+      g0[r] = g.x;
+      g1[r] = g.y;
+      s0 += g.x;
+      s1 += g.y;
+    }
+    if (p.gbd0) red_add2(p.gbd0 + n, s0, s1);
+    if ((Sd & 3) == 0) {
+      for (int j = 0; j < Sd; j += 4) {
+        float a[4] = {0.f, 0.f, 0.f, 0.f}, b[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          const float4 zz = *reinterpret_cast<const float4*>(sZ + r * Sd + j);
+          a[0] = fmaf(g0[r], zz.x, a[0]); a[1] = fmaf(g0[r], zz.y, a[1]); a[2] = fmaf(g0[r], zz.z, a[2]); a[3] = fmaf(g0[r], zz.w, a[3]);
+          b[0] = fmaf(g1[r], zz.x, b[0]); b[1] = fmaf(g1[r], zz.y, b[1]); b[2] = fmaf(g1[r], zz.z, b[2]); b[3] = fmaf(g1[r], zz.w, b[3]);
+        }
+        red_add4(p.gWd0 + (int64_t)n * Sd + j, a[0], a[1], a[2], a[3]);
+        red_add4(p.gWd0 + (int64_t)(n + 1) * Sd + j, b[0], b[1], b[2], b[3]);
+      }
+    } else {
+      for (int j = 0; j < Sd; ++j) {
+        float a = 0.f, b = 0.f;
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          const float zz = sZ[r * Sd + j];
+          a = fmaf(g0[r], zz, a);
+          b = fmaf(g1[r], zz, b);
+        }
+        atomicAdd(p.gWd0 + (int64_t)n * Sd + j, a);
+        atomicAdd(p.gWd0 + (int64_t)(n + 1) * Sd + j, b);
+      }
+    }
+  }
+  __syncthreads();
+
+  // ---- reverse sweep of the manifold chain: one warp per component, lane = row ----
+  for (int ci = warp; ci < C; ci += kLatThreads / 32) {
+    float gR = 0.f;
+    const ItemInfo c = info[ci];
+    if (lane < rows)
+      dispatch_item<true, MAXN, false>(c, sML + lane * P, sEPS + lane * Sn, nullptr, nullptr, nullptr, nullptr,
+                                       sGZ + lane * Sd, p.gkl, sGML + lane * P, &gR, false);
+    if (p.gradius) {
+      gR = warp_sum(gR) * radius_d(c.rp);
+      if (lane == 0 && gR != 0.f) atomicAdd(p.gradius + ci, gR);
+    }
+  }
+  __syncthreads();
+
+  // ---- heads: gWh[q][k] += sum_r gml[r][q] h[r][k];  gh[r][k] = (sum_q gml[r][q] Wh[q][k]) 1[h[r][k] > 0] ----
+  if (p.gbh)
+    for (int q = tid; q < P; q += blockDim.x) {
+      float s = 0.f;
+#pragma unroll
+      for (int r = 0; r < R; ++r) s += sGML[r * P + q];
+      atomicAdd(p.gbh + q, s);
+    }
+  for (int k = 2 * tid; k < H; k += 2 * kLatThreads) {
+    float h0[R], h1[R], y0[R], y1[R];
+    uint32_t mask = 0;
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      float2 hv = make_float2(0.f, 0.f);
+      if (r < rows) {
+        hv = planes_load2(sH + r * p.h_ld + k, h_elems, hpl);
+        // relu'(h): the leading plane is bf16(h) and h >= 0, so h > 0 <=> its bits are a positive number
+        const uint32_t w = *reinterpret_cast<const uint32_t*>(sH + r * p.h_ld + k);
+        const uint32_t lo = w & 0xFFFFu, hi = w >> 16;
+        mask |= (uint32_t)(((lo & 0x8000u) == 0) && ((lo & 0x7FFFu) != 0)) << (2 * r);
+        mask |= (uint32_t)(((hi & 0x8000u) == 0) && ((hi & 0x7FFFu) != 0)) << (2 * r + 1);
+      }
+      h0[r] = hv.x;
+      h1[r] = hv.y;
+      y0[r] = 0.f;
+      y1[r] = 0.f;
+    }
+    for (int q = 0; q < P; ++q) {
+      const float2 w = __ldg(reinterpret_cast<const float2*>(p.Wh + (int64_t)q * H + k));
+      float a = 0.f, b = 0.f;
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        const float g = sGML[r * P + q];
+        y0[r] = fmaf(g, w.x, y0[r]);
+        y1[r] = fmaf(g, w.y, y1[r]);
+        a = fmaf(g, h0[r], a);
+        b = fmaf(g, h1[r], b);
+      }
+      red_add2(p.gWh + (int64_t)q * H + k, a, b);
+    }
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+      if (r < rows)
+        planes_store2(p.gh + (row0 + r) * p.gh_ld + k, p.gh_stride, p.gh_planes, ((mask >> (2 * r)) & 1u) ? y0[r] : 0.f,
+                      ((mask >> (2 * r + 1)) & 1u) ? y1[r] : 0.f);
+  }
+}
+#endif
+
+// ------------------------------------------------------------------------------------------------ host side
+static inline int lat_align(int x, int a) { return (x + a - 1) / a * a; }
+
+static int launch_latent(LatParams& p, void* stream) {
+  constexpr bool bwd = MVAE_LAT_BWD != 0;
+  DeviceInfo di;
+  int rc = get_device_info(&di);
+  if (rc != MVAE_OK) return rc;
+  const mvae_pm_desc& D = p.desc;
+  const int P = D.ld_ml, Sn = D.ld_eps, Sd = D.ld_z, C = D.C, R = kLatRows;
+  int maxn = 0;
+  bool dyn = false;
+  for (int i = 0; i < C; ++i) {
+    const int n = D.comp[i].n;
+    dyn = dyn || !(n >= 1 && n <= 8 && n != 7);
+    maxn = n > maxn ? n : maxn;
+  }
+  // shared-memory layout
+  int o = lat_align(C * (int)sizeof(ItemInfo), 128);
+  p.off_a = o;
+  o += lat_align((bwd ? p.gdd_planes * R * p.gdd_ld : p.h_planes * R * p.h_ld) * 2, 128);
+  p.off_b = o;
+  if (bwd) o += lat_align((p.h_planes < 2 ? p.h_planes : 2) * R * p.h_ld * 2, 128);
+  p.off_ml = o;
+  o += lat_align(R * P * 4, 16);
+  p.off_eps = o;
+  o += lat_align(R * Sn * 4, 16);
+  p.off_z = o;
+  o += lat_align(R * Sd * 4, 16);
+  p.off_kl = o;
+  if (!bwd) o += lat_align(R * C * 4, 16);
+  p.off_gz = o;
+  if (bwd) o += lat_align(R * Sd * 4, 16);
+  p.off_gml = o;
+  if (bwd) o += lat_align(R * P * 4, 16);
+  p.off_bar = o;
+  o += 16;
+  const size_t smem = (size_t)o;
+  if (smem > (size_t)di.max_smem_optin) return MVAE_ERR_UNSUPPORTED;
+  const int small = (bwd ? (Sd > P ? Sd : P) : P);
+  void (*kern)(LatParams);
+#if MVAE_LAT_BWD
+#define MVAE_LAT_K(MN, SM) latent_backward_kernel<MN, SM>
+#else
+#define MVAE_LAT_K(MN, SM) latent_forward_kernel<MN, SM>
+#endif
+#define MVAE_LAT_PICK(MN) (small <= 16 ? MVAE_LAT_K(MN, 16) : small <= 32 ? MVAE_LAT_K(MN, 32) : MVAE_LAT_K(MN, 64))
+  if (dyn) kern = MVAE_LAT_PICK(0);
+  else if (maxn <= 2) kern = MVAE_LAT_PICK(2);
+  else kern = MVAE_LAT_PICK(8);
+#undef MVAE_LAT_PICK
+#undef MVAE_LAT_K
+  if (smem > 48 * 1024) MVAE_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int64_t grid = (p.B + R - 1) / R;
+  if (grid > 0x7fffffff) return MVAE_ERR_UNSUPPORTED;
+  kern<<<(unsigned)grid, kLatThreads, smem, as_stream(stream)>>>(p);
+  MVAE_LAUNCH_CHECK();
+  return MVAE_OK;
+}
+
+}  // namespace mvae

@@ -195,20 +195,28 @@ class FusedFeedForwardVAE(nn.Module):
         """Re-home every parameter as a view into one flat fp32 buffer (and its gradient into one flat bucket)."""
         dev = self.device
         net = self._net_params()
-        n_net = sum(p.numel() for _, p in net)
         C = self.desc.C
-        flat = torch.empty(n_net, device=dev, dtype=torch.float32)
+        # Offsets: the head weights and the head biases stay contiguous blocks ([P, H] and [P]); every other tensor
+        # (and the head-bias block) starts on a 16-byte boundary so that the kernels can use 128-bit accesses.
+        # The few padding floats are zero parameters with zero gradients.
+        n_heads = 2 * len(self.components)
+        offsets, off = [], 0
+        for i, (name, p) in enumerate(net):
+            if i == n_heads or i >= 2 * n_heads:
+                off = (off + 3) // 4 * 4
+            offsets.append(off)
+            off += p.numel()
+        n_net = (off + 3) // 4 * 4
+        flat = torch.zeros(n_net, device=dev, dtype=torch.float32)
         rflat = torch.ones(C, device=dev, dtype=torch.float32)
         bucket = torch.zeros(n_net + C + 3 + C, device=dev, dtype=torch.float32)
-        off = 0
         self._slices = {}
-        for name, p in net:
+        for (name, p), off in zip(net, offsets):
             n = p.numel()
             flat[off:off + n].copy_(p.data.reshape(-1).to(dev, torch.float32))
             p.data = flat[off:off + n].view(p.shape)
             p.grad = bucket[off:off + n].view(p.shape)
             self._slices[name] = (off, n)
-            off += n
         self._radius_mask = torch.zeros(C, device=dev, dtype=torch.float32)
         for i, c in enumerate(self.components):
             _, rp = c.radius_parameter()
@@ -248,6 +256,8 @@ class FusedFeedForwardVAE(nn.Module):
         self._planes_stale = True
         self._ws = {}
         self._graphs = {}
+        # heads + manifold chain + fc_d0 as one kernel per direction (mvae_latent_forward / _backward)
+        self.fused_latent = (H % 8 == 0) and P <= 64 and Sd <= 64
 
     def _apply(self, fn, *args, **kwargs):
         out = super()._apply(fn, *args, **kwargs)
@@ -289,14 +299,20 @@ class FusedFeedForwardVAE(nn.Module):
             self.refresh_weight_planes()
         ops.split_planes(ws.x, ws.xp)
         ops.gemm(ws.xp, self.We0p, B, H, D, epilogue=L.EPI_BIAS_RELU, bias=self.fc_e0.bias.data, out_planes=ws.hp)
-        # heads: N = P is tiny -> CUDA-core row dots in exact fp32 (h read from its 3 planes)
-        ops.skinny_rowdot((ws.hp, 3), self.Wh, H, 1, K=H, N=P, bias=self.bh, out=ws.ml)
-        out = {"z": ws.z, "kl": ws.kl, "mu": ws.mu, "sigma": ws.sigma}
-        ops.pm_forward(self.desc, ws.ml, ws.eps, self._rflat, want_mu_sigma=want_mu_sigma,
-                       flag=ws.flag if self.check_finite else None, out=out)
-        # fc_d0: K = total_z_dim is tiny -> CUDA-core expansion in exact fp32, relu, planes of dd for the logits GEMM
-        ops.skinny_expand(ws.z, self.fc_d0.weight.data, Sd, 1, K=Sd, N=H, bias=self.fc_d0.bias.data, act=ops.ACT_RELU,
-                          out_planes=ws.ddp)
+        if self.fused_latent and not want_mu_sigma:
+            # heads + manifold chain + fc_d0/relu in ONE kernel: ml, z, kl kept for the backward pass / statistics
+            ops.latent_forward(self.desc, ws.hp, self.Wh, self.bh, ws.eps, self._rflat, self.fc_d0.weight.data,
+                               self.fc_d0.bias.data, ws.ml, ws.z, ws.kl, ws.ddp,
+                               flag=ws.flag if self.check_finite else None)
+        else:
+            # heads: N = P is tiny -> CUDA-core row dots in exact fp32 (h read from its 3 planes)
+            ops.skinny_rowdot((ws.hp, 3), self.Wh, H, 1, K=H, N=P, bias=self.bh, out=ws.ml)
+            out = {"z": ws.z, "kl": ws.kl, "mu": ws.mu, "sigma": ws.sigma}
+            ops.pm_forward(self.desc, ws.ml, ws.eps, self._rflat, want_mu_sigma=want_mu_sigma,
+                           flag=ws.flag if self.check_finite else None, out=out)
+            # fc_d0: K = total_z_dim is tiny -> CUDA-core expansion in exact fp32, relu, planes of dd for the logits GEMM
+            ops.skinny_expand(ws.z, self.fc_d0.weight.data, Sd, 1, K=Sd, N=H, bias=self.fc_d0.bias.data,
+                              act=ops.ACT_RELU, out_planes=ws.ddp)
         ws.bce.zero_()
         epi = L.EPI_BCE_ROWSUM if self.recon_kind == "bce" else L.EPI_NLL_ROWSUM
         ops.gemm(ws.ddp, self.Wlp, B, D, H, epilogue=epi, bias=self.fc_logits.bias.data, aux=ws.x, rowsum=ws.bce,
@@ -311,16 +327,23 @@ class FusedFeedForwardVAE(nn.Module):
         ops.gemm(ws.gLp, ws.ddp, D, H + 1, B, a_major=MN, b_major=MN, split_k=0, out_f32=self.gWl, out_col=self.gbl,
                  col_split=H)
         ops.gemm(ws.gLp, self.Wlp, B, H, D, b_major=MN, epilogue=L.EPI_RELU_MASK, mask=ws.ddp, out_planes=ws.gddp)
-        # fc_d0 (skinny): gW[h, j] = sum_b gdd[b, h] z[b, j], gb[h] = sum_b gdd[b, h];  gz = gdd W
-        ops.skinny_wgrad(ws.z, Sd, (ws.gddp, 2), H, self.gWd0, 1, Sd, small_ones=True, out_row=self.gbd0)
-        ops.skinny_rowdot((ws.gddp, 2), self.fc_d0.weight.data, 1, Sd, K=H, N=Sd, bias=None, out=ws.gz)
-        # latent: d(-ELBO)/d kl = beta
-        ops.pm_backward(self.desc, ws.ml, ws.eps, self._rflat, ws.gz, None, beta, gml=ws.gml, gradius=self._gradius)
-        if self._any_fixed_radius:
-            self._gradius.mul_(self._radius_mask)  # requires_grad=False radii (fixed curvature) get no gradient
-        # heads (skinny): gWh[p, k] = sum_b gml[b, p] h[b, k] (+ bias from h's ones column);  gh = (gml Wh) * 1[h > 0]
-        ops.skinny_wgrad(ws.gml, P, (ws.hp, 2), H + 1, self.gWh, H, 1, out_col=self.gbh, col_split=H)
-        ops.skinny_expand(ws.gml, self.Wh, 1, H, K=P, N=H, act=ops.ACT_MASK, mask=ws.hp, out_planes=ws.ghp)
+        if self.fused_latent:
+            # fc_d0 dgrad + wgrad, manifold reverse sweep (d(-ELBO)/d kl = beta), heads dgrad + wgrad: ONE kernel
+            ops.latent_backward(self.desc, ws.gddp, ws.hp, self.Wh, self.fc_d0.weight.data, ws.ml, ws.eps, self._rflat,
+                                ws.z, beta, ws.ghp, self.gWd0, self.gbd0, self.gWh, self.gbh, self._gradius)
+            if self._any_fixed_radius:
+                self._gradius.mul_(self._radius_mask)  # requires_grad=False radii (fixed curvature) get no gradient
+        else:
+            # fc_d0 (skinny): gW[h, j] = sum_b gdd[b, h] z[b, j], gb[h] = sum_b gdd[b, h];  gz = gdd W
+            ops.skinny_wgrad(ws.z, Sd, (ws.gddp, 2), H, self.gWd0, 1, Sd, small_ones=True, out_row=self.gbd0)
+            ops.skinny_rowdot((ws.gddp, 2), self.fc_d0.weight.data, 1, Sd, K=H, N=Sd, bias=None, out=ws.gz)
+            # latent: d(-ELBO)/d kl = beta
+            ops.pm_backward(self.desc, ws.ml, ws.eps, self._rflat, ws.gz, None, beta, gml=ws.gml, gradius=self._gradius)
+            if self._any_fixed_radius:
+                self._gradius.mul_(self._radius_mask)  # requires_grad=False radii (fixed curvature) get no gradient
+            # heads (skinny): gWh[p, k] = sum_b gml[b, p] h[b, k] (+ bias from h's ones column);  gh = (gml Wh) * 1[h > 0]
+            ops.skinny_wgrad(ws.gml, P, (ws.hp, 2), H + 1, self.gWh, H, 1, out_col=self.gbh, col_split=H)
+            ops.skinny_expand(ws.gml, self.Wh, 1, H, K=P, N=H, act=ops.ACT_MASK, mask=ws.hp, out_planes=ws.ghp)
         # fc_e0 (no dgrad into x)
         ops.gemm(ws.ghp, ws.xp, H, D + 1, B, a_major=MN, b_major=MN, split_k=0, out_f32=self.gWe0,
                  out_col=self.gbe0, col_split=D, b_planes=2)

@@ -23,7 +23,7 @@ for _ in range(3):
 torch.cuda.synchronize()
 
 calls = []
-NAMES = ["split_planes", "gemm", "skinny_rowdot", "skinny_expand", "skinny_wgrad", "pm_forward", "pm_backward",
+NAMES = ["split_planes", "gemm", "latent_forward", "latent_backward", "skinny_rowdot", "skinny_expand", "skinny_wgrad", "pm_forward", "pm_backward",
          "elbo_reduce", "adam_step_dev", "sgd_step", "recon_loss"]
 orig = {n: getattr(ops, n) for n in NAMES if hasattr(ops, n)}
 

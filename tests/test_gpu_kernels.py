@@ -440,3 +440,57 @@ def test_skinny_wgrad(dev, B, S, Wd):
     out3 = torch.zeros(S, Wd, device=dev)
     ops.skinny_wgrad(small, S, wide, Wd, out3, Wd, 1)
     assert ((out3.double() - ref2).abs().max() / ref2.abs().max()).item() < 2e-6
+
+
+# ------------------------------------------------------------------------------------------ fused latent block
+@pytest.mark.parametrize("sig,B,H,scalar", [("h2,s2,e2", 4096, 400, False), ("h6,h6,s6,s6,e6", 1003, 400, False),
+                                            ("p2", 17, 64, False), ("h3,s5,p4,e1", 300, 136, True),
+                                            ("e2", 128, 400, False)])
+def test_latent_fused_matches_separate_kernels(dev, oracle, sig, B, H, scalar):
+    """mvae_latent_forward / _backward (heads + manifold chain + fc_d0 in one launch per direction) against the float64
+    oracle for the manifold part and float64 matmuls for the dense parts; ragged batches, scalar parametrization."""
+    from mvae_b200 import ops
+    desc = ops.make_desc(sig, scalar_parametrization=scalar)
+    odesc = oracle.make_desc(sig, scalar_parametrization=scalar)
+    P, Sn, Sd, C = desc.ld_ml, desc.ld_eps, desc.ld_z, desc.C
+    g = torch.Generator(device=dev).manual_seed(B + H)
+    h = torch.randn(B, H, device=dev, generator=g).clamp(min=0)           # relu output: about half the units are off
+    Wh = torch.randn(P, H, device=dev, generator=g) / H**0.5
+    bh = torch.randn(P, device=dev, generator=g) * 0.1
+    Wd0 = torch.randn(H, Sd, device=dev, generator=g) / Sd**0.5
+    bd0 = torch.randn(H, device=dev, generator=g) * 0.1
+    eps = torch.randn(B, Sn, device=dev, generator=g)
+    R = torch.full((C,), 1.7, device=dev)
+    hp = _planes_of(h, dev, planes=3, ones_col=True)
+    ml = torch.full((B, P), float("nan"), device=dev)
+    z = torch.full((B, Sd), float("nan"), device=dev)
+    kl = torch.full((B, C), float("nan"), device=dev)
+    ddp = ops.PlaneBuf(B, H, 2, dev, ones_col=True)
+    ops.latent_forward(desc, hp, Wh, bh, eps, R, Wd0, bd0, ml, z, kl, ddp)
+    ml_ref = h.double() @ Wh.double().t() + bh.double()
+    assert ((ml.double() - ml_ref).abs().max() / ml_ref.abs().max()).item() < 2e-6
+    ref = oracle.pm_forward(odesc, ml.double().cpu().numpy(), eps.double().cpu().numpy(), R.double().cpu().numpy())
+    assert normwise(z.cpu().numpy(), ref["z"]) < FWD_TOL
+    err = np.abs(kl.cpu().numpy() - ref["kl"]) / np.maximum(1.0, np.abs(ref["kl"]))
+    assert np.quantile(err, 0.99) < 5e-5
+    dd_ref = (z.double() @ Wd0.double().t() + bd0.double()).clamp(min=0)
+    assert ((ddp.to_float().double() - dd_ref).abs().max() / dd_ref.abs().max()).item() < 2e-5
+    assert torch.equal(ddp.t[0, :, H].float(), torch.ones(B, device=dev))  # ones column untouched
+    # backward
+    gdd = torch.randn(B, H, device=dev, generator=g) * (dd_ref > 0)
+    gddp = _planes_of(gdd.float(), dev, planes=2)
+    ghp = ops.PlaneBuf(B, H, 2, dev)
+    gWd0, gbd0 = torch.zeros(H, Sd, device=dev), torch.zeros(H, device=dev)
+    gWh, gbh, gR = torch.zeros(P, H, device=dev), torch.zeros(P, device=dev), torch.zeros(C, device=dev)
+    ops.latent_backward(desc, gddp, hp, Wh, Wd0, ml, eps, R, z, 0.7, ghp, gWd0, gbd0, gWh, gbh, gR)
+    gdd64 = gddp.to_float().double()
+    gz_ref = (gdd64 @ Wd0.double()).cpu().numpy()
+    gml_ref, gR_ref = oracle.pm_backward(odesc, ml.double().cpu().numpy(), eps.double().cpu().numpy(),
+                                         R.double().cpu().numpy(), gz_ref, None, 0.7)
+    gml64 = torch.from_numpy(gml_ref).to(dev)
+    gh_ref = (gml64 @ Wh.double()) * (h > 0)
+    assert ((ghp.to_float().double() - gh_ref).abs().max() / gh_ref.abs().max()).item() < 1e-4
+    for got, want in ((gWd0, gdd64.t() @ z.double()), (gbd0, gdd64.sum(0)), (gWh, gml64.t() @ h.double()),
+                      (gbh, gml64.sum(0))):
+        assert ((got.double() - want).norm() / want.norm()).item() < 1e-4
+    assert np.all(np.abs(gR.cpu().numpy() - gR_ref) <= 2e-4 * np.maximum(1.0, np.abs(gml_ref).sum()))
