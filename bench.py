@@ -271,9 +271,15 @@ def run_ours(args):
                                     device=dev)  # MNIST-shaped batches are binarised (0/1): one exact bf16 plane
     model.use_cuda_graph = not args.no_graph
     opt = vae.FusedCurvatureOptimizer(model, 1e-3, fixed_curvature=fixed, should_do_curvature_step=lambda: True)
+    collective = "none"
     if world > 1:
+        # one exchange per step: fused into the optimizer kernel over NVLink peer memory (default), or NCCL all-reduce
+        if os.environ.get("MVAE_DP", "p2p") != "nccl" and parallel.attach_p2p(model, opt):
+            collective = "peer-memory kernel: gradient reduce-scatter + Adam + parameter all-gather (mvae_dp_adam_step)"
+        else:
+            parallel.attach(model)
+            collective = "NCCL all-reduce(SUM) of the gradient/statistics bucket, then Adam"
         parallel.broadcast_parameters(model)
-        parallel.attach(model)
     C, Sn, Sd, P = model.desc.C, model.desc.ld_eps, model.desc.ld_z, model.desc.ld_ml
     # distinct batches per rank, rotated so that consecutive steps never see the same input
     n_rot = 4
@@ -361,7 +367,8 @@ def run_ours(args):
             "data": "synthetic",
             "config": {"workload": desc, "signature": sig, "batch_per_gpu": B, "global_batch": gb, "in_dim": D,
                        "h_dim": H, "parallelism": f"dp{world}", "l2": "flushed between timed steps (256 MiB memset)",
-                       "cuda_graph": bool(model.use_cuda_graph), "optimizer": "Adam(1e-3) + SGD(1e-4) on radii"},
+                       "cuda_graph": bool(model.use_cuda_graph), "optimizer": "Adam(1e-3) + SGD(1e-4) on radii",
+                       "collective": collective},
             "e2e": {"value": gb / (e2e_ms / 1e3), "unit": UNIT, "ms_per_step": e2e_ms,
                     "h2d_bytes_per_step": B * D * 4, "d2h_bytes_per_step": (3 + C) * 4,
                     "api": "model.train_epoch(optimizer, pinned host batches, beta): H2D of batch i+1 overlaps step i",

@@ -286,6 +286,45 @@ int mvae_adam_step_dev(int64_t n, float* param, const float* grad, float* exp_av
 /* Plain SGD step p -= lr * grad_scale * g (torch.optim.SGD defaults — the curvature optimizers of train.py:346-355). */
 int mvae_sgd_step(int64_t n, float* param, const float* grad, float lr, float grad_scale, void* stream);
 
+/* ------------------------------------------------------------------- data-parallel step over peer memory */
+/* The reference has no distributed mode.  Data parallelism here shards the batch by rank; the
+ * only exchange of a step is the SUM of the flat bucket [network grads (n_net) | radius grads (C) | ELBO statistics
+ * (3 + C)] (the reference's ELBO is a sum over the batch, stats.py:200-202).  mvae_dp_adam_step does that exchange and
+ * the optimizer update (Adam on the network parameters, SGD on the radii: train.py:327-360, utils.py:148-180) in ONE
+ * kernel over NVLink peer memory: reduce-scatter of the gradients with peer loads, Adam on the rank's slice (its
+ * moments are the only optimizer state the rank keeps current), all-gather of the new parameters with peer stores.
+ *
+ * Every rank allocates one region with mvae_dp_alloc, exports it (mvae_dp_ipc_export), and opens its peers' regions
+ * (mvae_dp_ipc_open) after exchanging the 64-byte handles out of band (e.g. torch.distributed.all_gather_object).
+ * bucket[r] / flat[r] / flags[r] are rank r's gradient bucket, parameter buffer and flag slots (MVAE_DP_MAX_RANKS slots
+ * of 128 bytes, zero-initialised) as mapped in THIS process. */
+#define MVAE_DP_MAX_RANKS 8
+#define MVAE_DP_HANDLE_BYTES 64
+typedef struct mvae_dp_comm {
+  int32_t rank, world;
+  float* bucket[MVAE_DP_MAX_RANKS];
+  float* flat[MVAE_DP_MAX_RANKS];
+  uint32_t* flags[MVAE_DP_MAX_RANKS];
+} mvae_dp_comm;
+
+int mvae_dp_alloc(size_t bytes, void** dev_ptr);           /* cudaMalloc + zero fill (synchronises once, at set-up) */
+int mvae_dp_free(void* dev_ptr);
+int mvae_dp_ipc_export(void* dev_ptr, uint8_t* handle_out /* [MVAE_DP_HANDLE_BYTES] */);
+int mvae_dp_ipc_open(const uint8_t* handle, void** peer_ptr);
+int mvae_dp_ipc_close(void* peer_ptr);
+
+/* One data-parallel optimizer step.  n_net (multiple of 4) network parameters, n_tail = C + 3 + C tail entries.
+ * exp_avg / exp_avg_sq: full-size moment buffers of which this rank updates its slice only.  step_dev: device step
+ * counter (incremented here).  radius [C] (may be NULL): raw radius parameters, stepped with radius_lr (0 = the
+ * curvature optimizers do not step) on the summed gradient times radius_mask (NULL = ones).  tail_out [n_tail]: the
+ * summed tail (radius grads, then bce, kl, elbo, kl_c sums).  sync_words: 4 zero-initialised device words private to
+ * this rank ([3] != 0 afterwards = a peer did not arrive within ~2 s; results are then undefined).
+ * Captured in a CUDA graph like any other launch; all ranks must launch it the same number of times. */
+int mvae_dp_adam_step(const mvae_dp_comm* comm, int64_t n_net, int32_t n_tail, int32_t C, float* exp_avg,
+                      float* exp_avg_sq, float lr, float beta1, float beta2, float eps, int32_t* step_dev,
+                      float* radius, float radius_lr, const float* radius_mask, float* tail_out, uint32_t* sync_words,
+                      void* stream);
+
 /* Device attributes the host layer needs for grid sizing / reporting. */
 int mvae_device_info(int32_t* sm_count, int32_t* cc_major, int32_t* cc_minor);
 

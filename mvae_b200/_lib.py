@@ -47,6 +47,14 @@ class GemmArgs(ctypes.Structure):
                 ("mask", ctypes.c_void_p), ("ld_mask", ctypes.c_int64), ("rowsum", ctypes.c_void_p)]
 
 
+DP_MAX_RANKS, DP_HANDLE_BYTES = 8, 64
+
+
+class DpComm(ctypes.Structure):
+    _fields_ = [("rank", ctypes.c_int32), ("world", ctypes.c_int32), ("bucket", ctypes.c_void_p * DP_MAX_RANKS),
+                ("flat", ctypes.c_void_p * DP_MAX_RANKS), ("flags", ctypes.c_void_p * DP_MAX_RANKS)]
+
+
 _vp, _i32, _i64, _f32 = ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64, ctypes.c_float
 
 # name -> (restype, argtypes); every symbol include/mvae_b200.h declares
@@ -78,6 +86,13 @@ PROTOTYPES = {
     "mvae_adam_step": (ctypes.c_int, [_i64, _vp, _vp, _vp, _vp, _f32, _f32, _f32, _f32, _i32, _f32, _vp]),
     "mvae_adam_step_dev": (ctypes.c_int, [_i64, _vp, _vp, _vp, _vp, _f32, _f32, _f32, _f32, _vp, _f32, _vp]),
     "mvae_sgd_step": (ctypes.c_int, [_i64, _vp, _vp, _f32, _f32, _vp]),
+    "mvae_dp_alloc": (ctypes.c_int, [ctypes.c_size_t, ctypes.POINTER(ctypes.c_void_p)]),
+    "mvae_dp_free": (ctypes.c_int, [_vp]),
+    "mvae_dp_ipc_export": (ctypes.c_int, [_vp, ctypes.c_char_p]),
+    "mvae_dp_ipc_open": (ctypes.c_int, [ctypes.c_char_p, ctypes.POINTER(ctypes.c_void_p)]),
+    "mvae_dp_ipc_close": (ctypes.c_int, [_vp]),
+    "mvae_dp_adam_step": (ctypes.c_int, [ctypes.POINTER(DpComm), _i64, _i32, _i32, _vp, _vp, _f32, _f32, _f32, _f32, _vp,
+                                         _vp, _f32, _vp, _vp, _vp, _vp]),
     "mvae_device_info": (ctypes.c_int, [ctypes.POINTER(_i32), ctypes.POINTER(_i32), ctypes.POINTER(_i32)]),
 }
 

@@ -350,3 +350,13 @@ def skinny_wgrad(small, S: int, wide, Wd: int, out, out_stride_s: int, out_strid
                                    _ptr(out_row), _ptr(out_col), col_split, _stream())
     L.check(rc, "mvae_skinny_wgrad")
     _LAUNCHES[0] += 1
+
+
+def dp_adam_step(comm: "L.DpComm", n_net: int, n_tail: int, C: int, exp_avg, exp_avg_sq, lr: float, beta1: float,
+                 beta2: float, eps: float, step_dev, radius, radius_lr: float, radius_mask, tail_out, sync_words):
+    """Gradient reduce-scatter + Adam + parameter all-gather over peer memory in one kernel (mvae_dp_adam_step)."""
+    rc = L.lib().mvae_dp_adam_step(ctypes.byref(comm), n_net, n_tail, C, _ptr(exp_avg), _ptr(exp_avg_sq), lr, beta1,
+                                   beta2, eps, _ptr(step_dev), _ptr(radius), radius_lr, _ptr(radius_mask),
+                                   _ptr(tail_out), _ptr(sync_words), _stream())
+    L.check(rc, "mvae_dp_adam_step")
+    _LAUNCHES[0] += 1

@@ -51,3 +51,101 @@ def broadcast_parameters(model, src: int = 0, group=None) -> None:
         dist.broadcast(model._flat, src=src, group=group)
         dist.broadcast(model._rflat, src=src, group=group)
         model.mark_parameters_changed()
+
+
+# ---------------------------------------------------------------------------------------------- peer-memory path
+class _DeviceRegion:
+    """A cudaMalloc'ed region exposed to torch through the CUDA array interface (zero-copy views)."""
+
+    def __init__(self, ptr: int, nbytes: int, owner=None):
+        self.ptr, self.nbytes, self.owner = ptr, nbytes, owner
+
+    def view(self, offset_bytes: int, count: int, dtype, device):
+        itemsize = torch.empty((), dtype=dtype).element_size()
+        typestr = {torch.float32: "<f4", torch.int32: "<i4", torch.uint8: "|u1"}[dtype]
+
+        class _Holder:
+            pass
+
+        h = _Holder()
+        h.__cuda_array_interface__ = {"shape": (count,), "typestr": typestr, "data": (self.ptr + offset_bytes, False),
+                                      "version": 3}
+        h._region = self  # keeps the allocation alive as long as the tensor lives
+        assert offset_bytes + count * itemsize <= self.nbytes
+        return torch.as_tensor(h, device=device)
+
+
+def attach_p2p(model, optimizer, group=None) -> bool:
+    """Data-parallel step over NVLink peer memory (mvae_dp_adam_step): the model's parameter buffer and gradient
+    bucket are re-homed into a cudaMalloc'ed region that every peer maps through CUDA IPC; the optimizer's step then
+    does gradient reduce-scatter + Adam + parameter all-gather in ONE kernel instead of all-reduce -> Adam.
+    Single node, world size <= 8.  Returns False (and leaves the model untouched) if the peers cannot be mapped."""
+    import ctypes
+
+    from . import _lib as L
+    if not (dist.is_initialized() and dist.get_world_size(group) > 1):
+        return False
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    if world > L.DP_MAX_RANKS:
+        return False
+    lib = L.lib()
+    dev = model.device
+    n_flat, n_bucket = model.flat_sizes()
+    al = lambda x: (x + 255) // 256 * 256  # noqa: E731
+    off_bucket = 0
+    off_flat = off_bucket + al(4 * n_bucket)
+    off_flags = off_flat + al(4 * n_flat)
+    nbytes = off_flags + L.DP_MAX_RANKS * 128
+    ptr = ctypes.c_void_p()
+    ok = True
+    try:
+        L.check(lib.mvae_dp_alloc(nbytes, ctypes.byref(ptr)), "mvae_dp_alloc")
+        handle = ctypes.create_string_buffer(L.DP_HANDLE_BYTES)
+        L.check(lib.mvae_dp_ipc_export(ptr, handle), "mvae_dp_ipc_export")
+        mine = bytes(handle.raw)
+    except L.MvaeError:
+        ok, mine = False, b""
+    handles = [None] * world
+    dist.all_gather_object(handles, mine if ok else None, group=group)
+    if any(h is None for h in handles):
+        return False
+    bases = []
+    for r in range(world):
+        if r == rank:
+            bases.append(ptr.value)
+            continue
+        pp = ctypes.c_void_p()
+        rc = lib.mvae_dp_ipc_open(handles[r], ctypes.byref(pp))
+        bases.append(pp.value if rc == 0 else None)
+    all_ok = [None] * world
+    dist.all_gather_object(all_ok, all(b is not None for b in bases), group=group)
+    if not all(all_ok):
+        return False
+    region = _DeviceRegion(ptr.value, nbytes)
+    flat = region.view(off_flat, n_flat, torch.float32, dev)
+    bucket = region.view(off_bucket, n_bucket, torch.float32, dev)
+    model._flatten(storage=(flat, bucket))
+    comm = L.DpComm()
+    comm.rank, comm.world = rank, world
+    for r in range(world):
+        comm.bucket[r] = bases[r] + off_bucket
+        comm.flat[r] = bases[r] + off_flat
+        comm.flags[r] = bases[r] + off_flags
+    C = model.desc.C
+    optimizer._dp = comm
+    optimizer._dp_tail = torch.zeros(2 * C + 3, device=dev, dtype=torch.float32)
+    optimizer._dp_sync = torch.zeros(4, device=dev, dtype=torch.int32)
+    # moments follow the re-homed parameters (fresh optimizer state), statistics are read from the summed tail
+    optimizer.exp_avg = torch.zeros_like(model._flat)
+    optimizer.exp_avg_sq = torch.zeros_like(model._flat)
+    model._stats_report = optimizer._dp_tail[C:]
+    model._grad_hook = None
+    model._dp_region = region
+    torch.cuda.synchronize(dev)
+    dist.barrier(group=group)  # every peer has mapped every region before the first step
+    return True
+
+
+def dp_error_word(optimizer) -> int:
+    """0 unless a peer failed to arrive at a barrier of mvae_dp_adam_step within its time limit."""
+    return 0 if optimizer._dp_sync is None else int(optimizer._dp_sync[3].item())

@@ -191,7 +191,11 @@ class FusedFeedForwardVAE(nn.Module):
                 ("fc_logits.weight", self.fc_logits.weight), ("fc_logits.bias", self.fc_logits.bias)]
         return heads_w + heads_b + rest
 
-    def _flatten(self) -> None:
+    def flat_sizes(self) -> Tuple[int, int]:
+        """(floats of the flat parameter buffer, floats of the gradient / statistics bucket)."""
+        return self._n_net, self._n_net + 2 * self.desc.C + 3
+
+    def _flatten(self, storage=None) -> None:
         """Re-home every parameter as a view into one flat fp32 buffer (and its gradient into one flat bucket)."""
         dev = self.device
         net = self._net_params()
@@ -207,9 +211,16 @@ class FusedFeedForwardVAE(nn.Module):
             offsets.append(off)
             off += p.numel()
         n_net = (off + 3) // 4 * 4
-        flat = torch.zeros(n_net, device=dev, dtype=torch.float32)
+        if storage is None:
+            flat = torch.zeros(n_net, device=dev, dtype=torch.float32)
+            bucket = torch.zeros(n_net + C + 3 + C, device=dev, dtype=torch.float32)
+        else:  # buffers provided by the caller (peer-mapped memory of the data-parallel step, parallel.attach_p2p)
+            flat, bucket = storage
+            assert flat.numel() == n_net and bucket.numel() == n_net + C + 3 + C
+            assert flat.data_ptr() % 16 == 0 and bucket.data_ptr() % 16 == 0
+            flat.zero_()
+            bucket.zero_()
         rflat = torch.ones(C, device=dev, dtype=torch.float32)
-        bucket = torch.zeros(n_net + C + 3 + C, device=dev, dtype=torch.float32)
         self._slices = {}
         for (name, p), off in zip(net, offsets):
             n = p.numel()
@@ -232,6 +243,7 @@ class FusedFeedForwardVAE(nn.Module):
         self._gnet = bucket[:n_net]
         self._gradius = bucket[n_net:n_net + C]
         self._stats = bucket[n_net + C:]
+        self._stats_report = self._stats  # where the step's (rank-summed) statistics are read from
         H, D, P, Sd = self.h_dim, self.in_dim, self.desc.ld_ml, self.desc.ld_z
 
         def view(buf, name, shape):
@@ -435,7 +447,7 @@ class FusedFeedForwardVAE(nn.Module):
         ws = self._workspace(x_mb.shape[0])
         self._stage(ws, x_mb, eps)
         self._step_kernels(optimizer, ws, beta)
-        stats = BatchStats(self._stats.clone() if not sync_stats else self._stats, beta)
+        stats = BatchStats(self._stats_report.clone() if not sync_stats else self._stats_report, beta)
         self._last_ws = ws
         out = (None, ws.z, None)
         if sync_stats:
@@ -478,7 +490,7 @@ class FusedFeedForwardVAE(nn.Module):
             self._slot_ready = [torch.cuda.Event(), torch.cuda.Event()]
             self._slot_free = [torch.cuda.Event(), torch.cuda.Event()]
         copy = self._copy_stream
-        ring_n, nst = 64, self._stats.numel()
+        ring_n, nst = 64, self._stats_report.numel()
         if getattr(self, "_stats_ring", None) is None:
             self._stats_ring = torch.zeros(ring_n, nst, dtype=torch.float32).pin_memory()
             self._ring_ev = [torch.cuda.Event() for _ in range(ring_n)]
@@ -530,7 +542,7 @@ class FusedFeedForwardVAE(nn.Module):
             self._slot_free[slot].record(main)
             if i >= ring_n:
                 drain(i - ring_n)
-            ring[i % ring_n].copy_(self._stats, non_blocking=True)
+            ring[i % ring_n].copy_(self._stats_report, non_blocking=True)
             ring_ev[i % ring_n].record(main)
             i += 1
             if x_next is not None and x_next.shape[0] != B:  # ragged last batch: its own workspace, no overlap
@@ -622,6 +634,7 @@ class FusedCurvatureOptimizer:
         self.step_count = 0
         self.step_dev = torch.zeros(1, device=model._flat.device, dtype=torch.int32)  # 1-based after the first step
         self.param_groups = [{"params": [p for _, p in model._net_params()], "lr": learning_rate}]
+        self._dp = self._dp_tail = self._dp_sync = None  # set by parallel.attach_p2p
 
     def zero_grad(self) -> None:
         pass  # the backward kernels overwrite / zero the bucket themselves
@@ -634,6 +647,14 @@ class FusedCurvatureOptimizer:
         graph and replayed."""
         m = self.model
         self.step_count += 1
+        if self._dp is not None:
+            # data parallel over NVLink peer memory: gradient reduce-scatter + Adam on this rank's slice + parameter
+            # all-gather + the radii's SGD step, one kernel (mvae_dp_adam_step)
+            ops.dp_adam_step(self._dp, m._n_net, 2 * m.desc.C + 3, m.desc.C, self.exp_avg, self.exp_avg_sq, self.lr,
+                             self.betas[0], self.betas[1], self.eps, self.step_dev, m._rflat,
+                             self.curvature_lr if self.curvature_step_enabled() else 0.0, m._radius_mask,
+                             self._dp_tail, self._dp_sync)
+            return
         ops.adam_step_dev(m._flat, m._gnet, self.exp_avg, self.exp_avg_sq, self.lr, self.step_dev, self.betas[0],
                           self.betas[1], self.eps)
         if self.curvature_step_enabled():
