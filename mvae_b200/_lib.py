@@ -86,6 +86,9 @@ PROTOTYPES = {
     "mvae_adam_step": (ctypes.c_int, [_i64, _vp, _vp, _vp, _vp, _f32, _f32, _f32, _f32, _i32, _f32, _vp]),
     "mvae_adam_step_dev": (ctypes.c_int, [_i64, _vp, _vp, _vp, _vp, _f32, _f32, _f32, _f32, _vp, _f32, _vp]),
     "mvae_sgd_step": (ctypes.c_int, [_i64, _vp, _vp, _f32, _f32, _vp]),
+    "mvae_opt_step_fused": (ctypes.c_int, [_i64, _vp, _vp, _vp, _vp, _f32, _f32, _f32, _f32, _vp, _vp, _vp, _vp, _vp,
+                                           _f32, _i32, _i32, ctypes.POINTER(_i64), ctypes.POINTER(_i32),
+                                           ctypes.POINTER(Planes), _vp]),
     "mvae_dp_alloc": (ctypes.c_int, [ctypes.c_size_t, ctypes.POINTER(ctypes.c_void_p)]),
     "mvae_dp_free": (ctypes.c_int, [_vp]),
     "mvae_dp_ipc_export": (ctypes.c_int, [_vp, ctypes.c_char_p]),

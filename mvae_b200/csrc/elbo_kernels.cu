@@ -3,6 +3,7 @@
 // accesses, warp-shuffle reductions, one atomic per CTA per output word.
 #include <cuda_bf16.h>
 #include <math.h>
+#include <string.h>
 
 #include "mvae_common.cuh"
 
@@ -114,6 +115,46 @@ __global__ void __launch_bounds__(256) elbo_kernel(int64_t B, int C, const float
     if (sh[i] != 0.f) atomicAdd(out + i, sh[i]);
 }
 
+// Small batches (the training configurations): ONE CTA of 1024 threads, block reduction, results written directly —
+// no memset, no atomics, deterministic summation order.
+__global__ void __launch_bounds__(1024) elbo_small_kernel(int B, int C, const float* __restrict__ bce,
+                                                          const float* __restrict__ kl, float beta,
+                                                          float* __restrict__ out) {
+  extern __shared__ float sh[];  // [32][3 + C] per-warp partials
+  const int nout = 3 + C, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float sb = 0.f, sk = 0.f, se = 0.f;
+  for (int b = threadIdx.x; b < B; b += blockDim.x) {
+    float klb = 0.f;
+    for (int c = 0; c < C; ++c) klb += kl[(int64_t)b * C + c];
+    const float bb = bce[b];
+    sb += bb;
+    sk += klb;
+    se += -bb - beta * klb;
+  }
+  sb = warp_sum(sb);
+  sk = warp_sum(sk);
+  se = warp_sum(se);
+  if (lane == 0) {
+    sh[warp * nout + 0] = sb;
+    sh[warp * nout + 1] = sk;
+    sh[warp * nout + 2] = se;
+  }
+  // per-component sums: warp w sweeps components w, w + 32, ...
+  for (int c = warp; c < C; c += 32) {
+    float acc = 0.f;
+    for (int b = lane; b < B; b += 32) acc += kl[(int64_t)b * C + c];
+    acc = warp_sum(acc);
+    if (lane == 0) sh[32 * nout + c] = acc;
+  }
+  __syncthreads();
+  if (threadIdx.x < 3) {
+    float acc = 0.f;
+    for (int w = 0; w < 32; ++w) acc += sh[w * nout + threadIdx.x];
+    out[threadIdx.x] = acc;
+  }
+  for (int c = threadIdx.x; c < C; c += blockDim.x) out[3 + c] = sh[32 * nout + c];
+}
+
 // --------------------------------------------------------------------------------------------- optimizers
 // torch.optim.Adam single-tensor semantics (no amsgrad / weight decay): exp_avg.lerp_(g, 1-b1);
 // exp_avg_sq.mul_(b2).addcmul_(g, g, 1-b2); denom = sqrt(v)/sqrt(bc2) + eps; p -= (lr/bc1) * m / denom.
@@ -200,6 +241,110 @@ __global__ void __launch_bounds__(256) split_kernel(const float* __restrict__ sr
   }
 }
 
+// Row-major only (no transposed copy), K % 8 == 0: a thread converts 8 consecutive values — two 128-bit loads, one
+// 128-bit store per plane.
+__global__ void __launch_bounds__(256) split_rows_kernel(const float* __restrict__ src, int64_t ld_src, int R, int K8,
+                                                         mvae_planes dst) {
+  const int64_t total = (int64_t)R * K8;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int r = (int)(i / K8), k = (int)(i - (int64_t)r * K8) * 8;
+    const float4 a = __ldg(reinterpret_cast<const float4*>(src + (int64_t)r * ld_src + k));
+    const float4 b = __ldg(reinterpret_cast<const float4*>(src + (int64_t)r * ld_src + k) + 1);
+    float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    for (int pl = 0; pl < dst.planes; ++pl) {
+      uint32_t w[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+        w[j] = *reinterpret_cast<const uint32_t*>(&h);
+        v[2 * j] -= __uint_as_float(w[j] << 16);
+        v[2 * j + 1] -= __uint_as_float(w[j] & 0xFFFF0000u);
+      }
+      *reinterpret_cast<uint4*>(dst.base + pl * dst.plane_stride + (int64_t)r * dst.ld + k) =
+          make_uint4(w[0], w[1], w[2], w[3]);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------- fused optimizer step
+// Adam over the flat parameter bucket (128-bit accesses) + the split-bf16 planes of the weight matrices that feed the
+// tensor-core GEMMs, written from the freshly updated values + the radii's SGD step + the device step counter: what
+// used to be five launches (bump, Adam, SGD, two plane splits) at the end of every step.
+struct PlaneTarget {
+  int64_t begin, end;  // float range [begin, end) of the flat bucket holding a [rows, cols] matrix (both % 4 == 0)
+  int cols, ld, planes;
+  uint16_t* base;
+  int64_t plane_stride;
+};
+struct OptParams {
+  int64_t n4;
+  float* p;
+  const float* g;
+  float* m;
+  float* v;
+  float lr, b1, b2, eps;
+  int32_t* step_dev;
+  uint32_t* done;  // zero-initialised counter (last-CTA-done pattern)
+  float* radius;
+  const float* gradius;
+  const float* radius_mask;
+  float radius_lr;
+  int C;
+  int n_targets;
+  PlaneTarget t[4];
+};
+__global__ void __launch_bounds__(256) opt_fused_kernel(const __grid_constant__ OptParams q) {
+  const double st = (double)(*q.step_dev + 1);
+  const float step_size = (float)((double)q.lr / (1.0 - pow((double)q.b1, st)));
+  const float inv_bc2_sqrt = (float)(1.0 / sqrt(1.0 - pow((double)q.b2, st)));
+  const float w1 = 1.f - q.b1, w2 = 1.f - q.b2;
+  if (blockIdx.x == 0 && q.radius && q.radius_lr != 0.f)
+    for (int t = threadIdx.x; t < q.C; t += blockDim.x)
+      q.radius[t] = q.radius[t] - q.radius_lr * (q.gradius[t] * (q.radius_mask ? q.radius_mask[t] : 1.f));
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < q.n4; i += (int64_t)gridDim.x * blockDim.x) {
+    const float4 g = reinterpret_cast<const float4*>(q.g)[i];
+    float4 mi = reinterpret_cast<float4*>(q.m)[i], vi = reinterpret_cast<float4*>(q.v)[i];
+    float4 pi = reinterpret_cast<float4*>(q.p)[i];
+#define MVAE_ADAM1(c)                                       \
+  mi.c = mi.c + (g.c - mi.c) * w1;                          \
+  vi.c = vi.c * q.b2 + w2 * (g.c * g.c);                    \
+  pi.c = pi.c - step_size * (mi.c / (sqrtf(vi.c) * inv_bc2_sqrt + q.eps));
+    MVAE_ADAM1(x) MVAE_ADAM1(y) MVAE_ADAM1(z) MVAE_ADAM1(w)
+#undef MVAE_ADAM1
+    reinterpret_cast<float4*>(q.m)[i] = mi;
+    reinterpret_cast<float4*>(q.v)[i] = vi;
+    reinterpret_cast<float4*>(q.p)[i] = pi;
+    const int64_t idx = 4 * i;
+#pragma unroll
+    for (int t = 0; t < 4; ++t)
+      if (t < q.n_targets && idx >= q.t[t].begin && idx < q.t[t].end) {
+        const int64_t rel = idx - q.t[t].begin;
+        const int64_t r = rel / q.t[t].cols;
+        const int c = (int)(rel - r * q.t[t].cols);
+        float v4[4] = {pi.x, pi.y, pi.z, pi.w};
+        for (int pl = 0; pl < q.t[t].planes; ++pl) {
+          const __nv_bfloat162 h0 = __floats2bfloat162_rn(v4[0], v4[1]), h1 = __floats2bfloat162_rn(v4[2], v4[3]);
+          const uint32_t u0 = *reinterpret_cast<const uint32_t*>(&h0), u1 = *reinterpret_cast<const uint32_t*>(&h1);
+          *reinterpret_cast<uint2*>(q.t[t].base + pl * q.t[t].plane_stride + r * q.t[t].ld + c) = make_uint2(u0, u1);
+          v4[0] -= __uint_as_float(u0 << 16);
+          v4[1] -= __uint_as_float(u0 & 0xFFFF0000u);
+          v4[2] -= __uint_as_float(u1 << 16);
+          v4[3] -= __uint_as_float(u1 & 0xFFFF0000u);
+        }
+      }
+  }
+  // the last CTA to finish bumps the step counter (every CTA has read it by then)
+  __shared__ bool last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) last = atomicAdd(q.done, 1u) == gridDim.x - 1;
+  __syncthreads();
+  if (last && threadIdx.x == 0) {
+    *q.step_dev += 1;
+    *q.done = 0u;
+  }
+}
+
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
 static int planes_ok(const mvae_planes* p, int rows, int cols) {
@@ -241,9 +386,14 @@ extern "C" int mvae_elbo_reduce(int64_t B, int32_t C, const float* bce, const fl
                                 void* stream) {
   if (B < 0 || C < 1 || C > MVAE_MAX_COMPONENTS || !out) return MVAE_ERR_INVALID_ARGUMENT;
   cudaStream_t s = as_stream(stream);
+  if (B > 0 && (!bce || !kl)) return MVAE_ERR_INVALID_ARGUMENT;
+  if (B > 0 && B <= 65536) {
+    elbo_small_kernel<<<1, 1024, sizeof(float) * (33 * (3 + C)), s>>>((int)B, C, bce, kl, beta, out);
+    MVAE_LAUNCH_CHECK();
+    return MVAE_OK;
+  }
   MVAE_CUDA_TRY(cudaMemsetAsync(out, 0, sizeof(float) * (3 + C), s));
   if (B == 0) return MVAE_OK;
-  if (!bce || !kl) return MVAE_ERR_INVALID_ARGUMENT;
   DeviceInfo di;
   int rc = get_device_info(&di);
   if (rc != MVAE_OK) return rc;
@@ -322,10 +472,77 @@ extern "C" int mvae_split_planes(const float* src, int64_t ld_src, int32_t R, in
     if (rc != MVAE_OK) return rc;
     t = *dst_transposed;
   }
+  if (!dst_transposed && (K & 7) == 0 && (ld_src & 3) == 0 && aligned16(src)) {
+    DeviceInfo di;
+    int rc = get_device_info(&di);
+    if (rc != MVAE_OK) return rc;
+    const int64_t want = ((int64_t)R * (K / 8) + 255) / 256;
+    const int g1 = (int)(want < (int64_t)di.sm_count * 8 ? want : (int64_t)di.sm_count * 8);
+    split_rows_kernel<<<g1, 256, 0, as_stream(stream)>>>(src, ld_src, R, K / 8, d);
+    MVAE_LAUNCH_CHECK();
+    return MVAE_OK;
+  }
   dim3 grid((K + 31) / 32, (R + 31) / 32);
   if (grid.y > 65535) return MVAE_ERR_UNSUPPORTED;
   split_kernel<<<grid, 256, 0, as_stream(stream)>>>(src, ld_src, R, K, d, t, dst != nullptr,
                                                     dst_transposed != nullptr);
+  MVAE_LAUNCH_CHECK();
+  return MVAE_OK;
+}
+
+extern "C" int mvae_opt_step_fused(int64_t n, float* param, const float* grad, float* exp_avg, float* exp_avg_sq,
+                                   float lr, float beta1, float beta2, float eps, int32_t* step_dev,
+                                   uint32_t* done_counter, float* radius, const float* gradius,
+                                   const float* radius_mask, float radius_lr, int32_t C, int32_t n_targets,
+                                   const int64_t* target_begin, const int32_t* target_rows,
+                                   const mvae_planes* targets, void* stream) {
+  if (n < 0 || (n & 3) || !step_dev || !done_counter || n_targets < 0 || n_targets > 4 || C < 0)
+    return MVAE_ERR_INVALID_ARGUMENT;
+  if (n > 0 && (!param || !grad || !exp_avg || !exp_avg_sq)) return MVAE_ERR_INVALID_ARGUMENT;
+  if (!aligned16(param) || !aligned16(grad) || !aligned16(exp_avg) || !aligned16(exp_avg_sq)) return MVAE_ERR_ALIGNMENT;
+  if (radius && radius_lr != 0.f && !gradius) return MVAE_ERR_INVALID_ARGUMENT;
+  OptParams q;
+  memset(&q, 0, sizeof(q));
+  q.n4 = n / 4;
+  q.p = param;
+  q.g = grad;
+  q.m = exp_avg;
+  q.v = exp_avg_sq;
+  q.lr = lr;
+  q.b1 = beta1;
+  q.b2 = beta2;
+  q.eps = eps;
+  q.step_dev = step_dev;
+  q.done = done_counter;
+  q.radius = radius;
+  q.gradius = gradius;
+  q.radius_mask = radius_mask;
+  q.radius_lr = radius_lr;
+  q.C = C;
+  q.n_targets = n_targets;
+  for (int t = 0; t < n_targets; ++t) {
+    if (!target_begin || !target_rows || !targets) return MVAE_ERR_INVALID_ARGUMENT;
+    const mvae_planes& pl = targets[t];
+    int rc = planes_ok(&pl, target_rows[t], pl.cols);
+    if (rc != MVAE_OK) return rc;
+    if ((target_begin[t] & 3) || (pl.cols & 3) || target_begin[t] < 0 ||
+        target_begin[t] + (int64_t)target_rows[t] * pl.cols > n)
+      return MVAE_ERR_ALIGNMENT;
+    q.t[t].begin = target_begin[t];
+    q.t[t].end = target_begin[t] + (int64_t)target_rows[t] * pl.cols;
+    q.t[t].cols = pl.cols;
+    q.t[t].ld = pl.ld;
+    q.t[t].planes = pl.planes;
+    q.t[t].base = pl.base;
+    q.t[t].plane_stride = pl.planes > 1 ? pl.plane_stride : 0;
+  }
+  DeviceInfo di;
+  int rc = get_device_info(&di);
+  if (rc != MVAE_OK) return rc;
+  const int64_t want = (q.n4 + 255) / 256;
+  int grid = (int)(want < (int64_t)di.sm_count * 4 ? want : (int64_t)di.sm_count * 4);
+  if (grid < 1) grid = 1;
+  opt_fused_kernel<<<grid, 256, 0, as_stream(stream)>>>(q);
   MVAE_LAUNCH_CHECK();
   return MVAE_OK;
 }

@@ -360,3 +360,19 @@ def dp_adam_step(comm: "L.DpComm", n_net: int, n_tail: int, C: int, exp_avg, exp
                                    _ptr(tail_out), _ptr(sync_words), _stream())
     L.check(rc, "mvae_dp_adam_step")
     _LAUNCHES[0] += 1
+
+
+def opt_step_fused(param, grad, exp_avg, exp_avg_sq, lr, beta1, beta2, eps, step_dev, done_counter, radius, gradius,
+                   radius_mask, radius_lr: float, targets):
+    """Adam + radii SGD + weight-plane refresh + step counter in one launch (mvae_opt_step_fused).
+    targets: list of (flat offset, rows, PlaneBuf)."""
+    nt = len(targets)
+    begins = (ctypes.c_int64 * max(nt, 1))(*[t[0] for t in targets])
+    rows = (ctypes.c_int32 * max(nt, 1))(*[t[1] for t in targets])
+    planes = (L.Planes * max(nt, 1))(*[t[2].struct() for t in targets])
+    C = radius.numel() if radius is not None else 0
+    rc = L.lib().mvae_opt_step_fused(param.numel(), _ptr(param), _ptr(grad), _ptr(exp_avg), _ptr(exp_avg_sq), lr, beta1,
+                                     beta2, eps, _ptr(step_dev), _ptr(done_counter), _ptr(radius), _ptr(gradius),
+                                     _ptr(radius_mask), radius_lr, C, nt, begins, rows, planes, _stream())
+    L.check(rc, "mvae_opt_step_fused")
+    _LAUNCHES[0] += 1

@@ -470,7 +470,7 @@ class FusedFeedForwardVAE(nn.Module):
             if not fused:
                 self._attach_grads()
             optimizer.step()
-            self._planes_stale = True
+            self._planes_stale = not getattr(optimizer, "planes_fresh", False)
 
     @torch.no_grad()
     def train_epoch(self, optimizer, batches, beta: float, eps_batches=None) -> List[BatchStatsFloat]:
@@ -589,7 +589,8 @@ class FusedFeedForwardVAE(nn.Module):
             saved = optimizer.step_count
             with torch.cuda.graph(gb):
                 optimizer.step()
-                self.refresh_weight_planes()
+                if not getattr(optimizer, "planes_fresh", False):
+                    self.refresh_weight_planes()
             optimizer.step_count = saved  # capture does not execute
             n2 = ops.launch_count()
             entry = self._graphs[key] = (ga, gb, n1 - n0, n2 - n1)
@@ -635,6 +636,8 @@ class FusedCurvatureOptimizer:
         self.step_dev = torch.zeros(1, device=model._flat.device, dtype=torch.int32)  # 1-based after the first step
         self.param_groups = [{"params": [p for _, p in model._net_params()], "lr": learning_rate}]
         self._dp = self._dp_tail = self._dp_sync = None  # set by parallel.attach_p2p
+        self._done = torch.zeros(1, device=model._flat.device, dtype=torch.int32)
+        self.planes_fresh = False  # True after a step that also refreshed the model's weight planes
 
     def zero_grad(self) -> None:
         pass  # the backward kernels overwrite / zero the bucket themselves
@@ -654,11 +657,16 @@ class FusedCurvatureOptimizer:
                              self.betas[0], self.betas[1], self.eps, self.step_dev, m._rflat,
                              self.curvature_lr if self.curvature_step_enabled() else 0.0, m._radius_mask,
                              self._dp_tail, self._dp_sync)
+            self.planes_fresh = False
             return
-        ops.adam_step_dev(m._flat, m._gnet, self.exp_avg, self.exp_avg_sq, self.lr, self.step_dev, self.betas[0],
-                          self.betas[1], self.eps)
-        if self.curvature_step_enabled():
-            ops.sgd_step(m._rflat, m._gradius, self.curvature_lr)  # fixed radii receive no gradient (masked below)
+        # Adam + the radii's SGD step + the refresh of the GEMM weight planes + the step counter: one launch
+        # (fixed radii receive no gradient: radius_mask)
+        targets = [(m._slices["fc_e0.weight"][0], m.h_dim, m.We0p), (m._slices["fc_logits.weight"][0], m.in_dim, m.Wlp)]
+        ops.opt_step_fused(m._flat, m._gnet, self.exp_avg, self.exp_avg_sq, self.lr, self.betas[0], self.betas[1],
+                           self.eps, self.step_dev, self._done, m._rflat, m._gradius, m._radius_mask,
+                           self.curvature_lr if self.curvature_step_enabled() else 0.0, targets)
+        m._planes_stale = False
+        self.planes_fresh = True
 
     def state_dict(self):
         return {"exp_avg": self.exp_avg, "exp_avg_sq": self.exp_avg_sq, "step": int(self.step_dev.item())}
