@@ -207,6 +207,12 @@ typedef struct mvae_gemm_args {
   const uint16_t* mask;    /* RELU_MASK: bf16 [M, ld_mask] (plane 0 of the activation) */
   int64_t ld_mask;
   float* rowsum;           /* BCE/NLL: [M] accumulated (+=) row sums                   */
+  /* Tile policy overrides (0 = automatic), for callers that time a few candidates once per shape and keep the best
+   * (the shapes of this workload are launch- and L2-bound, the best tile depends on M, N, K and the operand layout):
+   * tile_n = BLOCK_N (multiple of 16, 16..256); ctas_per_sm = 1 (deep pipeline) or 2 (co-resident CTAs overlap
+   * epilogue and main loop).  Requests that do not fit shared memory fall back to the automatic choice. */
+  int32_t tile_n;
+  int32_t ctas_per_sm;
 } mvae_gemm_args;
 
 int mvae_gemm(const mvae_gemm_args* args, void* stream);

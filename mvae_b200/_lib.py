@@ -44,7 +44,8 @@ class GemmArgs(ctypes.Structure):
                 ("split_k", ctypes.c_int32), ("bias", ctypes.c_void_p), ("out_f32", ctypes.c_void_p),
                 ("ld_out", ctypes.c_int64), ("out_col", ctypes.c_void_p), ("col_split", ctypes.c_int32),
                 ("out_planes", Planes), ("aux", ctypes.c_void_p), ("ld_aux", ctypes.c_int64),
-                ("mask", ctypes.c_void_p), ("ld_mask", ctypes.c_int64), ("rowsum", ctypes.c_void_p)]
+                ("mask", ctypes.c_void_p), ("ld_mask", ctypes.c_int64), ("rowsum", ctypes.c_void_p),
+                ("tile_n", ctypes.c_int32), ("ctas_per_sm", ctypes.c_int32)]
 
 
 DP_MAX_RANKS, DP_HANDLE_BYTES = 8, 64

@@ -14,6 +14,8 @@
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <mutex>
@@ -567,6 +569,13 @@ extern "C" int mvae_gemm(const mvae_gemm_args* a, void* stream) {
     const int64_t tiles = (int64_t)((a->M + kBlockM - 1) / kBlockM) * ((a->N + p.block_n - 1) / p.block_n);
     if (tiles * (a->split_k > 1 ? a->split_k : 1) <= di.sm_count && a->split_k != 0) smem_budget = smem_one;
   }
+  // caller's tile policy (mvae_gemm_args.tile_n / ctas_per_sm), honoured when it fits
+  if (a->ctas_per_sm == 1) smem_budget = smem_one;
+  if (a->ctas_per_sm == 2) smem_budget = smem_two;
+  if (a->tile_n >= 16 && a->tile_n <= 256 && (a->tile_n & 15) == 0 && stage_bytes_of(a->tile_n) <= smem_budget)
+    p.block_n = a->tile_n;
+  else if (a->ctas_per_sm == 1 && stage_bytes_of(p.block_n) > smem_budget)
+    smem_budget = smem_one;
   p.b_tile_bytes = p.b_major == MVAE_K_MAJOR ? p.block_n * 128 : round_up(p.block_n, 64) * 128;
   const int stage_bytes = p.a_planes * kATileBytes + p.b_planes * p.b_tile_bytes;
   p.kb_total = (a->K + kBlockK - 1) / kBlockK;

@@ -251,9 +251,14 @@ def split_planes(src: torch.Tensor, dst: Optional[PlaneBuf] = None, dst_t: Optio
 def gemm(a: PlaneBuf, b: PlaneBuf, M: int, N: int, K: int, a_major: int = L.K_MAJOR, b_major: int = L.K_MAJOR,
          epilogue: int = L.EPI_STORE, split_k: int = 1, bias=None, out_f32=None, ld_out: Optional[int] = None,
          out_col=None, col_split: int = -1, out_planes: Optional[PlaneBuf] = None, aux=None, mask: Optional[PlaneBuf] = None,
-         rowsum=None, a_planes: Optional[int] = None, b_planes: Optional[int] = None):
-    """D[M,N] = sum_k A[m,k] B[n,k] on tcgen05 tensor cores with a fused epilogue (mvae_gemm)."""
+         rowsum=None, a_planes: Optional[int] = None, b_planes: Optional[int] = None, tile: Optional[tuple] = None):
+    """D[M,N] = sum_k A[m,k] B[n,k] on tcgen05 tensor cores with a fused epilogue (mvae_gemm).
+    tile = (BLOCK_N, CTAs per SM[, split_k]) overrides the automatic tile policy (0 = automatic)."""
     g = L.GemmArgs()
+    if tile is not None:
+        g.tile_n, g.ctas_per_sm = int(tile[0]), int(tile[1])
+        if len(tile) > 2 and split_k != 1 and epilogue == L.EPI_STORE:
+            split_k = int(tile[2])
     g.a = a.struct(rows=M if a_major == L.K_MAJOR else K, cols=K if a_major == L.K_MAJOR else M, planes=a_planes)
     g.b = b.struct(rows=N if b_major == L.K_MAJOR else K, cols=K if b_major == L.K_MAJOR else N, planes=b_planes)
     g.a_major, g.b_major = a_major, b_major

@@ -18,6 +18,7 @@ Parameters keep the reference's names and shapes (state_dict round-trips, SURVEY
 into one flat fp32 buffer; gradients are views into one flat bucket [net grads | radius grads | ELBO stats] so that
 data-parallel training needs a single SUM all-reduce per step (mvae_b200/parallel.py).
 """
+import os
 from typing import List, Optional, Tuple
 
 import torch
@@ -172,6 +173,7 @@ class FusedFeedForwardVAE(nn.Module):
             raise NotImplementedError("product manifolds with more than 64 head outputs / latent coordinates")
         self._ws = {}
         self._graphs = {}
+        self._gemm_tiles = {}
         self._eps_override: Optional[Tensor] = None
         self._flat = None
         self.check_finite = False
@@ -268,6 +270,7 @@ class FusedFeedForwardVAE(nn.Module):
         self._planes_stale = True
         self._ws = {}
         self._graphs = {}
+        self._gemm_tiles = {}
         # heads + manifold chain + fc_d0 as one kernel per direction (mvae_latent_forward / _backward)
         self.fused_latent = (H % 8 == 0) and P <= 64 and Sd <= 64
 
@@ -310,7 +313,8 @@ class FusedFeedForwardVAE(nn.Module):
         if self._planes_stale:
             self.refresh_weight_planes()
         ops.split_planes(ws.x, ws.xp)
-        ops.gemm(ws.xp, self.We0p, B, H, D, epilogue=L.EPI_BIAS_RELU, bias=self.fc_e0.bias.data, out_planes=ws.hp)
+        self._gemm("e0_fwd", ws.xp, self.We0p, B, H, D, epilogue=L.EPI_BIAS_RELU, bias=self.fc_e0.bias.data,
+                   out_planes=ws.hp)
         if self.fused_latent and not want_mu_sigma:
             # heads + manifold chain + fc_d0/relu in ONE kernel: ml, z, kl kept for the backward pass / statistics
             ops.latent_forward(self.desc, ws.hp, self.Wh, self.bh, ws.eps, self._rflat, self.fc_d0.weight.data,
@@ -327,7 +331,7 @@ class FusedFeedForwardVAE(nn.Module):
                               act=ops.ACT_RELU, out_planes=ws.ddp)
         ws.bce.zero_()
         epi = L.EPI_BCE_ROWSUM if self.recon_kind == "bce" else L.EPI_NLL_ROWSUM
-        ops.gemm(ws.ddp, self.Wlp, B, D, H, epilogue=epi, bias=self.fc_logits.bias.data, aux=ws.x, rowsum=ws.bce,
+        self._gemm("logits_fwd", ws.ddp, self.Wlp, B, D, H, epilogue=epi, bias=self.fc_logits.bias.data, aux=ws.x, rowsum=ws.bce,
                  out_planes=ws.gLp if train else None, out_f32=logits)
         ops.elbo_reduce(ws.bce, ws.kl, beta, out=self._stats)
 
@@ -336,9 +340,10 @@ class FusedFeedForwardVAE(nn.Module):
         self._bucket[:self._n_net + C].zero_()
         MN = L.MN_MAJOR
         # fc_logits: gW = gL^T dd (+ bias from the ones column of dd), then gdd = (gL W) * 1[dd > 0]
-        ops.gemm(ws.gLp, ws.ddp, D, H + 1, B, a_major=MN, b_major=MN, split_k=0, out_f32=self.gWl, out_col=self.gbl,
+        self._gemm("logits_wgrad", ws.gLp, ws.ddp, D, H + 1, B, a_major=MN, b_major=MN, split_k=0, out_f32=self.gWl, out_col=self.gbl,
                  col_split=H)
-        ops.gemm(ws.gLp, self.Wlp, B, H, D, b_major=MN, epilogue=L.EPI_RELU_MASK, mask=ws.ddp, out_planes=ws.gddp)
+        self._gemm("logits_dgrad", ws.gLp, self.Wlp, B, H, D, b_major=MN, epilogue=L.EPI_RELU_MASK, mask=ws.ddp,
+                   out_planes=ws.gddp)
         if self.fused_latent:
             # fc_d0 dgrad + wgrad, manifold reverse sweep (d(-ELBO)/d kl = beta), heads dgrad + wgrad: ONE kernel
             ops.latent_backward(self.desc, ws.gddp, ws.hp, self.Wh, self.fc_d0.weight.data, ws.ml, ws.eps, self._rflat,
@@ -357,8 +362,52 @@ class FusedFeedForwardVAE(nn.Module):
             ops.skinny_wgrad(ws.gml, P, (ws.hp, 2), H + 1, self.gWh, H, 1, out_col=self.gbh, col_split=H)
             ops.skinny_expand(ws.gml, self.Wh, 1, H, K=P, N=H, act=ops.ACT_MASK, mask=ws.hp, out_planes=ws.ghp)
         # fc_e0 (no dgrad into x)
-        ops.gemm(ws.ghp, ws.xp, H, D + 1, B, a_major=MN, b_major=MN, split_k=0, out_f32=self.gWe0,
+        self._gemm("e0_wgrad", ws.ghp, ws.xp, H, D + 1, B, a_major=MN, b_major=MN, split_k=0, out_f32=self.gWe0,
                  out_col=self.gbe0, col_split=D, b_planes=2)
+
+    # ------------------------------------------------------------------------------------------ GEMM tile policy
+    # The five big GEMMs of a step are launch- and L2-bound at these shapes and their best tile (BLOCK_N, CTAs per SM,
+    # split-K) depends on M, N, K and the operand layouts: each call site times a handful of candidates ONCE per batch
+    # size (CUDA events, first eager step) and keeps the fastest.  MVAE_GEMM_AUTOTUNE=0 keeps the automatic policy.
+    _GEMM_TILES = [None, (48, 2), (64, 2), (96, 1), (112, 1), (112, 2), (128, 1), (208, 1)]
+    _GEMM_TILES_SPLITK = [None, (64, 2, 0), (64, 2, 4), (64, 2, 6), (80, 1, 0), (96, 1, 0), (112, 1, 0), (128, 1, 0)]
+    autotune_gemm = os.environ.get("MVAE_GEMM_AUTOTUNE", "1") != "0"
+
+    def _gemm(self, site: str, a, b, M: int, N: int, K: int, **kw) -> None:
+        key = (site, M, N, K)
+        if key not in self._gemm_tiles:
+            if self.autotune_gemm and not torch.cuda.is_current_stream_capturing():
+                self._gemm_tiles[key] = self._tune_gemm(a, b, M, N, K, kw)
+            else:
+                return ops.gemm(a, b, M, N, K, **kw)
+        ops.gemm(a, b, M, N, K, tile=self._gemm_tiles[key], **kw)
+
+    def _tune_gemm(self, a, b, M: int, N: int, K: int, kw) -> Optional[tuple]:
+        acc = [t for t in (kw.get("rowsum"), kw.get("out_f32") if kw.get("split_k", 1) != 1 else None,
+                           kw.get("out_col") if kw.get("split_k", 1) != 1 else None) if t is not None]
+        saved = [t.clone() for t in acc]  # accumulating outputs are restored afterwards
+        cands = self._GEMM_TILES_SPLITK if kw.get("split_k", 1) != 1 else self._GEMM_TILES
+        best, best_ms = None, float("inf")
+        n0 = ops.launch_count()
+        for tile in cands:
+            try:
+                for _ in range(2):
+                    ops.gemm(a, b, M, N, K, tile=tile, **kw)
+                s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                s.record()
+                for _ in range(8):
+                    ops.gemm(a, b, M, N, K, tile=tile, **kw)
+                e.record()
+                e.synchronize()
+            except L.MvaeError:
+                continue
+            ms = s.elapsed_time(e)
+            if ms < best_ms:
+                best, best_ms = tile, ms
+        for t, sv in zip(acc, saved):
+            t.copy_(sv)
+        ops.add_launches(n0 - ops.launch_count())  # tuning launches are not part of any step
+        return best
 
     def _stage(self, ws: _Workspace, x: Tensor, eps: Optional[Tensor]) -> None:
         ws.x.copy_(x.reshape(ws.B, self.in_dim), non_blocking=True)  # H2D if x lives on the host

@@ -1,4 +1,4 @@
-"""Per-kernel time of one train step with a warm L2 (as inside the step's CUDA graph): every op of the step is recorded
+"""GEMM-only variant of step_breakdown.py (tile-policy sweeps through MVAE_GEMM_TUNE): per-kernel time of one train step with a warm L2 (as inside the step's CUDA graph): every op of the step is recorded
 once, then captured alone in a CUDA graph (REP back-to-back launches) and timed with CUDA events.
 usage: python scripts/step_breakdown.py [workload]"""
 import os
@@ -23,8 +23,7 @@ for _ in range(3):
 torch.cuda.synchronize()
 
 calls = []
-NAMES = ["split_planes", "gemm", "opt_step_fused", "latent_forward", "latent_backward", "skinny_rowdot", "skinny_expand", "skinny_wgrad", "pm_forward", "pm_backward",
-         "elbo_reduce", "adam_step_dev", "sgd_step", "recon_loss"]
+NAMES = ["gemm"]
 orig = {n: getattr(ops, n) for n in NAMES if hasattr(ops, n)}
 
 
@@ -73,5 +72,5 @@ for i, (name, fn, a, k) in enumerate(calls):
     rows.append((name, shape, us))
     total += us
 for name, shape, us in rows:
-    print(f"{name:16s} {us:8.2f} us  {100 * us / total:5.1f}%  {shape}")
-print(f"sum {total:.1f} us over {len(rows)} ops (+ torch memsets / normal_ not listed)")
+    print(f"{os.environ.get('MVAE_GEMM_TUNE', 'auto'):10s} {us:8.2f} us  {shape}")
+print(f"{os.environ.get('MVAE_GEMM_TUNE', 'auto'):10s} sum {total:.1f} us")
