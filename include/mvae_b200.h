@@ -337,11 +337,13 @@ int mvae_dp_ipc_close(void* peer_ptr);
  * curvature optimizers do not step) on the summed gradient times radius_mask (NULL = ones).  tail_out [n_tail]: the
  * summed tail (radius grads, then bce, kl, elbo, kl_c sums).  sync_words: 4 zero-initialised device words private to
  * this rank ([3] != 0 afterwards = a peer did not arrive within ~2 s; results are then undefined).
+ * targets: weight matrices whose split-bf16 planes are refreshed from the gathered parameters (as mvae_opt_step_fused).
  * Captured in a CUDA graph like any other launch; all ranks must launch it the same number of times. */
 int mvae_dp_adam_step(const mvae_dp_comm* comm, int64_t n_net, int32_t n_tail, int32_t C, float* exp_avg,
                       float* exp_avg_sq, float lr, float beta1, float beta2, float eps, int32_t* step_dev,
                       float* radius, float radius_lr, const float* radius_mask, float* tail_out, uint32_t* sync_words,
-                      void* stream);
+                      int32_t n_targets, const int64_t* target_begin, const int32_t* target_rows,
+                      const mvae_planes* targets, void* stream);
 
 /* Device attributes the host layer needs for grid sizing / reporting. */
 int mvae_device_info(int32_t* sm_count, int32_t* cc_major, int32_t* cc_minor);

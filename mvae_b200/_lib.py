@@ -96,7 +96,8 @@ PROTOTYPES = {
     "mvae_dp_ipc_open": (ctypes.c_int, [ctypes.c_char_p, ctypes.POINTER(ctypes.c_void_p)]),
     "mvae_dp_ipc_close": (ctypes.c_int, [_vp]),
     "mvae_dp_adam_step": (ctypes.c_int, [ctypes.POINTER(DpComm), _i64, _i32, _i32, _vp, _vp, _f32, _f32, _f32, _f32, _vp,
-                                         _vp, _f32, _vp, _vp, _vp, _vp]),
+                                         _vp, _f32, _vp, _vp, _vp, _i32, ctypes.POINTER(_i64), ctypes.POINTER(_i32),
+                                         ctypes.POINTER(Planes), _vp]),
     "mvae_device_info": (ctypes.c_int, [ctypes.POINTER(_i32), ctypes.POINTER(_i32), ctypes.POINTER(_i32)]),
 }
 

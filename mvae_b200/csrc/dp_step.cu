@@ -19,6 +19,7 @@
 // Everything the kernel needs to know about the step (Adam step count, barrier epoch) lives on the device, so the launch
 // is captured once in the step's CUDA graph.  Spin loops are bounded (clock64) and raise an error word instead of
 // hanging the GPU if a peer never arrives.
+#include <cuda_bf16.h>
 #include <math.h>
 #include <string.h>
 
@@ -28,6 +29,13 @@ namespace mvae {
 
 constexpr int kDpThreads = 512;
 constexpr int kDpFlagStride = 32;  // uint32 per flag slot (one 128-byte line each)
+
+struct DpPlaneTarget {
+  int64_t begin, end;  // float range of the flat parameter buffer holding a [rows, cols] matrix (both % 4 == 0)
+  int cols, ld, planes;
+  uint16_t* base;
+  int64_t plane_stride;
+};
 
 struct DpParams {
   mvae_dp_comm comm;
@@ -44,6 +52,8 @@ struct DpParams {
   float* tail_out;
   uint32_t* sync;    // local: [0] epoch, [1] arrival counter, [2] release word, [3] error
   long long spin_limit;
+  int n_targets;     // weight matrices whose split-bf16 planes are refreshed after the all-gather
+  DpPlaneTarget t[4];
 };
 
 __device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
@@ -185,6 +195,27 @@ __global__ void __launch_bounds__(kDpThreads) dp_adam_kernel(const __grid_consta
     p.sync[0] = epoch + 1u;
     *p.step_dev = step;
   }
+  // ---- every slice of the parameters has arrived: refresh the split-bf16 planes of the GEMM weights locally ----
+  for (int t = 0; t < p.n_targets; ++t) {
+    const DpPlaneTarget& tg = p.t[t];
+    const int64_t n4 = (tg.end - tg.begin) >> 2;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+      const float4 w = ld_peer4(p.comm.flat[rank] + tg.begin + 4 * i);  // peers wrote it: not through L1
+      const int64_t rel = 4 * i;
+      const int64_t r = rel / tg.cols;
+      const int c = (int)(rel - r * tg.cols);
+      float v4[4] = {w.x, w.y, w.z, w.w};
+      for (int pl = 0; pl < tg.planes; ++pl) {
+        const __nv_bfloat162 h0 = __floats2bfloat162_rn(v4[0], v4[1]), h1 = __floats2bfloat162_rn(v4[2], v4[3]);
+        const uint32_t u0 = *reinterpret_cast<const uint32_t*>(&h0), u1 = *reinterpret_cast<const uint32_t*>(&h1);
+        *reinterpret_cast<uint2*>(tg.base + pl * tg.plane_stride + r * tg.ld + c) = make_uint2(u0, u1);
+        v4[0] -= __uint_as_float(u0 << 16);
+        v4[1] -= __uint_as_float(u0 & 0xFFFF0000u);
+        v4[2] -= __uint_as_float(u1 << 16);
+        v4[3] -= __uint_as_float(u1 & 0xFFFF0000u);
+      }
+    }
+  }
 }
 
 }  // namespace mvae
@@ -233,7 +264,8 @@ extern "C" int mvae_dp_ipc_close(void* peer_ptr) {
 extern "C" int mvae_dp_adam_step(const mvae_dp_comm* comm, int64_t n_net, int32_t n_tail, int32_t C, float* exp_avg,
                                  float* exp_avg_sq, float lr, float beta1, float beta2, float eps, int32_t* step_dev,
                                  float* radius, float radius_lr, const float* radius_mask, float* tail_out,
-                                 uint32_t* sync_words, void* stream) {
+                                 uint32_t* sync_words, int32_t n_targets, const int64_t* target_begin,
+                                 const int32_t* target_rows, const mvae_planes* targets, void* stream) {
   if (!comm || comm->world < 1 || comm->world > MVAE_DP_MAX_RANKS || comm->rank < 0 || comm->rank >= comm->world ||
       n_net < 0 || (n_net & 3) || n_tail < 0 || C < 0 || C > n_tail || !exp_avg || !exp_avg_sq || !step_dev ||
       !tail_out || !sync_words)
@@ -267,6 +299,24 @@ extern "C" int mvae_dp_adam_step(const mvae_dp_comm* comm, int64_t n_net, int32_
   p.radius_mask = radius_mask;
   p.tail_out = tail_out;
   p.sync = sync_words;
+  if (n_targets < 0 || n_targets > 4 || (n_targets > 0 && (!target_begin || !target_rows || !targets)))
+    return MVAE_ERR_INVALID_ARGUMENT;
+  p.n_targets = n_targets;
+  for (int t = 0; t < n_targets; ++t) {
+    const mvae_planes& pl = targets[t];
+    if (!pl.base || pl.planes < 1 || pl.planes > 3 || pl.rows != target_rows[t] || pl.ld < pl.cols)
+      return MVAE_ERR_INVALID_ARGUMENT;
+    if ((target_begin[t] & 3) || (pl.cols & 3) || (pl.ld & 7) || (pl.plane_stride & 7) || target_begin[t] < 0 ||
+        target_begin[t] + (int64_t)target_rows[t] * pl.cols > n_net || (reinterpret_cast<uintptr_t>(pl.base) & 15))
+      return MVAE_ERR_ALIGNMENT;
+    p.t[t].begin = target_begin[t];
+    p.t[t].end = target_begin[t] + (int64_t)target_rows[t] * pl.cols;
+    p.t[t].cols = pl.cols;
+    p.t[t].ld = pl.ld;
+    p.t[t].planes = pl.planes;
+    p.t[t].base = pl.base;
+    p.t[t].plane_stride = pl.planes > 1 ? pl.plane_stride : 0;
+  }
   p.spin_limit = 4000000000ll;  // ~2 s of SM clocks: a peer that has not arrived by then never will
   // The CTAs spin on each other, so all of them must be resident at once: a FIXED grid of at most one CTA per SM
   // (the barrier counters assume the same grid on every launch; 64 registers x 512 threads fit one SM).

@@ -358,11 +358,17 @@ def skinny_wgrad(small, S: int, wide, Wd: int, out, out_stride_s: int, out_strid
 
 
 def dp_adam_step(comm: "L.DpComm", n_net: int, n_tail: int, C: int, exp_avg, exp_avg_sq, lr: float, beta1: float,
-                 beta2: float, eps: float, step_dev, radius, radius_lr: float, radius_mask, tail_out, sync_words):
-    """Gradient reduce-scatter + Adam + parameter all-gather over peer memory in one kernel (mvae_dp_adam_step)."""
+                 beta2: float, eps: float, step_dev, radius, radius_lr: float, radius_mask, tail_out, sync_words,
+                 targets=()):
+    """Gradient reduce-scatter + Adam + parameter all-gather over peer memory + weight-plane refresh in one kernel
+    (mvae_dp_adam_step).  targets: list of (flat offset, rows, PlaneBuf)."""
+    nt = len(targets)
+    begins = (ctypes.c_int64 * max(nt, 1))(*[t[0] for t in targets])
+    rows = (ctypes.c_int32 * max(nt, 1))(*[t[1] for t in targets])
+    planes = (L.Planes * max(nt, 1))(*[t[2].struct() for t in targets])
     rc = L.lib().mvae_dp_adam_step(ctypes.byref(comm), n_net, n_tail, C, _ptr(exp_avg), _ptr(exp_avg_sq), lr, beta1,
                                    beta2, eps, _ptr(step_dev), _ptr(radius), radius_lr, _ptr(radius_mask),
-                                   _ptr(tail_out), _ptr(sync_words), _stream())
+                                   _ptr(tail_out), _ptr(sync_words), nt, begins, rows, planes, _stream())
     L.check(rc, "mvae_dp_adam_step")
     _LAUNCHES[0] += 1
 

@@ -699,18 +699,19 @@ class FusedCurvatureOptimizer:
         graph and replayed."""
         m = self.model
         self.step_count += 1
+        targets = [(m._slices["fc_e0.weight"][0], m.h_dim, m.We0p), (m._slices["fc_logits.weight"][0], m.in_dim, m.Wlp)]
         if self._dp is not None:
             # data parallel over NVLink peer memory: gradient reduce-scatter + Adam on this rank's slice + parameter
             # all-gather + the radii's SGD step, one kernel (mvae_dp_adam_step)
             ops.dp_adam_step(self._dp, m._n_net, 2 * m.desc.C + 3, m.desc.C, self.exp_avg, self.exp_avg_sq, self.lr,
                              self.betas[0], self.betas[1], self.eps, self.step_dev, m._rflat,
                              self.curvature_lr if self.curvature_step_enabled() else 0.0, m._radius_mask,
-                             self._dp_tail, self._dp_sync)
-            self.planes_fresh = False
+                             self._dp_tail, self._dp_sync, targets)
+            m._planes_stale = False
+            self.planes_fresh = True
             return
         # Adam + the radii's SGD step + the refresh of the GEMM weight planes + the step counter: one launch
         # (fixed radii receive no gradient: radius_mask)
-        targets = [(m._slices["fc_e0.weight"][0], m.h_dim, m.We0p), (m._slices["fc_logits.weight"][0], m.in_dim, m.Wlp)]
         ops.opt_step_fused(m._flat, m._gnet, self.exp_avg, self.exp_avg_sq, self.lr, self.betas[0], self.betas[1],
                            self.eps, self.step_dev, self._done, m._rflat, m._gradius, m._radius_mask,
                            self.curvature_lr if self.curvature_step_enabled() else 0.0, targets)

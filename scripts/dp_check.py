@@ -20,6 +20,7 @@ def build(use_graph):
     m = vae.FusedFeedForwardVAE(H, components.parse_components(sig, False),
                                 data.GenericDataset(B, D, "bce", binary_inputs=True), False, device=dev)
     m.use_cuda_graph = use_graph
+    m.autotune_gemm = False  # identical tiles in every mode: local gradients are then bit-identical across modes
     o = vae.FusedCurvatureOptimizer(m, 1e-3, fixed_curvature=False, should_do_curvature_step=lambda: True)
     return m, o
 
