@@ -1,4 +1,6 @@
 // api.cu — status strings, ABI version, cached device attributes of libmvae_b200.so.
+#include <stdlib.h>
+
 #include <mutex>
 
 #include "mvae_common.cuh"
@@ -29,6 +31,14 @@ int get_device_info(DeviceInfo* out) {
   *out = cache[dev];
   if (out->cc_major != 10) return MVAE_ERR_NOT_SM100;
   return MVAE_OK;
+}
+
+bool pdl_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("MVAE_PDL");  // opt-in: measured neutral on the captured step (profiles/), kept for eager use
+    return e && e[0] == '1';
+  }();
+  return on;
 }
 
 }  // namespace mvae

@@ -121,6 +121,8 @@ __global__ void __launch_bounds__(1024) elbo_small_kernel(int B, int C, const fl
                                                           const float* __restrict__ kl, float beta,
                                                           float* __restrict__ out) {
   extern __shared__ float sh[];  // [32][3 + C] per-warp partials
+  pdl_launch_dependents();
+  pdl_wait();
   const int nout = 3 + C, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   float sb = 0.f, sk = 0.f, se = 0.f;
   for (int b = threadIdx.x; b < B; b += blockDim.x) {
@@ -245,6 +247,8 @@ __global__ void __launch_bounds__(256) split_kernel(const float* __restrict__ sr
 // 128-bit store per plane.
 __global__ void __launch_bounds__(256) split_rows_kernel(const float* __restrict__ src, int64_t ld_src, int R, int K8,
                                                          mvae_planes dst) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int64_t total = (int64_t)R * K8;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int r = (int)(i / K8), k = (int)(i - (int64_t)r * K8) * 8;
@@ -294,6 +298,8 @@ struct OptParams {
   PlaneTarget t[4];
 };
 __global__ void __launch_bounds__(256) opt_fused_kernel(const __grid_constant__ OptParams q) {
+  pdl_launch_dependents();
+  pdl_wait();
   const double st = (double)(*q.step_dev + 1);
   const float step_size = (float)((double)q.lr / (1.0 - pow((double)q.b1, st)));
   const float inv_bc2_sqrt = (float)(1.0 / sqrt(1.0 - pow((double)q.b2, st)));
@@ -388,7 +394,8 @@ extern "C" int mvae_elbo_reduce(int64_t B, int32_t C, const float* bce, const fl
   cudaStream_t s = as_stream(stream);
   if (B > 0 && (!bce || !kl)) return MVAE_ERR_INVALID_ARGUMENT;
   if (B > 0 && B <= 65536) {
-    elbo_small_kernel<<<1, 1024, sizeof(float) * (33 * (3 + C)), s>>>((int)B, C, bce, kl, beta, out);
+    MVAE_CUDA_TRY(launch_pdl(elbo_small_kernel, dim3(1), dim3(1024), sizeof(float) * (33 * (3 + C)), s, (int)B, C, bce, kl,
+                             beta, out));
     MVAE_LAUNCH_CHECK();
     return MVAE_OK;
   }
@@ -478,7 +485,7 @@ extern "C" int mvae_split_planes(const float* src, int64_t ld_src, int32_t R, in
     if (rc != MVAE_OK) return rc;
     const int64_t want = ((int64_t)R * (K / 8) + 255) / 256;
     const int g1 = (int)(want < (int64_t)di.sm_count * 8 ? want : (int64_t)di.sm_count * 8);
-    split_rows_kernel<<<g1, 256, 0, as_stream(stream)>>>(src, ld_src, R, K / 8, d);
+    MVAE_CUDA_TRY(launch_pdl(split_rows_kernel, dim3(g1), dim3(256), 0, as_stream(stream), src, ld_src, R, K / 8, d));
     MVAE_LAUNCH_CHECK();
     return MVAE_OK;
   }
@@ -542,7 +549,7 @@ extern "C" int mvae_opt_step_fused(int64_t n, float* param, const float* grad, f
   const int64_t want = (q.n4 + 255) / 256;
   int grid = (int)(want < (int64_t)di.sm_count * 4 ? want : (int64_t)di.sm_count * 4);
   if (grid < 1) grid = 1;
-  opt_fused_kernel<<<grid, 256, 0, as_stream(stream)>>>(q);
+  MVAE_CUDA_TRY(launch_pdl(opt_fused_kernel, dim3(grid), dim3(256), 0, as_stream(stream), q));
   MVAE_LAUNCH_CHECK();
   return MVAE_OK;
 }

@@ -224,6 +224,7 @@ __global__ void __launch_bounds__(kGemmThreads, 2)
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot_ptr;
+  pdl_wait();  // everything above is independent of the previous kernel; operands and epilogue inputs are not
 
   if (warp == 0) {
     // ===================================== TMA producer =====================================
@@ -357,6 +358,7 @@ __global__ void __launch_bounds__(kGemmThreads, 2)
     prefetch(0);
     mbar_wait(tmem_full_bar, 0);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    pdl_launch_dependents();  // main loop done: the next kernel's CTAs may take the SM resources this CTA frees soon
     float row_acc = 0.f;
     for (int c = 0; c < p.block_n; c += 16) {
       const int n = n0 + c;
@@ -633,7 +635,7 @@ extern "C" int mvae_gemm(const mvae_gemm_args* a, void* stream) {
   });
   MVAE_CUDA_TRY(attr_err);
   dim3 grid((a->M + kBlockM - 1) / kBlockM, (a->N + p.block_n - 1) / p.block_n, split);
-  gemm_tcgen05_kernel<<<grid, kGemmThreads, smem, as_stream(stream)>>>(map_a, map_b, p);
+  MVAE_CUDA_TRY(launch_pdl(gemm_tcgen05_kernel, grid, dim3(kGemmThreads), smem, as_stream(stream), map_a, map_b, p));
   MVAE_LAUNCH_CHECK();
   return MVAE_OK;
 }

@@ -204,10 +204,13 @@ __global__ void __launch_bounds__(kLatThreads) latent_forward_kernel(const __gri
   const int rows = (int)min((int64_t)R, p.B - row0);
   const int plane_elems = R * p.h_ld;
 
-  stage_items(info, p.desc, p.radius);
   if (tid == 0) {
     pm_mbar_init(bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  pdl_wait();  // the radii (previous optimizer step) and h (previous GEMM) are read from here on
+  stage_items(info, p.desc, p.radius);
+  if (tid == 0) {
     const uint32_t bytes = (uint32_t)(rows * p.h_ld) * 2u;
     pm_mbar_expect_tx(bar, bytes * (uint32_t)p.h_planes);
     for (int pl = 0; pl < p.h_planes; ++pl)
@@ -250,6 +253,7 @@ __global__ void __launch_bounds__(kLatThreads) latent_forward_kernel(const __gri
   for (int i = tid; i < rows * Sd; i += blockDim.x) p.z[row0 * Sd + i] = sZ[i];
   for (int i = tid; i < rows * C; i += blockDim.x) p.kl[row0 * C + i] = sKL[i];
 
+  pdl_launch_dependents();
   // ---- fc_d0 + relu -> planes: thread per column pair, the 16 rows unrolled in registers ----
   for (int n = 2 * tid; n < H; n += 2 * kLatThreads) {
     float a0[R], a1[R];
@@ -297,10 +301,13 @@ __global__ void __launch_bounds__(kLatThreads) latent_backward_kernel(const __gr
   const int g_elems = R * p.gdd_ld, h_elems = R * p.h_ld;
   const int hpl = p.h_planes < 2 ? p.h_planes : 2;
 
-  stage_items(info, p.desc, p.radius);
   if (tid == 0) {
     pm_mbar_init(bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  pdl_wait();
+  stage_items(info, p.desc, p.radius);
+  if (tid == 0) {
     const uint32_t gb = (uint32_t)(rows * p.gdd_ld) * 2u, hb = (uint32_t)(rows * p.h_ld) * 2u;
     pm_mbar_expect_tx(bar, gb * (uint32_t)p.gdd_planes + hb * (uint32_t)hpl);
     for (int pl = 0; pl < p.gdd_planes; ++pl)
@@ -383,6 +390,7 @@ __global__ void __launch_bounds__(kLatThreads) latent_backward_kernel(const __gr
   }
   __syncthreads();
 
+  pdl_launch_dependents();
   // ---- heads: gWh[q][k] += sum_r gml[r][q] h[r][k];  gh[r][k] = (sum_q gml[r][q] Wh[q][k]) 1[h[r][k] > 0] ----
   if (p.gbh)
     for (int q = tid; q < P; q += blockDim.x) {
@@ -487,7 +495,7 @@ static int launch_latent(LatParams& p, void* stream) {
   if (smem > 48 * 1024) MVAE_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int64_t grid = (p.B + R - 1) / R;
   if (grid > 0x7fffffff) return MVAE_ERR_UNSUPPORTED;
-  kern<<<(unsigned)grid, kLatThreads, smem, as_stream(stream)>>>(p);
+  MVAE_CUDA_TRY(launch_pdl(kern, dim3((unsigned)grid), dim3(kLatThreads), smem, as_stream(stream), p));
   MVAE_LAUNCH_CHECK();
   return MVAE_OK;
 }

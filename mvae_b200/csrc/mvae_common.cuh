@@ -46,6 +46,35 @@ static inline FastDiv make_fastdiv(uint32_t d) {
   f.magic = d <= 1 ? 0u : (uint32_t)(((1ull << 32) + d - 1) / d);
   return f;
 }
+// ---------------------------------------------------------------------------------------------------------
+// Programmatic dependent launch.  A train step is ~14 kernels of 5-30 us each inside one CUDA graph: with plain stream
+// order every kernel boundary costs launch latency plus the drain of the previous grid.  Kernels launched through
+// launch_pdl() may be scheduled while their predecessor is still running; they call pdl_launch_dependents() first (so
+// that THEIR successor can be scheduled early too), do whatever does not depend on the predecessor (barrier / TMEM
+// set-up), and then pdl_wait(), which returns once the predecessor grid has completed and its writes are visible.
+// Opt-in with MVAE_PDL=1 (inside the step's CUDA graph the launch latency is already hidden: measured neutral).
+bool pdl_enabled();
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                                     Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+#endif
+
 #ifdef __CUDACC__
 __device__ __forceinline__ uint32_t fastdiv(uint32_t n, FastDiv f) { return f.d <= 1 ? n : __umulhi(n, f.magic); }
 
