@@ -399,7 +399,11 @@ def run_ours(args):
                                                       out={"z": ws.z, "kl": ws.kl}), 20, flush)
         ach = Bbig * bytes_fwd / (ms_f * 1e-3) / 1e9
         line["roofline"] = {"kernel": "pm_forward_kernel", "bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"],
-                            "unit": "GB/s", "frac": ach / peaks["hbm_gbs"], "traffic": None,
+                            "unit": "GB/s", "frac": ach / peaks["hbm_gbs"],
+                            # dram__bytes_read.sum + dram__bytes_write.sum of this launch (same shape, 2^22 samples) from
+                            # the ncu --set full capture summarised in profiles/r01_ncu_prof_pm_d_pm2.md
+                            "traffic": (302.07e6 + 152.17e6) if (sig == "h2,s2,e2") else None,
+                            "algorithmic_bytes": Bbig * bytes_fwd,
                             "bytes_per_sample": bytes_fwd, "samples_per_launch": Bbig, "us_per_launch": ms_f * 1e3,
                             "us_at_config_batch": ms_f_cfg * 1e3, "peak_source": peaks["source"]}
         achb = Bbig * bytes_bwd / (ms_b * 1e-3) / 1e9
