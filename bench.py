@@ -263,6 +263,7 @@ def run_ours(args):
         raise SystemExit("bench.py needs a CUDA device (the mvae_b200 path has no CPU fallback)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa_bound = world > 1 and os.environ.get("MVAE_NUMA_BIND", "1") != "0" and parallel.bind_to_gpu_numa_node(local)
     sig, B, D, H, recon, fixed, desc = WORKLOADS[args.workload]
     peaks = measured_peaks()
     torch.manual_seed(0)
@@ -368,7 +369,7 @@ def run_ours(args):
             "config": {"workload": desc, "signature": sig, "batch_per_gpu": B, "global_batch": gb, "in_dim": D,
                        "h_dim": H, "parallelism": f"dp{world}", "l2": "flushed between timed steps (256 MiB memset)",
                        "cuda_graph": bool(model.use_cuda_graph), "optimizer": "Adam(1e-3) + SGD(1e-4) on radii",
-                       "collective": collective},
+                       "collective": collective, "numa_bound": bool(numa_bound)},
             "e2e": {"value": gb / (e2e_ms / 1e3), "unit": UNIT, "ms_per_step": e2e_ms,
                     "h2d_bytes_per_step": B * D * 4, "d2h_bytes_per_step": (3 + C) * 4,
                     "api": "model.train_epoch(optimizer, pinned host batches, beta): H2D of batch i+1 overlaps step i",

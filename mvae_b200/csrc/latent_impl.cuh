@@ -15,7 +15,7 @@
 // plane: one bulk asynchronous copy (TMA) per plane lands them in shared memory, where they serve both access
 // patterns — warp-per-row dot products (lanes along the hidden dimension, shuffle reduction) and thread-per-column
 // outer products (rows unrolled in registers).  The manifold arithmetic is pm_math.cuh through dispatch_item, one warp
-// per component, lane = row.  Weight gradients are accumulated per CTA in registers over its 16 rows and leave as
+// per component, lane = row.  Weight gradients are accumulated per CTA in registers over its rows and leave as
 // vector reductions (red.global.add.v2/.v4.f32).  All arithmetic is exact fp32 FMA on values reconstructed from the
 // planes (the sum of the bf16 planes is the fp32 value the producing GEMM computed, to 2^-24 with three planes).
 #pragma once
@@ -29,7 +29,7 @@
 
 namespace mvae {
 
-constexpr int kLatRows = 16;      // rows per CTA
+constexpr int kLatRows = 16;      // rows per CTA (8: twice the weight-gradient reductions, measured slower)
 constexpr int kLatThreads = 256;  // 8 warps
 
 struct LatParams {
@@ -399,13 +399,18 @@ __global__ void __launch_bounds__(kLatThreads) latent_backward_kernel(const __gr
       for (int r = 0; r < R; ++r) s += sGML[r * P + q];
       atomicAdd(p.gbh + q, s);
     }
-  for (int k = 2 * tid; k < H; k += 2 * kLatThreads) {
+  // (H % 4 == 0 and a 16-byte aligned gWh: lanes 2i, 2i+1 cover 4 consecutive floats; the loop bound is warp-uniform
+  // up to the last pair, whose partner then holds zeros)
+  const bool pair4 = (H & 3) == 0 && (reinterpret_cast<uintptr_t>(p.gWh) & 15) == 0;
+  for (int k0 = 0; k0 < H; k0 += 2 * kLatThreads) {
+    const int k = k0 + 2 * tid;
+    const bool live = k < H;
     float h0[R], h1[R], y0[R], y1[R];
     uint32_t mask = 0;
 #pragma unroll
     for (int r = 0; r < R; ++r) {
       float2 hv = make_float2(0.f, 0.f);
-      if (r < rows) {
+      if (r < rows && live) {
         hv = planes_load2(sH + r * p.h_ld + k, h_elems, hpl);
         // relu'(h): the leading plane is bf16(h) and h >= 0, so h > 0 <=> its bits are a positive number
         const uint32_t w = *reinterpret_cast<const uint32_t*>(sH + r * p.h_ld + k);
@@ -419,7 +424,7 @@ __global__ void __launch_bounds__(kLatThreads) latent_backward_kernel(const __gr
       y1[r] = 0.f;
     }
     for (int q = 0; q < P; ++q) {
-      const float2 w = __ldg(reinterpret_cast<const float2*>(p.Wh + (int64_t)q * H + k));
+      const float2 w = live ? __ldg(reinterpret_cast<const float2*>(p.Wh + (int64_t)q * H + k)) : make_float2(0.f, 0.f);
       float a = 0.f, b = 0.f;
 #pragma unroll
       for (int r = 0; r < R; ++r) {
@@ -429,11 +434,18 @@ __global__ void __launch_bounds__(kLatThreads) latent_backward_kernel(const __gr
         a = fmaf(g, h0[r], a);
         b = fmaf(g, h1[r], b);
       }
-      red_add2(p.gWh + (int64_t)q * H + k, a, b);
+      // adjacent lanes own adjacent column pairs: the even lane issues ONE 128-bit reduction for both (the
+      // reductions, not the arithmetic, bound this phase)
+      const float a2 = __shfl_down_sync(0xffffffffu, a, 1), b2 = __shfl_down_sync(0xffffffffu, b, 1);
+      if (pair4) {
+        if ((lane & 1) == 0 && live) red_add4(p.gWh + (int64_t)q * H + k, a, b, a2, b2);
+      } else if (live) {
+        red_add2(p.gWh + (int64_t)q * H + k, a, b);
+      }
     }
 #pragma unroll
     for (int r = 0; r < R; ++r)
-      if (r < rows)
+      if (r < rows && live)
         planes_store2(p.gh + (row0 + r) * p.gh_ld + k, p.gh_stride, p.gh_planes, ((mask >> (2 * r)) & 1u) ? y0[r] : 0.f,
                       ((mask >> (2 * r + 1)) & 1u) ? y1[r] : 0.f);
   }

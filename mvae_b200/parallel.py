@@ -27,6 +27,24 @@ def init_from_env(backend: str = None) -> tuple:
     return rank, world, local
 
 
+def bind_to_gpu_numa_node(local_rank: int) -> bool:
+    """Pin this process to the CPUs NVML reports as local to its GPU, so that the pinned host batches it allocates
+    afterwards (first touch) sit on the socket the GPU's PCIe root hangs off: with one process per GPU and eight
+    12.8 MB host->device copies per 0.25 ms step, cross-socket traffic is what saturates first."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        try:
+            uuid = str(torch.cuda.get_device_properties(local_rank).uuid)
+            h = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid).encode())
+        except Exception:
+            h = pynvml.nvmlDeviceGetHandleByIndex(local_rank)
+        pynvml.nvmlDeviceSetCpuAffinity(h)
+        return True
+    except Exception:
+        return False
+
+
 def shard_bounds(batch: int, rank: int, world: int) -> tuple:
     """Contiguous batch split: rank r owns rows [r*B/N, (r+1)*B/N) — remainder to the first ranks."""
     base, rem = divmod(batch, world)
