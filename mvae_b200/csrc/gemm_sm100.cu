@@ -376,7 +376,15 @@ __global__ void __launch_bounds__(kGemmThreads, 2)
       for (int j = 0; j < 16; ++j) y[j] = __uint_as_float(r[j]) + s_bias[c + j];
       switch (p.epilogue) {
         case MVAE_EPI_STORE: {
-          if (p.atomic_out) {
+          if (p.atomic_out && vec_out && n + 16 <= p.N && !(p.col_split >= n && p.col_split < n + 16)) {
+            // split-K partial sums: four 128-bit reductions per row and chunk instead of sixteen scalar atomics
+            float* dst = p.out_f32 + (int64_t)m * p.ld_out + n;
+#pragma unroll
+            for (int j = 0; j < 16; j += 4)
+              asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(dst + j), "f"(y[j]), "f"(y[j + 1]),
+                           "f"(y[j + 2]), "f"(y[j + 3])
+                           : "memory");
+          } else if (p.atomic_out) {
 #pragma unroll
             for (int j = 0; j < 16; ++j)
               if (n + j < p.N) {
