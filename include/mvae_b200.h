@@ -250,20 +250,21 @@ int mvae_skinny_wgrad(int64_t B, int32_t S, int32_t Wd, const float* small, int6
  *   ml = h Wh^T + bh            all fc_mean / fc_logvar heads (component.py:64,69), Wh [P, H], P = desc->ld_ml
  *   z, kl = mvae_pm_forward(ml, eps, radius)
  *   dd = relu(z Wd0^T + bd0)    fc_d0 (ffnn_vae.py:56), Wd0 [H, Sd], Sd = desc->ld_z, written as split planes
- * h: split planes of relu(fc_e0(x)) [B, H] (all of its planes are read).  Requirements: H % 8 == 0, P <= 64, Sd <= 64,
- * Wh 16-byte aligned.  Outputs ml [B, P], z [B, Sd], kl [B, C] are kept for the backward pass / the statistics. */
-int mvae_latent_forward(const mvae_pm_desc* desc, int64_t B, int32_t H, const mvae_planes* h, const float* Wh,
+ * h: relu(fc_e0(x)) as fp32 [B, ld_h] (the producing GEMM's epilogue writes it; 16-byte aligned, ld_h % 4 == 0).
+ * Requirements: H % 8 == 0, P <= 64, Sd <= 64, Wh 16-byte aligned.  Outputs ml [B, P], z [B, Sd], kl [B, C] are kept for the backward pass / the statistics. */
+int mvae_latent_forward(const mvae_pm_desc* desc, int64_t B, int32_t H, const float* h, int64_t ld_h, const float* Wh,
                         const float* bh, const float* eps, const float* radius, const float* Wd0, const float* bd0,
                         float* ml, float* z, float* kl, const mvae_planes* dd_out, uint32_t* nonfinite_flag,
                         void* stream);
 
-/* backward of the block for d(loss)/d(dd) = gdd (already masked by relu'(dd)) and d(loss)/d(kl) = gkl_scalar:
+/* backward of the block for d(loss)/d(dd) = gdd (fp32 [B, ld_gdd], already masked by relu'(dd)) and
+ * d(loss)/d(kl) = gkl_scalar:
  *   gz = gdd Wd0;  gml = mvae_pm_backward(ml, eps, radius, gz, gkl_scalar);  gh = (gml Wh) * 1[h > 0]  -> planes
  *   gWd0 [H, Sd] += gdd^T z;  gbd0 [H] += colsum(gdd);  gWh [P, H] += gml^T h;  gbh [P] += colsum(gml);
  *   gradius [C] += dR          (all ACCUMULATED: zero them first)
  * Requirements as above plus Wd0 / gWd0 16-byte and Wh / gWh / gbd0 8-byte aligned. */
-int mvae_latent_backward(const mvae_pm_desc* desc, int64_t B, int32_t H, const mvae_planes* gdd, const mvae_planes* h,
-                         const float* Wh, const float* Wd0, const float* ml, const float* eps, const float* radius,
+int mvae_latent_backward(const mvae_pm_desc* desc, int64_t B, int32_t H, const float* gdd, int64_t ld_gdd,
+                         const float* h, int64_t ld_h, const float* Wh, const float* Wd0, const float* ml, const float* eps, const float* radius,
                          const float* z, float gkl_scalar, const mvae_planes* gh_out, float* gWd0, float* gbd0,
                          float* gWh, float* gbh, float* gradius, void* stream);
 

@@ -77,11 +77,10 @@ PROTOTYPES = {
                                           ctypes.POINTER(Planes), _vp, _i64, _vp]),
     "mvae_skinny_wgrad": (ctypes.c_int, [_i64, _i32, _i32, _vp, _i64, _i32, _vp, _i64, ctypes.POINTER(Planes), _vp, _i64,
                                          _i64, _vp, _vp, _i32, _vp]),
-    "mvae_latent_forward": (ctypes.c_int, [ctypes.POINTER(PmDesc), _i64, _i32, ctypes.POINTER(Planes), _vp, _vp, _vp, _vp,
+    "mvae_latent_forward": (ctypes.c_int, [ctypes.POINTER(PmDesc), _i64, _i32, _vp, _i64, _vp, _vp, _vp, _vp,
                                            _vp, _vp, _vp, _vp, _vp, ctypes.POINTER(Planes), _vp, _vp]),
-    "mvae_latent_backward": (ctypes.c_int, [ctypes.POINTER(PmDesc), _i64, _i32, ctypes.POINTER(Planes),
-                                            ctypes.POINTER(Planes), _vp, _vp, _vp, _vp, _vp, _vp, _f32,
-                                            ctypes.POINTER(Planes), _vp, _vp, _vp, _vp, _vp, _vp]),
+    "mvae_latent_backward": (ctypes.c_int, [ctypes.POINTER(PmDesc), _i64, _i32, _vp, _i64, _vp, _i64, _vp, _vp, _vp,
+                                            _vp, _vp, _vp, _f32, ctypes.POINTER(Planes), _vp, _vp, _vp, _vp, _vp, _vp]),
     "mvae_recon_loss": (ctypes.c_int, [_i32, _i64, _i32, _vp, _vp, _vp, _vp, _vp]),
     "mvae_elbo_reduce": (ctypes.c_int, [_i64, _i32, _vp, _vp, _f32, _vp, _vp]),
     "mvae_adam_step": (ctypes.c_int, [_i64, _vp, _vp, _vp, _vp, _f32, _f32, _f32, _f32, _i32, _f32, _vp]),

@@ -6,19 +6,18 @@ using namespace mvae;
 
 static bool lat_aligned(const void* p, uintptr_t a) { return (reinterpret_cast<uintptr_t>(p) & (a - 1)) == 0; }
 
-extern "C" int mvae_latent_forward(const mvae_pm_desc* desc, int64_t B, int32_t H, const mvae_planes* h, const float* Wh,
+extern "C" int mvae_latent_forward(const mvae_pm_desc* desc, int64_t B, int32_t H, const float* h, int64_t ld_h, const float* Wh,
                                    const float* bh, const float* eps, const float* radius, const float* Wd0,
                                    const float* bd0, float* ml, float* z, float* kl, const mvae_planes* dd_out,
                                    uint32_t* nonfinite_flag, void* stream) {
-  if (!desc || desc->C < 1 || desc->C > MVAE_MAX_COMPONENTS || B < 0 || H < 8 || !h || !h->base || !Wh || !bh || !eps ||
+  if (!desc || desc->C < 1 || desc->C > MVAE_MAX_COMPONENTS || B < 0 || H < 8 || !h || !Wh || !bh || !eps ||
       !Wd0 || !bd0 || !ml || !z || !kl || !dd_out || !dd_out->base)
     return MVAE_ERR_INVALID_ARGUMENT;
   if (desc->ld_ml > 64 || desc->ld_z > 64 || (H & 7)) return MVAE_ERR_UNSUPPORTED;
-  if (h->planes < 1 || h->planes > 3 || dd_out->planes < 1 || dd_out->planes > 3 || h->ld < H || dd_out->ld < H ||
-      h->rows < B || dd_out->rows < B)
+  if (dd_out->planes < 1 || dd_out->planes > 3 || ld_h < H || dd_out->ld < H || dd_out->rows < B)
     return MVAE_ERR_INVALID_ARGUMENT;
-  if ((h->ld & 7) || (h->plane_stride & 7) || (dd_out->ld & 1) || (dd_out->plane_stride & 1) ||
-      !lat_aligned(h->base, 16) || !lat_aligned(dd_out->base, 4) || !lat_aligned(Wh, 16))
+  if ((ld_h & 3) || ld_h > 0x7fffffff || (dd_out->ld & 1) || (dd_out->plane_stride & 1) || !lat_aligned(h, 16) ||
+      !lat_aligned(dd_out->base, 4) || !lat_aligned(Wh, 16))
     return MVAE_ERR_ALIGNMENT;
   if (B == 0) return MVAE_OK;
   LatParams p;
@@ -26,10 +25,8 @@ extern "C" int mvae_latent_forward(const mvae_pm_desc* desc, int64_t B, int32_t 
   p.desc = *desc;
   p.B = B;
   p.H = H;
-  p.h = h->base;
-  p.h_stride = h->planes > 1 ? h->plane_stride : 0;
-  p.h_ld = h->ld;
-  p.h_planes = h->planes;
+  p.h = h;
+  p.h_ld = (int)ld_h;
   p.Wh = Wh;
   p.bh = bh;
   p.Wd0 = Wd0;

@@ -11,13 +11,12 @@
 // [B, P] / [B, Sd] / [B, H] intermediates through L2; fused, the per-sample intermediates (ml on the way back, gz, gml)
 // never leave shared memory and the activations h / gdd are read exactly once.
 //
-// A CTA owns R = 16 consecutive rows.  Their rows of the split-bf16 planes of h (or gdd and h) are contiguous per
-// plane: one bulk asynchronous copy (TMA) per plane lands them in shared memory, where they serve both access
+// A CTA owns R = 16 consecutive rows.  Their rows of h (or gdd and h; fp32, written by the producing GEMM's epilogue
+// for this kernel alone) are contiguous: one bulk asynchronous copy (TMA) lands them in shared memory, where they serve both access
 // patterns — warp-per-row dot products (lanes along the hidden dimension, shuffle reduction) and thread-per-column
 // outer products (rows unrolled in registers).  The manifold arithmetic is pm_math.cuh through dispatch_item, one warp
 // per component, lane = row.  Weight gradients are accumulated per CTA in registers over its rows and leave as
-// vector reductions (red.global.add.v2/.v4.f32).  All arithmetic is exact fp32 FMA on values reconstructed from the
-// planes (the sum of the bf16 planes is the fp32 value the producing GEMM computed, to 2^-24 with three planes).
+// vector reductions (red.global.add.v2/.v4.f32).  All arithmetic is exact fp32 FMA.
 #pragma once
 #include <cuda_bf16.h>
 
@@ -36,10 +35,9 @@ struct LatParams {
   mvae_pm_desc desc;
   int64_t B;
   int H;                       // hidden width (multiple of 8)
-  // h planes (forward: 3 read for the heads; backward: planes 0,1 for the weight gradient, plane 0 for the relu mask)
-  const uint16_t* h;
-  int64_t h_stride;
-  int h_ld, h_planes;
+  // h = relu(fc_e0(x)) as fp32 [B, h_ld] (forward: heads; backward: heads weight gradient and the relu mask)
+  const float* h;
+  int h_ld;
   const float* Wh;             // [P, H]
   const float* bh;             // [P]
   const float* Wd0;            // [H, Sd]
@@ -55,9 +53,8 @@ struct LatParams {
   int dd_ld, dd_planes;
   uint32_t* flag;
   // backward
-  const uint16_t* gdd;
-  int64_t gdd_stride;
-  int gdd_ld, gdd_planes;
+  const float* gdd;            // fp32 [B, gdd_ld]
+  int gdd_ld;
   const float* ml_in;
   const float* z_in;
   float gkl;
@@ -77,33 +74,10 @@ struct LatParams {
 __device__ __forceinline__ float bf16lo(uint32_t w) { return __uint_as_float(w << 16); }
 __device__ __forceinline__ float bf16hi(uint32_t w) { return __uint_as_float(w & 0xFFFF0000u); }
 
-// sum of `planes` bf16 planes for 8 consecutive columns of one row held in shared memory
-__device__ __forceinline__ void planes_load8(const uint16_t* s, int plane_elems, int planes, float (&v)[8]) {
-#pragma unroll
-  for (int j = 0; j < 8; ++j) v[j] = 0.f;
-#pragma unroll
-  for (int p = 0; p < 3; ++p)
-    if (p < planes) {
-      const uint4 q = *reinterpret_cast<const uint4*>(s + p * plane_elems);
-      const uint32_t w[4] = {q.x, q.y, q.z, q.w};
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        v[2 * j] += bf16lo(w[j]);
-        v[2 * j + 1] += bf16hi(w[j]);
-      }
-    }
-}
-// sum of `planes` planes for a column pair
-__device__ __forceinline__ float2 planes_load2(const uint16_t* s, int plane_elems, int planes) {
-  float2 r = make_float2(0.f, 0.f);
-#pragma unroll
-  for (int p = 0; p < 3; ++p)
-    if (p < planes) {
-      const uint32_t w = *reinterpret_cast<const uint32_t*>(s + p * plane_elems);
-      r.x += bf16lo(w);
-      r.y += bf16hi(w);
-    }
-  return r;
+// 8 consecutive fp32 columns of one row held in shared memory
+__device__ __forceinline__ void row_load8(const float* s, float (&v)[8]) {
+  const float4 a = *reinterpret_cast<const float4*>(s), b = *reinterpret_cast<const float4*>(s + 4);
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
 }
 // split a column pair into bf16 planes and store it (32-bit stores, coalesced across the warp)
 __device__ __forceinline__ void planes_store2(uint16_t* dst, int64_t stride, int planes, float a, float b) {
@@ -122,17 +96,17 @@ __device__ __forceinline__ void red_add4(float* p, float a, float b, float c, fl
   asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
-// out[r][n] = sum_k rowvec[k] * W[n][k] for ONE row held as planes in shared memory; lanes stride the K = H columns in
+// out[r][n] = sum_k rowvec[k] * W[n][k] for ONE fp32 row held in shared memory; lanes stride the K = H columns in
 // chunks of 8, W rows are read with 128-bit loads through L1 (every warp of every CTA reads the same few KB).
 template <int NMAX>
-__device__ __forceinline__ void row_dot_WnK(const uint16_t* srow, int plane_elems, int planes, int H,
-                                            const float* __restrict__ W, int N, float (&acc)[NMAX]) {
+__device__ __forceinline__ void row_dot_WnK(const float* srow, int H, const float* __restrict__ W, int N,
+                                            float (&acc)[NMAX]) {
   const int lane = threadIdx.x & 31;
 #pragma unroll
   for (int n = 0; n < NMAX; ++n) acc[n] = 0.f;
   for (int c = lane; 8 * c < H; c += 32) {
     float v[8];
-    planes_load8(srow + 8 * c, plane_elems, planes, v);
+    row_load8(srow + 8 * c, v);
 #pragma unroll
     for (int n = 0; n < NMAX; ++n)
       if (n < N) {
@@ -151,15 +125,15 @@ __device__ __forceinline__ void row_dot_WnK(const uint16_t* srow, int plane_elem
 
 // out[r][j] = sum_h rowvec[h] * W[h][j] (W row-major [H, J], J small): the dgrad of fc_d0 into z
 template <int JMAX>
-__device__ __forceinline__ void row_dot_WKn(const uint16_t* srow, int plane_elems, int planes, int H,
-                                            const float* __restrict__ W, int J, float (&acc)[JMAX]) {
+__device__ __forceinline__ void row_dot_WKn(const float* srow, int H, const float* __restrict__ W, int J,
+                                            float (&acc)[JMAX]) {
   const int lane = threadIdx.x & 31;
 #pragma unroll
   for (int j = 0; j < JMAX; ++j) acc[j] = 0.f;
   const bool vec = (J & 3) == 0;
   for (int c = lane; 8 * c < H; c += 32) {
     float v[8];
-    planes_load8(srow + 8 * c, plane_elems, planes, v);
+    row_load8(srow + 8 * c, v);
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       const float* wr = W + (int64_t)(8 * c + i) * J;
@@ -193,7 +167,7 @@ __global__ void __launch_bounds__(kLatThreads) latent_forward_kernel(const __gri
   constexpr int R = kLatRows;
   const int C = p.desc.C, P = p.desc.ld_ml, Sn = p.desc.ld_eps, Sd = p.desc.ld_z, H = p.H;
   ItemInfo* info = reinterpret_cast<ItemInfo*>(smem);
-  uint16_t* sH = reinterpret_cast<uint16_t*>(smem + p.off_a);
+  float* sH = reinterpret_cast<float*>(smem + p.off_a);
   float* sML = reinterpret_cast<float*>(smem + p.off_ml);
   float* sEPS = reinterpret_cast<float*>(smem + p.off_eps);
   float* sZ = reinterpret_cast<float*>(smem + p.off_z);
@@ -202,7 +176,6 @@ __global__ void __launch_bounds__(kLatThreads) latent_forward_kernel(const __gri
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int64_t row0 = (int64_t)blockIdx.x * R;
   const int rows = (int)min((int64_t)R, p.B - row0);
-  const int plane_elems = R * p.h_ld;
 
   if (tid == 0) {
     pm_mbar_init(bar, 1);
@@ -211,10 +184,9 @@ __global__ void __launch_bounds__(kLatThreads) latent_forward_kernel(const __gri
   pdl_wait();  // the radii (previous optimizer step) and h (previous GEMM) are read from here on
   stage_items(info, p.desc, p.radius);
   if (tid == 0) {
-    const uint32_t bytes = (uint32_t)(rows * p.h_ld) * 2u;
-    pm_mbar_expect_tx(bar, bytes * (uint32_t)p.h_planes);
-    for (int pl = 0; pl < p.h_planes; ++pl)
-      pm_bulk_g2s(pm_smem_u32(sH + pl * plane_elems), p.h + pl * p.h_stride + row0 * p.h_ld, bytes, bar);
+    const uint32_t bytes = (uint32_t)(rows * p.h_ld) * 4u;
+    pm_mbar_expect_tx(bar, bytes);
+    pm_bulk_g2s(pm_smem_u32(sH), p.h + row0 * p.h_ld, bytes, bar);
   }
   for (int i = tid; i < rows * Sn; i += blockDim.x) sEPS[i] = __ldg(p.eps + row0 * Sn + i);
   __syncthreads();
@@ -223,7 +195,7 @@ __global__ void __launch_bounds__(kLatThreads) latent_forward_kernel(const __gri
   // ---- heads: ml[r][p] = <h[r], Wh[p]> + bh[p]; one warp per row ----
   for (int r = warp; r < rows; r += kLatThreads / 32) {
     float acc[SMAX];
-    row_dot_WnK<SMAX>(sH + r * p.h_ld, plane_elems, p.h_planes, H, p.Wh, P, acc);
+    row_dot_WnK<SMAX>(sH + r * p.h_ld, H, p.Wh, P, acc);
     if (lane == 0) {
 #pragma unroll
       for (int n = 0; n < SMAX; ++n)
@@ -287,8 +259,8 @@ __global__ void __launch_bounds__(kLatThreads) latent_backward_kernel(const __gr
   constexpr int R = kLatRows;
   const int C = p.desc.C, P = p.desc.ld_ml, Sn = p.desc.ld_eps, Sd = p.desc.ld_z, H = p.H;
   ItemInfo* info = reinterpret_cast<ItemInfo*>(smem);
-  uint16_t* sG = reinterpret_cast<uint16_t*>(smem + p.off_a);
-  uint16_t* sH = reinterpret_cast<uint16_t*>(smem + p.off_b);
+  float* sG = reinterpret_cast<float*>(smem + p.off_a);
+  float* sH = reinterpret_cast<float*>(smem + p.off_b);
   float* sML = reinterpret_cast<float*>(smem + p.off_ml);
   float* sEPS = reinterpret_cast<float*>(smem + p.off_eps);
   float* sZ = reinterpret_cast<float*>(smem + p.off_z);
@@ -298,8 +270,6 @@ __global__ void __launch_bounds__(kLatThreads) latent_backward_kernel(const __gr
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int64_t row0 = (int64_t)blockIdx.x * R;
   const int rows = (int)min((int64_t)R, p.B - row0);
-  const int g_elems = R * p.gdd_ld, h_elems = R * p.h_ld;
-  const int hpl = p.h_planes < 2 ? p.h_planes : 2;
 
   if (tid == 0) {
     pm_mbar_init(bar, 1);
@@ -308,12 +278,10 @@ __global__ void __launch_bounds__(kLatThreads) latent_backward_kernel(const __gr
   pdl_wait();
   stage_items(info, p.desc, p.radius);
   if (tid == 0) {
-    const uint32_t gb = (uint32_t)(rows * p.gdd_ld) * 2u, hb = (uint32_t)(rows * p.h_ld) * 2u;
-    pm_mbar_expect_tx(bar, gb * (uint32_t)p.gdd_planes + hb * (uint32_t)hpl);
-    for (int pl = 0; pl < p.gdd_planes; ++pl)
-      pm_bulk_g2s(pm_smem_u32(sG + pl * g_elems), p.gdd + pl * p.gdd_stride + row0 * p.gdd_ld, gb, bar);
-    for (int pl = 0; pl < hpl; ++pl)
-      pm_bulk_g2s(pm_smem_u32(sH + pl * h_elems), p.h + pl * p.h_stride + row0 * p.h_ld, hb, bar);
+    const uint32_t gb = (uint32_t)(rows * p.gdd_ld) * 4u, hb = (uint32_t)(rows * p.h_ld) * 4u;
+    pm_mbar_expect_tx(bar, gb + hb);
+    pm_bulk_g2s(pm_smem_u32(sG), p.gdd + row0 * p.gdd_ld, gb, bar);
+    pm_bulk_g2s(pm_smem_u32(sH), p.h + row0 * p.h_ld, hb, bar);
   }
   for (int i = tid; i < R * P; i += blockDim.x) {
     sML[i] = i < rows * P ? __ldg(p.ml_in + row0 * P + i) : 0.f;
@@ -327,7 +295,7 @@ __global__ void __launch_bounds__(kLatThreads) latent_backward_kernel(const __gr
   // ---- gz[r][j] = sum_h gdd[r][h] Wd0[h][j]; one warp per row ----
   for (int r = warp; r < rows; r += kLatThreads / 32) {
     float acc[SMAX];
-    row_dot_WKn<SMAX>(sG + r * p.gdd_ld, g_elems, p.gdd_planes, H, p.Wd0, Sd, acc);
+    row_dot_WKn<SMAX>(sG + r * p.gdd_ld, H, p.Wd0, Sd, acc);
     if (lane == 0) {
 #pragma unroll
       for (int j = 0; j < SMAX; ++j)
@@ -341,7 +309,7 @@ __global__ void __launch_bounds__(kLatThreads) latent_backward_kernel(const __gr
 #pragma unroll
     for (int r = 0; r < R; ++r) {
       float2 g = make_float2(0.f, 0.f);
-      if (r < rows) g = planes_load2(sG + r * p.gdd_ld + n, g_elems, p.gdd_planes);
+      if (r < rows) g = *reinterpret_cast<const float2*>(sG + r * p.gdd_ld + n);
       g0[r] = g.x;
       g1[r] = g.y;
       s0 += g.x;
@@ -411,12 +379,9 @@ __global__ void __launch_bounds__(kLatThreads) latent_backward_kernel(const __gr
     for (int r = 0; r < R; ++r) {
       float2 hv = make_float2(0.f, 0.f);
       if (r < rows && live) {
-        hv = planes_load2(sH + r * p.h_ld + k, h_elems, hpl);
-        // relu'(h): the leading plane is bf16(h) and h >= 0, so h > 0 <=> its bits are a positive number
-        const uint32_t w = *reinterpret_cast<const uint32_t*>(sH + r * p.h_ld + k);
-        const uint32_t lo = w & 0xFFFFu, hi = w >> 16;
-        mask |= (uint32_t)(((lo & 0x8000u) == 0) && ((lo & 0x7FFFu) != 0)) << (2 * r);
-        mask |= (uint32_t)(((hi & 0x8000u) == 0) && ((hi & 0x7FFFu) != 0)) << (2 * r + 1);
+        hv = *reinterpret_cast<const float2*>(sH + r * p.h_ld + k);
+        mask |= (uint32_t)(hv.x > 0.f) << (2 * r);  // relu'(h)
+        mask |= (uint32_t)(hv.y > 0.f) << (2 * r + 1);
       }
       h0[r] = hv.x;
       h1[r] = hv.y;
@@ -472,9 +437,9 @@ static int launch_latent(LatParams& p, void* stream) {
   // shared-memory layout
   int o = lat_align(C * (int)sizeof(ItemInfo), 128);
   p.off_a = o;
-  o += lat_align((bwd ? p.gdd_planes * R * p.gdd_ld : p.h_planes * R * p.h_ld) * 2, 128);
+  o += lat_align((bwd ? R * p.gdd_ld : R * p.h_ld) * 4, 128);
   p.off_b = o;
-  if (bwd) o += lat_align((p.h_planes < 2 ? p.h_planes : 2) * R * p.h_ld * 2, 128);
+  if (bwd) o += lat_align(R * p.h_ld * 4, 128);
   p.off_ml = o;
   o += lat_align(R * P * 4, 16);
   p.off_eps = o;

@@ -297,25 +297,26 @@ def _wide(x):
     return None, 0, st
 
 
-def latent_forward(desc: L.PmDesc, h: "PlaneBuf", Wh, bh, eps, radius, Wd0, bd0, ml, z, kl, dd: "PlaneBuf",
+def latent_forward(desc: L.PmDesc, h: torch.Tensor, Wh, bh, eps, radius, Wd0, bd0, ml, z, kl, dd: "PlaneBuf",
                    flag: Optional[torch.Tensor] = None):
-    """heads + product-manifold forward + fc_d0/relu in one launch (mvae_latent_forward)."""
+    """heads + product-manifold forward + fc_d0/relu in one launch (mvae_latent_forward); h: fp32 [B, H]."""
     B, H = ml.shape[0], Wh.shape[1]
-    hs, ds = h.struct(), dd.struct()
-    rc = L.lib().mvae_latent_forward(ctypes.byref(desc), B, H, ctypes.byref(hs), _ptr(Wh), _ptr(bh), _ptr(eps),
+    ds = dd.struct()
+    rc = L.lib().mvae_latent_forward(ctypes.byref(desc), B, H, _ptr(h), h.stride(0), _ptr(Wh), _ptr(bh), _ptr(eps),
                                      _ptr(radius), _ptr(Wd0), _ptr(bd0), _ptr(ml), _ptr(z), _ptr(kl), ctypes.byref(ds),
                                      _ptr(flag), _stream())
     L.check(rc, "mvae_latent_forward")
     _LAUNCHES[0] += 1
 
 
-def latent_backward(desc: L.PmDesc, gdd: "PlaneBuf", h: "PlaneBuf", Wh, Wd0, ml, eps, radius, z, gkl_scalar: float,
-                    gh: "PlaneBuf", gWd0, gbd0, gWh, gbh, gradius):
+def latent_backward(desc: L.PmDesc, gdd: torch.Tensor, h: torch.Tensor, Wh, Wd0, ml, eps, radius, z,
+                    gkl_scalar: float, gh: "PlaneBuf", gWd0, gbd0, gWh, gbh, gradius):
     """fc_d0 dgrad/wgrad + product-manifold backward + heads dgrad/wgrad in one launch (mvae_latent_backward).
     The gradient outputs are ACCUMULATED."""
     B, H = ml.shape[0], Wh.shape[1]
-    gs, hs, os_ = gdd.struct(), h.struct(), gh.struct()
-    rc = L.lib().mvae_latent_backward(ctypes.byref(desc), B, H, ctypes.byref(gs), ctypes.byref(hs), _ptr(Wh), _ptr(Wd0),
+    os_ = gh.struct()
+    rc = L.lib().mvae_latent_backward(ctypes.byref(desc), B, H, _ptr(gdd), gdd.stride(0), _ptr(h), h.stride(0), _ptr(Wh),
+                                      _ptr(Wd0),
                                       _ptr(ml), _ptr(eps), _ptr(radius), _ptr(z), float(gkl_scalar), ctypes.byref(os_),
                                       _ptr(gWd0), _ptr(gbd0), _ptr(gWh), _ptr(gbh), _ptr(gradius), _stream())
     L.check(rc, "mvae_latent_backward")

@@ -138,6 +138,9 @@ class _Workspace:
         self.gml = torch.zeros(B, P, **f)
         self.ghp = ops.PlaneBuf(B, H, 2, dev)
         self.flag = torch.zeros(1, device=dev, dtype=torch.int32)
+        # fused latent block: the fc_e0 / logits-dgrad epilogues write h and gdd as fp32 for it (no planes needed)
+        self.h32 = torch.zeros(B, H, **f)
+        self.gdd32 = torch.zeros(B, H, **f)
 
     @property
     def x(self) -> Tensor:
@@ -313,11 +316,17 @@ class FusedFeedForwardVAE(nn.Module):
         if self._planes_stale:
             self.refresh_weight_planes()
         ops.split_planes(ws.x, ws.xp)
-        self._gemm("e0_fwd", ws.xp, self.We0p, B, H, D, epilogue=L.EPI_BIAS_RELU, bias=self.fc_e0.bias.data,
-                   out_planes=ws.hp)
-        if self.fused_latent and not want_mu_sigma:
+        fused = self.fused_latent and not want_mu_sigma
+        if fused:
+            self._gemm("e0_fwd32", ws.xp, self.We0p, B, H, D, epilogue=L.EPI_BIAS_RELU, bias=self.fc_e0.bias.data,
+                       out_f32=ws.h32)
+        else:
+            self._gemm("e0_fwd", ws.xp, self.We0p, B, H, D, epilogue=L.EPI_BIAS_RELU, bias=self.fc_e0.bias.data,
+                       out_planes=ws.hp)
+        ws.fused = fused
+        if fused:
             # heads + manifold chain + fc_d0/relu in ONE kernel: ml, z, kl kept for the backward pass / statistics
-            ops.latent_forward(self.desc, ws.hp, self.Wh, self.bh, ws.eps, self._rflat, self.fc_d0.weight.data,
+            ops.latent_forward(self.desc, ws.h32, self.Wh, self.bh, ws.eps, self._rflat, self.fc_d0.weight.data,
                                self.fc_d0.bias.data, ws.ml, ws.z, ws.kl, ws.ddp,
                                flag=ws.flag if self.check_finite else None)
         else:
@@ -342,11 +351,15 @@ class FusedFeedForwardVAE(nn.Module):
         # fc_logits: gW = gL^T dd (+ bias from the ones column of dd), then gdd = (gL W) * 1[dd > 0]
         self._gemm("logits_wgrad", ws.gLp, ws.ddp, D, H + 1, B, a_major=MN, b_major=MN, split_k=0, out_f32=self.gWl, out_col=self.gbl,
                  col_split=H)
-        self._gemm("logits_dgrad", ws.gLp, self.Wlp, B, H, D, b_major=MN, epilogue=L.EPI_RELU_MASK, mask=ws.ddp,
-                   out_planes=ws.gddp)
+        if self.fused_latent:
+            self._gemm("logits_dgrad32", ws.gLp, self.Wlp, B, H, D, b_major=MN, epilogue=L.EPI_RELU_MASK, mask=ws.ddp,
+                       out_f32=ws.gdd32)
+        else:
+            self._gemm("logits_dgrad", ws.gLp, self.Wlp, B, H, D, b_major=MN, epilogue=L.EPI_RELU_MASK, mask=ws.ddp,
+                       out_planes=ws.gddp)
         if self.fused_latent:
             # fc_d0 dgrad + wgrad, manifold reverse sweep (d(-ELBO)/d kl = beta), heads dgrad + wgrad: ONE kernel
-            ops.latent_backward(self.desc, ws.gddp, ws.hp, self.Wh, self.fc_d0.weight.data, ws.ml, ws.eps, self._rflat,
+            ops.latent_backward(self.desc, ws.gdd32, ws.h32, self.Wh, self.fc_d0.weight.data, ws.ml, ws.eps, self._rflat,
                                 ws.z, beta, ws.ghp, self.gWd0, self.gbd0, self.gWh, self.gbh, self._gradius)
             if self._any_fixed_radius:
                 self._gradius.mul_(self._radius_mask)  # requires_grad=False radii (fixed curvature) get no gradient

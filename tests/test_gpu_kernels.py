@@ -461,12 +461,11 @@ def test_latent_fused_matches_separate_kernels(dev, oracle, sig, B, H, scalar):
     bd0 = torch.randn(H, device=dev, generator=g) * 0.1
     eps = torch.randn(B, Sn, device=dev, generator=g)
     R = torch.full((C,), 1.7, device=dev)
-    hp = _planes_of(h, dev, planes=3, ones_col=True)
     ml = torch.full((B, P), float("nan"), device=dev)
     z = torch.full((B, Sd), float("nan"), device=dev)
     kl = torch.full((B, C), float("nan"), device=dev)
     ddp = ops.PlaneBuf(B, H, 2, dev, ones_col=True)
-    ops.latent_forward(desc, hp, Wh, bh, eps, R, Wd0, bd0, ml, z, kl, ddp)
+    ops.latent_forward(desc, h, Wh, bh, eps, R, Wd0, bd0, ml, z, kl, ddp)
     ml_ref = h.double() @ Wh.double().t() + bh.double()
     assert ((ml.double() - ml_ref).abs().max() / ml_ref.abs().max()).item() < 2e-6
     ref = oracle.pm_forward(odesc, ml.double().cpu().numpy(), eps.double().cpu().numpy(), R.double().cpu().numpy())
@@ -478,12 +477,12 @@ def test_latent_fused_matches_separate_kernels(dev, oracle, sig, B, H, scalar):
     assert torch.equal(ddp.t[0, :, H].float(), torch.ones(B, device=dev))  # ones column untouched
     # backward
     gdd = torch.randn(B, H, device=dev, generator=g) * (dd_ref > 0)
-    gddp = _planes_of(gdd.float(), dev, planes=2)
+    gdd = gdd.float().contiguous()
     ghp = ops.PlaneBuf(B, H, 2, dev)
     gWd0, gbd0 = torch.zeros(H, Sd, device=dev), torch.zeros(H, device=dev)
     gWh, gbh, gR = torch.zeros(P, H, device=dev), torch.zeros(P, device=dev), torch.zeros(C, device=dev)
-    ops.latent_backward(desc, gddp, hp, Wh, Wd0, ml, eps, R, z, 0.7, ghp, gWd0, gbd0, gWh, gbh, gR)
-    gdd64 = gddp.to_float().double()
+    ops.latent_backward(desc, gdd, h, Wh, Wd0, ml, eps, R, z, 0.7, ghp, gWd0, gbd0, gWh, gbh, gR)
+    gdd64 = gdd.double()
     gz_ref = (gdd64 @ Wd0.double()).cpu().numpy()
     gml_ref, gR_ref = oracle.pm_backward(odesc, ml.double().cpu().numpy(), eps.double().cpu().numpy(),
                                          R.double().cpu().numpy(), gz_ref, None, 0.7)

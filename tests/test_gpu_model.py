@@ -128,8 +128,9 @@ def test_train_step_vs_oracle(dev, oracle, sig, B, D, H, recon, fixed, fused_lat
     # only be a handful — and the oracle's backward pass then takes the same decisions, so that every gradient is
     # compared at the tight bar.
     decisions = {}
-    for name, planes, pre in (("h", ws.hp, fwd["h_pre"]), ("dd", ws.ddp, fwd["dd_pre"])):
-        on = planes.to_float().cpu().numpy() > 0
+    h_dev = ws.h32 if fused_latent else ws.hp.to_float()  # the fused latent block reads h as fp32, not as planes
+    for name, act, pre in (("h", h_dev, fwd["h_pre"]), ("dd", ws.ddp.to_float(), fwd["dd_pre"])):
+        on = act.cpu().numpy() > 0
         diff = on != (pre > 0)
         assert diff.sum() <= 4, (name, int(diff.sum()))
         assert np.all(np.abs(pre[diff]) <= 2e-6 * np.abs(pre).max()), (name, np.abs(pre[diff]).max())
