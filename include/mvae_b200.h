@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define MVAE_ABI_VERSION 1
+#define MVAE_ABI_VERSION 2
 #define MVAE_MAX_COMPONENTS 96
 
 /* ------------------------------------------------------------------------------------------------ status */
@@ -213,6 +213,10 @@ typedef struct mvae_gemm_args {
    * epilogue and main loop).  Requests that do not fit shared memory fall back to the automatic choice. */
   int32_t tile_n;
   int32_t ctas_per_sm;
+  /* BCE/NLL: when > 0 the targets have only aux_rows rows and row m reads x[m % aux_rows] — the importance-sampling
+   * path decodes n samples per input row ([n*B, .] activations against [B, D] targets; vae.py:108-109 materialises
+   * x.repeat((n, 1, 1)) instead). */
+  int64_t aux_rows;
 } mvae_gemm_args;
 
 int mvae_gemm(const mvae_gemm_args* args, void* stream);
@@ -278,6 +282,31 @@ int mvae_recon_loss(int32_t kind, int64_t B, int32_t D, const float* logits, con
 /* ELBO reduction (stats.py:144-202): out = [bce_sum, kl_sum, elbo, kl_c sums (C)] with
  * elbo = sum_b(-bce_b - beta * sum_c kl_bc).  Warp-shuffle + block reduce; `out` [3+C] is overwritten. */
 int mvae_elbo_reduce(int64_t B, int32_t C, const float* bce, const float* kl, float beta, float* out, void* stream);
+
+/* ------------------------------------------------------ importance-weighted log-likelihood (evaluation) */
+/* ModelVAE.log_likelihood (vae.py:82-123) draws n samples per input row.  The encoder runs once; per chunk of `ns`
+ * samples mvae_iwae_latent does Component.encode's manifold part + rsample_log_probs of EVERY component
+ * (sampling_procedures.py:47-50,106-110; wrapped_normal.py:70-103; EuclideanNormal.log_prob
+ * wrapped_distributions.py:39-42) from the ONE set of head pre-activations ml [B, ld_ml]:
+ *   eps  [ns, B, ld_eps]  standard normal draws
+ *   z    [ns, B, ld_z]    samples, concat order of vae.py:105
+ *   diff [ns, B]          sum_c (log q_c(z|x) - log p_c(z))   (single-sample Monte-Carlo terms for every component,
+ *                         Euclidean ones included — unlike the analytic KL of the training path)
+ *   zsum [B, ld_z]        += sum_s z   (atomic accumulate; feeds cov_norm, vae.py:119-121) — may be NULL
+ * ld_ml <= 64 and ld_z <= 64. */
+int mvae_iwae_latent(const mvae_pm_desc* desc, int64_t B, int32_t ns, const float* ml, const float* eps,
+                     const float* radius, float* z, float* diff, float* zsum, void* stream);
+
+/* log_p_x[b] = logsumexp_s(-recon[s,b] - diff[s,b]) - log n;  mi[b] = logsumexp_s(diff[s,b]) - log n
+ * (vae.py:111-117); recon, diff [n, B]. */
+int mvae_iwae_reduce(int32_t n, int64_t B, const float* recon, const float* diff, float* log_p_x, float* mi,
+                     void* stream);
+
+/* cov_norm (vae.py:119-121): with zbar[b] = zsum[b] / n,
+ *   || sum_b (x[b] - mean_b x)^T (zbar[b] - mean_b zbar) ||_F  ->  out[0].
+ * work: [B * Sd + D * Sd] floats of scratch.  Three small launches. */
+int mvae_iwae_cov_norm(int64_t B, int32_t D, int32_t Sd, int32_t n, const float* x, const float* zsum, float* work,
+                       float* out, void* stream);
 
 /* Fused Adam (torch.optim.Adam defaults: betas .9/.999, eps 1e-8, no weight decay — train.py:343) over a flat
  * fp32 parameter bucket.  step is 1-based.  grad_scale multiplies the gradient first. */

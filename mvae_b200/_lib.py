@@ -11,7 +11,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libmvae_b200.so")
 
 MAX_COMPONENTS = 96
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 # mvae_manifold
 EUCLIDEAN, HYPERBOLOID, SPHERE, POINCARE, PROJ_SPHERE = 0, 1, 2, 3, 4
@@ -45,7 +45,7 @@ class GemmArgs(ctypes.Structure):
                 ("ld_out", ctypes.c_int64), ("out_col", ctypes.c_void_p), ("col_split", ctypes.c_int32),
                 ("out_planes", Planes), ("aux", ctypes.c_void_p), ("ld_aux", ctypes.c_int64),
                 ("mask", ctypes.c_void_p), ("ld_mask", ctypes.c_int64), ("rowsum", ctypes.c_void_p),
-                ("tile_n", ctypes.c_int32), ("ctas_per_sm", ctypes.c_int32)]
+                ("tile_n", ctypes.c_int32), ("ctas_per_sm", ctypes.c_int32), ("aux_rows", ctypes.c_int64)]
 
 
 DP_MAX_RANKS, DP_HANDLE_BYTES = 8, 64
@@ -83,6 +83,9 @@ PROTOTYPES = {
                                             _vp, _vp, _vp, _f32, ctypes.POINTER(Planes), _vp, _vp, _vp, _vp, _vp, _vp]),
     "mvae_recon_loss": (ctypes.c_int, [_i32, _i64, _i32, _vp, _vp, _vp, _vp, _vp]),
     "mvae_elbo_reduce": (ctypes.c_int, [_i64, _i32, _vp, _vp, _f32, _vp, _vp]),
+    "mvae_iwae_latent": (ctypes.c_int, [ctypes.POINTER(PmDesc), _i64, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "mvae_iwae_reduce": (ctypes.c_int, [_i32, _i64, _vp, _vp, _vp, _vp, _vp]),
+    "mvae_iwae_cov_norm": (ctypes.c_int, [_i64, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp]),
     "mvae_adam_step": (ctypes.c_int, [_i64, _vp, _vp, _vp, _vp, _f32, _f32, _f32, _f32, _i32, _f32, _vp]),
     "mvae_adam_step_dev": (ctypes.c_int, [_i64, _vp, _vp, _vp, _vp, _f32, _f32, _f32, _f32, _vp, _f32, _vp]),
     "mvae_sgd_step": (ctypes.c_int, [_i64, _vp, _vp, _f32, _f32, _vp]),

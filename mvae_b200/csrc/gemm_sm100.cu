@@ -56,6 +56,7 @@ struct GemmParams {
   int op_planes;
   const float* aux;
   int64_t ld_aux;
+  int64_t aux_rows;  // > 0: targets repeat every aux_rows rows (row m reads x[m % aux_rows])
   const uint16_t* mask;
   int64_t ld_mask;
   float* rowsum;
@@ -310,6 +311,7 @@ __global__ void __launch_bounds__(kGemmThreads, 2)
     const bool vec_aux = p.aux && ((p.ld_aux & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.aux) & 15) == 0);
     const bool is_loss = p.epilogue == MVAE_EPI_BCE_ROWSUM || p.epilogue == MVAE_EPI_NLL_ROWSUM;
     const bool is_mask = p.epilogue == MVAE_EPI_RELU_MASK;
+    const int64_t m_aux = p.aux_rows > 0 ? (int64_t)m % p.aux_rows : (int64_t)m;
     // operands of the epilogue that do not depend on the accumulator are fetched one chunk ahead
     float t_nxt[16];
     uint32_t mk_nxt = 0;
@@ -317,7 +319,7 @@ __global__ void __launch_bounds__(kGemmThreads, 2)
       const int n = n0 + c;
       if (!row_ok || n >= p.N) return;
       if (is_loss) {
-        const float* xr = p.aux + (int64_t)m * p.ld_aux + n;
+        const float* xr = p.aux + m_aux * p.ld_aux + n;
         if (vec_aux && n + 16 <= p.N) {
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
@@ -621,6 +623,7 @@ extern "C" int mvae_gemm(const mvae_gemm_args* a, void* stream) {
   p.op_planes = a->out_planes.base ? a->out_planes.planes : 0;
   p.aux = a->aux;
   p.ld_aux = a->ld_aux;
+  p.aux_rows = a->aux_rows > 0 ? a->aux_rows : 0;
   p.mask = a->mask;
   p.ld_mask = a->ld_mask;
   p.rowsum = a->rowsum;

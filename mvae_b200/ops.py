@@ -185,6 +185,46 @@ def elbo_reduce(bce, kl, beta: float, out: Optional[torch.Tensor] = None):
     return out
 
 
+# ------------------------------------------------------------------------------------------ IWAE log-likelihood
+def iwae_latent(desc: L.PmDesc, ml, eps, radius, z, diff, zsum: Optional[torch.Tensor] = None):
+    """z [ns, B, ld_z] and diff [ns, B] = sum_c (log q_c - log p_c) for ns samples per row of ml [B, ld_ml]
+    (mvae_iwae_latent); zsum [B, ld_z] accumulates sum_s z."""
+    ns, B = eps.shape[0], ml.shape[0]
+    assert eps.shape == (ns, B, desc.ld_eps) and z.shape == (ns, B, desc.ld_z) and diff.shape == (ns, B)
+    rc = L.lib().mvae_iwae_latent(ctypes.byref(desc), B, ns, _ptr(_f32(ml, "ml")), _ptr(_f32(eps, "eps")),
+                                  _ptr(radius), _ptr(z), _ptr(diff), _ptr(zsum), _stream())
+    L.check(rc, "mvae_iwae_latent")
+    _LAUNCHES[0] += 1
+
+
+def iwae_reduce(recon, diff, log_p_x: Optional[torch.Tensor] = None, mi: Optional[torch.Tensor] = None):
+    """(logsumexp_s(-recon - diff) - log n, logsumexp_s(diff) - log n) over [n, B] inputs (mvae_iwae_reduce)."""
+    n, B = diff.shape
+    if log_p_x is None:
+        log_p_x = torch.empty(B, device=diff.device)
+    if mi is None:
+        mi = torch.empty(B, device=diff.device)
+    rc = L.lib().mvae_iwae_reduce(n, B, _ptr(_f32(recon, "recon")), _ptr(_f32(diff, "diff")), _ptr(log_p_x), _ptr(mi),
+                                  _stream())
+    L.check(rc, "mvae_iwae_reduce")
+    _LAUNCHES[0] += 1
+    return log_p_x, mi
+
+
+def iwae_cov_norm(x, zsum, n: int, out: Optional[torch.Tensor] = None):
+    """cov_norm of vae.py:119-121 from x [B, D] and zsum [B, Sd] = sum over the n samples of z (mvae_iwae_cov_norm)."""
+    B, D = x.shape
+    Sd = zsum.shape[1]
+    work = torch.empty(B * Sd + D * Sd, device=x.device)
+    if out is None:
+        out = torch.empty(1, device=x.device)
+    rc = L.lib().mvae_iwae_cov_norm(B, D, Sd, n, _ptr(_f32(x, "x")), _ptr(_f32(zsum, "zsum")), _ptr(work), _ptr(out),
+                                    _stream())
+    L.check(rc, "mvae_iwae_cov_norm")
+    _LAUNCHES[0] += 3
+    return out
+
+
 def adam_step(param, grad, exp_avg, exp_avg_sq, lr, step, beta1=0.9, beta2=0.999, eps=1e-8, grad_scale=1.0):
     rc = L.lib().mvae_adam_step(param.numel(), _ptr(param), _ptr(grad), _ptr(exp_avg), _ptr(exp_avg_sq), float(lr),
                                 float(beta1), float(beta2), float(eps), int(step), float(grad_scale), _stream())
@@ -251,7 +291,8 @@ def split_planes(src: torch.Tensor, dst: Optional[PlaneBuf] = None, dst_t: Optio
 def gemm(a: PlaneBuf, b: PlaneBuf, M: int, N: int, K: int, a_major: int = L.K_MAJOR, b_major: int = L.K_MAJOR,
          epilogue: int = L.EPI_STORE, split_k: int = 1, bias=None, out_f32=None, ld_out: Optional[int] = None,
          out_col=None, col_split: int = -1, out_planes: Optional[PlaneBuf] = None, aux=None, mask: Optional[PlaneBuf] = None,
-         rowsum=None, a_planes: Optional[int] = None, b_planes: Optional[int] = None, tile: Optional[tuple] = None):
+         rowsum=None, a_planes: Optional[int] = None, b_planes: Optional[int] = None, tile: Optional[tuple] = None,
+         aux_rows: int = 0):
     """D[M,N] = sum_k A[m,k] B[n,k] on tcgen05 tensor cores with a fused epilogue (mvae_gemm).
     tile = (BLOCK_N, CTAs per SM[, split_k]) overrides the automatic tile policy (0 = automatic)."""
     g = L.GemmArgs()
@@ -275,6 +316,7 @@ def gemm(a: PlaneBuf, b: PlaneBuf, M: int, N: int, K: int, a_major: int = L.K_MA
     if aux is not None:
         g.aux = aux.data_ptr()
         g.ld_aux = aux.stride(0)
+        g.aux_rows = int(aux_rows)
     if mask is not None:
         g.mask = mask.t.data_ptr()
         g.ld_mask = mask.ld

@@ -73,23 +73,37 @@ class BatchStatsFloat:
         stats.add_scalar(prefix + "/bce", self.bce)
         stats.add_scalar(prefix + "/kl", self.kl)
         stats.add_scalar(prefix + "/elbo", self.elbo)
+        if self.log_likelihood is not None:
+            stats.add_scalar(prefix + "/log_likelihood", self.log_likelihood)
+        if self.mutual_info is not None:
+            stats.add_scalar(prefix + "/mutual_info", self.mutual_info)
+        if self.cov_norm is not None:
+            stats.add_scalar(prefix + "/cov_norm", self.cov_norm)
 
 
 class BatchStats:
     """mt/mvae/stats.py:144-212 over the device vector [bce_sum, kl_sum, elbo, kl_c...] of mvae_elbo_reduce."""
 
     def __init__(self, stats_vec: Tensor, beta: float, bce_rows: Optional[Tensor] = None,
-                 kl_rows: Optional[Tensor] = None) -> None:
+                 kl_rows: Optional[Tensor] = None, likelihood=None) -> None:
         self._vec = stats_vec
         self._beta = beta
         self._bce = bce_rows
         self._component_kl = None if kl_rows is None else [kl_rows[:, i] for i in range(kl_rows.shape[1])]
+        # likelihood = (log_p_x [B], mi [B], cov_norm [1]) of log_likelihood(); reported summed over the batch
+        # (stats.py:177-186).  The two sums are one more launch of the ELBO reduction kernel.
+        self._log_likelihood, self._mutual_info, self._cov_norm = likelihood if likelihood is not None else (None,) * 3
+        self._lsum = None
+        if likelihood is not None:
+            self._lsum = ops.elbo_reduce(self._log_likelihood, self._mutual_info.reshape(-1, 1), 0.0)
 
     bce = property(lambda self: self._vec[0])
     kl = property(lambda self: self._vec[1])
     elbo = property(lambda self: self._vec[2])
     beta = property(lambda self: self._beta)
-    log_likelihood = mutual_info = cov_norm = None
+    log_likelihood = property(lambda self: None if self._lsum is None else self._lsum[0])
+    mutual_info = property(lambda self: None if self._lsum is None else self._lsum[1])
+    cov_norm = property(lambda self: None if self._cov_norm is None else self._cov_norm.reshape(()))
 
     @property
     def component_kl(self) -> List[Tensor]:
@@ -97,7 +111,10 @@ class BatchStats:
 
     def convert_to_float(self) -> BatchStatsFloat:
         h = self._vec.detach().cpu().tolist()  # one D2H copy (the reference does 3 + C .item() syncs)
-        return BatchStatsFloat(h[0], h[1], h[2], h[3:], self._beta)
+        if self._lsum is None:
+            return BatchStatsFloat(h[0], h[1], h[2], h[3:], self._beta)
+        ll, mi = self._lsum[:2].cpu().tolist()
+        return BatchStatsFloat(h[0], h[1], h[2], h[3:], self._beta, ll, mi, float(self._cov_norm.reshape(-1)[0].item()))
 
 
 def _recon_kind_of(dataset) -> str:
@@ -492,13 +509,68 @@ class FusedFeedForwardVAE(nn.Module):
     def compute_batch_stats(self, x_mb: Tensor, x_mb_: Tensor, reparametrized: List[Reparametrized], beta: float,
                             likelihood_n: int = 0) -> BatchStats:
         """vae.py:125-147: bce row sums of the given logits + the per-component KL of `reparametrized` -> BatchStats."""
-        if likelihood_n:
-            raise NotImplementedError("log_likelihood (IWAE, vae.py:82-123) is outside the round-1 hot path")
         x_mb = x_mb.to(self.device).float().contiguous()
         bce, _ = ops.recon_loss(self.recon_kind, x_mb_.float().contiguous(), x_mb)
         kl = torch.stack([r.kl for r in reparametrized], dim=-1).contiguous()
         vec = ops.elbo_reduce(bce, kl, beta)
-        return BatchStats(vec, beta, bce, kl)
+        likelihood = self.log_likelihood(x_mb, n=likelihood_n) if likelihood_n else None
+        return BatchStats(vec, beta, bce, kl, likelihood)
+
+    # ------------------------------------------------------------------------------------------ IWAE log-likelihood
+    iwae_chunk_rows = 1 << 17  # rows (samples x batch) decoded per launch group; bounds the activation workspace
+
+    @torch.no_grad()
+    def log_likelihood(self, x: Tensor, n: int = 500, eps: Optional[Tensor] = None) -> Tuple[Tensor, Tensor, Tensor]:
+        """vae.py:82-123: importance-weighted Monte-Carlo estimate with n samples per row ->
+        (log_p_x [B], mi [B], cov_norm scalar).  `eps` [n, B, sum(n_i)] optionally supplies the standard-normal draws
+        (component order = column order, as everywhere else).
+
+        The encoder and the heads run ONCE (the reference does too, :93); per chunk of samples:
+        mvae_iwae_latent (z and sum_c log q - log p for every component, from the head pre-activations) ->
+        fc_d0 + relu -> logits GEMM with the reconstruction row sums in its epilogue (targets indexed modulo B: no
+        x.repeat((n, 1, 1)), no [n, B, D] logits in HBM) ; then ONE streaming logsumexp over the sample axis for both
+        estimates, and cov_norm from sum_s z (the sample mean commutes with the bilinear form of :119-121)."""
+        B, D, H, P, Sd, Sn = x.shape[0], self.in_dim, self.h_dim, self.desc.ld_ml, self.desc.ld_z, self.desc.ld_eps
+        ws = self._workspace(B)
+        ws.x.copy_(x.reshape(B, D), non_blocking=True)
+        if self._planes_stale:
+            self.refresh_weight_planes()
+        ops.split_planes(ws.x, ws.xp)
+        self._gemm("e0_fwd", ws.xp, self.We0p, B, H, D, epilogue=L.EPI_BIAS_RELU, bias=self.fc_e0.bias.data,
+                   out_planes=ws.hp)
+        ops.skinny_rowdot((ws.hp, 3), self.Wh, H, 1, K=H, N=P, bias=self.bh, out=ws.ml)
+        nc = max(1, min(n, self.iwae_chunk_rows // max(B, 1)))
+        lw = self._iwae_workspace(B, nc, n)
+        lw["recon"].zero_()
+        lw["zsum"].zero_()
+        epi = L.EPI_BCE_ROWSUM if self.recon_kind == "bce" else L.EPI_NLL_ROWSUM
+        for s0 in range(0, n, nc):
+            k = min(nc, n - s0)
+            e = lw["eps"][:k]
+            if eps is None:
+                e.normal_()
+            else:
+                e.copy_(eps[s0:s0 + k], non_blocking=True)
+            z = lw["z"][:k]
+            ops.iwae_latent(self.desc, ws.ml, e, self._rflat, z, lw["diff"][s0:s0 + k], lw["zsum"])
+            ops.skinny_expand(z.view(k * B, Sd), self.fc_d0.weight.data, Sd, 1, K=Sd, N=H, bias=self.fc_d0.bias.data,
+                              act=ops.ACT_RELU, out_planes=lw["ddp"])
+            self._gemm("iwae_logits", lw["ddp"], self.Wlp, k * B, D, H, epilogue=epi, bias=self.fc_logits.bias.data,
+                       aux=ws.x, aux_rows=B, rowsum=lw["recon"][s0:s0 + k])
+        log_p_x, mi = ops.iwae_reduce(lw["recon"], lw["diff"])
+        cov_norm = ops.iwae_cov_norm(ws.x, lw["zsum"], n)
+        return log_p_x, mi, cov_norm.reshape(())
+
+    def _iwae_workspace(self, B: int, nc: int, n: int) -> dict:
+        key = (B, nc, n)
+        lw = self._iwae_ws.get(key) if hasattr(self, "_iwae_ws") else None
+        if lw is None:
+            f = dict(device=self.device, dtype=torch.float32)
+            lw = {"eps": torch.empty(nc, B, self.desc.ld_eps, **f), "z": torch.empty(nc, B, self.desc.ld_z, **f),
+                  "ddp": ops.PlaneBuf(nc * B, self.h_dim, 2, self.device), "recon": torch.zeros(n, B, **f),
+                  "diff": torch.empty(n, B, **f), "zsum": torch.zeros(B, self.desc.ld_z, **f)}
+            self._iwae_ws = {key: lw}  # one likelihood workspace at a time (it can be hundreds of MB)
+        return lw
 
     @torch.no_grad()
     def train_step(self, optimizer, x_mb: Tensor, beta: float, eps: Optional[Tensor] = None,

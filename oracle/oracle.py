@@ -213,6 +213,38 @@ class OracleVAE:
                     r[i] = params[k]
         return r
 
+    def log_likelihood(self, params, x, eps):
+        """ModelVAE.log_likelihood (vae.py:82-123) with the draws supplied: eps [n, B, sum(n_i)] ->
+        dict(log_p_x [B], mi [B], cov_norm, log_q [n,B], log_p [n,B], log_p_x_z [n,B], z [n,B,Sd])."""
+        dt = x.dtype
+        n, B = eps.shape[0], x.shape[0]
+        Wh, bh = self.heads_matrix(params)
+        R = self.radii(params, dt)
+        h = linear(x, params["fc_e0.weight"], params["fc_e0.bias"], relu=True)      # vae.py:93
+        ml = linear(h, Wh, bh)
+        lq = np.zeros((n, B), dtype=dt)
+        lp = np.zeros((n, B), dtype=dt)
+        lpxz = np.zeros((n, B), dtype=dt)
+        zs = np.zeros((n, B, self.desc.ld_z), dtype=dt)
+        for s in range(n):
+            f = pm_forward(self.desc, ml, eps[s], R, want=("z", "logq", "logp"))    # :97-104 rsample_log_probs
+            lq[s], lp[s], zs[s] = f["logq"].sum(-1), f["logp"].sum(-1), f["z"]
+            dd = linear(f["z"], params["fc_d0.weight"], params["fc_d0.bias"], relu=True)
+            logits = linear(dd, params["fc_logits.weight"], params["fc_logits.bias"])  # :107
+            lpxz[s] = -recon(self.recon_kind, logits, x)[0]                          # :109
+
+        def lse(a):
+            m = a.max(0)
+            return m + np.log(np.exp(a - m).sum(0))
+
+        log_p_x = lse(lpxz + lp - lq) - np.log(n)                                    # :113-114
+        mi = lse(lq - lp) - np.log(n)                                                # :117
+        xc = x - x.mean(0, keepdims=True)                                            # :119-121
+        zc = zs - zs.mean(1, keepdims=True)
+        cov = np.einsum("bd,sbj->dj", xc, zc) / n
+        return {"log_p_x": log_p_x, "mi": mi, "cov_norm": np.sqrt((cov * cov).sum()), "log_q": lq, "log_p": lp,
+                "log_p_x_z": lpxz, "z": zs}
+
     def step(self, params, x, eps, beta=1.0, backward=True, relu_decisions=None):
         """relu_decisions = {"h": bool [B,H], "dd": bool [B,H]} (optional): the backward pass uses these relu masks
         instead of its own (h > 0), (dd > 0).  relu'(0) is a convention and a pre-activation within float32 rounding

@@ -165,6 +165,15 @@ def _ref_model_step(model, x, eps_list, beta):
     return res
 
 
+def ref_log_likelihood(model, x, eps_list, n):
+    """The reference's own ModelVAE.log_likelihood (vae.py:82-123) with the draws injected:
+    eps_list[i] is [n, B, n_i] for component i (one Normal.rsample(sample_shape) per component, in order)."""
+    with default_dtype(x.dtype), torch.no_grad(), injected_noise(eps_list):
+        ll, mi, cov = model.log_likelihood(x, n=n)
+    return {"log_p_x": ll.detach().cpu().numpy(), "mi": mi.detach().cpu().numpy(),
+            "cov_norm": np.asarray(cov.detach().cpu().numpy())}
+
+
 def ref_product_manifold(model_sig, m, l, eps, radii, gz, gkl, scalar_parametrization=False):
     """Reference L0-L2 path for a product manifold from head pre-activations.
 

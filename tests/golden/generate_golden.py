@@ -8,6 +8,8 @@ Fixtures (all small, float64 unless the key ends in _f32):
                     plus the reference's own float32 run of the same inputs (suffix _f32)
   model_<name>.npz  whole ModelVAE.forward + compute_batch_stats + backward (vae.py:69-80,125-160) on a tiny FeedForwardVAE
   ops_<letter>.npz  standalone Manifold ops (ops/*.py) for h,s,p,e at R=2
+  loglik_<name>.npz ModelVAE.log_likelihood (vae.py:82-123: IWAE estimate, mutual information, cov_norm) of a tiny
+                    FeedForwardVAE with the n x B draws injected
   kat.json          known-answer vectors re-derived here
 """
 import json
@@ -78,6 +80,36 @@ def gen_model(name, sig, in_dim, h_dim, B, recon, fixed_curvature, radius, scala
             "scalar_parametrization": bool(scalar), "beta": beta}
     np.savez_compressed(os.path.join(HERE, f"model_{name}.npz"), meta=json.dumps(meta), **out)
     print("model", name, sig, "elbo", float(out["elbo"]))
+
+
+def gen_loglik(name, sig, in_dim, h_dim, B, n, recon, radius, scalar=False, seed=11):
+    out = {}
+    for dtype, sfx in ((torch.float64, ""), (torch.float32, "_f32")):
+        model = rh.build_model(sig, in_dim, h_dim, False, scalar, recon, seed, torch.float64)
+        for c in model.components:
+            for pn in ("_nradius", "_pradius"):
+                if hasattr(c, pn):
+                    getattr(c, pn).data.fill_(radius)
+        model = model.to(dtype)
+        g = torch.Generator().manual_seed(seed + 1)
+        if recon == "bce":
+            x = (torch.rand(B, in_dim, generator=g, dtype=torch.float64) < 0.3).to(dtype)
+        else:
+            x = torch.randn(B, in_dim, generator=g, dtype=torch.float64).to(dtype)
+        eps = rh.draw_eps(model, B, seed + 2, dtype, n_samples=n)
+        res = rh.ref_log_likelihood(model, x, eps, n)
+        if sfx == "":
+            out.update(res)
+            out["x"] = x.numpy()
+            out["eps"] = torch.cat(eps, -1).numpy()
+            for pname, prm in model.named_parameters():
+                out["param." + pname] = prm.detach().numpy()
+        else:
+            out.update({k + sfx: v for k, v in res.items()})
+    meta = {"sig": sig, "in_dim": in_dim, "h_dim": h_dim, "recon": recon, "scalar_parametrization": bool(scalar), "n": n}
+    np.savez_compressed(os.path.join(HERE, f"loglik_{name}.npz"), meta=json.dumps(meta), **out)
+    print("loglik", name, sig, "sum ll", float(out["log_p_x"].sum()), "sum mi", float(out["mi"].sum()), "cov_norm",
+          float(out["cov_norm"]))
 
 
 def gen_ops(letter, n=3, B=16, R=2.0, seed=5):
@@ -168,8 +200,19 @@ def gen_kat():
     print("kat written")
 
 
+def gen_logliks():
+    gen_loglik("h2_s2_e2_bce", "h2,s2,e2", in_dim=20, h_dim=16, B=12, n=7, recon="bce", radius=1.0)
+    gen_loglik("h2_p2_nll", "h2,p2", in_dim=10, h_dim=16, B=9, n=5, recon="nll", radius=2.0)
+    gen_loglik("cfg3_small_bce", "h6,h6,s6,s6,e6", in_dim=24, h_dim=32, B=8, n=6, recon="bce", radius=10.0)
+    gen_loglik("scalar_s3_p2_e3_bce", "s3,p2,e3", in_dim=18, h_dim=16, B=10, n=4, recon="bce", radius=1.5, scalar=True)
+
+
 if __name__ == "__main__":
+    if "--only-loglik" in sys.argv:  # added later: leaves the other committed fixtures byte-identical
+        gen_logliks()
+        sys.exit(0)
     gen_kat()
+    gen_logliks()
     gen_pm("h2_s2_e2_R1", "h2,s2,e2", [1.0, 1.0, 0.0])
     gen_pm("cfg3_R10", "h6,h6,s6,s6,e6", [10.0, 10.0, 10.0, 10.0, 0.0], seed=1)
     gen_pm("cfg3_Rmixed", "h6,h6,s6,s6,e6", [1.5, 0.7, 2.0, 1.0, 0.0], seed=2, scale_m=0.6)

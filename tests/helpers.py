@@ -22,6 +22,10 @@ def model_golden_names():
     return sorted(f[:-4] for f in os.listdir(GOLDEN) if f.startswith("model_") and f.endswith(".npz"))
 
 
+def loglik_golden_names():
+    return sorted(f[:-4] for f in os.listdir(GOLDEN) if f.startswith("loglik_") and f.endswith(".npz"))
+
+
 def pack_ml(desc, m, l, dtype=None):
     """Component-ordered [m | l] matrices (reference layout) -> packed ml rows [m_0|l_0|m_1|l_1|...]."""
     dtype = dtype or m.dtype

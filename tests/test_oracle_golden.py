@@ -6,7 +6,7 @@ import os
 import numpy as np
 import pytest
 
-from helpers import (GOLDEN, load_golden, model_golden_names, normwise, pack_ml, pm_golden_names, radii_array,
+from helpers import (GOLDEN, load_golden, loglik_golden_names, model_golden_names, normwise, pack_ml, pm_golden_names, radii_array,
                      unpack_gml)
 
 F64_TOL = 1e-9   # oracle(float64) vs reference(float64): same operations, different summation order only
@@ -120,3 +120,23 @@ def test_elbo_and_recon(oracle):
     np.testing.assert_allclose(out[1], kl.sum())
     np.testing.assert_allclose(out[2], (-rs - 0.7 * kl.sum(-1)).sum())
     np.testing.assert_allclose(out[3:], kl.sum(0))
+
+
+@pytest.mark.parametrize("name", loglik_golden_names())
+def test_log_likelihood_vs_reference(oracle, name):
+    """OracleVAE.log_likelihood against the reference's own ModelVAE.log_likelihood (vae.py:82-123) run with the
+    same injected n x B draws: IWAE estimate, mutual information and cov_norm."""
+    g, meta = load_golden(name)
+    params = {k[len("param."):]: v for k, v in g.items() if k.startswith("param.")}
+    o = oracle.OracleVAE(meta["sig"], meta["in_dim"], meta["h_dim"], meta["recon"], meta["scalar_parametrization"])
+    r = o.log_likelihood(params, g["x"], g["eps"])
+    assert r["log_p_x"].shape == g["log_p_x"].shape == (g["x"].shape[0],)
+    assert normwise(r["log_p_x"], g["log_p_x"]) < F64_TOL
+    assert normwise(r["mi"], g["mi"]) < F64_TOL
+    assert abs(r["cov_norm"] - float(g["cov_norm"])) < F64_TOL * float(g["cov_norm"])
+    # float32 oracle against the float64 truth and the reference's float32 run
+    p32 = {k: v.astype(np.float32) for k, v in params.items()}
+    r32 = o.log_likelihood(p32, g["x"].astype(np.float32), g["eps"].astype(np.float32))
+    for k in ("log_p_x", "mi"):
+        assert normwise(r32[k], g[k]) < max(F32_TOL, 3 * normwise(g[k + "_f32"], g[k])), k
+    assert abs(r32["cov_norm"] - float(g["cov_norm"])) < 1e-4 * float(g["cov_norm"])
