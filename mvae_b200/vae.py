@@ -328,10 +328,27 @@ class FusedFeedForwardVAE(nn.Module):
         return ws
 
     # ------------------------------------------------------------------------------------------ kernel sequences
-    def _forward_kernels(self, ws: _Workspace, beta: float, train: bool, want_mu_sigma: bool, logits: Optional[Tensor]):
+    def _side_stream(self) -> "torch.cuda.Stream":
+        st = getattr(self, "_side", None)
+        if st is None:
+            st = self._side = torch.cuda.Stream(device=self.device)
+        return st
+
+    def _forward_kernels(self, ws: _Workspace, beta: float, train: bool, want_mu_sigma: bool, logits: Optional[Tensor],
+                         draw_eps: bool = False):
         B, D, H, P, Sd = ws.B, self.in_dim, self.h_dim, self.desc.ld_ml, self.desc.ld_z
         if self._planes_stale:
             self.refresh_weight_planes()
+        # Fork: the noise draw and the memsets of the accumulating outputs do not depend on the encoder — they run on a
+        # side stream (a parallel branch of the step's CUDA graph) next to split(x) + fc_e0.
+        main, side = torch.cuda.current_stream(self.device), self._side_stream()
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            if draw_eps:
+                ws.eps.normal_()
+            ws.bce.zero_()
+            if train:
+                self._bucket[:self._n_net + self.desc.C].zero_()
         ops.split_planes(ws.x, ws.xp)
         fused = self.fused_latent and not want_mu_sigma
         if fused:
@@ -341,6 +358,7 @@ class FusedFeedForwardVAE(nn.Module):
             self._gemm("e0_fwd", ws.xp, self.We0p, B, H, D, epilogue=L.EPI_BIAS_RELU, bias=self.fc_e0.bias.data,
                        out_planes=ws.hp)
         ws.fused = fused
+        main.wait_stream(side)  # join: eps drawn, bce / gradient bucket zeroed
         if fused:
             # heads + manifold chain + fc_d0/relu in ONE kernel: ml, z, kl kept for the backward pass / statistics
             ops.latent_forward(self.desc, ws.h32, self.Wh, self.bh, ws.eps, self._rflat, self.fc_d0.weight.data,
@@ -355,19 +373,26 @@ class FusedFeedForwardVAE(nn.Module):
             # fc_d0: K = total_z_dim is tiny -> CUDA-core expansion in exact fp32, relu, planes of dd for the logits GEMM
             ops.skinny_expand(ws.z, self.fc_d0.weight.data, Sd, 1, K=Sd, N=H, bias=self.fc_d0.bias.data,
                               act=ops.ACT_RELU, out_planes=ws.ddp)
-        ws.bce.zero_()
         epi = L.EPI_BCE_ROWSUM if self.recon_kind == "bce" else L.EPI_NLL_ROWSUM
         self._gemm("logits_fwd", ws.ddp, self.Wlp, B, D, H, epilogue=epi, bias=self.fc_logits.bias.data, aux=ws.x, rowsum=ws.bce,
                  out_planes=ws.gLp if train else None, out_f32=logits)
-        ops.elbo_reduce(ws.bce, ws.kl, beta, out=self._stats)
+        if not train:  # training: the reduction runs beside the backward GEMMs (_backward_kernels)
+            ops.elbo_reduce(ws.bce, ws.kl, beta, out=self._stats)
 
     def _backward_kernels(self, ws: _Workspace, beta: float):
         B, D, H, P, Sd, C = ws.B, self.in_dim, self.h_dim, self.desc.ld_ml, self.desc.ld_z, self.desc.C
-        self._bucket[:self._n_net + C].zero_()
         MN = L.MN_MAJOR
-        # fc_logits: gW = gL^T dd (+ bias from the ones column of dd), then gdd = (gL W) * 1[dd > 0]
-        self._gemm("logits_wgrad", ws.gLp, ws.ddp, D, H + 1, B, a_major=MN, b_major=MN, split_k=0, out_f32=self.gWl, out_col=self.gbl,
-                 col_split=H)
+        # Fork: the ELBO reduction and the weight gradient of fc_logits depend only on the forward pass; they run as a
+        # parallel branch beside  logits dgrad -> latent backward -> fc_e0 wgrad  (each of these GEMMs fills about half
+        # of the SMs on its own).  The gradient bucket was zeroed by the forward pass's side branch.
+        main, side = torch.cuda.current_stream(self.device), self._side_stream()
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            ops.elbo_reduce(ws.bce, ws.kl, beta, out=self._stats)
+            # fc_logits: gW = gL^T dd (+ bias from the ones column of dd)
+            self._gemm("logits_wgrad", ws.gLp, ws.ddp, D, H + 1, B, a_major=MN, b_major=MN, split_k=0, out_f32=self.gWl,
+                       out_col=self.gbl, col_split=H)
+        # gdd = (gL W) * 1[dd > 0]
         if self.fused_latent:
             self._gemm("logits_dgrad32", ws.gLp, self.Wlp, B, H, D, b_major=MN, epilogue=L.EPI_RELU_MASK, mask=ws.ddp,
                        out_f32=ws.gdd32)
@@ -394,6 +419,7 @@ class FusedFeedForwardVAE(nn.Module):
         # fc_e0 (no dgrad into x)
         self._gemm("e0_wgrad", ws.ghp, ws.xp, H, D + 1, B, a_major=MN, b_major=MN, split_k=0, out_f32=self.gWe0,
                  out_col=self.gbe0, col_split=D, b_planes=2)
+        main.wait_stream(side)  # join
 
     # ------------------------------------------------------------------------------------------ GEMM tile policy
     # The five big GEMMs of a step are launch- and L2-bound at these shapes and their best tile (BLOCK_N, CTAs per SM,
@@ -439,14 +465,16 @@ class FusedFeedForwardVAE(nn.Module):
         ops.add_launches(n0 - ops.launch_count())  # tuning launches are not part of any step
         return best
 
-    def _stage(self, ws: _Workspace, x: Tensor, eps: Optional[Tensor]) -> None:
+    def _stage(self, ws: _Workspace, x: Tensor, eps: Optional[Tensor]) -> bool:
+        """Input batch (and supplied noise) into the workspace.  Returns True when the noise has to be drawn: the
+        forward kernels then do it on their side branch (inside the step's CUDA graph)."""
         ws.x.copy_(x.reshape(ws.B, self.in_dim), non_blocking=True)  # H2D if x lives on the host
         if eps is None:
             eps = self._eps_override
         if eps is None:
-            ws.eps.normal_()
-        else:
-            ws.eps.copy_(eps, non_blocking=True)
+            return True
+        ws.eps.copy_(eps, non_blocking=True)
+        return False
 
     # ------------------------------------------------------------------------------------------ reference API
     def encode(self, x: Tensor) -> Tensor:
@@ -498,10 +526,10 @@ class FusedFeedForwardVAE(nn.Module):
         the stats vector (see compute_batch_stats)."""
         x = x.to(self.device, non_blocking=True)
         ws = self._workspace(x.shape[0])
-        self._stage(ws, x, eps)
+        draw = self._stage(ws, x, eps)
         if ws.logits is None:
             ws.logits = torch.empty(ws.B, self.in_dim, device=self.device)
-        self._forward_kernels(ws, beta, train=False, want_mu_sigma=True, logits=ws.logits)
+        self._forward_kernels(ws, beta, train=False, want_mu_sigma=True, logits=ws.logits, draw_eps=draw)
         self._last_ws = ws
         return self._reparametrized(ws), ws.z, ws.logits
 
@@ -579,8 +607,8 @@ class FusedFeedForwardVAE(nn.Module):
         step, stats to floats.  Returns (BatchStatsFloat | BatchStats, (reparametrized, concat_z, x_mb_)); x_mb_
         (the logits) is not materialised in training — call forward() when it is needed."""
         ws = self._workspace(x_mb.shape[0])
-        self._stage(ws, x_mb, eps)
-        self._step_kernels(optimizer, ws, beta)
+        draw = self._stage(ws, x_mb, eps)
+        self._step_kernels(optimizer, ws, beta, draw)
         stats = BatchStats(self._stats_report.clone() if not sync_stats else self._stats_report, beta)
         self._last_ws = ws
         out = (None, ws.z, None)
@@ -590,14 +618,14 @@ class FusedFeedForwardVAE(nn.Module):
             return stats.convert_to_float(), out
         return stats, out
 
-    def _step_kernels(self, optimizer, ws: _Workspace, beta: float) -> None:
+    def _step_kernels(self, optimizer, ws: _Workspace, beta: float, draw_eps: bool = False) -> None:
         fused = isinstance(optimizer, FusedCurvatureOptimizer)
         if fused and self.use_cuda_graph:
-            self._graphed_step(optimizer, ws, beta)
+            self._graphed_step(optimizer, ws, beta, draw_eps)
         else:
             if not fused:
                 optimizer.zero_grad()
-            self._forward_kernels(ws, beta, train=True, want_mu_sigma=False, logits=None)
+            self._forward_kernels(ws, beta, train=True, want_mu_sigma=False, logits=None, draw_eps=draw_eps)
             self._backward_kernels(ws, beta)
             if self._grad_hook is not None:
                 self._grad_hook(self._bucket)  # data-parallel: one SUM all-reduce over [grads | radius grads | stats]
@@ -668,11 +696,9 @@ class FusedFeedForwardVAE(nn.Module):
             if x_next is not None and x_next.shape[0] == B:
                 prefetch(ws, 1 - slot, x_next, first=(i == 0))
             eps = next(eps_it) if eps_it is not None else self._eps_override
-            if eps is None:
-                ws.eps.normal_()
-            else:
+            if eps is not None:
                 ws.eps.copy_(eps, non_blocking=True)
-            self._step_kernels(optimizer, ws, beta)
+            self._step_kernels(optimizer, ws, beta, eps is None)
             self._slot_free[slot].record(main)
             if i >= ring_n:
                 drain(i - ring_n)
@@ -696,12 +722,13 @@ class FusedFeedForwardVAE(nn.Module):
     _grad_hook = None
     use_cuda_graph = False
 
-    def _graphed_step(self, optimizer: "FusedCurvatureOptimizer", ws: _Workspace, beta: float) -> None:
+    def _graphed_step(self, optimizer: "FusedCurvatureOptimizer", ws: _Workspace, beta: float,
+                      draw_eps: bool = False) -> None:
         """Replay the whole step from CUDA graphs (launch-bound otherwise: ~30 kernels of a few microseconds).
         Graph A = forward + backward into the gradient bucket; [the data-parallel all-reduce runs between the two,
         eagerly]; graph B = optimizer step + refresh of the weight planes.  Keyed by everything baked into launch
         parameters: batch size, beta, and whether the curvature optimizers step."""
-        key = (ws.B, ws.slot, float(beta), optimizer.curvature_step_enabled(), id(optimizer))
+        key = (ws.B, ws.slot, float(beta), optimizer.curvature_step_enabled(), id(optimizer), bool(draw_eps))
         entry = self._graphs.get(key)
         if entry is None:
             if self._planes_stale:
@@ -710,13 +737,13 @@ class FusedFeedForwardVAE(nn.Module):
             side = torch.cuda.Stream(device=self.device)
             side.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(side):
-                self._forward_kernels(ws, beta, train=True, want_mu_sigma=False, logits=None)
+                self._forward_kernels(ws, beta, train=True, want_mu_sigma=False, logits=None, draw_eps=draw_eps)
                 self._backward_kernels(ws, beta)
             torch.cuda.current_stream().wait_stream(side)
             n0 = ops.launch_count()
             ga = torch.cuda.CUDAGraph()
             with torch.cuda.graph(ga):
-                self._forward_kernels(ws, beta, train=True, want_mu_sigma=False, logits=None)
+                self._forward_kernels(ws, beta, train=True, want_mu_sigma=False, logits=None, draw_eps=draw_eps)
                 self._backward_kernels(ws, beta)
             n1 = ops.launch_count()
             gb = torch.cuda.CUDAGraph()
