@@ -126,7 +126,7 @@ typedef enum mvae_op {
   MVAE_OP_DISTANCE = 6,            /* x, y points -> out [B,1] geodesic distance (poincare.py:96-105; tests/mvae/ops/test_hyperbolics.py:46, test_spherical.py:45, test_euclidean.py:41) */
   MVAE_OP_MOBIUS_ADD = 7,          /* Poincare / projected sphere only: x (+) y (poincare.py:100, spherical_projected.py:107-113) */
   MVAE_OP_MOBIUS_SCALAR_MUL = 8,   /* Poincare only: x[B,d], y[B,1] scalar r -> r (x) x. No reference call site: parity unpinned. */
-  MVAE_OP_LOGDET = 9,              /* x = u (h,s: [B,d]) -> out [B,1] (hyperbolics.py:58, spherical.py:58) */
+  MVAE_OP_LOGDET = 9,              /* x = u (h,s: [B,d]) -> out [B,1] (hyperbolics.py:58, spherical.py:58); d: x = z, y = mu (spherical_projected.py:58-92) */
   MVAE_OP_TO_POINCARE = 10,        /* h: lorentz_to_poincare (hyperbolics.py:151); s: spherical_to_projected (spherical.py:132) */
   MVAE_OP_FROM_POINCARE = 11       /* p: poincare_to_lorentz (poincare.py:167); d: projected_to_spherical (spherical_projected.py:191) */
 } mvae_op;

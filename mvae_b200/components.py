@@ -14,7 +14,7 @@ from torch import Tensor
 
 from . import _lib as L
 from .distributions import EuclideanNormal, WrappedNormal
-from .manifolds import Euclidean, Hyperboloid, Manifold, PoincareBall, Sphere
+from .manifolds import Euclidean, Hyperboloid, Manifold, PoincareBall, Sphere, StereographicallyProjectedSphere
 
 
 class Component(torch.nn.Module):
@@ -143,6 +143,22 @@ class SphericalComponent(Component):
         return self.dim - 1
 
 
+class StereographicallyProjectedSphereComponent(Component):
+    """component.py:170-189: the sphere in stereographic coordinates (dim = n), learnable `_pradius`."""
+    letter, kind = "d", L.PROJ_SPHERE
+
+    def __init__(self, dim: int, fixed_curvature: bool, radius: float = 1.0) -> None:
+        super().__init__(dim, fixed_curvature)
+        self._pradius = torch.nn.Parameter(torch.tensor(radius), requires_grad=not fixed_curvature)
+
+    def create_manifold(self) -> Manifold:
+        return StereographicallyProjectedSphere(lambda: self._pradius)
+
+    @property
+    def true_dim(self) -> int:
+        return self.dim
+
+
 class EuclideanComponent(Component):
     """component.py:192-203: always fixed curvature."""
     letter, kind = "e", L.EUCLIDEAN
@@ -158,7 +174,8 @@ class EuclideanComponent(Component):
         return self.dim
 
 
-space_creator_map = {"h": HyperbolicComponent, "s": SphericalComponent, "p": PoincareComponent, "e": EuclideanComponent}
+space_creator_map = {"h": HyperbolicComponent, "s": SphericalComponent, "d": StereographicallyProjectedSphereComponent,
+                     "p": PoincareComponent, "e": EuclideanComponent}
 
 
 def parse_component_str(space_str: str) -> Tuple[int, str, int]:
@@ -172,7 +189,7 @@ def parse_component_str(space_str: str) -> Tuple[int, str, int]:
 
 
 def parse_components(arg: str, fixed_curvature: bool) -> List[Component]:
-    """mt/mvae/utils.py:103-140.  Letters h, s, p, e (d / u / c are outside this hot path: SURVEY.md §8f)."""
+    """mt/mvae/utils.py:103-140.  Letters h, s, d, p, e (u / c are outside this hot path: SURVEY.md §8f)."""
     arg = arg.lower().strip()
     if not arg:
         return []

@@ -109,6 +109,41 @@ __device__ __forceinline__ float p_logdet_rt(int n, const float* z, const float*
   return h_logdet_rt(n + 1, uu, R);
 }
 
+// ---- stereographically projected sphere 'd' (spherical_projected.py; geoopt mobius_add at c = -1/R^2, :107-113) ----
+__device__ __forceinline__ float d_lambda(int n, const float* x, float c) {  // lambda_x_c :123-124
+  return 2.f / fmaxf(1.f + c * dot(n, x, x), kPMin);
+}
+__device__ __forceinline__ void d_expmap(int n, const float* at, const float* x, float R, float* out) {  // :141-147
+  const float c = 1.f / (R * R);
+  const float r = fmaxf(sqrtf(dot(n, x, x)), kPMin) / R;
+  const float k = tanf(r * d_lambda(n, at, c) / 2.f);
+  float rhs[kOpMaxD];
+  for (int j = 0; j < n; ++j) rhs[j] = k * x[j] / r;
+  mobius_add_rt(n, at, rhs, -c, out, 1.f);
+}
+__device__ __forceinline__ void d_logmap(int n, const float* at, const float* x, float R, float* out) {  // :157-162
+  const float c = 1.f / (R * R);
+  float sub[kOpMaxD];
+  mobius_add_rt(n, at, x, -c, sub, -1.f);
+  const float nm = fmaxf(sqrtf(dot(n, sub, sub)), kPMin) / R;
+  const float k = 2.f / d_lambda(n, at, c) * atanf(nm);
+  for (int j = 0; j < n; ++j) out[j] = k * (sub[j] / nm);
+}
+__device__ __forceinline__ void d2s_rt(int n, const float* y, float R, float* out) {  // projected_to_spherical :190-195
+  const float nrm = sqrtf(dot(n, y, y));
+  const float yn2 = nrm * nrm, r2 = R * R;
+  out[0] = R * (r2 - yn2) / (yn2 + r2);
+  for (int j = 0; j < n; ++j) out[j + 1] = 2.f * r2 * y[j] / (yn2 + r2);
+}
+// StereographicallyProjectedSphere.logdet (:58-92)
+__device__ __forceinline__ float d_logdet_rt(int n, const float* z, const float* mu, float R) {
+  float zs[kOpMaxD], ms[kOpMaxD], uu[kOpMaxD];
+  d2s_rt(n, z, R, zs);
+  d2s_rt(n, mu, R, ms);
+  s_inv_exp_rt(n + 1, zs, ms, R, uu);
+  return s_logdet_rt(n + 1, uu, R);
+}
+
 // sample_projection_mu0(v, at) -> z, u   (hyperbolics.py:138-142, spherical.py:119-123, poincare.py:152-157, euclidean.py:90-93)
 __device__ __forceinline__ void sample_projection(int man, int n, const float* v, const float* at, float R, float* z,
                                                   float* u) {
@@ -136,6 +171,10 @@ __device__ __forceinline__ void sample_projection(int man, int n, const float* v
     float lam = lambda_x(n, at, c);
     for (int j = 0; j < n; ++j) u[j] = v[j] / lam;
     p_expmap(n, at, u, c, z);
+  } else if (man == MVAE_PROJ_SPHERE) {  // spherical_projected.py:176-179
+    float lam = d_lambda(n, at, 1.f / (R * R));
+    for (int j = 0; j < n; ++j) u[j] = v[j] / lam;
+    d_expmap(n, at, u, R, z);
   } else {
     for (int j = 0; j < n; ++j) {
       u[j] = v[j];
@@ -160,6 +199,10 @@ __device__ __forceinline__ void inv_sample_projection(int man, int n, const floa
     float c = 1.f / (R * R);
     p_logmap(n, at, z, c, u);
     float lam = lambda_x(n, at, c);
+    for (int j = 0; j < n; ++j) v[j] = u[j] * lam;
+  } else if (man == MVAE_PROJ_SPHERE) {  // spherical_projected.py:182-186
+    d_logmap(n, at, z, R, u);
+    float lam = d_lambda(n, at, 1.f / (R * R));
     for (int j = 0; j < n; ++j) v[j] = u[j] * lam;
   } else {
     for (int j = 0; j < n; ++j) {
@@ -200,6 +243,10 @@ __global__ void __launch_bounds__(128) manifold_op_kernel(const OpParams p) {
         float un = fmaxf(sqrtf(dot(n, x, x)), kPMin);
         float th = tanh_c(sc * un);
         for (int j = 0; j < n; ++j) o[j] = th * x[j] / (sc * un);
+      } else if (man == MVAE_PROJ_SPHERE) {  // spherical_projected.py:150-154
+        float r = fmaxf(sqrtf(dot(n, x, x)), kPMin) / R;
+        float tn = tanf(r);
+        for (int j = 0; j < n; ++j) o[j] = tn * x[j] / r;
       } else {
         for (int j = 0; j < n; ++j) o[j] = x[j] / 2.f;
       }
@@ -222,6 +269,10 @@ __global__ void __launch_bounds__(128) manifold_op_kernel(const OpParams p) {
         float xc;
         float at = artanh_go(sc * yn, &xc);
         for (int j = 0; j < n; ++j) o[j] = x[j] / yn / sc * at;
+      } else if (man == MVAE_PROJ_SPHERE) {  // spherical_projected.py:165-168
+        float nx = fmaxf(sqrtf(dot(n, x, x)), kPMin) / R;
+        float at = atanf(nx);
+        for (int j = 0; j < n; ++j) o[j] = at * (x[j] / nx);
       } else {
         for (int j = 0; j < n; ++j) o[j] = 2.f * x[j];
       }
@@ -240,6 +291,8 @@ __global__ void __launch_bounds__(128) manifold_op_kernel(const OpParams p) {
         for (int k = 0; k < d; ++k) o[k] = c1 * y[k] + s1 * (x[k] / t);
       } else if (man == MVAE_POINCARE) {
         p_expmap(n, y, x, c, o);
+      } else if (man == MVAE_PROJ_SPHERE) {
+        d_expmap(n, y, x, R, o);
       } else {
         for (int j = 0; j < n; ++j) o[j] = y[j] + x[j] / 2.f;
       }
@@ -248,6 +301,7 @@ __global__ void __launch_bounds__(128) manifold_op_kernel(const OpParams p) {
       if (man == MVAE_HYPERBOLOID) h_inv_exp_rt(d, x, y, R, o);
       else if (man == MVAE_SPHERE) s_inv_exp_rt(d, x, y, R, o);
       else if (man == MVAE_POINCARE) p_logmap(n, y, x, c, o);
+      else if (man == MVAE_PROJ_SPHERE) d_logmap(n, y, x, R, o);
       else
         for (int j = 0; j < n; ++j) o[j] = 2.f * (x[j] - y[j]);
     } break;
@@ -263,6 +317,9 @@ __global__ void __launch_bounds__(128) manifold_op_kernel(const OpParams p) {
       } else if (man == MVAE_POINCARE) {
         float f = fmaxf(1.f - c * dot(n, y, y), kPMin);
         for (int j = 0; j < n; ++j) o[j] = x[j] * f;
+      } else if (man == MVAE_PROJ_SPHERE) {  // (2 / lambda_dst) x, spherical_projected.py:133-134
+        float f = 2.f / d_lambda(n, y, c);
+        for (int j = 0; j < n; ++j) o[j] = f * x[j];
       } else {
         for (int j = 0; j < n; ++j) o[j] = x[j];
       }
@@ -279,6 +336,9 @@ __global__ void __launch_bounds__(128) manifold_op_kernel(const OpParams p) {
       } else if (man == MVAE_POINCARE) {
         float f = fmaxf(1.f - c * dot(n, y, y), kPMin);
         for (int j = 0; j < n; ++j) o[j] = x[j] / f;
+      } else if (man == MVAE_PROJ_SPHERE) {  // (lambda_src / 2) x, spherical_projected.py:137-138
+        float f = d_lambda(n, y, c) / 2.f;
+        for (int j = 0; j < n; ++j) o[j] = f * x[j];
       } else {
         for (int j = 0; j < n; ++j) o[j] = x[j];
       }
@@ -294,13 +354,18 @@ __global__ void __launch_bounds__(128) manifold_op_kernel(const OpParams p) {
         float sub[kOpMaxD];
         mobius_add_rt(n, x, y, c, sub, -1.f);
         o[0] = atanh_g(sc * sqrtf(dot(n, sub, sub))) * 2.f / sc;
+      } else if (man == MVAE_PROJ_SPHERE) {  // spherical_projected_distance, spherical_projected.py:95-102 (K = c)
+        float dd = 0.f;
+        for (int j = 0; j < n; ++j) dd += (x[j] - y[j]) * (x[j] - y[j]);
+        float arg = 1.f - 2.f * c * dd / ((1.f + c * dot(n, x, x)) * (1.f + c * dot(n, y, y)));
+        o[0] = 1.f / sqrt_g(c) * acosf(fminf(arg, 1.f));
       } else {
         float s = 0.f;
         for (int j = 0; j < n; ++j) s += (x[j] - y[j]) * (x[j] - y[j]);
         o[0] = 2.f * sqrtf(s);
       }
     } break;
-    case MVAE_OP_MOBIUS_ADD: mobius_add_rt(n, x, y, c, o, 1.f); break;
+    case MVAE_OP_MOBIUS_ADD: mobius_add_rt(n, x, y, man == MVAE_PROJ_SPHERE ? -c : c, o, 1.f); break;
     case MVAE_OP_MOBIUS_SCALAR_MUL: {
       // r (x)_c x = tanh(r artanh(sqrt_c |x|)) x / (sqrt_c |x|)   (no reference call site: parity unpinned)
       float sc = powf(c, 0.5f);
@@ -309,11 +374,18 @@ __global__ void __launch_bounds__(128) manifold_op_kernel(const OpParams p) {
       float k = tanh_c(y[0] * artanh_go(sc * xn, &xc));
       for (int j = 0; j < n; ++j) o[j] = k * x[j] / (xn * sc);
     } break;
-    case MVAE_OP_LOGDET: o[0] = man == MVAE_HYPERBOLOID ? h_logdet_rt(d, x, R) : s_logdet_rt(d, x, R); break;
+    case MVAE_OP_LOGDET:
+      o[0] = man == MVAE_HYPERBOLOID ? h_logdet_rt(d, x, R)
+             : man == MVAE_SPHERE    ? s_logdet_rt(d, x, R)
+                                     : d_logdet_rt(n, x, y, R);  // 'd': x = z, y = mu
+      break;
     case MVAE_OP_TO_POINCARE:
       for (int j = 0; j < n; ++j) o[j] = R * x[j + 1] / (R + x[0]);
       break;
-    default: p2l_rt(n, x, R, o); break;  // MVAE_OP_FROM_POINCARE
+    default:  // MVAE_OP_FROM_POINCARE
+      if (man == MVAE_PROJ_SPHERE) d2s_rt(n, x, R, o);
+      else p2l_rt(n, x, R, o);
+      break;
   }
   for (int k = 0; k < p.out_w; ++k) p.out[b * p.out_w + k] = o[k];
 }
@@ -365,6 +437,7 @@ __global__ void __launch_bounds__(128) wn_kernel(const WnParams p) {
   if (man == MVAE_HYPERBOLOID) ld = h_logdet_rt(d, u, R);
   else if (man == MVAE_SPHERE) ld = s_logdet_rt(d, u, R);
   else if (man == MVAE_POINCARE) ld = p_logdet_rt(n, z, loc, R);
+  else if (man == MVAE_PROJ_SPHERE) ld = d_logdet_rt(n, z, loc, R);
   p.logp[b] = normal_lp(n, v, sg) - ld;
 }
 
@@ -372,7 +445,7 @@ static int amb_dim(int man, int n) { return (man == MVAE_HYPERBOLOID || man == M
 
 static int check_manifold(int man, int n) {
   if (man < MVAE_EUCLIDEAN || man > MVAE_PROJ_SPHERE || n < 1) return MVAE_ERR_INVALID_ARGUMENT;
-  if (man == MVAE_PROJ_SPHERE || n > kDynMaxN) return MVAE_ERR_UNSUPPORTED;
+  if (n > kDynMaxN) return MVAE_ERR_UNSUPPORTED;
   return MVAE_OK;
 }
 
@@ -409,7 +482,7 @@ extern "C" int mvae_manifold_op(int32_t op, int32_t manifold, int32_t n, int64_t
     case MVAE_OP_INV_PT_MU0: p.x_w = d; p.y_w = d; p.out_w = d; need_y = true; break;
     case MVAE_OP_DISTANCE: p.x_w = d; p.y_w = d; p.out_w = 1; need_y = true; break;
     case MVAE_OP_MOBIUS_ADD:
-      if (manifold != MVAE_POINCARE) return MVAE_ERR_UNSUPPORTED;
+      if (manifold != MVAE_POINCARE && manifold != MVAE_PROJ_SPHERE) return MVAE_ERR_UNSUPPORTED;
       p.x_w = d; p.y_w = d; p.out_w = d; need_y = true;
       break;
     case MVAE_OP_MOBIUS_SCALAR_MUL:
@@ -417,6 +490,10 @@ extern "C" int mvae_manifold_op(int32_t op, int32_t manifold, int32_t n, int64_t
       p.x_w = d; p.y_w = 1; p.out_w = d; need_y = true;
       break;
     case MVAE_OP_LOGDET:
+      if (manifold == MVAE_PROJ_SPHERE) {  // logdet(mu, z) through the sphere: x = z, y = mu
+        p.x_w = d; p.y_w = d; p.out_w = 1; need_y = true;
+        break;
+      }
       if (!amb) return MVAE_ERR_UNSUPPORTED;
       p.x_w = d; p.out_w = 1;
       break;
@@ -425,7 +502,7 @@ extern "C" int mvae_manifold_op(int32_t op, int32_t manifold, int32_t n, int64_t
       p.x_w = d; p.out_w = n;
       break;
     default:
-      if (manifold != MVAE_POINCARE) return MVAE_ERR_UNSUPPORTED;
+      if (manifold != MVAE_POINCARE && manifold != MVAE_PROJ_SPHERE) return MVAE_ERR_UNSUPPORTED;
       p.x_w = n; p.out_w = n + 1;
       break;
   }

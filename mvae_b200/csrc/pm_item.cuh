@@ -86,7 +86,8 @@ __device__ __forceinline__ bool run_item(int n_rt, int l_n, const CompConst& K, 
   if (TYPE == MVAE_EUCLIDEAN) comp_e<N, BWD>(n, l_n, m, l, e, o, gz, gkl, gm, gl);
   else if (TYPE == MVAE_HYPERBOLOID) comp_hsp<N, BWD, kHyp, WANT_MS>(n, l_n, m, l, e, K, o, gz, gkl, gm, gl, &gR);
   else if (TYPE == MVAE_SPHERE) comp_hsp<N, BWD, kSph, WANT_MS>(n, l_n, m, l, e, K, o, gz, gkl, gm, gl, &gR);
-  else comp_hsp<N, BWD, kPoi, WANT_MS>(n, l_n, m, l, e, K, o, gz, gkl, gm, gl, &gR);
+  else if (TYPE == MVAE_POINCARE) comp_hsp<N, BWD, kPoi, WANT_MS>(n, l_n, m, l, e, K, o, gz, gkl, gm, gl, &gR);
+  else comp_hsp<N, BWD, kPsp, WANT_MS>(n, l_n, m, l, e, K, o, gz, gkl, gm, gl, &gR);
   if (BWD) {
     *gR_acc += gR;
     if (N > 0) {
@@ -168,12 +169,15 @@ __device__ __forceinline__ bool dispatch_item(const ItemInfo& c, const float* ml
 #define MVAE_PM_H(NN) MVAE_PM_ITEM(MVAE_HYPERBOLOID, NN)
 #define MVAE_PM_S(NN) MVAE_PM_ITEM(MVAE_SPHERE, NN)
 #define MVAE_PM_P(NN) MVAE_PM_ITEM(MVAE_POINCARE, NN)
+#define MVAE_PM_D(NN) MVAE_PM_ITEM(MVAE_PROJ_SPHERE, NN)
   switch (c.type) {
     case MVAE_EUCLIDEAN: MVAE_PM_FOR_DIMS(MAXN, c.n, MVAE_PM_E) break;
     case MVAE_HYPERBOLOID: MVAE_PM_FOR_DIMS(MAXN, c.n, MVAE_PM_H) break;
     case MVAE_SPHERE: MVAE_PM_FOR_DIMS(MAXN, c.n, MVAE_PM_S) break;
-    default: MVAE_PM_FOR_DIMS(MAXN, c.n, MVAE_PM_P) break;
+    case MVAE_POINCARE: MVAE_PM_FOR_DIMS(MAXN, c.n, MVAE_PM_P) break;
+    default: MVAE_PM_FOR_DIMS(MAXN, c.n, MVAE_PM_D) break;
   }
+#undef MVAE_PM_D
 #undef MVAE_PM_E
 #undef MVAE_PM_H
 #undef MVAE_PM_S

@@ -15,7 +15,6 @@ static int validate_desc(const mvae_pm_desc* d) {
   for (int i = 0; i < d->C; ++i) {
     const mvae_component& c = d->comp[i];
     if (c.type < MVAE_EUCLIDEAN || c.type > MVAE_PROJ_SPHERE) return MVAE_ERR_INVALID_ARGUMENT;
-    if (c.type == MVAE_PROJ_SPHERE) return MVAE_ERR_UNSUPPORTED;
     if (c.n < 1) return MVAE_ERR_INVALID_ARGUMENT;
     if (c.n > pm::kDynMaxN) return MVAE_ERR_UNSUPPORTED;
     const int d_expect = (c.type == MVAE_HYPERBOLOID || c.type == MVAE_SPHERE) ? c.n + 1 : c.n;

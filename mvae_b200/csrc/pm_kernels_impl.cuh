@@ -307,12 +307,15 @@ __device__ __forceinline__ void pm_kernel_body(const PmParams& p) {
 #define MVAE_PM_LOOP_H(NN) pm_tile_loop<BWD, MAXN, WANT_MS, MVAE_HYPERBOLOID, NN>(p, smem, info, my_ci, smem0, bar0);
 #define MVAE_PM_LOOP_S(NN) pm_tile_loop<BWD, MAXN, WANT_MS, MVAE_SPHERE, NN>(p, smem, info, my_ci, smem0, bar0);
 #define MVAE_PM_LOOP_P(NN) pm_tile_loop<BWD, MAXN, WANT_MS, MVAE_POINCARE, NN>(p, smem, info, my_ci, smem0, bar0);
+#define MVAE_PM_LOOP_D(NN) pm_tile_loop<BWD, MAXN, WANT_MS, MVAE_PROJ_SPHERE, NN>(p, smem, info, my_ci, smem0, bar0);
     switch (type) {
       case MVAE_EUCLIDEAN: MVAE_PM_FOR_DIMS(MAXN, n, MVAE_PM_LOOP_E) break;
       case MVAE_HYPERBOLOID: MVAE_PM_FOR_DIMS(MAXN, n, MVAE_PM_LOOP_H) break;
       case MVAE_SPHERE: MVAE_PM_FOR_DIMS(MAXN, n, MVAE_PM_LOOP_S) break;
-      default: MVAE_PM_FOR_DIMS(MAXN, n, MVAE_PM_LOOP_P) break;
+      case MVAE_POINCARE: MVAE_PM_FOR_DIMS(MAXN, n, MVAE_PM_LOOP_P) break;
+      default: MVAE_PM_FOR_DIMS(MAXN, n, MVAE_PM_LOOP_D) break;
     }
+#undef MVAE_PM_LOOP_D
 #undef MVAE_PM_LOOP_E
 #undef MVAE_PM_LOOP_H
 #undef MVAE_PM_LOOP_S
@@ -391,7 +394,8 @@ static int launch_pm(PmParams& p, void* stream) {
   cudaFuncAttributes fa;
   MVAE_CUDA_TRY(cudaFuncGetAttributes(&fa, kern));
   auto cost_of = [&](const mvae_component& c) {  // issue slots per item, from the SASS of the static variants
-    const int base = c.type == MVAE_EUCLIDEAN ? 20 : c.type == MVAE_SPHERE ? 125 : c.type == MVAE_POINCARE ? 115 : 105;
+    const int base = c.type == MVAE_EUCLIDEAN ? 20 : c.type == MVAE_SPHERE ? 125 : c.type == MVAE_POINCARE ? 115 :
+                     c.type == MVAE_PROJ_SPHERE ? 140 : 105;
     return (bwd ? 3 : 2) * (base + (c.type == MVAE_EUCLIDEAN ? 15 : 25) * c.n) / 2;
   };
   int wc[MVAE_MAX_COMPONENTS];

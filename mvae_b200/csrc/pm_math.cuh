@@ -325,15 +325,24 @@ PM_DEV void comp_e(int n, int l_n, const float* m, const float* l, const float* 
 // takes H._logdet of the log map, whose norm is dist(mu, z) = |v|: the same Fq(t).  log p (:160-164): |logmap_0(z)|
 // lambda_0 = 2R artanh(|z|/R) = R r with geoopt's artanh clamp (|z|/R <= 1 - 1e-5, i.e. r <= 12.206), while the
 // log-det sees the unclamped r.  geoopt's tanh clamp (+-15) bounds a and t/2.
-enum { kHyp = 0, kSph = 1, kPoi = 2 };
+// Stereographically projected sphere ('d', spherical_projected.py; d = n): the same construction over the sphere.
+// exp_map_mu0 (:150-154) gives mu = R tan(a) mh = the sphere point at distance 2|m| seen through spherical_to_projected
+// (spherical.py:132-133); sample_projection_mu0 (:176-179, exp_map :141-147 with geoopt's mobius_add at c = -1/R^2)
+// lands at geodesic distance |v| from mu in the conformal direction of v: z_D = R Z_tail / (R + Z_0), Z the sphere
+// sample at a -> 2a.  logdet (:58-92) maps z and mu back to the sphere and takes S._logdet of the log map, whose norm
+// is dist(mu, z) = R acos(cos t) — the WRAPPED angle tw in [0, pi], not t (they differ once |v| > pi R).  log p
+// (:182-186, :157-162): |x| = 2R atan(|z|/R) = R r, r = dist(mu0, Z)/R; no clamps besides MIN_NORM on norms.
+enum { kHyp = 0, kSph = 1, kPoi = 2, kPsp = 3 };
 
 template <int N, bool BWD, int KIND, bool WANT_MS>
 PM_DEV void comp_hsp(int n, int l_n, const float* m, const float* l, const float* e, const CompConst& K,
                      CompOut<N>& o, const float* gz, float gkl, float* gm, float* gl, float* gR_out) {
   PM_UN(N);
   constexpr int CN = Cap<N>::n;
-  constexpr bool HYP = KIND != kSph;  // hyperbolic trigonometry
+  constexpr bool HYP = KIND == kHyp || KIND == kPoi;  // hyperbolic trigonometry
   constexpr bool POI = KIND == kPoi;
+  constexpr bool PSP = KIND == kPsp;
+  constexpr bool PROJ = POI || PSP;  // conformal model of H / S: a -> 2a, projected coordinates, MIN_NORM clamps
   const float R = K.R, iR = K.iR;
   // ---- encode ----
   float nm2 = 0.f;
@@ -341,12 +350,12 @@ PM_DEV void comp_hsp(int n, int l_n, const float* m, const float* l, const float
   for (int j = 0; j < CN; ++j)
     if (j < n) nm2 = fmaf(m[j], m[j], nm2);
   const float nm = f_sqrt(nm2);
-  const float nmin = POI ? kPMin : 1e-12f;  // geoopt MIN_NORM | F.normalize eps
+  const float nmin = PROJ ? kPMin : 1e-12f;  // geoopt MIN_NORM | F.normalize eps
   const float dn = fmaxf(nm, nmin);
   const float idn = f_rcp(dn);
-  const float a = (POI ? dn : nm) * iR;
+  const float a = (PROJ ? dn : nm) * iR;
   const bool a_sat = POI && a > 15.f;       // geoopt tanh clamp (plain: zero gradient beyond)
-  const float aa = POI ? 2.f * fminf(a, 15.f) : a;
+  const float aa = POI ? 2.f * fminf(a, 15.f) : (PSP ? 2.f * a : a);
   float ca, sa;
   if (HYP) coshsinh_pos(aa, &ca, &sa);
   else sincos_cw(aa, &sa, &ca);
@@ -399,9 +408,9 @@ PM_DEV void comp_hsp(int n, int l_n, const float* m, const float* l, const float
       zt[j] = fmaf(A, v[j], Bm * m[j]);
       zt2 = fmaf(zt[j], zt[j], zt2);
     }
-  const float iRz = POI ? f_rcp(R + z0) : 0.f;
-  const float pj = POI ? R * iRz : 1.f;  // lorentz_to_poincare
-  if (POI) {
+  const float iRz = PROJ ? f_rcp(R + z0) : 0.f;
+  const float pj = PROJ ? R * iRz : 1.f;  // lorentz_to_poincare | spherical_to_projected
+  if (PROJ) {
     PM_UNROLL
     for (int j = 0; j < CN; ++j)
       if (j < n) z[j] = pj * zt[j];
@@ -413,8 +422,8 @@ PM_DEV void comp_hsp(int n, int l_n, const float* m, const float* l, const float
   }
   if (WANT_MS) {
     float* mu = o.mu;
-    if (POI) {
-      const float Ta = R * sa * f_rcp(ca + 1.f) * idn;  // tanh(a) = sinh(2a) / (cosh(2a) + 1)
+    if (PROJ) {
+      const float Ta = R * sa * f_rcp(ca + 1.f) * idn;  // tanh(a) = sinh(2a) / (cosh(2a) + 1), tan(a) likewise
       PM_UNROLL
       for (int j = 0; j < CN; ++j)
         if (j < n) mu[j] = Ta * m[j];
@@ -431,7 +440,7 @@ PM_DEV void comp_hsp(int n, int l_n, const float* m, const float* l, const float
   const float rl_min = kSqrtClamp * iR;
   const float s2 = zt2 * iR2;
   const float s = f_sqrt(s2);
-  float r, rq, as_ = 0.f, alpha = 0.f, snr = 0.f, csr = 0.f, irl = 0.f, D;
+  float r, rq, as_ = 0.f, alpha = 0.f, snr = 0.f, csr = 0.f, irl = 0.f, tw = 0.f, D;
   bool r_clamped = false, at_clamped = false;
   if (HYP) {
     as_ = f_sqrt(1.f + s2);
@@ -450,8 +459,10 @@ PM_DEV void comp_hsp(int n, int l_n, const float* m, const float* l, const float
     snr = s * inv_q;                                       // sin r and cos r without going through r
     csr = alpha * inv_q;
     // G(x) = log clamp(|sin x|, 1e-5) - log clamp(x, 1e-5) (spherical.py:58-67); G(t) - G(r) under one logarithm
+    // 'd' measures the posterior's log-det at the wrapped angle tw = acos(cos t) (|sin| is the same)
+    tw = PSP ? atan2_pos(fabsf(st), ct) : t;
     const float num = fmaxf(fabsf(st), 1e-5f) * fmaxf(r, 1e-5f);
-    const float den = fmaxf(fabsf(snr), 1e-5f) * fmaxf(t, 1e-5f);
+    const float den = fmaxf(fabsf(snr), 1e-5f) * fmaxf(tw, 1e-5f);
     D = f_lg2(num * f_rcp(den)) * kLn2;
     rq = r;
   }
@@ -494,7 +505,7 @@ PM_DEV void comp_hsp(int n, int l_n, const float* m, const float* l, const float
   const float k_zt = s > 0.f ? g_s * iR2 * f_rcp(s) : 0.f;
   gR += -g_s * s * iR;
   float g_z0 = 0.f;
-  if (POI) {
+  if (PROJ) {
     // z_j = R Z_j / (R + Z_0)
     PM_UNROLL
     for (int j = 0; j < CN; ++j)
@@ -505,10 +516,10 @@ PM_DEV void comp_hsp(int n, int l_n, const float* m, const float* l, const float
       }
   } else {
     g_z0 = gz[0];
-    if (!HYP) {
-      g_z0 = fmaf(g_alpha, iR, g_z0);
-      gR += -g_alpha * alpha * iR;
-    }
+  }
+  if (!HYP) {
+    g_z0 = fmaf(g_alpha, iR, g_z0);
+    gR += -g_alpha * alpha * iR;
   }
   // z0 = R ct ca + sgn A sa p ;  Bc = R ct sa + A cam1 p ; z_tail = A v + Bc mh
   float g_A = 0.f, g_Bm = 0.f;
@@ -516,7 +527,7 @@ PM_DEV void comp_hsp(int n, int l_n, const float* m, const float* l, const float
   PM_UNROLL
   for (int j = 0; j < CN; ++j)
     if (j < n) {
-      G[j] = fmaf(k_zt, zt[j], POI ? pj * gz[j] : gz[j + 1]);
+      G[j] = fmaf(k_zt, zt[j], PROJ ? pj * gz[j] : gz[j + 1]);
       g_A = fmaf(G[j], v[j], g_A);
       g_Bm = fmaf(G[j], m[j], g_Bm);
     }
@@ -541,7 +552,11 @@ PM_DEV void comp_hsp(int n, int l_n, const float* m, const float* l, const float
       g_t += fmaf(-g_ct, st, g_st * ct);
       float dG = 0.f;
       if (fabsf(st) >= 1e-5f) dG = ct * f_rcp(st);
-      if (t >= 1e-5f) dG -= it;
+      if (PSP) {
+        if (tw >= 1e-5f) dG -= (st >= 0.f ? 1.f : -1.f) * f_rcp(tw);  // d(tw)/dt = sign(sin t)
+      } else if (t >= 1e-5f) {
+        dG -= it;
+      }
       g_t = fmaf(-gkl * nm1, dG, g_t);
     }
   }
@@ -555,10 +570,10 @@ PM_DEV void comp_hsp(int n, int l_n, const float* m, const float* l, const float
   float g_a;
   if (POI) g_a = a_sat ? 0.f : 2.f * fmaf(g_ca, sa, g_sa * ca);
   else if (HYP) g_a = fmaf(g_ca, sa, g_sa * ca) * (a <= kMaxHyp ? 1.f : 1e-8f);
-  else g_a = fmaf(-g_ca, sa, g_sa * ca);
+  else g_a = (PSP ? 2.f : 1.f) * fmaf(-g_ca, sa, g_sa * ca);
   gR += -g_a * a * iR;
-  float g_nm = POI ? 0.f : g_a * iR;   // P: a = max(|m|, MIN_NORM) / R
-  float g_dn = POI ? g_a * iR : 0.f;
+  float g_nm = PROJ ? 0.f : g_a * iR;   // P, D: a = max(|m|, MIN_NORM) / R
+  float g_dn = PROJ ? g_a * iR : 0.f;
   // v = eps * sigma ; p = <mh, v> ; mh = m / dn ; z_tail = A v + Bc mh
   float g_s_[CN];
   const float g_pm = g_p * idn, twoSv = 2.f * g_Sv;

@@ -40,7 +40,7 @@ class WrappedNormal(VaeDistribution):
 
     def __init__(self, loc: Tensor, scale: Tensor, manifold: Manifold) -> None:
         self.dim = loc.shape[-1]
-        tangent_dim = self.dim if manifold.kind in (L.POINCARE, L.EUCLIDEAN) else self.dim - 1
+        tangent_dim = self.dim if manifold.kind in (L.POINCARE, L.PROJ_SPHERE, L.EUCLIDEAN) else self.dim - 1
         if scale.shape[-1] > 1 and scale.shape[-1] != tangent_dim:
             raise ValueError("Invalid scale dimension: neither isotropic nor elliptical.")
         if scale.shape[-1] == 1:

@@ -1,5 +1,6 @@
 """Host-side mirror of the reference's `Manifold` interface (mt/mvae/ops/manifold.py:22-75) and its concrete
-manifolds (mt/mvae/ops/{hyperbolics.py:26-55, spherical.py:26-55, poincare.py:28-89, euclidean.py:24-59}).
+manifolds (mt/mvae/ops/{hyperbolics.py:26-55, spherical.py:26-55, poincare.py:28-89, euclidean.py:24-59,
+spherical_projected.py:28-92}).
 
 Every method runs a device kernel of libmvae_b200.so through mvae_manifold_op (include/mvae_b200.h); inputs are
 float32 CUDA tensors of shape [..., dim].  These standalone ops are forward-only (no autograd): gradients of the
@@ -76,8 +77,10 @@ class Manifold:
         v = self.inverse_parallel_transport_mu0(u, at_point)
         if self.kind in (L.HYPERBOLOID, L.SPHERE):
             v = v[..., 1:]
-        elif self.kind == L.POINCARE:
-            v = 2.0 * v  # poincare.py:160-164: v_ * lambda_x; the inverse PT kernel returns v_ / (1 - c|x|^2)
+        elif self.kind in (L.POINCARE, L.PROJ_SPHERE):
+            # poincare.py:160-164 / spherical_projected.py:182-186: v_ * lambda_x; the inverse PT kernel returns
+            # v_ * lambda_x / 2
+            v = 2.0 * v
         return u, v
 
     def logdet(self, mu: Tensor, std: Tensor, z: Tensor, data: Tuple[Tensor, ...]) -> Tensor:
@@ -176,6 +179,29 @@ class PoincareBall(RadiusManifold):
     @property
     def curvature(self) -> Tensor:
         return -super().curvature
+
+
+class StereographicallyProjectedSphere(RadiusManifold):
+    """mt/mvae/ops/spherical_projected.py:28-92 ('d': the sphere of radius R in stereographic coordinates; geoopt's
+    mobius_add at c = -1/R^2)."""
+    kind = L.PROJ_SPHERE
+
+    def mu_0(self, shape: torch.Size, **kwargs: Any) -> Tensor:
+        return torch.zeros(shape, **kwargs)
+
+    def mobius_add(self, x: Tensor, y: Tensor) -> Tensor:
+        """mob_add (spherical_projected.py:107-113)."""
+        return self._op(L.OP_MOBIUS_ADD, x, y)
+
+    def to_spherical(self, x: Tensor) -> Tensor:
+        """projected_to_spherical (spherical_projected.py:190-195)."""
+        return self._op(L.OP_FROM_POINCARE, x)
+
+    def logdet(self, mu: Tensor, std: Tensor, z: Tensor, data: Tuple[Tensor, ...]) -> Tensor:
+        # spherical_projected.py:58-92: S._logdet of the sphere's log map of z at mu
+        lead = z.shape[:-1]
+        mu_b = mu.expand(*lead, mu.shape[-1]).reshape(-1, mu.shape[-1]).contiguous()
+        return self._op(L.OP_LOGDET, z.reshape(-1, z.shape[-1]).contiguous(), mu_b).reshape(lead)
 
 
 class Euclidean(Manifold):

@@ -39,7 +39,7 @@ def _f32(t: torch.Tensor, name: str) -> torch.Tensor:
 
 
 def parse_signature(sig: str):
-    """'2h3,s2,e2' -> ([types], [dims]); grammar of mt/mvae/utils.py:78-140 (letters e,h,s,p; 'd','u' unsupported)."""
+    """'2h3,s2,e2' -> ([types], [dims]); grammar of mt/mvae/utils.py:78-140 (letters e,h,s,p,d; 'u','c' unsupported)."""
     types, dims = [], []
     for tok in sig.lower().strip().split(","):
         tok = tok.strip().split("-")[0]

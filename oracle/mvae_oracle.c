@@ -23,6 +23,8 @@ MATHFN(_f64, double, mexp, exp)
 MATHFN(_f64, double, msin, sin)
 MATHFN(_f64, double, mcos, cos)
 MATHFN(_f64, double, macos, acos)
+MATHFN(_f64, double, mtan, tan)
+MATHFN(_f64, double, matan, atan)
 static inline double mpow_f64(double x, double y) { return pow(x, y); }
 #define real double
 #define SFX(n) n##_f64
@@ -41,6 +43,8 @@ MATHFN(_f32, float, mexp, expf)
 MATHFN(_f32, float, msin, sinf)
 MATHFN(_f32, float, mcos, cosf)
 MATHFN(_f32, float, macos, acosf)
+MATHFN(_f32, float, mtan, tanf)
+MATHFN(_f32, float, matan, atanf)
 static inline float mpow_f32(float x, float y) { return powf(x, y); }
 #define real float
 #define SFX(n) n##_f32

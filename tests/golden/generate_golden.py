@@ -114,12 +114,14 @@ def gen_loglik(name, sig, in_dim, h_dim, B, n, recon, radius, scalar=False, seed
 
 def gen_ops(letter, n=3, B=16, R=2.0, seed=5):
     from mt.mvae.ops import Hyperboloid, Sphere, PoincareBall, Euclidean
-    from mt.mvae.ops import hyperbolics as H, spherical as S, poincare as P
+    from mt.mvae.ops import hyperbolics as H, spherical as S, poincare as P, spherical_projected as SP
+    from mt.mvae.ops import StereographicallyProjectedSphere
     from mt.mvae.distributions import WrappedNormal
     with rh.default_dtype(torch.float64):
         Rt = torch.tensor(R, dtype=torch.float64)
         man = {"h": lambda: Hyperboloid(lambda: Rt), "s": lambda: Sphere(lambda: Rt),
-               "p": lambda: PoincareBall(lambda: Rt), "e": lambda: Euclidean()}[letter]()
+               "p": lambda: PoincareBall(lambda: Rt), "e": lambda: Euclidean(),
+               "d": lambda: StereographicallyProjectedSphere(lambda: Rt)}[letter]()
         g = torch.Generator().manual_seed(seed)
         t1 = torch.randn(B, n, generator=g, dtype=torch.float64) * 0.8
         t2 = torch.randn(B, n, generator=g, dtype=torch.float64) * 0.8
@@ -161,6 +163,16 @@ def gen_ops(letter, n=3, B=16, R=2.0, seed=5):
             out["distance"] = P.poincare_distance(x, y, radius=Rt)
             out["mobius_add"] = P.pm.mobius_add(x, y, c=P._c(Rt))
             out["from_poincare"] = P.poincare_to_lorentz(x, Rt)
+            out["logdet_zmu"] = man.logdet(x, scale, z, (u, vv))
+        elif letter == "d":
+            pt = man.parallel_transport_mu0(v, x)
+            out["pt_mu0"] = pt
+            out["inv_pt_mu0"] = man.inverse_parallel_transport_mu0(pt, x)
+            out["exp_map"] = SP.exp_map(pt, x, radius=Rt)
+            out["inv_exp_map"] = SP.inverse_exp_map(y, x, radius=Rt)
+            out["distance"] = SP.spherical_projected_distance(x, y, K=SP._c(Rt))
+            out["mobius_add"] = SP.mob_add(x, y, SP._c(Rt))
+            out["from_poincare"] = SP.projected_to_spherical(x, Rt)
             out["logdet_zmu"] = man.logdet(x, scale, z, (u, vv))
         else:
             from mt.mvae.ops import euclidean as E
@@ -207,12 +219,28 @@ def gen_logliks():
     gen_loglik("scalar_s3_p2_e3_bce", "s3,p2,e3", in_dim=18, h_dim=16, B=10, n=4, recon="bce", radius=1.5, scalar=True)
 
 
+def gen_ds():
+    """'d' (stereographically projected sphere, spherical_projected.py) fixtures."""
+    gen_pm("d2_s2_d3_e2", "d2,s2,d3,e2", [1.0, 1.3, 2.0, 0.0], seed=21, scale_m=0.7)
+    gen_pm("d6_p2_R", "d6,p2", [3.0, 1.5], seed=22, scale_m=0.8)
+    gen_pm("scalar_d2_h2", "d2,h2", [0.9, 1.1], seed=23, scalar=True, scale_m=0.5)
+    gen_pm("d1_d40", "d1,d40", [1.0, 4.0], B=8, seed=24, scale_m=0.3)
+    gen_model("d2_h2_e2_bce", "d2,h2,e2", in_dim=20, h_dim=16, B=12, recon="bce", fixed_curvature=False, radius=1.5,
+              seed=25)
+    gen_loglik("d2_s2_bce", "d2,s2", in_dim=16, h_dim=16, B=9, n=5, recon="bce", radius=1.2, seed=26)
+    gen_ops("d")
+
+
 if __name__ == "__main__":
+    if "--only-d" in sys.argv:
+        gen_ds()
+        sys.exit(0)
     if "--only-loglik" in sys.argv:  # added later: leaves the other committed fixtures byte-identical
         gen_logliks()
         sys.exit(0)
     gen_kat()
     gen_logliks()
+    gen_ds()
     gen_pm("h2_s2_e2_R1", "h2,s2,e2", [1.0, 1.0, 0.0])
     gen_pm("cfg3_R10", "h6,h6,s6,s6,e6", [10.0, 10.0, 10.0, 10.0, 0.0], seed=1)
     gen_pm("cfg3_Rmixed", "h6,h6,s6,s6,e6", [1.5, 0.7, 2.0, 1.0, 0.0], seed=2, scale_m=0.6)

@@ -24,7 +24,8 @@ static void run(const mvae_component& c, float rp, const float* ml, const float*
     case MVAE_EUCLIDEAN: comp_e<N, BWD>(n, c.l_n, m, l, e, o, gzc, gkl, gm, gl); break;
     case MVAE_HYPERBOLOID: comp_hsp<N, BWD, kHyp, true>(n, c.l_n, m, l, e, K, o, gzc, gkl, gm, gl, &g); break;
     case MVAE_SPHERE: comp_hsp<N, BWD, kSph, true>(n, c.l_n, m, l, e, K, o, gzc, gkl, gm, gl, &g); break;
-    default: comp_hsp<N, BWD, kPoi, true>(n, c.l_n, m, l, e, K, o, gzc, gkl, gm, gl, &g); break;
+    case MVAE_POINCARE: comp_hsp<N, BWD, kPoi, true>(n, c.l_n, m, l, e, K, o, gzc, gkl, gm, gl, &g); break;
+    default: comp_hsp<N, BWD, kPsp, true>(n, c.l_n, m, l, e, K, o, gzc, gkl, gm, gl, &g); break;
   }
   if (BWD) {
     *gR += g * radius_d(rp);
