@@ -51,7 +51,12 @@ typedef enum mvae_manifold {
   MVAE_HYPERBOLOID = 1, /* 'h'  mt/mvae/ops/hyperbolics.py + WrappedNormalProcedure (:91-116)   */
   MVAE_SPHERE = 2,      /* 's'  mt/mvae/ops/spherical.py   + WrappedNormalProcedure             */
   MVAE_POINCARE = 3,    /* 'p'  mt/mvae/ops/poincare.py (+geoopt 0.1.0) + WrappedNormalProcedure */
-  MVAE_PROJ_SPHERE = 4  /* 'd'  mt/mvae/ops/spherical_projected.py + WrappedNormalProcedure     */
+  MVAE_PROJ_SPHERE = 4, /* 'd'  mt/mvae/ops/spherical_projected.py + WrappedNormalProcedure     */
+  MVAE_UNIVERSAL = 5    /* 'u'  mt/mvae/ops/universal.py + UniversalSamplingProcedure (sampling_procedures.py:184-206):
+                                the component's entry of `radius` holds its raw CURVATURE parameter kappa; the kernels
+                                branch per launch on its sign — kappa < -1e-6: Poincare ball, kappa > 1e-6: projected
+                                sphere, both with R = 1/sqrt|kappa| (universal.py:30-31,64-74), else Euclidean — and
+                                return d/dkappa in the component's slot of the radius gradient */
 } mvae_manifold;
 
 /* One latent component.  n = true (tangent) dimension; d = ambient dimension of loc/z
@@ -283,6 +288,20 @@ int mvae_recon_loss(int32_t kind, int64_t B, int32_t D, const float* logits, con
  * elbo = sum_b(-bce_b - beta * sum_c kl_bc).  Warp-shuffle + block reduce; `out` [3+C] is overwritten. */
 int mvae_elbo_reduce(int64_t B, int32_t C, const float* bce, const float* kl, float beta, float* out, void* stream);
 
+/* ------------------------------------------------------------------------------------ input pipeline */
+/* Dynamic binarisation of image batches on the device.  The reference does it per sample on the CPU inside its
+ * DataLoader (ImageDynamicBinarization, mt/data/image_reconstruction.py:37-53) and ships float batches; here the batch
+ * travels as stored (uint8 grayscale src [B, ld_src]) and one kernel produces
+ *   x [B, ld_x] fp32 (reconstruction targets) and / or x_planes (plane 0 of the fc_e0 operand; 0 / 1 are exact in bf16)
+ *   x[b,k] = (v > u[b,k]) ? 1 : 0,  v = src/255 as float32 (ToTensor), v <- 1 - v if invert
+ * mode 0: dynamic — u [B, D] supplied (bit-exact against the reference's comparison for the same draws), or NULL =
+ *         drawn in the kernel (Philox4x32-10: key `seed`, offset 8 * *offset_dev; the device word is read, not advanced,
+ *         so the call can be captured in a CUDA graph — the caller increments it once per step);
+ * mode 1: fixed threshold 0.5 (the reference's evaluation transform). */
+int mvae_binarize(const uint8_t* src, int64_t ld_src, int64_t B, int32_t D, int32_t mode, int32_t invert, const float* u,
+                  uint64_t seed, const uint64_t* offset_dev, float* x, int64_t ld_x, const mvae_planes* x_planes,
+                  void* stream);
+
 /* ------------------------------------------------------ importance-weighted log-likelihood (evaluation) */
 /* ModelVAE.log_likelihood (vae.py:82-123) draws n samples per input row.  The encoder runs once; per chunk of `ns`
  * samples mvae_iwae_latent does Component.encode's manifold part + rsample_log_probs of EVERY component
@@ -318,6 +337,11 @@ int mvae_adam_step(int64_t n, float* param, const float* grad, float* exp_avg, f
  * captured once in a CUDA graph and replayed. */
 int mvae_adam_step_dev(int64_t n, float* param, const float* grad, float* exp_avg, float* exp_avg_sq, float lr,
                        float beta1, float beta2, float eps, int32_t* step_dev, float grad_scale, void* stream);
+
+/* torch.nn.utils.clip_grad_norm_(params, max_norm, norm_type=2) over the n <= 4096 scalar gradients selected by mask
+ * (mask[i] != 0): the reference clips the "curvature"-named parameters of universal components in every train step
+ * (vae.py:161-163).  grad[i] *= min(1, max_norm / (||grad . mask||_2 + 1e-6)) for the selected entries. */
+int mvae_clip_grad_norm(int32_t n, float* grad, const float* mask, float max_norm, void* stream);
 
 /* Plain SGD step p -= lr * grad_scale * g (torch.optim.SGD defaults — the curvature optimizers of train.py:346-355). */
 int mvae_sgd_step(int64_t n, float* param, const float* grad, float lr, float grad_scale, void* stream);

@@ -14,8 +14,8 @@ MAX_COMPONENTS = 96
 ABI_VERSION = 2
 
 # mvae_manifold
-EUCLIDEAN, HYPERBOLOID, SPHERE, POINCARE, PROJ_SPHERE = 0, 1, 2, 3, 4
-TYPE_OF_LETTER = {"e": EUCLIDEAN, "h": HYPERBOLOID, "s": SPHERE, "p": POINCARE, "d": PROJ_SPHERE}
+EUCLIDEAN, HYPERBOLOID, SPHERE, POINCARE, PROJ_SPHERE, UNIVERSAL = 0, 1, 2, 3, 4, 5
+TYPE_OF_LETTER = {"e": EUCLIDEAN, "h": HYPERBOLOID, "s": SPHERE, "p": POINCARE, "d": PROJ_SPHERE, "u": UNIVERSAL}
 # mvae_op
 (OP_EXP_MAP_MU0, OP_INV_EXP_MAP_MU0, OP_EXP_MAP, OP_INV_EXP_MAP, OP_PT_MU0, OP_INV_PT_MU0, OP_DISTANCE, OP_MOBIUS_ADD,
  OP_MOBIUS_SCALAR_MUL, OP_LOGDET, OP_TO_POINCARE, OP_FROM_POINCARE) = range(12)
@@ -83,11 +83,14 @@ PROTOTYPES = {
                                             _vp, _vp, _vp, _f32, ctypes.POINTER(Planes), _vp, _vp, _vp, _vp, _vp, _vp]),
     "mvae_recon_loss": (ctypes.c_int, [_i32, _i64, _i32, _vp, _vp, _vp, _vp, _vp]),
     "mvae_elbo_reduce": (ctypes.c_int, [_i64, _i32, _vp, _vp, _f32, _vp, _vp]),
+    "mvae_binarize": (ctypes.c_int, [_vp, _i64, _i64, _i32, _i32, _i32, _vp, ctypes.c_uint64, _vp, _vp, _i64,
+                                     ctypes.POINTER(Planes), _vp]),
     "mvae_iwae_latent": (ctypes.c_int, [ctypes.POINTER(PmDesc), _i64, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "mvae_iwae_reduce": (ctypes.c_int, [_i32, _i64, _vp, _vp, _vp, _vp, _vp]),
     "mvae_iwae_cov_norm": (ctypes.c_int, [_i64, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp]),
     "mvae_adam_step": (ctypes.c_int, [_i64, _vp, _vp, _vp, _vp, _f32, _f32, _f32, _f32, _i32, _f32, _vp]),
     "mvae_adam_step_dev": (ctypes.c_int, [_i64, _vp, _vp, _vp, _vp, _f32, _f32, _f32, _f32, _vp, _f32, _vp]),
+    "mvae_clip_grad_norm": (ctypes.c_int, [_i32, _vp, _vp, _f32, _vp]),
     "mvae_sgd_step": (ctypes.c_int, [_i64, _vp, _vp, _f32, _f32, _vp]),
     "mvae_opt_step_fused": (ctypes.c_int, [_i64, _vp, _vp, _vp, _vp, _f32, _f32, _f32, _f32, _vp, _vp, _vp, _vp, _vp,
                                            _f32, _i32, _i32, ctypes.POINTER(_i64), ctypes.POINTER(_i32),

@@ -14,7 +14,8 @@ from torch import Tensor
 
 from . import _lib as L
 from .distributions import EuclideanNormal, WrappedNormal
-from .manifolds import Euclidean, Hyperboloid, Manifold, PoincareBall, Sphere, StereographicallyProjectedSphere
+from .manifolds import (Euclidean, Hyperboloid, Manifold, PoincareBall, Sphere, StereographicallyProjectedSphere,
+                        Universal)
 
 
 class Component(torch.nn.Module):
@@ -42,10 +43,15 @@ class Component(torch.nn.Module):
         return self.fc_mean.weight.device
 
     def radius_parameter(self):
-        for name in ("_nradius", "_pradius"):
+        """(name, parameter) of the component's curvature parameter: a raw radius, or the raw curvature of 'u'."""
+        for name in ("_nradius", "_pradius", "_curvature"):
             if hasattr(self, name):
                 return name, getattr(self, name)
         return None, None
+
+    def effective_kind(self) -> int:
+        """Manifold the component currently lives on (differs from `kind` only for 'u')."""
+        return self.kind
 
     def encode(self, x: Tensor) -> Tuple[Tensor, Tensor]:
         """component.py:63-75."""
@@ -56,11 +62,12 @@ class Component(torch.nn.Module):
 
     def reparametrize(self, z_mean: Tensor, std: Tensor):
         """WrappedNormalProcedure / EuclideanNormalProcedure.reparametrize (sampling_procedures.py:93-99,147-151)."""
-        if self.kind == L.EUCLIDEAN:
+        if self.effective_kind() == L.EUCLIDEAN:
             return EuclideanNormal(z_mean, std), EuclideanNormal(torch.zeros_like(z_mean), torch.ones_like(std))
-        q_z = WrappedNormal(z_mean, std, self.manifold)
-        mu_0 = self.manifold.mu_0(z_mean.shape, device=z_mean.device, dtype=z_mean.dtype)
-        p_z = WrappedNormal(mu_0, torch.ones_like(q_z.scale), self.manifold)
+        man = self.manifold.manifold if self.kind == L.UNIVERSAL else self.manifold
+        q_z = WrappedNormal(z_mean, std, man)
+        mu_0 = man.mu_0(z_mean.shape, device=z_mean.device, dtype=z_mean.dtype)
+        p_z = WrappedNormal(mu_0, torch.ones_like(q_z.scale), man)
         return q_z, p_z
 
     def forward(self, x: Tensor):
@@ -70,7 +77,7 @@ class Component(torch.nn.Module):
 
     def kl_loss(self, q_z, p_z, z: Tensor, data) -> Tensor:
         """sampling_procedures.py:101-116 (log q - log p, one-sample MC) and :153-155 (analytic for Euclidean)."""
-        if self.kind == L.EUCLIDEAN:
+        if self.effective_kind() == L.EUCLIDEAN:
             return torch.distributions.kl.kl_divergence(q_z, p_z).sum(dim=-1)
         return q_z.log_prob_from_parts(z, data) - p_z.log_prob(z)
 
@@ -159,6 +166,28 @@ class StereographicallyProjectedSphereComponent(Component):
         return self.dim
 
 
+class UniversalComponent(Component):
+    """component.py:225-242: learnable `_curvature` (kappa); the manifold is the Poincare ball, the projected sphere or
+    the Euclidean plane according to its sign (universal.py), the sampling procedure follows
+    (UniversalSamplingProcedure, sampling_procedures.py:184-206)."""
+    letter, kind = "u", L.UNIVERSAL
+
+    def __init__(self, dim: int, fixed_curvature: bool, curvature: float = 0.0, eps: float = 1e-6) -> None:
+        super().__init__(dim, fixed_curvature)
+        self._curvature = torch.nn.Parameter(torch.tensor(curvature), requires_grad=not fixed_curvature)
+        self._eps = eps
+
+    def create_manifold(self) -> Manifold:
+        return Universal(lambda: self._curvature, eps=self._eps)
+
+    def effective_kind(self) -> int:
+        return {-1: L.POINCARE, 0: L.EUCLIDEAN, 1: L.PROJ_SPHERE}[self.manifold._choice]
+
+    @property
+    def true_dim(self) -> int:
+        return self.dim
+
+
 class EuclideanComponent(Component):
     """component.py:192-203: always fixed curvature."""
     letter, kind = "e", L.EUCLIDEAN
@@ -175,7 +204,7 @@ class EuclideanComponent(Component):
 
 
 space_creator_map = {"h": HyperbolicComponent, "s": SphericalComponent, "d": StereographicallyProjectedSphereComponent,
-                     "p": PoincareComponent, "e": EuclideanComponent}
+                     "p": PoincareComponent, "e": EuclideanComponent, "u": UniversalComponent}
 
 
 def parse_component_str(space_str: str) -> Tuple[int, str, int]:
@@ -189,7 +218,7 @@ def parse_component_str(space_str: str) -> Tuple[int, str, int]:
 
 
 def parse_components(arg: str, fixed_curvature: bool) -> List[Component]:
-    """mt/mvae/utils.py:103-140.  Letters h, s, d, p, e (u / c are outside this hot path: SURVEY.md §8f)."""
+    """mt/mvae/utils.py:103-140.  Letters h, s, d, p, e, u ('c' is outside this hot path: SURVEY.md §8f)."""
     arg = arg.lower().strip()
     if not arg:
         return []

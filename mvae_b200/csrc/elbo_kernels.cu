@@ -497,6 +497,41 @@ extern "C" int mvae_split_planes(const float* src, int64_t ld_src, int32_t R, in
   return MVAE_OK;
 }
 
+namespace mvae {
+__global__ void __launch_bounds__(128) clip_grad_norm_kernel(int n, float* __restrict__ g, const float* __restrict__ mask,
+                                                             float max_norm) {
+  __shared__ float red[4];
+  __shared__ float coef;
+  float acc = 0.f;
+  for (int i = threadIdx.x; i < n; i += 128) {
+    const float v = mask[i] != 0.f ? g[i] : 0.f;
+    acc = fmaf(v, v, acc);
+  }
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const float norm = sqrtf(red[0] + red[1] + red[2] + red[3]);
+    coef = fminf(max_norm / (norm + 1e-6f), 1.f);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < n; i += 128)
+    if (mask[i] != 0.f) g[i] *= coef;
+}
+}  // namespace mvae
+
+extern "C" int mvae_clip_grad_norm(int32_t n, float* grad, const float* mask, float max_norm, void* stream) {
+  if (n < 0 || n > 4096 || !(max_norm > 0.f)) return MVAE_ERR_INVALID_ARGUMENT;
+  DeviceInfo di;
+  int rc = get_device_info(&di);
+  if (rc != MVAE_OK) return rc;
+  if (n == 0) return MVAE_OK;
+  if (!grad || !mask) return MVAE_ERR_INVALID_ARGUMENT;
+  clip_grad_norm_kernel<<<1, 128, 0, as_stream(stream)>>>(n, grad, mask, max_norm);
+  MVAE_LAUNCH_CHECK();
+  return MVAE_OK;
+}
+
 extern "C" int mvae_opt_step_fused(int64_t n, float* param, const float* grad, float* exp_avg, float* exp_avg_sq,
                                    float lr, float beta1, float beta2, float eps, int32_t* step_dev,
                                    uint32_t* done_counter, float* radius, const float* gradius,

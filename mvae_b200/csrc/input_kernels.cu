@@ -1,0 +1,155 @@
+// input_kernels.cu — dynamic binarisation of image batches on the device (mvae_binarize, include/mvae_b200.h).
+//
+// The reference binarises every image on the CPU inside its DataLoader (ImageDynamicBinarization,
+// mt/data/image_reconstruction.py:37-53: x > U(0,1) per pixel in training, x > 0.5 in evaluation, after ToTensor's
+// uint8 / 255) and ships float batches: 4 bytes per pixel over PCIe.  Here the batch travels as the dataset stores it
+// (uint8 grayscale, 1 byte per pixel) and ONE kernel produces both consumers of the step from it: the fp32 targets of
+// the reconstruction loss and the bf16 operand plane of fc_e0 (0 / 1 are exact in bf16) — it replaces the plane-split
+// launch of the float path.  The uniforms are either supplied (parity tests: bit-exact against the reference's
+// comparison given the same draws) or drawn in the kernel with Philox4x32-10 (key = seed, subsequence = pixel group,
+// offset = 8 x the step counter read from device memory, so the launch is CUDA-graph replayable).
+#include <cuda_bf16.h>
+#include <curand_kernel.h>
+
+#include "mvae_common.cuh"
+
+namespace mvae {
+
+struct BinParams {
+  const uint8_t* src;
+  int64_t ld_src;
+  int64_t B;
+  int D;
+  int mode;    // 0 dynamic (x > u), 1 fixed (x > 0.5)
+  int invert;  // x <- 1 - x first
+  const float* u;
+  unsigned long long seed;
+  const unsigned long long* offset_dev;
+  float* x;
+  int64_t ld_x;
+  uint16_t* plane;  // plane 0 of the fc_e0 operand, or nullptr
+  int64_t ld_plane;
+};
+
+__device__ __forceinline__ float pixel_value(uint8_t v, int invert) {
+  const float x = (float)v / 255.f;  // ToTensor: uint8 -> float32, div(255)
+  return invert ? 1.f - x : x;
+}
+
+// One thread per group of 8 consecutive pixels of a row (D % 8 == 0, 8-byte aligned rows): one 64-bit load, two Philox
+// blocks, two 128-bit fp32 stores, one 128-bit bf16 store.
+__global__ void __launch_bounds__(256) binarize8_kernel(const BinParams p) {
+  const int K8 = p.D >> 3;
+  const int64_t total = p.B * K8;
+  const unsigned long long step = (p.mode == 0 && !p.u && p.offset_dev) ? *p.offset_dev : 0ull;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / K8;
+    const int k = (int)(i - r * K8) * 8;
+    const uint2 raw = __ldg(reinterpret_cast<const uint2*>(p.src + r * p.ld_src + k));
+    float thr[8];
+    if (p.mode != 0) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) thr[j] = 0.5f;
+    } else if (p.u) {
+      const float4 a = __ldg(reinterpret_cast<const float4*>(p.u + r * p.D + k));
+      const float4 b = __ldg(reinterpret_cast<const float4*>(p.u + r * p.D + k) + 1);
+      thr[0] = a.x; thr[1] = a.y; thr[2] = a.z; thr[3] = a.w;
+      thr[4] = b.x; thr[5] = b.y; thr[6] = b.z; thr[7] = b.w;
+    } else {
+      curandStatePhilox4_32_10_t st;
+      curand_init(p.seed, (unsigned long long)i, step * 8ull, &st);
+      const float4 a = curand_uniform4(&st), b = curand_uniform4(&st);  // (0, 1]; torch.rand is [0, 1)
+      thr[0] = 1.f - a.x; thr[1] = 1.f - a.y; thr[2] = 1.f - a.z; thr[3] = 1.f - a.w;
+      thr[4] = 1.f - b.x; thr[5] = 1.f - b.y; thr[6] = 1.f - b.z; thr[7] = 1.f - b.w;
+    }
+    float y[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const uint8_t v = (uint8_t)(((j < 4 ? raw.x : raw.y) >> (8 * (j & 3))) & 0xFFu);
+      y[j] = pixel_value(v, p.invert) > thr[j] ? 1.f : 0.f;
+    }
+    if (p.x) {
+      float4* dst = reinterpret_cast<float4*>(p.x + r * p.ld_x + k);
+      dst[0] = make_float4(y[0], y[1], y[2], y[3]);
+      dst[1] = make_float4(y[4], y[5], y[6], y[7]);
+    }
+    if (p.plane) {
+      uint32_t w[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j)  // bf16(1.0) = 0x3F80
+        w[j] = (y[2 * j] != 0.f ? 0x3F80u : 0u) | (y[2 * j + 1] != 0.f ? 0x3F800000u : 0u);
+      *reinterpret_cast<uint4*>(p.plane + r * p.ld_plane + k) = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+  }
+}
+
+// General shapes: one thread per pixel (the Philox stream is the same function of the pixel group, so both kernels
+// binarise identically).
+__global__ void __launch_bounds__(256) binarize1_kernel(const BinParams p) {
+  const int64_t total = p.B * p.D;
+  const int K8 = (p.D + 7) >> 3;
+  const unsigned long long step = (p.mode == 0 && !p.u && p.offset_dev) ? *p.offset_dev : 0ull;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / p.D;
+    const int k = (int)(i - r * p.D);
+    float thr = 0.5f;
+    if (p.mode == 0) {
+      if (p.u) {
+        thr = __ldg(p.u + r * p.D + k);
+      } else {
+        curandStatePhilox4_32_10_t st;
+        curand_init(p.seed, (unsigned long long)(r * K8 + (k >> 3)), step * 8ull, &st);
+        const float4 a = curand_uniform4(&st), b = curand_uniform4(&st);
+        const float t8[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+        thr = 1.f - t8[k & 7];
+      }
+    }
+    const float y = pixel_value(__ldg(p.src + r * p.ld_src + k), p.invert) > thr ? 1.f : 0.f;
+    if (p.x) p.x[r * p.ld_x + k] = y;
+    if (p.plane) p.plane[r * p.ld_plane + k] = y != 0.f ? (uint16_t)0x3F80u : (uint16_t)0u;
+  }
+}
+
+}  // namespace mvae
+
+using namespace mvae;
+
+extern "C" int mvae_binarize(const uint8_t* src, int64_t ld_src, int64_t B, int32_t D, int32_t mode, int32_t invert,
+                             const float* u, uint64_t seed, const uint64_t* offset_dev, float* x, int64_t ld_x,
+                             const mvae_planes* x_planes, void* stream) {
+  if (!src || B < 0 || D < 1 || ld_src < D || mode < 0 || mode > 1 || (!x && !x_planes))
+    return MVAE_ERR_INVALID_ARGUMENT;
+  if (x && ld_x < D) return MVAE_ERR_INVALID_ARGUMENT;
+  if (x_planes && (!x_planes->base || x_planes->planes < 1 || x_planes->rows < B || x_planes->ld < D))
+    return MVAE_ERR_INVALID_ARGUMENT;
+  DeviceInfo di;
+  int rc = get_device_info(&di);
+  if (rc != MVAE_OK) return rc;
+  if (B == 0) return MVAE_OK;
+  BinParams p;
+  memset(&p, 0, sizeof(p));
+  p.src = src;
+  p.ld_src = ld_src;
+  p.B = B;
+  p.D = D;
+  p.mode = mode;
+  p.invert = invert ? 1 : 0;
+  p.u = u;
+  p.seed = (unsigned long long)seed;
+  p.offset_dev = reinterpret_cast<const unsigned long long*>(offset_dev);
+  p.x = x;
+  p.ld_x = ld_x;
+  p.plane = x_planes ? x_planes->base : nullptr;
+  p.ld_plane = x_planes ? x_planes->ld : 0;
+  auto al = [](const void* q, uintptr_t a) { return (reinterpret_cast<uintptr_t>(q) & (a - 1)) == 0; };
+  const bool fast = (D % 8 == 0) && (ld_src % 8 == 0) && al(src, 8) && (!x || ((ld_x % 4 == 0) && al(x, 16))) &&
+                    (!u || al(u, 16)) && (!p.plane || ((p.ld_plane % 8 == 0) && al(p.plane, 16)));
+  const int64_t work = fast ? B * (D / 8) : B * (int64_t)D;
+  int64_t blocks = (work + 255) / 256;
+  const int64_t cap = (int64_t)di.sm_count * 16;
+  if (blocks > cap) blocks = cap;
+  if (fast) binarize8_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(p);
+  else binarize1_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(p);
+  MVAE_LAUNCH_CHECK();
+  return MVAE_OK;
+}

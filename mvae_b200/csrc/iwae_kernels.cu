@@ -261,7 +261,7 @@ extern "C" int mvae_iwae_latent(const mvae_pm_desc* desc, int64_t B, int32_t ns,
   int maxn = 0;
   for (int i = 0; i < desc->C; ++i) {
     const mvae_component& c = desc->comp[i];
-    if (c.type < MVAE_EUCLIDEAN || c.type > MVAE_PROJ_SPHERE || c.n < 1) return MVAE_ERR_INVALID_ARGUMENT;
+    if (c.type < MVAE_EUCLIDEAN || c.type > MVAE_UNIVERSAL || c.n < 1) return MVAE_ERR_INVALID_ARGUMENT;
     any_curved = any_curved || c.type != MVAE_EUCLIDEAN;
     dyn = dyn || !(c.n >= 1 && c.n <= 8 && c.n != 7);
     maxn = c.n > maxn ? c.n : maxn;

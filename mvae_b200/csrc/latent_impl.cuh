@@ -352,7 +352,7 @@ __global__ void __launch_bounds__(kLatThreads) latent_backward_kernel(const __gr
       dispatch_item<true, MAXN, false>(c, sML + lane * P, sEPS + lane * Sn, nullptr, nullptr, nullptr, nullptr,
                                        sGZ + lane * Sd, p.gkl, sGML + lane * P, &gR, false);
     if (p.gradius) {
-      gR = warp_sum(gR) * radius_d(c.rp);
+      gR = warp_sum(gR) * c.dfac;
       if (lane == 0 && gR != 0.f) atomicAdd(p.gradius + ci, gR);
     }
   }

@@ -66,7 +66,7 @@ struct __align__(16) ItemInfo {
   int m_off, l_off, eps_off, z_off;
   CompConst K;  // R, 1/R
   float rp;
-  int pad;
+  float dfac;   // d(radius)/d(raw parameter): clamp(relu(.)) for radius parameters, d|kappa|^(-1/2)/dkappa for 'u'
 };
 
 // One (component, sample) item with every operand pointer final (component offsets applied): m, l, e [, gz] in the input
@@ -200,8 +200,23 @@ __device__ __forceinline__ void stage_items(ItemInfo* info, const mvae_pm_desc& 
     ii.eps_off = c.eps_off;
     ii.z_off = c.z_off;
     ii.rp = (radius && c.type != MVAE_EUCLIDEAN) ? __ldg(radius + i) : 1.f;
+    if (c.type == MVAE_UNIVERSAL) {
+      // universal.py:64-74: the manifold is chosen by the sign of the learnable curvature (the reference does it with a
+      // host-side `if` on every call); radius = relu(1 / sqrt(|kappa|)) (:30-31)
+      const float kappa = ii.rp, ak = fabsf(kappa);
+      if (ak > 1e-6f) {
+        ii.type = kappa < 0.f ? MVAE_POINCARE : MVAE_PROJ_SPHERE;
+        ii.rp = rsqrtf(ak);
+        ii.dfac = (kappa < 0.f ? 0.5f : -0.5f) * ii.rp / ak;
+      } else {
+        ii.type = MVAE_EUCLIDEAN;
+        ii.rp = 1.f;
+        ii.dfac = 0.f;
+      }
+    } else {
+      ii.dfac = radius_d(ii.rp);
+    }
     ii.K = make_const(ii.rp);
-    ii.pad = 0;
     info[i] = ii;
   }
 }

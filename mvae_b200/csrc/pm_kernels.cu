@@ -14,7 +14,7 @@ static int validate_desc(const mvae_pm_desc* d) {
   if (d->ld_ml > 16384 || d->ld_z > 16384) return MVAE_ERR_UNSUPPORTED;
   for (int i = 0; i < d->C; ++i) {
     const mvae_component& c = d->comp[i];
-    if (c.type < MVAE_EUCLIDEAN || c.type > MVAE_PROJ_SPHERE) return MVAE_ERR_INVALID_ARGUMENT;
+    if (c.type < MVAE_EUCLIDEAN || c.type > MVAE_UNIVERSAL) return MVAE_ERR_INVALID_ARGUMENT;
     if (c.n < 1) return MVAE_ERR_INVALID_ARGUMENT;
     if (c.n > pm::kDynMaxN) return MVAE_ERR_UNSUPPORTED;
     const int d_expect = (c.type == MVAE_HYPERBOLOID || c.type == MVAE_SPHERE) ? c.n + 1 : c.n;
@@ -41,7 +41,7 @@ extern "C" int mvae_pm_desc_init(mvae_pm_desc* D, int32_t C, const int32_t* type
   int ml = 0, e = 0, z = 0;
   for (int i = 0; i < C; ++i) {
     mvae_component* c = &D->comp[i];
-    if (dims[i] < 1 || types[i] < MVAE_EUCLIDEAN || types[i] > MVAE_PROJ_SPHERE) return MVAE_ERR_INVALID_ARGUMENT;
+    if (dims[i] < 1 || types[i] < MVAE_EUCLIDEAN || types[i] > MVAE_UNIVERSAL) return MVAE_ERR_INVALID_ARGUMENT;
     c->type = types[i];
     c->n = dims[i];
     c->d = (types[i] == MVAE_HYPERBOLOID || types[i] == MVAE_SPHERE) ? dims[i] + 1 : dims[i];

@@ -220,7 +220,7 @@ __device__ __forceinline__ void pm_tile_loop(const PmParams& p, float* smem, con
               c, sin_ + p.in_ml + sidx * ld_ml, sin_ + p.in_eps + sidx * ld_eps, sout + p.out_a + sidx * ld_z,
               sout + p.out_b + sidx * C + ci, sout + p.out_c + sidx * ld_z, sout + p.out_d + sidx * ld_eps,
               sin_ + p.in_gz + sidx * ld_z, gkl, sout + p.out_a + sidx * ld_ml, &gR, check);
-          gR *= radius_d(c.rp);
+          gR *= c.dfac;
         }
         if (BWD && p.gradius) {
           gR = warp_sum(gR);
@@ -275,7 +275,7 @@ __device__ __forceinline__ void pm_tile_loop(const PmParams& p, float* smem, con
   if (tid == 0) pm_bulk_wait_all0();  // shared memory must outlive the last bulk store
   if (BWD) {
     if (SINGLE && p.gradius) {
-      const float g = warp_sum(gR_acc * radius_d(mine.rp));
+      const float g = warp_sum(gR_acc * mine.dfac);
       if (lane == 0 && g != 0.f) atomicAdd(p.gradius + my_ci, g);
     }
   } else if (p.flag) {
@@ -395,7 +395,7 @@ static int launch_pm(PmParams& p, void* stream) {
   MVAE_CUDA_TRY(cudaFuncGetAttributes(&fa, kern));
   auto cost_of = [&](const mvae_component& c) {  // issue slots per item, from the SASS of the static variants
     const int base = c.type == MVAE_EUCLIDEAN ? 20 : c.type == MVAE_SPHERE ? 125 : c.type == MVAE_POINCARE ? 115 :
-                     c.type == MVAE_PROJ_SPHERE ? 140 : 105;
+                     (c.type == MVAE_PROJ_SPHERE || c.type == MVAE_UNIVERSAL) ? 140 : 105;
     return (bwd ? 3 : 2) * (base + (c.type == MVAE_EUCLIDEAN ? 15 : 25) * c.n) / 2;
   };
   int wc[MVAE_MAX_COMPONENTS];

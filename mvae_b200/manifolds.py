@@ -204,6 +204,74 @@ class StereographicallyProjectedSphere(RadiusManifold):
         return self._op(L.OP_LOGDET, z.reshape(-1, z.shape[-1]).contiguous(), mu_b).reshape(lead)
 
 
+class Universal(Manifold):
+    """mt/mvae/ops/universal.py:27-86: the sign of the learnable curvature picks the manifold on every call —
+    PoincareBall (kappa < -eps), StereographicallyProjectedSphere (kappa > eps) or Euclidean — with
+    radius = relu(1 / sqrt(|kappa|)).  Standalone ops delegate to the chosen manifold (one host read of kappa, like the
+    reference's `if`); the fused kernels take the same branch on the device (MVAE_UNIVERSAL)."""
+    kind = L.UNIVERSAL
+
+    def __init__(self, curvature: Callable[[], Tensor], eps: float = 1e-6) -> None:
+        super().__init__()
+        self._curvature = curvature
+        self.eps = eps
+        self._manifolds = {-1: PoincareBall(lambda: self.radius), 0: Euclidean(),
+                           1: StereographicallyProjectedSphere(lambda: self.radius)}
+
+    @property
+    def curvature(self) -> Tensor:
+        return self._curvature()
+
+    @property
+    def radius(self) -> Tensor:
+        return torch.relu(1.0 / torch.sqrt(torch.clamp(self.curvature.detach().abs(), min=1e-9)))
+
+    @property
+    def _choice(self) -> int:
+        k = float(self._curvature().detach())
+        return -1 if k < -self.eps else (1 if k > self.eps else 0)
+
+    @property
+    def manifold(self) -> Manifold:
+        return self._manifolds[self._choice]
+
+    def _radius_param(self):
+        return self.manifold._radius_param()
+
+    def exp_map_mu0(self, x: Tensor) -> Tensor:
+        return self.manifold.exp_map_mu0(x)
+
+    def inverse_exp_map_mu0(self, x: Tensor) -> Tensor:
+        return self.manifold.inverse_exp_map_mu0(x)
+
+    def exp_map(self, x: Tensor, at_point: Tensor) -> Tensor:
+        return self.manifold.exp_map(x, at_point)
+
+    def inverse_exp_map(self, x: Tensor, at_point: Tensor) -> Tensor:
+        return self.manifold.inverse_exp_map(x, at_point)
+
+    def parallel_transport_mu0(self, x: Tensor, dst: Tensor) -> Tensor:
+        return self.manifold.parallel_transport_mu0(x, dst)
+
+    def inverse_parallel_transport_mu0(self, x: Tensor, src: Tensor) -> Tensor:
+        return self.manifold.inverse_parallel_transport_mu0(x, src)
+
+    def distance(self, x: Tensor, y: Tensor) -> Tensor:
+        return self.manifold.distance(x, y)
+
+    def mu_0(self, shape: torch.Size, **kwargs: Any) -> Tensor:
+        return self.manifold.mu_0(shape, **kwargs)
+
+    def sample_projection_mu0(self, x: Tensor, at_point: Tensor) -> Tuple[Tensor, Tuple[Tensor, Tensor]]:
+        return self.manifold.sample_projection_mu0(x, at_point)
+
+    def inverse_sample_projection_mu0(self, x_proj: Tensor, at_point: Tensor) -> Tuple[Tensor, Tensor]:
+        return self.manifold.inverse_sample_projection_mu0(x_proj, at_point)
+
+    def logdet(self, mu: Tensor, std: Tensor, z: Tensor, data: Tuple[Tensor, ...]) -> Tensor:
+        return self.manifold.logdet(mu, std, z, data)
+
+
 class Euclidean(Manifold):
     """mt/mvae/ops/euclidean.py:24-59 (note exp_map_mu0(x) = x/2)."""
     kind = L.EUCLIDEAN

@@ -39,7 +39,7 @@ def _f32(t: torch.Tensor, name: str) -> torch.Tensor:
 
 
 def parse_signature(sig: str):
-    """'2h3,s2,e2' -> ([types], [dims]); grammar of mt/mvae/utils.py:78-140 (letters e,h,s,p,d; 'u','c' unsupported)."""
+    """'2h3,s2,e2' -> ([types], [dims]); grammar of mt/mvae/utils.py:78-140 (letters e,h,s,p,d,u; 'c' unsupported)."""
     types, dims = [], []
     for tok in sig.lower().strip().split(","):
         tok = tok.strip().split("-")[0]
@@ -185,6 +185,28 @@ def elbo_reduce(bce, kl, beta: float, out: Optional[torch.Tensor] = None):
     return out
 
 
+# ------------------------------------------------------------------------------------------ input pipeline
+def binarize(src_u8: torch.Tensor, x: Optional[torch.Tensor] = None, planes: Optional["PlaneBuf"] = None,
+             u: Optional[torch.Tensor] = None, seed: int = 0, offset_dev: Optional[torch.Tensor] = None,
+             dynamic: bool = True, invert: bool = False):
+    """uint8 grayscale batch [B, D] -> binarised fp32 x and / or its bf16 operand plane (mvae_binarize).
+    dynamic: x/255 > u with u supplied or drawn in the kernel (Philox; offset_dev = int64 device step counter);
+    else the fixed evaluation threshold 0.5."""
+    if not src_u8.is_cuda or src_u8.dtype != torch.uint8:
+        raise L.MvaeError("binarize: expected a CUDA uint8 tensor")
+    B, D = src_u8.shape
+    if x is None and planes is None:
+        x = torch.empty(B, D, device=src_u8.device)
+    ps = planes.struct() if planes is not None else None
+    rc = L.lib().mvae_binarize(_ptr(src_u8), src_u8.stride(0), B, D, 0 if dynamic else 1, int(invert),
+                               _ptr(None if u is None else _f32(u, "u")), int(seed) & (2**64 - 1), _ptr(offset_dev),
+                               _ptr(x), x.stride(0) if x is not None else 0,
+                               ctypes.byref(ps) if ps is not None else None, _stream())
+    L.check(rc, "mvae_binarize")
+    _LAUNCHES[0] += 1
+    return x
+
+
 # ------------------------------------------------------------------------------------------ IWAE log-likelihood
 def iwae_latent(desc: L.PmDesc, ml, eps, radius, z, diff, zsum: Optional[torch.Tensor] = None):
     """z [ns, B, ld_z] and diff [ns, B] = sum_c (log q_c - log p_c) for ns samples per row of ml [B, ld_ml]
@@ -239,6 +261,13 @@ def adam_step_dev(param, grad, exp_avg, exp_avg_sq, lr, step_dev, beta1=0.9, bet
                                     _stream())
     L.check(rc, "mvae_adam_step_dev")
     _LAUNCHES[0] += 2
+
+
+def clip_grad_norm(grad, mask, max_norm: float = 1.0):
+    """In-place clip_grad_norm_ (2-norm) over the entries of `grad` selected by `mask` (mvae_clip_grad_norm)."""
+    rc = L.lib().mvae_clip_grad_norm(grad.numel(), _ptr(grad), _ptr(mask), float(max_norm), _stream())
+    L.check(rc, "mvae_clip_grad_norm")
+    _LAUNCHES[0] += 1
 
 
 def sgd_step(param, grad, lr, grad_scale=1.0):

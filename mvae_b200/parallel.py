@@ -106,6 +106,8 @@ def attach_p2p(model, optimizer, group=None) -> bool:
     world, rank = dist.get_world_size(group), dist.get_rank(group)
     if world > L.DP_MAX_RANKS:
         return False
+    if getattr(model, "_clip_mask", None) is not None:
+        return False  # 'u' components: the gradient clip sits between the reduction and the update (NCCL path)
     lib = L.lib()
     dev = model.device
     n_flat, n_bucket = model.flat_sizes()

@@ -138,6 +138,11 @@ class _Workspace:
         # other (the CUDA graphs are keyed by slot, the buffers never move)
         self.xbuf = [torch.zeros(B, D, **f), torch.zeros(B, D, **f)]
         self.slot = 0
+        # uint8 image batches (binarised on the device, mvae_binarize): raw pixels per slot, allocated on first use;
+        # u8 = the current batch arrived as uint8; bin_ctr = Philox step counter of the dynamic binarisation
+        self.x8buf = None
+        self.u8 = False
+        self.bin_ctr = torch.zeros(1, device=dev, dtype=torch.int64)
         self.eps = torch.zeros(B, Sn, **f)
         self.xp = ops.PlaneBuf(B, D, m.input_planes, dev, ones_col=True)
         self.hp = ops.PlaneBuf(B, H, 3, dev, ones_col=True)   # 3 planes: feeds the heads at fp32 accuracy
@@ -162,6 +167,13 @@ class _Workspace:
     @property
     def x(self) -> Tensor:
         return self.xbuf[self.slot]
+
+    @property
+    def x8(self) -> Tensor:
+        if self.x8buf is None:
+            self.x8buf = [torch.zeros(self.B, self.xbuf[0].shape[1], device=self.xbuf[0].device, dtype=torch.uint8)
+                          for _ in range(2)]
+        return self.x8buf[self.slot]
 
 
 class FusedFeedForwardVAE(nn.Module):
@@ -259,6 +271,11 @@ class FusedFeedForwardVAE(nn.Module):
                 if rp.requires_grad:
                     rp.grad = bucket[n_net + i]
                     self._radius_mask[i] = 1.0
+        # universal components: the reference clips the 2-norm of their "curvature"-named gradients to 1 in every
+        # train step (vae.py:161-163); _clip_mask selects them in the radius-gradient vector
+        self._clip_mask = None
+        if any(c.kind == L.UNIVERSAL for c in self.components):
+            self._clip_mask = torch.tensor([1.0 if c.kind == L.UNIVERSAL else 0.0 for c in self.components], device=dev)
         self._any_fixed_radius = any((c.radius_parameter()[1] is not None) and (not c.radius_parameter()[1].requires_grad)
                                      for c in self.components)
         self._flat, self._rflat, self._bucket, self._n_net = flat, rflat, bucket, n_net
@@ -349,7 +366,13 @@ class FusedFeedForwardVAE(nn.Module):
             ws.bce.zero_()
             if train:
                 self._bucket[:self._n_net + self.desc.C].zero_()
-        ops.split_planes(ws.x, ws.xp)
+        if ws.u8:
+            # uint8 pixels -> binarised fp32 targets + the bf16 operand plane of fc_e0 in one kernel
+            # (image_reconstruction.py:37-53: dynamic in training, threshold 0.5 in evaluation)
+            ops.binarize(ws.x8, x=ws.x, planes=ws.xp, seed=self.binarize_seed, offset_dev=ws.bin_ctr,
+                         dynamic=train or self.binarize_eval_dynamic, invert=self.binarize_invert)
+        else:
+            ops.split_planes(ws.x, ws.xp)
         fused = self.fused_latent and not want_mu_sigma
         if fused:
             self._gemm("e0_fwd32", ws.xp, self.We0p, B, H, D, epilogue=L.EPI_BIAS_RELU, bias=self.fc_e0.bias.data,
@@ -388,6 +411,8 @@ class FusedFeedForwardVAE(nn.Module):
         main, side = torch.cuda.current_stream(self.device), self._side_stream()
         side.wait_stream(main)
         with torch.cuda.stream(side):
+            if ws.u8:
+                ws.bin_ctr.add_(1)  # next step's binarisation draws fresh uniforms
             ops.elbo_reduce(ws.bce, ws.kl, beta, out=self._stats)
             # fc_logits: gW = gL^T dd (+ bias from the ones column of dd)
             self._gemm("logits_wgrad", ws.gLp, ws.ddp, D, H + 1, B, a_major=MN, b_major=MN, split_k=0, out_f32=self.gWl,
@@ -468,13 +493,31 @@ class FusedFeedForwardVAE(nn.Module):
     def _stage(self, ws: _Workspace, x: Tensor, eps: Optional[Tensor]) -> bool:
         """Input batch (and supplied noise) into the workspace.  Returns True when the noise has to be drawn: the
         forward kernels then do it on their side branch (inside the step's CUDA graph)."""
-        ws.x.copy_(x.reshape(ws.B, self.in_dim), non_blocking=True)  # H2D if x lives on the host
+        self._stage_x(ws, ws.slot, x)  # H2D if x lives on the host
         if eps is None:
             eps = self._eps_override
         if eps is None:
             return True
         ws.eps.copy_(eps, non_blocking=True)
         return False
+
+    binarize_seed = 0              # Philox key of the on-device dynamic binarisation
+    binarize_invert = False        # ImageDynamicBinarization(invert=...) (Omniglot)
+    binarize_eval_dynamic = False  # forward() / log_likelihood() use the fixed 0.5 threshold like the reference's test loader
+
+    def _stage_x(self, ws: _Workspace, slot: int, x: Tensor) -> None:
+        """Copy a batch into input slot `slot`: float batches as they are, uint8 image batches (raw grayscale pixels,
+        what the dataset stores) into the slot's uint8 buffer — they are binarised on the device by the forward
+        kernels.  Marks which kind the slot's consumer has to read."""
+        if x.dtype == torch.uint8:
+            if self.input_planes != 1:
+                raise L.MvaeError("uint8 image batches need a dataset with binary_inputs=True (one operand plane)")
+            ws.x8  # allocate on first use
+            ws.x8buf[slot].copy_(x.reshape(ws.B, self.in_dim), non_blocking=True)
+            ws.u8 = True
+        else:
+            ws.xbuf[slot].copy_(x.reshape(ws.B, self.in_dim), non_blocking=True)
+            ws.u8 = False
 
     # ------------------------------------------------------------------------------------------ reference API
     def encode(self, x: Tensor) -> Tensor:
@@ -510,13 +553,13 @@ class FusedFeedForwardVAE(nn.Module):
             loc = ws.mu[:, d.z_off:d.z_off + d.d]
             scale = ws.sigma[:, d.eps_off:d.eps_off + d.n]
             z = ws.z[:, d.z_off:d.z_off + d.d]
-            if c.kind == L.EUCLIDEAN:
+            if c.effective_kind() == L.EUCLIDEAN:
                 q_z = EuclideanNormal(loc, scale)
                 p_z = EuclideanNormal(torch.zeros_like(loc), torch.ones_like(scale))
             else:
-                q_z = WrappedNormal(loc, scale, c.manifold)
-                p_z = WrappedNormal(c.manifold.mu_0(loc.shape, device=loc.device, dtype=loc.dtype),
-                                    torch.ones_like(scale), c.manifold)
+                man = c.manifold.manifold if c.kind == L.UNIVERSAL else c.manifold
+                q_z = WrappedNormal(loc, scale, man)
+                p_z = WrappedNormal(man.mu_0(loc.shape, device=loc.device, dtype=loc.dtype), torch.ones_like(scale), man)
             res.append(Reparametrized(q_z, p_z, z, ws.kl[:, i], ws.eps[:, d.eps_off:d.eps_off + d.n]))
         return res
 
@@ -560,10 +603,14 @@ class FusedFeedForwardVAE(nn.Module):
         estimates, and cov_norm from sum_s z (the sample mean commutes with the bilinear form of :119-121)."""
         B, D, H, P, Sd, Sn = x.shape[0], self.in_dim, self.h_dim, self.desc.ld_ml, self.desc.ld_z, self.desc.ld_eps
         ws = self._workspace(B)
-        ws.x.copy_(x.reshape(B, D), non_blocking=True)
+        self._stage_x(ws, ws.slot, x)
         if self._planes_stale:
             self.refresh_weight_planes()
-        ops.split_planes(ws.x, ws.xp)
+        if ws.u8:
+            ops.binarize(ws.x8, x=ws.x, planes=ws.xp, seed=self.binarize_seed, offset_dev=ws.bin_ctr,
+                         dynamic=self.binarize_eval_dynamic, invert=self.binarize_invert)
+        else:
+            ops.split_planes(ws.x, ws.xp)
         self._gemm("e0_fwd", ws.xp, self.We0p, B, H, D, epilogue=L.EPI_BIAS_RELU, bias=self.fc_e0.bias.data,
                    out_planes=ws.hp)
         ops.skinny_rowdot((ws.hp, 3), self.Wh, H, 1, K=H, N=P, bias=self.bh, out=ws.ml)
@@ -631,6 +678,8 @@ class FusedFeedForwardVAE(nn.Module):
                 self._grad_hook(self._bucket)  # data-parallel: one SUM all-reduce over [grads | radius grads | stats]
             if not fused:
                 self._attach_grads()
+                if self._clip_mask is not None:
+                    ops.clip_grad_norm(self._gradius, self._clip_mask, 1.0)
             optimizer.step()
             self._planes_stale = not getattr(optimizer, "planes_fresh", False)
 
@@ -669,7 +718,7 @@ class FusedFeedForwardVAE(nn.Module):
             else:
                 copy.wait_stream(main)
             with torch.cuda.stream(copy):
-                ws.xbuf[slot].copy_(x.reshape(ws.B, self.in_dim), non_blocking=True)
+                self._stage_x(ws, slot, x)
                 self._slot_ready[slot].record(copy)
 
         def drain(i):
@@ -725,10 +774,11 @@ class FusedFeedForwardVAE(nn.Module):
     def _graphed_step(self, optimizer: "FusedCurvatureOptimizer", ws: _Workspace, beta: float,
                       draw_eps: bool = False) -> None:
         """Replay the whole step from CUDA graphs (launch-bound otherwise: ~30 kernels of a few microseconds).
-        Graph A = forward + backward into the gradient bucket; [the data-parallel all-reduce runs between the two,
-        eagerly]; graph B = optimizer step + refresh of the weight planes.  Keyed by everything baked into launch
+        One graph holds forward + backward + optimizer step (+ refresh of the weight planes); with a gradient hook
+        (the NCCL data-parallel path) it is split in two and the all-reduce runs between them, eagerly.  Keyed by everything baked into launch
         parameters: batch size, beta, and whether the curvature optimizers step."""
-        key = (ws.B, ws.slot, float(beta), optimizer.curvature_step_enabled(), id(optimizer), bool(draw_eps))
+        key = (ws.B, ws.slot, float(beta), optimizer.curvature_step_enabled(), id(optimizer), bool(draw_eps), ws.u8,
+               self._grad_hook is None)
         entry = self._graphs.get(key)
         if entry is None:
             if self._planes_stale:
@@ -741,25 +791,35 @@ class FusedFeedForwardVAE(nn.Module):
                 self._backward_kernels(ws, beta)
             torch.cuda.current_stream().wait_stream(side)
             n0 = ops.launch_count()
+            one_graph = self._grad_hook is None  # nothing eager between backward and optimizer: ONE graph, one replay
+            saved = optimizer.step_count
+
+            def capture_opt():
+                optimizer.step()
+                if not getattr(optimizer, "planes_fresh", False):
+                    self.refresh_weight_planes()
+
             ga = torch.cuda.CUDAGraph()
             with torch.cuda.graph(ga):
                 self._forward_kernels(ws, beta, train=True, want_mu_sigma=False, logits=None, draw_eps=draw_eps)
                 self._backward_kernels(ws, beta)
+                if one_graph:
+                    capture_opt()
             n1 = ops.launch_count()
-            gb = torch.cuda.CUDAGraph()
-            saved = optimizer.step_count
-            with torch.cuda.graph(gb):
-                optimizer.step()
-                if not getattr(optimizer, "planes_fresh", False):
-                    self.refresh_weight_planes()
+            gb = None
+            if not one_graph:
+                gb = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(gb):
+                    capture_opt()
             optimizer.step_count = saved  # capture does not execute
             n2 = ops.launch_count()
             entry = self._graphs[key] = (ga, gb, n1 - n0, n2 - n1)
         ga, gb, la, lb = entry
         ga.replay()
-        if self._grad_hook is not None:
-            self._grad_hook(self._bucket)
-        gb.replay()
+        if gb is not None:
+            if self._grad_hook is not None:
+                self._grad_hook(self._bucket)
+            gb.replay()
         optimizer.step_count += 1
         ops.add_launches(la + lb)
         self._planes_stale = False
@@ -811,6 +871,8 @@ class FusedCurvatureOptimizer:
         graph and replayed."""
         m = self.model
         self.step_count += 1
+        if m._clip_mask is not None:
+            ops.clip_grad_norm(m._gradius, m._clip_mask, 1.0)  # vae.py:161-163, on the (rank-summed) gradient
         targets = [(m._slices["fc_e0.weight"][0], m.h_dim, m.We0p), (m._slices["fc_logits.weight"][0], m.in_dim, m.Wlp)]
         if self._dp is not None:
             # data parallel over NVLink peer memory: gradient reduce-scatter + Adam on this rank's slice + parameter

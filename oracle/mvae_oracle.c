@@ -61,6 +61,7 @@ int oracle_pm_desc_init(mvae_pm_desc* D, int32_t C, const int32_t* types, const 
   for (int i = 0; i < C; ++i) {
     mvae_component* c = &D->comp[i];
     if (dims[i] < 1) return -1;
+    if (types[i] < MVAE_EUCLIDEAN || types[i] > MVAE_UNIVERSAL) return -1;
     c->type = types[i];
     c->n = dims[i];
     c->d = (types[i] == MVAE_HYPERBOLOID || types[i] == MVAE_SPHERE) ? dims[i] + 1 : dims[i];

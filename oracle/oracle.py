@@ -13,7 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB_PATH = os.path.join(_HERE, "liboracle.so")
 
 MAX_COMPONENTS = 96
-TYPE_OF_LETTER = {"e": 0, "h": 1, "s": 2, "p": 3, "d": 4}
+TYPE_OF_LETTER = {"e": 0, "h": 1, "s": 2, "p": 3, "d": 4, "u": 5}
 
 
 class Component(ctypes.Structure):
@@ -207,7 +207,7 @@ class OracleVAE:
     def radii(self, params, dtype):
         r = np.ones(self.C, dtype=dtype)
         for i in range(self.C):
-            for nm in ("_nradius", "_pradius"):
+            for nm in ("_nradius", "_pradius", "_curvature"):  # 'u': the slot holds the raw curvature
                 k = f"components.{i}.{nm}"
                 if k in params:
                     r[i] = params[k]
@@ -289,7 +289,7 @@ class OracleVAE:
             g[f"components.{i}.fc_logvar.weight"] = gWh[row:row + c.l_n]
             g[f"components.{i}.fc_logvar.bias"] = gbh[row:row + c.l_n]
             row += c.l_n
-            for nm in ("_nradius", "_pradius"):
+            for nm in ("_nradius", "_pradius", "_curvature"):
                 if f"components.{i}.{nm}" in params:
                     g[f"components.{i}.{nm}"] = np.asarray(gR[i])
         gh = (gml @ Wh) * h_on

@@ -202,11 +202,11 @@ def _ref_product_manifold(model_sig, m, l, eps, radii, gz, gkl, scalar_parametri
     for i, c in enumerate(comps):
         n = c.true_dim
         ln = 1 if scalar_parametrization else n
-        for pname in ("_nradius", "_pradius"):
+        for pname in ("_nradius", "_pradius", "_curvature"):  # 'u': radii[i] is the curvature
             if hasattr(c, pname):
                 getattr(c, pname).data = torch.tensor(float(radii[i]), dtype=dtype)
                 Rs.append(getattr(c, pname))
-        if not (hasattr(c, "_nradius") or hasattr(c, "_pradius")):
+        if not (hasattr(c, "_nradius") or hasattr(c, "_pradius") or hasattr(c, "_curvature")):
             Rs.append(None)
         mi = m[:, mo:mo + n]
         li = l[:, lo:lo + ln]

@@ -60,10 +60,12 @@ def gen_pm(name, sig, radii, B=24, seed=0, scale_m=1.0, scalar=False):
 def gen_model(name, sig, in_dim, h_dim, B, recon, fixed_curvature, radius, scalar=False, seed=3, beta=1.0):
     for dtype, sfx in ((torch.float64, ""), (torch.float32, "_f32")):
         model = rh.build_model(sig, in_dim, h_dim, fixed_curvature, scalar, recon, seed, torch.float64)
-        for c in model.components:
+        for ci, c in enumerate(model.components):
             for pn in ("_nradius", "_pradius"):
                 if hasattr(c, pn):
                     getattr(c, pn).data.fill_(radius)
+            if hasattr(c, "_curvature"):  # 'u': alternate hyperbolic / spherical choices
+                c._curvature.data.fill_((-1.0) ** ci * 0.7)
         model = model.to(dtype)
         g = torch.Generator().manual_seed(seed + 1)
         if recon == "bce":
@@ -86,10 +88,12 @@ def gen_loglik(name, sig, in_dim, h_dim, B, n, recon, radius, scalar=False, seed
     out = {}
     for dtype, sfx in ((torch.float64, ""), (torch.float32, "_f32")):
         model = rh.build_model(sig, in_dim, h_dim, False, scalar, recon, seed, torch.float64)
-        for c in model.components:
+        for ci, c in enumerate(model.components):
             for pn in ("_nradius", "_pradius"):
                 if hasattr(c, pn):
                     getattr(c, pn).data.fill_(radius)
+            if hasattr(c, "_curvature"):  # 'u': alternate hyperbolic / spherical choices
+                c._curvature.data.fill_((-1.0) ** ci * 0.7)
         model = model.to(dtype)
         g = torch.Generator().manual_seed(seed + 1)
         if recon == "bce":
@@ -231,7 +235,20 @@ def gen_ds():
     gen_ops("d")
 
 
+def gen_us():
+    """'u' (universal, universal.py) fixtures: negative, positive and ~zero curvature choices."""
+    gen_pm("u2_u3_u2_h2", "u2,u3,u2,h2", [-0.8, 1.3, 5e-7, 1.0], seed=31, scale_m=0.5)
+    gen_pm("u6_u6", "u6,u6", [0.05, -2.0], seed=32, scale_m=0.6)
+    gen_pm("scalar_u2_u2", "u2,u2", [-0.3, 0.4], seed=33, scalar=True, scale_m=0.5)
+    gen_model("u2_u2_e2_bce", "u2,u2,e2", in_dim=20, h_dim=16, B=12, recon="bce", fixed_curvature=False, radius=1.0,
+              seed=35)
+    gen_loglik("u2_u2_bce", "u2,u2", in_dim=16, h_dim=16, B=9, n=5, recon="bce", radius=1.0, seed=36)
+
+
 if __name__ == "__main__":
+    if "--only-u" in sys.argv:
+        gen_us()
+        sys.exit(0)
     if "--only-d" in sys.argv:
         gen_ds()
         sys.exit(0)
@@ -241,6 +258,7 @@ if __name__ == "__main__":
     gen_kat()
     gen_logliks()
     gen_ds()
+    gen_us()
     gen_pm("h2_s2_e2_R1", "h2,s2,e2", [1.0, 1.0, 0.0])
     gen_pm("cfg3_R10", "h6,h6,s6,s6,e6", [10.0, 10.0, 10.0, 10.0, 0.0], seed=1)
     gen_pm("cfg3_Rmixed", "h6,h6,s6,s6,e6", [1.5, 0.7, 2.0, 1.0, 0.0], seed=2, scale_m=0.6)

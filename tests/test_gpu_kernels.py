@@ -49,7 +49,8 @@ def test_pm_forward_golden(dev, oracle, name):
     for k in ("z", "kl", "mu", "sigma"):
         got = out[k].cpu().numpy()
         assert normwise(got, g[k]) < FWD_TOL, (k, normwise(got, g[k]))
-        assert normwise(got, g[k + "_f32"]) < 2e-4, k
+        # against the reference's own float32 run — itself up to ~1e-3 from its float64 run on the small-radius fixtures
+        assert normwise(got, g[k + "_f32"]) < max(2e-4, 3 * normwise(g[k + "_f32"], g[k])), k
     assert int(flag.item()) == 0
     # mu/sigma are optional outputs: the result must not depend on asking for them
     out2 = ops.pm_forward(desc, _t(ml, dev), _t(g["eps"], dev), _t(R, dev))

@@ -76,8 +76,12 @@ def test_forward_and_gradients_match_reference(dev, name):
 
     bs, _ = model.train_step(NoOpt(), x, beta, eps=eps)
     assert abs(bs.elbo - g["elbo"]) < TOL_SUM * abs(g["elbo"])
+    # 'u' components: train_step clips the 2-norm of the "curvature"-named gradients to 1 (vae.py:161-163); the golden
+    # gradients come from a plain backward(), so the same clip is applied to them here
+    curv = [k for k, _ in model.named_parameters() if "curvature" in k]
+    clip = min(1.0, 1.0 / (float(np.sqrt(sum(float(g["grad." + k]) ** 2 for k in curv))) + 1e-6)) if curv else 1.0
     for k, p in model.named_parameters():
-        ref = g["grad." + k]
+        ref = g["grad." + k] * (clip if k in curv else 1.0)
         if "radius" in k:
             if meta["fixed_curvature"]:
                 continue
@@ -224,3 +228,133 @@ def test_peer_memory_data_parallel_step_two_gpus():
                         "--master-addr", "127.0.0.1", "--master-port", "29541", os.path.join(root, "scripts", "dp_check.py")],
                        capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "dp_check ok" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+def test_uint8_batches_binarised_on_device(dev, oracle):
+    """mvae_binarize (ImageDynamicBinarization, image_reconstruction.py:37-53, moved to the device): bit-exact against
+    the reference's comparison `ToTensor(x) > U` for supplied draws and against `> 0.5` in evaluation mode; the Philox
+    path is deterministic per (seed, step), fresh per step, and unbiased; and a train step fed uint8 pixels equals
+    the step fed the float batch the kernel produced (up to the order of the atomic reductions)."""
+    from mvae_b200 import components, data, ops, vae
+    g = torch.Generator().manual_seed(0)
+    for B, D in ((64, 784), (37, 19)):   # vectorised and general kernel
+        px = torch.randint(0, 256, (B, D), generator=g, dtype=torch.int32).to(torch.uint8)
+        u = torch.rand(B, D, generator=g)
+        v = px.to(torch.float32).div(255)                     # torchvision ToTensor
+        ref_dyn = (v.double() > u.double()).float()           # float64 default dtype of the reference (run.py:77)
+        ref_fix = (v > 0.5).float()
+        ref_inv = ((1 - v).double() > u.double()).float()
+        xp = ops.PlaneBuf(B, D, 1, dev, ones_col=True)
+        x = ops.binarize(px.to(dev), planes=xp, x=torch.empty(B, D, device=dev), u=u.to(dev))
+        assert torch.equal(x.cpu(), ref_dyn)
+        assert torch.equal(xp.t[0, :, :D].float().cpu(), ref_dyn) and bool((xp.t[0, :, D] == 1).all())
+        assert torch.equal(ops.binarize(px.to(dev), dynamic=False).cpu(), ref_fix)
+        assert torch.equal(ops.binarize(px.to(dev), u=u.to(dev), invert=True).cpu(), ref_inv)
+        ctr = torch.zeros(1, dtype=torch.int64, device=dev)
+        a = ops.binarize(px.to(dev), seed=7, offset_dev=ctr)
+        b = ops.binarize(px.to(dev), seed=7, offset_dev=ctr)
+        assert torch.equal(a, b)
+        ctr += 1
+        c = ops.binarize(px.to(dev), seed=7, offset_dev=ctr)
+        assert not torch.equal(a, c)
+        assert not torch.equal(a, ops.binarize(px.to(dev), seed=8, offset_dev=ctr - 1))
+    # unbiased: P(x = 1) = v for every pixel value (large sample, 5 sigma)
+    Bn = 1 << 16
+    px = torch.full((Bn, 8), 0, dtype=torch.uint8)
+    levels = torch.tensor([0, 1, 64, 100, 128, 200, 254, 255], dtype=torch.uint8)
+    px[:] = levels
+    ctr = torch.zeros(1, dtype=torch.int64, device=dev)
+    freq = ops.binarize(px.to(dev), seed=3, offset_dev=ctr).mean(0).cpu().double()
+    p = levels.double() / 255
+    assert bool(((freq - p).abs() <= 5 * (p * (1 - p) / Bn).sqrt() + 1e-12).all()), (freq, p)
+    # model level
+    torch.manual_seed(0)
+    B, D, H = 256, 784, 64
+    mk = lambda: vae.FusedFeedForwardVAE(H, components.parse_components("h2,s2,e2", False),
+                                         data.GenericDataset(B, D, "bce", binary_inputs=True), False, device=dev)
+    m1 = mk()
+    m2 = mk()
+    m2.load_state_dict(m1.state_dict())
+    px = torch.randint(0, 256, (B, D), generator=g, dtype=torch.int32).to(torch.uint8)
+    eps = torch.randn(B, m1.desc.ld_eps, generator=g).to(dev)
+    o1 = vae.FusedCurvatureOptimizer(m1, 1e-3, fixed_curvature=False, should_do_curvature_step=lambda: True)
+    o2 = vae.FusedCurvatureOptimizer(m2, 1e-3, fixed_curvature=False, should_do_curvature_step=lambda: True)
+    m1.binarize_seed = 11
+    s1, _ = m1.train_step(o1, px, 1.0, eps=eps)
+    x_float = m1._workspace(B).x.clone()   # what the kernel produced from the pixels
+    assert set(x_float.unique().tolist()) <= {0.0, 1.0} and 0.3 < float(x_float.mean()) < 0.7
+    s2, _ = m2.train_step(o2, x_float, 1.0, eps=eps)
+    assert abs(s1.elbo - s2.elbo) <= 1e-6 * abs(s2.elbo) and abs(s1.bce - s2.bce) <= 1e-6 * abs(s2.bce)
+    for (k, a), (_, b) in zip(m1.state_dict().items(), m2.state_dict().items()):
+        assert normwise(a.cpu().numpy(), b.cpu().numpy()) < 1e-5, k
+    # the next step draws different uniforms (device counter), evaluation uses the fixed threshold
+    m1.train_step(o1, px, 1.0, eps=eps)
+    assert not torch.equal(m1._workspace(B).x, x_float)
+    m1.forward(px, eps=eps)
+    assert torch.equal(m1._workspace(B).x.cpu(), (px.float().div(255) > 0.5).float())
+    # pipelined epoch with uint8 batches and CUDA graphs: runs, finite, statistics per batch
+    m1.use_cuda_graph = True
+    out = m1.train_epoch(o1, [px.pin_memory()] * 5, 1.0)
+    assert len(out) == 5 and all(np.isfinite(s.elbo) for s in out)
+    assert int(m1._workspace(B).bin_ctr.item()) >= 6
+
+
+def test_universal_components_train(dev, oracle):
+    """'u' (universal.py): the kernels branch on sign(kappa) per launch; one step's loss and every gradient (incl.
+    d/dkappa) against the float64 oracle; the fused optimizer (gradient clip of the curvature parameters, vae.py:161-163,
+    then SGD) moves kappa exactly like torch's clip_grad_norm_ + SGD; a curvature that crosses the +-eps band switches
+    manifolds without any re-setup."""
+    from mvae_b200 import components, data, vae
+    sig, B, D, H = "u2,u3,u2,e2", 512, 64, 32
+    kappas = [-0.7, 0.9, 5e-7]
+    torch.manual_seed(2)
+    model = vae.FusedFeedForwardVAE(H, components.parse_components(sig, False), data.GenericDataset(B, D, "bce"), False,
+                                    device=dev)
+    with torch.no_grad():
+        for c, k in zip(model.components, kappas):
+            c._curvature.fill_(k)
+    assert [c.effective_kind() for c in model.components] == [3, 4, 0, 0]
+    g = torch.Generator().manual_seed(4)
+    x = (torch.rand(B, D, generator=g) < 0.3).float()
+    eps = torch.randn(B, model.desc.ld_eps, generator=g)
+    params = {k: v.detach().cpu().double().numpy() for k, v in model.state_dict().items()}
+    ref = oracle.OracleVAE(sig, D, H, "bce", False).step(params, x.double().numpy(), eps.double().numpy(), beta=1.0)
+
+    class NoOpt:
+        def zero_grad(self):
+            pass
+
+        def step(self):
+            pass
+
+    kap_before = [float(c._curvature.detach()) for c in model.components[:3]]
+    bs, _ = model.train_step(NoOpt(), x, 1.0, eps=eps.to(dev))
+    assert abs(bs.elbo - ref["elbo"]) < TOL_SUM * abs(ref["elbo"])
+    gk = np.array([float(ref["grads"][f"components.{i}._curvature"]) for i in range(3)])
+    assert gk[2] == 0.0 and abs(gk[0]) > 0 and abs(gk[1]) > 0   # no gradient reaches kappa on the Euclidean branch
+    clip = min(1.0, 1.0 / (np.linalg.norm(gk) + 1e-6))
+    for k, p in model.named_parameters():
+        r = ref["grads"][k] * (clip if "curvature" in k else 1.0)
+        got = p.grad.detach().cpu().numpy()
+        assert normwise(got, r) < 3e-4, (k, normwise(got, r))
+    # fused optimizer: clip + SGD(1e-4) on kappa
+    opt = vae.FusedCurvatureOptimizer(model, 1e-3, fixed_curvature=False, should_do_curvature_step=lambda: True)
+    model.train_step(opt, x, 1.0, eps=eps.to(dev))
+    for i in range(3):
+        want = kap_before[i] - 1e-4 * clip * gk[i]
+        assert abs(float(model.components[i]._curvature.detach()) - want) < 2e-7 + 3e-4 * abs(1e-4 * clip * gk[i])
+    # crossing the band: the same model object continues on the other manifold
+    with torch.no_grad():
+        model.components[0]._curvature.fill_(0.4)
+        model.components[1]._curvature.fill_(0.0)
+    assert [c.effective_kind() for c in model.components] == [4, 0, 0, 0]
+    params = {k: v.detach().cpu().double().numpy() for k, v in model.state_dict().items()}
+    ref2 = oracle.OracleVAE(sig, D, H, "bce", False).step(params, x.double().numpy(), eps.double().numpy(), beta=1.0,
+                                                          backward=False)
+    model.use_cuda_graph = True
+    for _ in range(2):   # second call replays the CUDA graph captured by the first
+        rep, z, logits = model.forward(x, eps=eps.to(dev))
+        assert normwise(z.cpu().numpy(), ref2["z"]) < TOL
+        assert normwise(torch.stack([r.kl for r in rep], -1).cpu().numpy(), ref2["kl"]) < TOL
+    ll, mi, cov = model.log_likelihood(x.to(dev), n=4)
+    assert torch.isfinite(ll).all() and torch.isfinite(mi).all()

@@ -41,8 +41,11 @@ def test_pm_forward_backward_f32(oracle, name):
     R = radii_array(g["radii"], f32)
     f = oracle.pm_forward(desc, ml, g["eps"].astype(f32), R, want=("z", "kl", "mu", "sigma"))
     for k in ("z", "kl", "mu", "sigma"):
-        assert normwise(f[k], g[k + "_f32"]) < F32_TOL, k
-        assert normwise(f[k], g[k]) < F32_TOL, k
+        # where the reference's own float32 run is further than F32_TOL from its float64 run (small radii: the
+        # Poincare log-det cancels), a float32 restatement is held to a small multiple of that distance
+        tol = max(F32_TOL, 3 * normwise(g[k + "_f32"], g[k]))
+        assert normwise(f[k], g[k + "_f32"]) < tol, k
+        assert normwise(f[k], g[k]) < tol, k
     gml, gR = oracle.pm_backward(desc, ml, g["eps"].astype(f32), R, g["gz"].astype(f32), g["gkl"].astype(f32))
     gm, gl = unpack_gml(desc, gml)
     # the reference's float32 backward is itself only ~1e-3 normwise accurate on these inputs
