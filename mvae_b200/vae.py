@@ -309,7 +309,7 @@ class FusedFeedForwardVAE(nn.Module):
         self._graphs = {}
         self._gemm_tiles = {}
         # heads + manifold chain + fc_d0 as one kernel per direction (mvae_latent_forward / _backward)
-        self.fused_latent = (H % 8 == 0) and P <= 64 and Sd <= 64
+        self.fused_latent = (H % 8 == 0) and P <= 64 and Sd <= 64 and os.environ.get("MVAE_FUSED_LATENT", "1") != "0"
 
     def _apply(self, fn, *args, **kwargs):
         out = super()._apply(fn, *args, **kwargs)
@@ -874,6 +874,10 @@ class FusedCurvatureOptimizer:
         if m._clip_mask is not None:
             ops.clip_grad_norm(m._gradius, m._clip_mask, 1.0)  # vae.py:161-163, on the (rank-summed) gradient
         targets = [(m._slices["fc_e0.weight"][0], m.h_dim, m.We0p), (m._slices["fc_logits.weight"][0], m.in_dim, m.Wlp)]
+        # the fused kernels refresh a weight's planes with 128-bit accesses: rows must be a multiple of 4 floats wide
+        # (in_dim = 50 of the BDP data is not); such a matrix gets its own plane-split launch after the update
+        late = [(m.fc_e0.weight if t[2] is m.We0p else m.fc_logits.weight, t[2]) for t in targets if t[2].cols % 4]
+        targets = [t for t in targets if t[2].cols % 4 == 0]
         if self._dp is not None:
             # data parallel over NVLink peer memory: gradient reduce-scatter + Adam on this rank's slice + parameter
             # all-gather + the radii's SGD step, one kernel (mvae_dp_adam_step)
@@ -881,6 +885,8 @@ class FusedCurvatureOptimizer:
                              self.betas[0], self.betas[1], self.eps, self.step_dev, m._rflat,
                              self.curvature_lr if self.curvature_step_enabled() else 0.0, m._radius_mask,
                              self._dp_tail, self._dp_sync, targets)
+            for w, buf in late:
+                ops.split_planes(w.data, buf)
             m._planes_stale = False
             self.planes_fresh = True
             return
@@ -889,6 +895,8 @@ class FusedCurvatureOptimizer:
         ops.opt_step_fused(m._flat, m._gnet, self.exp_avg, self.exp_avg_sq, self.lr, self.betas[0], self.betas[1],
                            self.eps, self.step_dev, self._done, m._rflat, m._gradius, m._radius_mask,
                            self.curvature_lr if self.curvature_step_enabled() else 0.0, targets)
+        for w, buf in late:
+            ops.split_planes(w.data, buf)
         m._planes_stale = False
         self.planes_fresh = True
 

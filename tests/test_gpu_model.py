@@ -358,3 +358,28 @@ def test_universal_components_train(dev, oracle):
         assert normwise(torch.stack([r.kl for r in rep], -1).cpu().numpy(), ref2["kl"]) < TOL
     ll, mi, cov = model.log_likelihood(x.to(dev), n=4)
     assert torch.isfinite(ll).all() and torch.isfinite(mi).all()
+
+
+@pytest.mark.parametrize("graph", [False, True])
+def test_fused_optimizer_with_unaligned_input_width(dev, graph):
+    """BDP-shaped model (in_dim = 50: rows of fc_e0.weight are not a multiple of 4 floats): the fused optimizer refreshes
+    that matrix's operand planes with a separate launch; after every step the planes equal the updated weights."""
+    from mvae_b200 import components, data, vae
+    torch.manual_seed(1)
+    B, D, H = 300, 50, 64
+    model = vae.FusedFeedForwardVAE(H, components.parse_components("h2,p2", False), data.GenericDataset(B, D, "nll"),
+                                    False, device=dev)
+    model.use_cuda_graph = graph
+    opt = vae.FusedCurvatureOptimizer(model, 1e-3, fixed_curvature=False, should_do_curvature_step=lambda: True)
+    g = torch.Generator().manual_seed(2)
+    x = torch.randn(B, D, generator=g)
+    w0 = model.fc_e0.weight.detach().clone()
+    elbos = []
+    for _ in range(4):
+        bs, _ = model.train_step(opt, x, 1.0)
+        elbos.append(bs.elbo)
+        assert np.isfinite(bs.elbo)
+        assert normwise(model.We0p.to_float().cpu().numpy(), model.fc_e0.weight.detach().cpu().numpy()) < 1e-6
+        assert normwise(model.Wlp.to_float().cpu().numpy(), model.fc_logits.weight.detach().cpu().numpy()) < 1e-4
+    assert not torch.equal(w0, model.fc_e0.weight.detach())
+    assert elbos[-1] > elbos[0]
