@@ -309,7 +309,7 @@ class PlaneBuf:
 def split_planes(src: torch.Tensor, dst: Optional[PlaneBuf] = None, dst_t: Optional[PlaneBuf] = None):
     src = _f32(src, "src")
     R, K = src.shape
-    ds = dst.struct() if dst is not None else None
+    ds = dst.struct(rows=R) if dst is not None else None  # the leading R rows of a (possibly larger) plane buffer
     dt = dst_t.struct() if dst_t is not None else None
     rc = L.lib().mvae_split_planes(_ptr(src), src.stride(0), R, K, ctypes.byref(ds) if ds is not None else None,
                                    ctypes.byref(dt) if dt is not None else None, _stream())

@@ -155,7 +155,9 @@ class _Workspace:
         self.bce = torch.zeros(B, **f)
         self.logits = None  # allocated on first forward() that needs them
         self.gLp = ops.PlaneBuf(B, D, 2, dev)
-        self.gddp = ops.PlaneBuf(B, H, 2, dev)
+        # gdd feeds the reverse sweep of the manifold chain (ill conditioned near the log-det singularities): when it is
+        # consumed as planes (latent_gemm) it carries 3 of them
+        self.gddp = ops.PlaneBuf(B, H, 3 if m.latent_gemm else 2, dev)
         self.gz = torch.zeros(B, Sd, **f)
         self.gml = torch.zeros(B, P, **f)
         self.ghp = ops.PlaneBuf(B, H, 2, dev)
@@ -163,6 +165,10 @@ class _Workspace:
         # fused latent block: the fc_e0 / logits-dgrad epilogues write h and gdd as fp32 for it (no planes needed)
         self.h32 = torch.zeros(B, H, **f)
         self.gdd32 = torch.zeros(B, H, **f)
+        # wide product manifolds: the latent dense layers run on the tensor cores (FusedFeedForwardVAE.latent_gemm)
+        if m.latent_gemm:
+            self.zp = ops.PlaneBuf(B, Sd, 3, dev, ones_col=True)  # 3 planes: z feeds fc_d0 + relu at fp32 accuracy
+            self.gmlp = ops.PlaneBuf(B, P, 3, dev)  # 3 planes: the head weight gradients are read at fp32 accuracy
 
     @property
     def x(self) -> Tensor:
@@ -310,6 +316,15 @@ class FusedFeedForwardVAE(nn.Module):
         self._gemm_tiles = {}
         # heads + manifold chain + fc_d0 as one kernel per direction (mvae_latent_forward / _backward)
         self.fused_latent = (H % 8 == 0) and P <= 64 and Sd <= 64 and os.environ.get("MVAE_FUSED_LATENT", "1") != "0"
+        # Wide products (cfg3: 60 head outputs, 34 latent coordinates): the per-CTA weight-gradient reductions of the
+        # fused block and the CUDA-core skinny kernels both scale with P * B; there the heads and fc_d0 (forward, dgrad,
+        # wgrad) go through the tcgen05 GEMM instead — 3 operand planes where the result feeds a non-smooth function —
+        # around the standalone product-manifold kernels (measured at cfg3: 600 us fused / 460 us skinny -> ~130 us).
+        self.latent_gemm = (P > 16 or Sd > 16) and os.environ.get("MVAE_LATENT_GEMM", "1") != "0"
+        if self.latent_gemm:
+            self.fused_latent = False
+            self.Whp = ops.PlaneBuf(P, H, 3, dev)
+            self.Wd0p = ops.PlaneBuf(H, Sd, 3, dev)
 
     def _apply(self, fn, *args, **kwargs):
         out = super()._apply(fn, *args, **kwargs)
@@ -332,6 +347,9 @@ class FusedFeedForwardVAE(nn.Module):
     def refresh_weight_planes(self) -> None:
         ops.split_planes(self.fc_e0.weight.data, self.We0p)
         ops.split_planes(self.fc_logits.weight.data, self.Wlp)
+        if self.latent_gemm:
+            ops.split_planes(self.Wh, self.Whp)
+            ops.split_planes(self.fc_d0.weight.data, self.Wd0p)
         self._planes_stale = False
 
     def mark_parameters_changed(self) -> None:
@@ -364,6 +382,8 @@ class FusedFeedForwardVAE(nn.Module):
             if draw_eps:
                 ws.eps.normal_()
             ws.bce.zero_()
+            if self.latent_gemm:
+                ws.ml.zero_()  # the heads GEMM accumulates its K slices into it
             if train:
                 self._bucket[:self._n_net + self.desc.C].zero_()
         if ws.u8:
@@ -387,6 +407,16 @@ class FusedFeedForwardVAE(nn.Module):
             ops.latent_forward(self.desc, ws.h32, self.Wh, self.bh, ws.eps, self._rflat, self.fc_d0.weight.data,
                                self.fc_d0.bias.data, ws.ml, ws.z, ws.kl, ws.ddp,
                                flag=ws.flag if self.check_finite else None)
+        elif self.latent_gemm:
+            # wide product: heads and fc_d0 on the tensor cores (3 planes each side: fp32 accuracy ahead of the
+            # manifold maps / the relu), the standalone product-manifold kernel between them
+            self._heads_gemm(ws)
+            out = {"z": ws.z, "kl": ws.kl, "mu": ws.mu, "sigma": ws.sigma}
+            ops.pm_forward(self.desc, ws.ml, ws.eps, self._rflat, want_mu_sigma=want_mu_sigma,
+                           flag=ws.flag if self.check_finite else None, out=out)
+            ops.split_planes(ws.z, ws.zp)
+            self._gemm("d0_fwd", ws.zp, self.Wd0p, B, H, Sd, epilogue=L.EPI_BIAS_RELU, bias=self.fc_d0.bias.data,
+                       out_planes=ws.ddp)
         else:
             # heads: N = P is tiny -> CUDA-core row dots in exact fp32 (h read from its 3 planes)
             ops.skinny_rowdot((ws.hp, 3), self.Wh, H, 1, K=H, N=P, bias=self.bh, out=ws.ml)
@@ -430,6 +460,20 @@ class FusedFeedForwardVAE(nn.Module):
                                 ws.z, beta, ws.ghp, self.gWd0, self.gbd0, self.gWh, self.gbh, self._gradius)
             if self._any_fixed_radius:
                 self._gradius.mul_(self._radius_mask)  # requires_grad=False radii (fixed curvature) get no gradient
+        elif self.latent_gemm:
+            # fc_d0: gW = gdd^T z (+ bias from the ones column of z), gz = gdd W
+            self._gemm("d0_wgrad", ws.gddp, ws.zp, H, Sd + 1, B, a_major=MN, b_major=MN, split_k=0, out_f32=self.gWd0,
+                       out_col=self.gbd0, col_split=Sd, a_planes=2, b_planes=2)
+            self._gemm("d0_dgrad", ws.gddp, self.Wd0p, B, Sd, H, b_major=MN, out_f32=ws.gz)
+            ops.pm_backward(self.desc, ws.ml, ws.eps, self._rflat, ws.gz, None, beta, gml=ws.gml, gradius=self._gradius)
+            if self._any_fixed_radius:
+                self._gradius.mul_(self._radius_mask)  # requires_grad=False radii (fixed curvature) get no gradient
+            ops.split_planes(ws.gml, ws.gmlp)
+            # heads: gWh = gml^T h (+ bias from h's ones column);  gh = (gml Wh) * 1[h > 0]
+            self._gemm("heads_wgrad", ws.gmlp, ws.hp, P, H + 1, B, a_major=MN, b_major=MN, split_k=0, out_f32=self.gWh,
+                       out_col=self.gbh, col_split=H)
+            self._gemm("heads_dgrad", ws.gmlp, self.Whp, B, H, P, b_major=MN, epilogue=L.EPI_RELU_MASK, mask=ws.hp,
+                       out_planes=ws.ghp, a_planes=2, b_planes=2)
         else:
             # fc_d0 (skinny): gW[h, j] = sum_b gdd[b, h] z[b, j], gb[h] = sum_b gdd[b, h];  gz = gdd W
             ops.skinny_wgrad(ws.z, Sd, (ws.gddp, 2), H, self.gWd0, 1, Sd, small_ones=True, out_row=self.gbd0)
@@ -462,6 +506,15 @@ class FusedFeedForwardVAE(nn.Module):
             else:
                 return ops.gemm(a, b, M, N, K, **kw)
         ops.gemm(a, b, M, N, K, tile=self._gemm_tiles[key], **kw)
+
+    def _heads_gemm(self, ws: _Workspace) -> None:
+        """ml = h Wh^T + bh on the tensor cores (wide products), accumulated into a ZEROED ws.ml.  The head
+        pre-activations feed the manifold maps, whose gradients are ill conditioned near the log-det singularities, and
+        the tensor core truncates (does not round) every add into its fp32 accumulator: one CTA per 64-wide K slice,
+        combined by fp32 atomics (round to nearest), keeps the number of truncating adds per output at 24 instead of
+        6 * K / 16 (measured: gradient error of the sphere components 1.9e-4 -> fp32-level)."""
+        ops.gemm(ws.hp, self.Whp, ws.B, self.desc.ld_ml, self.h_dim, bias=self.bh, out_f32=ws.ml,
+                 split_k=(self.h_dim + 63) // 64)
 
     def _tune_gemm(self, a, b, M: int, N: int, K: int, kw) -> Optional[tuple]:
         acc = [t for t in (kw.get("rowsum"), kw.get("out_f32") if kw.get("split_k", 1) != 1 else None,
@@ -613,7 +666,11 @@ class FusedFeedForwardVAE(nn.Module):
             ops.split_planes(ws.x, ws.xp)
         self._gemm("e0_fwd", ws.xp, self.We0p, B, H, D, epilogue=L.EPI_BIAS_RELU, bias=self.fc_e0.bias.data,
                    out_planes=ws.hp)
-        ops.skinny_rowdot((ws.hp, 3), self.Wh, H, 1, K=H, N=P, bias=self.bh, out=ws.ml)
+        if self.latent_gemm:
+            ws.ml.zero_()
+            self._heads_gemm(ws)
+        else:
+            ops.skinny_rowdot((ws.hp, 3), self.Wh, H, 1, K=H, N=P, bias=self.bh, out=ws.ml)
         nc = max(1, min(n, self.iwae_chunk_rows // max(B, 1)))
         lw = self._iwae_workspace(B, nc, n)
         lw["recon"].zero_()
@@ -628,8 +685,13 @@ class FusedFeedForwardVAE(nn.Module):
                 e.copy_(eps[s0:s0 + k], non_blocking=True)
             z = lw["z"][:k]
             ops.iwae_latent(self.desc, ws.ml, e, self._rflat, z, lw["diff"][s0:s0 + k], lw["zsum"])
-            ops.skinny_expand(z.view(k * B, Sd), self.fc_d0.weight.data, Sd, 1, K=Sd, N=H, bias=self.fc_d0.bias.data,
-                              act=ops.ACT_RELU, out_planes=lw["ddp"])
+            if self.latent_gemm:
+                ops.split_planes(z.view(k * B, Sd), lw["zp"])
+                self._gemm("iwae_d0", lw["zp"], self.Wd0p, k * B, H, Sd, epilogue=L.EPI_BIAS_RELU,
+                           bias=self.fc_d0.bias.data, out_planes=lw["ddp"])
+            else:
+                ops.skinny_expand(z.view(k * B, Sd), self.fc_d0.weight.data, Sd, 1, K=Sd, N=H,
+                                  bias=self.fc_d0.bias.data, act=ops.ACT_RELU, out_planes=lw["ddp"])
             self._gemm("iwae_logits", lw["ddp"], self.Wlp, k * B, D, H, epilogue=epi, bias=self.fc_logits.bias.data,
                        aux=ws.x, aux_rows=B, rowsum=lw["recon"][s0:s0 + k])
         log_p_x, mi = ops.iwae_reduce(lw["recon"], lw["diff"])
@@ -644,6 +706,8 @@ class FusedFeedForwardVAE(nn.Module):
             lw = {"eps": torch.empty(nc, B, self.desc.ld_eps, **f), "z": torch.empty(nc, B, self.desc.ld_z, **f),
                   "ddp": ops.PlaneBuf(nc * B, self.h_dim, 2, self.device), "recon": torch.zeros(n, B, **f),
                   "diff": torch.empty(n, B, **f), "zsum": torch.zeros(B, self.desc.ld_z, **f)}
+            if self.latent_gemm:
+                lw["zp"] = ops.PlaneBuf(nc * B, self.desc.ld_z, 3, self.device)
             self._iwae_ws = {key: lw}  # one likelihood workspace at a time (it can be hundreds of MB)
         return lw
 
@@ -770,6 +834,7 @@ class FusedFeedForwardVAE(nn.Module):
 
     _grad_hook = None
     use_cuda_graph = False
+    latent_gemm = False
 
     def _graphed_step(self, optimizer: "FusedCurvatureOptimizer", ws: _Workspace, beta: float,
                       draw_eps: bool = False) -> None:
@@ -874,9 +939,15 @@ class FusedCurvatureOptimizer:
         if m._clip_mask is not None:
             ops.clip_grad_norm(m._gradius, m._clip_mask, 1.0)  # vae.py:161-163, on the (rank-summed) gradient
         targets = [(m._slices["fc_e0.weight"][0], m.h_dim, m.We0p), (m._slices["fc_logits.weight"][0], m.in_dim, m.Wlp)]
+        if m.latent_gemm:
+            targets += [(m._slices["components.0.fc_mean.weight"][0], m.desc.ld_ml, m.Whp),
+                        (m._slices["fc_d0.weight"][0], m.h_dim, m.Wd0p)]
         # the fused kernels refresh a weight's planes with 128-bit accesses: rows must be a multiple of 4 floats wide
         # (in_dim = 50 of the BDP data is not); such a matrix gets its own plane-split launch after the update
-        late = [(m.fc_e0.weight if t[2] is m.We0p else m.fc_logits.weight, t[2]) for t in targets if t[2].cols % 4]
+        src_of = {id(m.We0p): lambda: m.fc_e0.weight.data, id(m.Wlp): lambda: m.fc_logits.weight.data}
+        if m.latent_gemm:
+            src_of.update({id(m.Whp): lambda: m.Wh, id(m.Wd0p): lambda: m.fc_d0.weight.data})
+        late = [(src_of[id(t[2])](), t[2]) for t in targets if t[2].cols % 4]
         targets = [t for t in targets if t[2].cols % 4 == 0]
         if self._dp is not None:
             # data parallel over NVLink peer memory: gradient reduce-scatter + Adam on this rank's slice + parameter
@@ -886,7 +957,7 @@ class FusedCurvatureOptimizer:
                              self.curvature_lr if self.curvature_step_enabled() else 0.0, m._radius_mask,
                              self._dp_tail, self._dp_sync, targets)
             for w, buf in late:
-                ops.split_planes(w.data, buf)
+                ops.split_planes(w, buf)
             m._planes_stale = False
             self.planes_fresh = True
             return
@@ -896,7 +967,7 @@ class FusedCurvatureOptimizer:
                            self.eps, self.step_dev, self._done, m._rflat, m._gradius, m._radius_mask,
                            self.curvature_lr if self.curvature_step_enabled() else 0.0, targets)
         for w, buf in late:
-            ops.split_planes(w.data, buf)
+            ops.split_planes(w, buf)
         m._planes_stale = False
         self.planes_fresh = True
 

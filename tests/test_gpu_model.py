@@ -99,16 +99,23 @@ def test_forward_and_gradients_match_reference(dev, name):
     ("p2", 2048, 50, 400, "nll", False),                 # cfg4b
     ("h6,h6,s6,s6,e6", 1000, 784, 400, "bce", False),    # cfg3 model, ragged batch
 ])
-@pytest.mark.parametrize("fused_latent", [True, False])
-def test_train_step_vs_oracle(dev, oracle, sig, B, D, H, recon, fixed, fused_latent):
+@pytest.mark.parametrize("mode", ["fused", "skinny", "gemm"])
+def test_train_step_vs_oracle(dev, oracle, sig, B, D, H, recon, fixed, mode):
     """Full step at the BASELINE shapes: loss, statistics and every gradient against the float64 oracle, with the
-    latent block as one fused kernel per direction (the training path) and as separate kernels."""
+    latent block as one fused kernel per direction (the training path of narrow products), as separate CUDA-core
+    kernels, and with its dense layers on the tensor cores (the training path of wide products such as cfg3)."""
     from mvae_b200 import components, data, vae
     torch.manual_seed(0)
     comps = components.parse_components(sig, fixed)
     model = vae.FusedFeedForwardVAE(H, comps, data.GenericDataset(B, D, recon), False, device=dev)
-    assert model.fused_latent
-    model.fused_latent = fused_latent
+    if mode == "gemm":
+        if not model.latent_gemm:
+            pytest.skip("narrow product: the latent block stays fused")
+        assert not model.fused_latent
+    else:
+        model.latent_gemm = False
+        model.fused_latent = mode == "fused"
+    fused_latent = mode == "fused"
     g = torch.Generator().manual_seed(1)
     x = (torch.rand(B, D, generator=g) < 0.1307).float() if recon == "bce" else torch.randn(B, D, generator=g)
     eps = torch.randn(B, model.desc.ld_eps, generator=g)
