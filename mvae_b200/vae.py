@@ -461,17 +461,21 @@ class FusedFeedForwardVAE(nn.Module):
             if self._any_fixed_radius:
                 self._gradius.mul_(self._radius_mask)  # requires_grad=False radii (fixed curvature) get no gradient
         elif self.latent_gemm:
-            # fc_d0: gW = gdd^T z (+ bias from the ones column of z), gz = gdd W
-            self._gemm("d0_wgrad", ws.gddp, ws.zp, H, Sd + 1, B, a_major=MN, b_major=MN, split_k=0, out_f32=self.gWd0,
-                       out_col=self.gbd0, col_split=Sd, a_planes=2, b_planes=2)
+            # fc_d0: gW = gdd^T z (+ bias from the ones column of z) on the side branch, gz = gdd W on the main one
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                self._gemm("d0_wgrad", ws.gddp, ws.zp, H, Sd + 1, B, a_major=MN, b_major=MN, split_k=0,
+                           out_f32=self.gWd0, out_col=self.gbd0, col_split=Sd, a_planes=2, b_planes=2)
             self._gemm("d0_dgrad", ws.gddp, self.Wd0p, B, Sd, H, b_major=MN, out_f32=ws.gz)
             ops.pm_backward(self.desc, ws.ml, ws.eps, self._rflat, ws.gz, None, beta, gml=ws.gml, gradius=self._gradius)
             if self._any_fixed_radius:
                 self._gradius.mul_(self._radius_mask)  # requires_grad=False radii (fixed curvature) get no gradient
             ops.split_planes(ws.gml, ws.gmlp)
-            # heads: gWh = gml^T h (+ bias from h's ones column);  gh = (gml Wh) * 1[h > 0]
-            self._gemm("heads_wgrad", ws.gmlp, ws.hp, P, H + 1, B, a_major=MN, b_major=MN, split_k=0, out_f32=self.gWh,
-                       out_col=self.gbh, col_split=H)
+            # heads: gWh = gml^T h (+ bias from h's ones column) on the side branch;  gh = (gml Wh) * 1[h > 0]
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                self._gemm("heads_wgrad", ws.gmlp, ws.hp, P, H + 1, B, a_major=MN, b_major=MN, split_k=0,
+                           out_f32=self.gWh, out_col=self.gbh, col_split=H)
             self._gemm("heads_dgrad", ws.gmlp, self.Whp, B, H, P, b_major=MN, epilogue=L.EPI_RELU_MASK, mask=ws.hp,
                        out_planes=ws.ghp, a_planes=2, b_planes=2)
         else:
