@@ -7,8 +7,11 @@
 //               mbarrier-guarded ring of shared-memory stages; one k-block = 64 bf16 of K per operand plane.
 //   warp 1      allocates TMEM, then one elected lane issues tcgen05.mma (kind::f16, M=128, N=BLOCK_N, K=16) for
 //               every plane pair (i,j) with i+j < max(planes); tcgen05.commit releases stages / signals the epilogue.
-//   warps 2..5  epilogue: tcgen05.ld the fp32 accumulator (lane = row, column = n) and apply the fused epilogue
+//   warps 2..9  epilogue: tcgen05.ld the fp32 accumulator (lane = row, column = n) and apply the fused epilogue
 //               (bias, relu, relu-mask, BCE / Gaussian-NLL row sums + dloss/dlogits, split planes for the next GEMM).
+//               A warp may only read the TMEM lanes 32 (warp % 4) .. +31, so two warps share each lane quadrant and
+//               take alternating 16-column chunks: the epilogue of these short-K GEMMs is latency bound (MUFU chains
+//               of the BCE, dependent tcgen05.ld waits), and eight warps hide twice as much of it as four.
 // Operands may be K-major (row-major [rows, K]) or MN-major (row-major [K, rows], read through an MN-major UMMA
 // descriptor) so that dgrad and wgrad read the very same buffers as the forward pass — no transposes in HBM.
 #include <cuda.h>
@@ -27,7 +30,8 @@ namespace mvae {
 constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;             // bf16 elements per k-block = one 128-byte swizzle row
 constexpr int kUmmaK = 16;              // K of one tcgen05.mma kind::f16
-constexpr int kGemmThreads = 192;       // 6 warps
+constexpr int kEpiThreads = 256;        // 8 epilogue warps: two per TMEM lane quadrant, alternating 16-column chunks
+constexpr int kGemmThreads = 64 + kEpiThreads;  // + TMA producer warp + MMA issuer warp
 constexpr int kATileBytes = kBlockM * kBlockK * 2;  // 16 KiB per plane per stage
 constexpr int kMaxStages = 8;
 constexpr float kHalfLn2PiG = 0.9189385332046727f;
@@ -298,14 +302,15 @@ __global__ void __launch_bounds__(kGemmThreads, 2)
   } else {
     // ===================================== epilogue =====================================
     const int q = warp & 3;  // TMEM lane quadrant this warp may access
+    const int c_first = ((warp - 2) >> 2) * 16;  // first column chunk of this warp (the quadrant's other warp: +16)
     const int m = m0 + q * 32 + lane;
     const bool row_ok = m < p.M;
-    const int te = threadIdx.x - 64;  // 0..127 within the epilogue warps
+    const int te = threadIdx.x - 64;  // 0..255 within the epilogue warps
     // stage the bias slice of this tile in shared memory while the main loop runs (split-K: first slice only)
     {
       const float* bias = blockIdx.z == 0 ? p.bias : nullptr;
-      for (int i = te; i < p.block_n; i += 128) s_bias[i] = (bias && n0 + i < p.N) ? __ldg(bias + n0 + i) : 0.f;
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+      for (int i = te; i < p.block_n; i += kEpiThreads) s_bias[i] = (bias && n0 + i < p.N) ? __ldg(bias + n0 + i) : 0.f;
+      asm volatile("bar.sync 1, 256;" ::: "memory");
     }
     const bool vec_out = p.out_f32 && ((p.ld_out & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.out_f32) & 15) == 0);
     const bool vec_aux = p.aux && ((p.ld_aux & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.aux) & 15) == 0);
@@ -357,19 +362,19 @@ __global__ void __launch_bounds__(kGemmThreads, 2)
         mk_nxt = bits;
       }
     };
-    prefetch(0);
+    if (c_first < p.block_n) prefetch(c_first);
     mbar_wait(tmem_full_bar, 0);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     pdl_launch_dependents();  // main loop done: the next kernel's CTAs may take the SM resources this CTA frees soon
     float row_acc = 0.f;
-    for (int c = 0; c < p.block_n; c += 16) {
+    for (int c = c_first; c < p.block_n; c += 32) {
       const int n = n0 + c;
       if (n >= p.N) break;  // warp-uniform
       float t[16];
 #pragma unroll
       for (int j = 0; j < 16; ++j) t[j] = t_nxt[j];
       const uint32_t mk_cur = mk_nxt;
-      if (c + 16 < p.block_n) prefetch(c + 16);
+      if (c + 32 < p.block_n) prefetch(c + 32);
       uint32_t r[16];
       tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, r);
       if (!row_ok) continue;
