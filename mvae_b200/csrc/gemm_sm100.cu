@@ -107,6 +107,17 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint
       "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+__device__ __forceinline__ bool elect_one_sync() {
+  uint32_t pred;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "elect.sync _|p, 0xffffffff;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
@@ -264,7 +275,13 @@ __global__ void __launch_bounds__(kGemmThreads, 2)
     }
   } else if (warp == 1) {
     // ===================================== MMA issuer =====================================
-    if (lane == 0) {
+    // The warp stays converged through the k-block loop (every lane polls the barrier and derives the same shared-memory
+    // descriptors); the MMAs and commits themselves are issued by ONE lane chosen with elect.sync.  Written as
+    // `if (lane == 0) { whole loop }` the compiler cannot prove that a single lane is active and wraps every
+    // tcgen05.mma in an ELECT / BRA.U.ANY loop over the active lanes: ~25 dependent instructions per MMA on one warp,
+    // i.e. more cycles to ISSUE an MMA than the tensor core needs to execute it (the issuing thread, not the data, was
+    // what the epilogue warps were waiting for).
+    {
       const int pmax = max(p.a_planes, p.b_planes);
       // K-major: rows of 128 B, 8-row groups 1024 B apart (SBO); k-step = 32 B inside the swizzle row.
       // MN-major: 64-element column chunks 8192 B apart (LBO), 8-k-row groups 1024 B apart (SBO); k-step = 16 rows = 2048 B.
@@ -272,6 +289,8 @@ __global__ void __launch_bounds__(kGemmThreads, 2)
       const uint32_t b_lbo = p.b_major == MVAE_K_MAJOR ? 16u : 8192u;
       const uint32_t a_kstep = p.a_major == MVAE_K_MAJOR ? 32u : 2048u;
       const uint32_t b_kstep = p.b_major == MVAE_K_MAJOR ? 32u : 2048u;
+      // descriptors differ only in their 14-bit start-address field: build the constant part once
+      const uint64_t da_hi = make_desc(0u, a_lbo, 1024u), db_hi = make_desc(0u, b_lbo, 1024u);
       uint32_t accumulate = 0;
       for (int i = 0; i < nkb; ++i) {
         const int s = i % p.stages;
@@ -282,23 +301,26 @@ __global__ void __launch_bounds__(kGemmThreads, 2)
         const uint32_t sb = sa + p.a_planes * kATileBytes;
         const int k_left = p.K - (kb0 + i) * kBlockK;
         const int nks = k_left >= kBlockK ? kBlockK / kUmmaK : (k_left + kUmmaK - 1) / kUmmaK;
-        for (int pa = 0; pa < p.a_planes; ++pa)
-          for (int pb = 0; pb < p.b_planes; ++pb) {
-            if (pa + pb >= pmax) continue;
-            const uint32_t ta = sa + pa * kATileBytes;
-            const uint32_t tb = sb + pb * p.b_tile_bytes;
-            for (int ks = 0; ks < nks; ++ks) {
-              const uint64_t da = make_desc(ta + ks * a_kstep, a_lbo, 1024u);
-              const uint64_t db = make_desc(tb + ks * b_kstep, b_lbo, 1024u);
-              umma_bf16(tmem_base, da, db, p.idesc, accumulate);
-              accumulate = 1;
+        if (elect_one_sync()) {
+          for (int pa = 0; pa < p.a_planes; ++pa)
+            for (int pb = 0; pb < p.b_planes; ++pb) {
+              if (pa + pb >= pmax) continue;
+              const uint32_t ta = (sa + pa * kATileBytes) >> 4;
+              const uint32_t tb = (sb + pb * p.b_tile_bytes) >> 4;
+              for (int ks = 0; ks < nks; ++ks) {
+                const uint64_t da = da_hi | (uint64_t)((ta + ks * (a_kstep >> 4)) & 0x3FFFu);
+                const uint64_t db = db_hi | (uint64_t)((tb + ks * (b_kstep >> 4)) & 0x3FFFu);
+                umma_bf16(tmem_base, da, db, p.idesc, accumulate);
+                accumulate = 1;
+              }
             }
-          }
-        umma_commit(empty_bar(s));  // stage reusable once these MMAs retire
+          umma_commit(empty_bar(s));  // stage reusable once these MMAs retire
+          if (i == nkb - 1) umma_commit(tmem_full_bar);  // accumulator complete
+        }
+        accumulate = 1;
+        __syncwarp();
       }
-      umma_commit(tmem_full_bar);   // accumulator complete
     }
-    __syncwarp();
   } else {
     // ===================================== epilogue =====================================
     const int q = warp & 3;  // TMEM lane quadrant this warp may access
