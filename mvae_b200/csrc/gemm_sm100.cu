@@ -244,33 +244,38 @@ __global__ void __launch_bounds__(kGemmThreads, 2)
 
   if (warp == 0) {
     // ===================================== TMA producer =====================================
-    if (lane == 0) {
+    // converged warp, one elected lane issues (see the MMA issuer below for why not `if (lane == 0) { loop }`)
+    {
       const uint32_t tx_bytes = stage_bytes;
       for (int i = 0; i < nkb; ++i) {
         const int s = i % p.stages;
         const uint32_t ph = (uint32_t)(i / p.stages) & 1u;
         mbar_wait(empty_bar(s), ph ^ 1u);
-        mbar_expect_tx(full_bar(s), tx_bytes);
-        const int k = (kb0 + i) * kBlockK;
-        const uint32_t sa = base + s * stage_bytes;
-        const uint32_t sb = sa + p.a_planes * kATileBytes;
-        for (int pl = 0; pl < p.a_planes; ++pl) {
-          const uint32_t dst = sa + pl * kATileBytes;
-          if (p.a_major == MVAE_K_MAJOR) {
-            tma_load_3d(dst, &map_a, full_bar(s), k, m0, pl);
-          } else {
-            tma_load_3d(dst, &map_a, full_bar(s), m0, k, pl);
-            tma_load_3d(dst + 8192, &map_a, full_bar(s), m0 + 64, k, pl);
+        if (elect_one_sync()) {
+          mbar_expect_tx(full_bar(s), tx_bytes);
+          const int k = (kb0 + i) * kBlockK;
+          const uint32_t sa = base + s * stage_bytes;
+          const uint32_t sb = sa + p.a_planes * kATileBytes;
+          for (int pl = 0; pl < p.a_planes; ++pl) {
+            const uint32_t dst = sa + pl * kATileBytes;
+            if (p.a_major == MVAE_K_MAJOR) {
+              tma_load_3d(dst, &map_a, full_bar(s), k, m0, pl);
+            } else {
+              tma_load_3d(dst, &map_a, full_bar(s), m0, k, pl);
+              tma_load_3d(dst + 8192, &map_a, full_bar(s), m0 + 64, k, pl);
+            }
+          }
+          for (int pl = 0; pl < p.b_planes; ++pl) {
+            const uint32_t dst = sb + pl * p.b_tile_bytes;
+            if (p.b_major == MVAE_K_MAJOR) {
+              tma_load_3d(dst, &map_b, full_bar(s), k, n0, pl);
+            } else {
+              for (int c = 0; c * 8192 < p.b_tile_bytes; ++c)
+                tma_load_3d(dst + c * 8192, &map_b, full_bar(s), n0 + c * 64, k, pl);
+            }
           }
         }
-        for (int pl = 0; pl < p.b_planes; ++pl) {
-          const uint32_t dst = sb + pl * p.b_tile_bytes;
-          if (p.b_major == MVAE_K_MAJOR) {
-            tma_load_3d(dst, &map_b, full_bar(s), k, n0, pl);
-          } else {
-            for (int c = 0; c * 8192 < p.b_tile_bytes; ++c) tma_load_3d(dst + c * 8192, &map_b, full_bar(s), n0 + c * 64, k, pl);
-          }
-        }
+        __syncwarp();
       }
     }
   } else if (warp == 1) {
