@@ -391,6 +391,8 @@ class FusedFeedForwardVAE(nn.Module):
             # (image_reconstruction.py:37-53: dynamic in training, threshold 0.5 in evaluation)
             ops.binarize(ws.x8, x=ws.x, planes=ws.xp, seed=self.binarize_seed, offset_dev=ws.bin_ctr,
                          dynamic=train or self.binarize_eval_dynamic, invert=self.binarize_invert)
+            if self.input_planes > 1:  # binarised values are exact in plane 0: the residual planes are zero
+                ws.xp.t[1:, :, :self.in_dim].zero_()
         else:
             ops.split_planes(ws.x, ws.xp)
         fused = self.fused_latent and not want_mu_sigma
@@ -567,8 +569,6 @@ class FusedFeedForwardVAE(nn.Module):
         what the dataset stores) into the slot's uint8 buffer — they are binarised on the device by the forward
         kernels.  Marks which kind the slot's consumer has to read."""
         if x.dtype == torch.uint8:
-            if self.input_planes != 1:
-                raise L.MvaeError("uint8 image batches need a dataset with binary_inputs=True (one operand plane)")
             ws.x8  # allocate on first use
             ws.x8buf[slot].copy_(x.reshape(ws.B, self.in_dim), non_blocking=True)
             ws.u8 = True
