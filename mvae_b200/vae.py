@@ -666,6 +666,8 @@ class FusedFeedForwardVAE(nn.Module):
         if ws.u8:
             ops.binarize(ws.x8, x=ws.x, planes=ws.xp, seed=self.binarize_seed, offset_dev=ws.bin_ctr,
                          dynamic=self.binarize_eval_dynamic, invert=self.binarize_invert)
+            if self.input_planes > 1:
+                ws.xp.t[1:, :, :self.in_dim].zero_()
         else:
             ops.split_planes(ws.x, ws.xp)
         self._gemm("e0_fwd", ws.xp, self.We0p, B, H, D, epilogue=L.EPI_BIAS_RELU, bias=self.fc_e0.bias.data,
