@@ -24,11 +24,9 @@ def test_pm_forward_backward_f64(oracle, name):
         assert normwise(f[k], g[k]) < F64_TOL, k
     gml, gR = oracle.pm_backward(desc, ml, g["eps"], R, g["gz"], g["gkl"])
     gm, gl = unpack_gml(desc, gml)
-    # 'd' components: the oracle's gradients are five-point differences of its float64 forward, not a reverse sweep
-    has_d = any(desc.comp[i].type == oracle.TYPE_OF_LETTER["d"] for i in range(desc.C))
-    assert normwise(gm, g["gm"]) < (1e-7 if has_d else F64_TOL)
-    assert normwise(gl, g["gl"]) < (1e-7 if has_d else F64_TOL)
-    assert normwise(gR, g["gR"]) < (1e-7 if has_d else 1e-8)
+    assert normwise(gm, g["gm"]) < F64_TOL
+    assert normwise(gl, g["gl"]) < F64_TOL
+    assert normwise(gR, g["gR"]) < 1e-8
 
 
 @pytest.mark.parametrize("name", pm_golden_names())

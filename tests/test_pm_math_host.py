@@ -59,8 +59,8 @@ def _drop_pole_rows(oracle, sig, desc, radius, ml, eps, gz):
         c = desc.comp[i]
         if c.type == oracle.TYPE_OF_LETTER["d"]:
             keep &= np.abs(f["z"][:, c.z_off:c.z_off + c.d]).max(1) < 6.0 * radius[i]
-            # ... and the log-det (n-1) log|sin t| is singular at |v| = k pi R (k >= 1), where the oracle's finite-difference
-            # gradients of 'd' are not usable either
+            # ... and the log-det (n-1) log|sin t| is singular at |v| = k pi R (k >= 1): gradients blow up there and
+            # no float32 evaluation tracks the float64 one
             v = eps[:, c.eps_off:c.eps_off + c.n] * f["sigma"][:, c.eps_off:c.eps_off + c.n]
             t = np.linalg.norm(v, axis=1) / radius[i]
             keep &= (t < 1.5) | (np.abs(np.sin(t)) > 0.05)
