@@ -141,7 +141,7 @@ class _Workspace:
         # uint8 image batches (binarised on the device, mvae_binarize): raw pixels per slot, allocated on first use;
         # u8 = the current batch arrived as uint8; bin_ctr = Philox step counter of the dynamic binarisation
         self.x8buf = None
-        self.u8 = False
+        self._u8 = [False, False]  # per input slot (train_epoch stages batch i+1 while step i is being enqueued)
         self.bin_ctr = torch.zeros(1, device=dev, dtype=torch.int64)
         self.eps = torch.zeros(B, Sn, **f)
         self.xp = ops.PlaneBuf(B, D, m.input_planes, dev, ones_col=True)
@@ -173,6 +173,10 @@ class _Workspace:
     @property
     def x(self) -> Tensor:
         return self.xbuf[self.slot]
+
+    @property
+    def u8(self) -> bool:
+        return self._u8[self.slot]
 
     @property
     def x8(self) -> Tensor:
@@ -571,10 +575,10 @@ class FusedFeedForwardVAE(nn.Module):
         if x.dtype == torch.uint8:
             ws.x8  # allocate on first use
             ws.x8buf[slot].copy_(x.reshape(ws.B, self.in_dim), non_blocking=True)
-            ws.u8 = True
+            ws._u8[slot] = True
         else:
             ws.xbuf[slot].copy_(x.reshape(ws.B, self.in_dim), non_blocking=True)
-            ws.u8 = False
+            ws._u8[slot] = False
 
     # ------------------------------------------------------------------------------------------ reference API
     def encode(self, x: Tensor) -> Tensor:

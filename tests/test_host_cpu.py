@@ -107,3 +107,22 @@ def test_reference_arm_bench_line():
     assert d["value"] > 0 and d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
     assert d["config"]["workload"].startswith("MNIST e2")
+
+
+def test_input_slots_keep_their_own_batch_kind():
+    """train_epoch stages batch i+1 (host -> device) while step i is being enqueued: each input slot remembers whether
+    it holds uint8 pixels (binarised on the device) or a float batch.  Host-side bookkeeping only (CPU tensors)."""
+    from mvae_b200 import components, data, vae
+    m = vae.FusedFeedForwardVAE(16, components.parse_components("h2,e2", True),
+                                data.GenericDataset(4, 8, "bce", binary_inputs=True), False, device="cpu")
+    ws = vae._Workspace(m, 4)
+    xf = torch.rand(4, 8)
+    x8 = (torch.rand(4, 8) * 255).to(torch.uint8)
+    m._stage_x(ws, 0, x8)
+    m._stage_x(ws, 1, xf)
+    ws.slot = 0
+    assert ws.u8 and torch.equal(ws.x8, x8)
+    ws.slot = 1
+    assert not ws.u8 and torch.equal(ws.x, xf)
+    m._stage_x(ws, 1, x8.reshape(4, 2, 4))   # image-shaped batches are flattened like the reference's transform
+    assert ws.u8 and torch.equal(ws.x8, x8)
