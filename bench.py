@@ -47,6 +47,40 @@ def measured_peaks():
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "source": "fallback (B200_PROFILING.md)"}
 
 
+KERNEL_SOURCES = {  # files whose edits invalidate an ncu capture of the kernel
+    "pm_forward_kernel": ["pm_kernels_impl.cuh", "pm_item.cuh", "pm_math.cuh", "pm_params.cuh"],
+    "pm_backward_kernel": ["pm_kernels_impl.cuh", "pm_item.cuh", "pm_math.cuh", "pm_params.cuh"],
+    "gemm_tcgen05_kernel": ["gemm_sm100.cu"],
+}
+
+
+def source_hash(kernel):
+    import hashlib
+    h = hashlib.sha1()
+    for f in KERNEL_SOURCES[kernel]:
+        with open(os.path.join(ROOT, "mvae_b200", "csrc", f), "rb") as fh:
+            h.update(fh.read())
+    return h.hexdigest()[:12]
+
+
+def ncu_traffic(kernel, signature, samples):
+    """DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of `kernel` from the committed
+    `ncu --set full` capture, profiles/ncu_traffic.json (written by scripts/summarize_profiles.py together with a hash
+    of the kernel's sources).  None — with the reason — when there is no capture of this shape or the sources have
+    changed since: a number from another build is not reported as this build's."""
+    path = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if not os.path.exists(path):
+        return None, "no capture committed"
+    with open(path) as fh:
+        table = json.load(fh)
+    for row in table.get(kernel, []):
+        if row.get("signature") == signature and int(row.get("samples", -1)) == int(samples):
+            if row.get("source_hash") != source_hash(kernel):
+                return None, f"capture {row.get('capture')} predates the current kernel sources"
+            return float(row["dram_bytes"]), row.get("capture")
+    return None, "no capture of this shape"
+
+
 def synthetic_x(recon, B, D, seed):
     import torch
     g = torch.Generator().manual_seed(seed)
@@ -154,55 +188,51 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------ CPU arm
+def force_host_threads():
+    """All host threads for the CPU arm.  torch.distributed.run pre-sets OMP_NUM_THREADS=1 for its workers: override
+    it (and the BLAS variables) BEFORE numpy / torch / the OpenMP oracle are loaded."""
+    cores = os.cpu_count() or 1
+    for k in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
+        os.environ[k] = str(cores)
+    return cores
+
+
 def cpu_step_fn(workload, B, seed=0):
-    """One train step of the oracle port (forward + ELBO + backward + Adam) in float32 on the host cores."""
+    """One train step of the CPU arm (forward + ELBO + backward + Adam + radii SGD) in float32 on the host cores:
+    oracle/cpu_baseline.py.  Returns (step function, threads in use)."""
     import numpy as np
     import torch
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
-    import oracle as orc
+    import cpu_baseline
     sig, _, D, H, recon, fixed, _ = WORKLOADS[workload]
     from mvae_b200 import components
     torch.manual_seed(seed)
     comps = components.parse_components(sig, fixed)
-    types, dims = orc.parse_signature(sig)
-    ov = orc.OracleVAE(sig, D, H, recon, False)
     # reference-shaped parameters with nn.Linear default init (CPU only; no kernels involved)
     params = {}
     for i, c in enumerate(comps):
         c.init_layers(H, False)
-        params[f"components.{i}.fc_mean.weight"] = c.fc_mean.weight.detach().numpy().copy()
-        params[f"components.{i}.fc_mean.bias"] = c.fc_mean.bias.detach().numpy().copy()
-        params[f"components.{i}.fc_logvar.weight"] = c.fc_logvar.weight.detach().numpy().copy()
-        params[f"components.{i}.fc_logvar.bias"] = c.fc_logvar.bias.detach().numpy().copy()
+        for nm in ("fc_mean", "fc_logvar"):
+            params[f"components.{i}.{nm}.weight"] = getattr(c, nm).weight.detach().numpy().copy()
+            params[f"components.{i}.{nm}.bias"] = getattr(c, nm).bias.detach().numpy().copy()
         name, rp = c.radius_parameter()
-        if rp is not None:
+        if rp is not None and not fixed:
             params[f"components.{i}.{name}"] = np.asarray(1.0, dtype=np.float32)
     tz = sum(c.dim for c in comps)
     for nm, (o, i_) in (("fc_e0", (H, D)), ("fc_d0", (H, tz)), ("fc_logits", (D, H))):
         lin = torch.nn.Linear(i_, o)
         params[nm + ".weight"] = lin.weight.detach().numpy().copy()
         params[nm + ".bias"] = lin.bias.detach().numpy().copy()
-    x = synthetic_x(recon, B, D, seed).numpy()
-    rng = np.random.default_rng(seed)
-    m = {k: np.zeros_like(v) for k, v in params.items()}
-    v = {k: np.zeros_like(v) for k, v in params.items()}
-    state = {"t": 0}
+    cpu = cpu_baseline.CpuTrainStep(sig, D, H, recon, params)
+    x = synthetic_x(recon, B, D, seed)
+    g = torch.Generator().manual_seed(seed)
+    n_eps = cpu.desc.ld_eps
 
     def step():
-        eps = rng.standard_normal((B, ov.desc.ld_eps), dtype=np.float32)
-        out = ov.step(params, x, eps, beta=1.0)
-        state["t"] += 1
-        t = state["t"]
-        for k, g in out["grads"].items():
-            if "radius" in k:
-                continue
-            g = g.astype(np.float32)
-            m[k] = 0.9 * m[k] + 0.1 * g
-            v[k] = 0.999 * v[k] + 0.001 * g * g
-            params[k] = params[k] - (1e-3 / (1 - 0.9**t)) * m[k] / (np.sqrt(v[k]) / np.sqrt(1 - 0.999**t) + 1e-8)
-        return out["elbo"]
+        eps = torch.randn(B, n_eps, generator=g)
+        return cpu.step(x, eps, beta=1.0)["elbo"]
 
-    return step
+    return step, torch.get_num_threads()
 
 
 def run_reference(args):
@@ -212,12 +242,11 @@ def run_reference(args):
     import torch
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    os.environ.setdefault("OMP_NUM_THREADS", str(cores))
     sig, B, D, H, recon, fixed, desc = WORKLOADS[args.workload]
     # bounded sample: a step is a full train step on the first Bs rows of the workload's batch, Bs chosen so that the
     # whole run (warm-up + K steps) stays near two minutes of CPU time
     Bs = B
-    step = cpu_step_fn(args.workload, Bs)
+    step, threads = cpu_step_fn(args.workload, Bs)
     step()
     t0 = time.perf_counter()
     step()
@@ -227,7 +256,7 @@ def run_reference(args):
     if t1 * n_total > budget_s:
         Bs = int(B * budget_s / (t1 * n_total)) // 128 * 128
         Bs = min(B, max(128, Bs))
-        step = cpu_step_fn(args.workload, Bs)
+        step, threads = cpu_step_fn(args.workload, Bs)
     for _ in range(max(args.warmup, 1)):
         step()
     t0 = time.perf_counter()
@@ -236,14 +265,15 @@ def run_reference(args):
     dt = time.perf_counter() - t0
     ms = dt / args.steps * 1e3
     value = Bs / (ms / 1e3)
-    sample = (f"{args.steps} full train steps on {Bs} of the {B} rows of the batch ({desc}), float32, "
-              f"numpy BLAS + C/OpenMP oracle port")
+    sample = (f"{args.steps} full train steps on {Bs} of the {B} rows of the batch ({desc}), float32, ATen CPU dense "
+              f"layers + C/OpenMP oracle for the latent chain (oracle/cpu_baseline.py), {threads} threads")
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms, "steps_per_sec": 1e3 / ms, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": desc, "signature": sig, "batch_per_gpu": B, "global_batch": B, "in_dim": D,
                        "h_dim": H, "note": "CPU arm runs one replica of the per-GPU workload on the host cores"},
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample,
+                             "omp_num_threads": os.environ.get("OMP_NUM_THREADS")},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
@@ -263,6 +293,64 @@ def time_kernel(fn, iters, flush):
         e[i].record()
     torch.cuda.synchronize()
     return sum(a.elapsed_time(b) for a, b in zip(s, e)) / iters  # ms
+
+
+def step_rooflines(model, opt, x, peaks, flush, C, Sn, Sd, P, H, B):
+    """Rooflines of the kernels the TIMED STEP launches, at the config batch: every GEMM / latent / manifold launch of
+    one eager step is recorded, then re-issued alone with a cold L2 (CUDA events, 10 runs each).  GEMMs: algorithmic
+    fp32 flops 2 M N K against the measured bf16 tensor peak (the kernel issues 3 or 6 bf16 MMAs per product);
+    latent / manifold kernels: algorithmic bytes against the measured HBM bandwidth."""
+    import torch
+    from mvae_b200 import ops
+    names = ["gemm", "latent_forward", "latent_backward", "pm_forward", "pm_backward"]
+    orig = {n: getattr(ops, n) for n in names}
+    calls = []
+
+    def wrap(name, fn):
+        def inner(*a, **k):
+            calls.append((name, fn, a, k))
+            return fn(*a, **k)
+        return inner
+
+    graph = model.use_cuda_graph
+    model.use_cuda_graph = False
+    for n, f in orig.items():
+        setattr(ops, n, wrap(n, f))
+    try:
+        model.train_step(opt, x, 1.0, sync_stats=False)
+    finally:
+        for n, f in orig.items():
+            setattr(ops, n, f)
+        model.use_cuda_graph = graph
+    torch.cuda.synchronize()
+    n0 = ops.launch_count()
+    bytes_of = {  # algorithmic bytes per sample (fp32 unless planes): what the kernel must read and write once
+        "latent_forward": 4 * H + 4 * Sn + 4 * (P + Sd + C) + 2 * 2 * H,       # h, eps -> ml, z, kl, dd (2 planes)
+        "latent_backward": 4 * H + 4 * H + 4 * (P + Sn + Sd) + 2 * 2 * H,      # gdd, h, ml, eps, z -> gh (2 planes)
+        "pm_forward": 4 * (3 * Sn + Sd + C), "pm_backward": 4 * (5 * Sn + Sd)}
+    rows, gemm_flops, gemm_us = [], 0.0, 0.0
+    for name, fn, a, k in calls:
+        ms = time_kernel(lambda: fn(*a, **k), 10, flush)
+        if name == "gemm":
+            M, N, K = a[2], a[3], a[4]
+            fl = 2.0 * M * N * K
+            gemm_flops += fl
+            gemm_us += ms * 1e3
+            rows.append({"kernel": "gemm_tcgen05_kernel", "shape": [M, N, K], "epilogue": int(k.get("epilogue", 0)),
+                         "us": ms * 1e3, "tflops": fl / (ms * 1e-3) / 1e12,
+                         "frac": fl / (ms * 1e-3) / 1e12 / peaks["bf16_tflops"]})
+        else:
+            by = bytes_of[name] * B
+            rows.append({"kernel": name + "_kernel", "us": ms * 1e3, "gbs": by / (ms * 1e-3) / 1e9,
+                         "frac": by / (ms * 1e-3) / 1e9 / peaks["hbm_gbs"], "bytes_per_sample": bytes_of[name]})
+    ops.add_launches(n0 - ops.launch_count())
+    out = {"kernels": rows, "l2": "cold (flushed before every launch)"}
+    if gemm_us:
+        tf = gemm_flops / (gemm_us * 1e-6) / 1e12
+        out["gemm_total"] = {"launches": sum(1 for r in rows if r["kernel"].startswith("gemm")), "us": gemm_us,
+                             "tflops": tf, "peak": peaks["bf16_tflops"], "frac": tf / peaks["bf16_tflops"],
+                             "bound": "tensor", "unit": "TFLOP/s"}
+    return out
 
 
 def run_ours(args):
@@ -371,10 +459,41 @@ def run_ours(args):
         model.train_step(opt, xs_e2e[i % n_rot], 1.0)
     torch.cuda.synchronize()
     serial_s = (time.perf_counter() - t0) / n_serial
+    # strict drop-in pattern: the reference's literal call, `stats, _ = model.train_step(optimizer, x_mb, beta)` with the
+    # float32 batch its DataLoader yields, blocking on the statistics every step (train.py:197-198)
+    for i in range(3):
+        model.train_step(opt, xs_host[i % n_rot], 1.0)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(n_serial):
+        model.train_step(opt, xs_host[i % n_rot], 1.0)
+    torch.cuda.synchronize()
+    strict_s = (time.perf_counter() - t0) / n_serial
     if world > 1:
-        t = torch.tensor([e2e_s, serial_s, float_s], device=dev)
+        t = torch.tensor([e2e_s, serial_s, float_s, strict_s], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_s, serial_s, float_s = float(t[0].item()), float(t[1].item()), float(t[2].item())
+        e2e_s, serial_s, float_s, strict_s = (float(v) for v in t.tolist())
+
+    # ---------------- N > 1: the run proves itself ----------------
+    dp_check = None
+    if world > 1:
+        # (a) replicas bit-identical after everything above; (b) the sticky error word of mvae_dp_step;
+        # (c) one more step with supplied noise: the statistics the exchange produced (rank-summed inside the fused
+        #     kernel) against an NCCL all-reduce of every rank's own statistics
+        identical = parallel.replicas_identical(model)
+        g = torch.Generator(device=dev).manual_seed(4242 + rank)
+        eps_chk = torch.randn(B, Sn, device=dev, generator=g)
+        bs_chk, _ = model.train_step(opt, xs_dev[0], 1.0, eps=eps_chk)
+        local = model._stats.clone()          # this rank's [bce, kl, elbo, kl_c] (the tail of its own bucket)
+        if collective.startswith("NCCL"):
+            local = None                      # the bucket itself was all-reduced in place
+        rel = None
+        if local is not None:
+            dist.all_reduce(local, op=dist.ReduceOp.SUM)
+            rel = abs(bs_chk.elbo - float(local[2].item())) / abs(float(local[2].item()))
+        dp_check = {"replicas_identical": bool(identical and parallel.replicas_identical(model)),
+                    "elbo_vs_nccl_rel": rel, "dp_error_word": parallel.dp_error_word(opt),
+                    "overlap": bool(getattr(opt, "dp_overlap", False) and opt._dp is not None)}
     e2e_ms = e2e_s / args.steps * 1e3
     float_ms = float_s / args.steps * 1e3
 
@@ -401,9 +520,14 @@ def run_ours(args):
                     "float32_batches": {"value": gb / (float_ms / 1e3), "ms_per_step": float_ms,
                                         "h2d_bytes_per_step": B * D * 4},
                     "serial": {"value": gb / serial_s, "ms_per_step": serial_s * 1e3,
-                               "api": "model.train_step(optimizer, x_host, beta), blocking"}},
+                               "api": "model.train_step(optimizer, x_host, beta), blocking"},
+                    "strict": {"value": gb / strict_s, "ms_per_step": strict_s * 1e3, "h2d_bytes_per_step": B * D * 4,
+                               "api": "the reference's literal call pattern: model.train_step(optimizer, float32 host "
+                                      "batch, beta), blocking on the statistics every step (train.py:197-198)"}},
             "gpu_launches": int(launches), "clocks": clocks, "elbo_per_sample": float(bs.elbo) / gb,
             "peaks": peaks["source"]}
+    if dp_check is not None:
+        line["dp_check"] = dp_check
 
     # ---------------- roofline of the fused product-manifold kernel (HBM bound) ----------------
     if not args.skip_roofline:
@@ -426,17 +550,20 @@ def run_ours(args):
         ms_f_cfg = time_kernel(lambda: ops.pm_forward(model.desc, ws.ml, ws.eps, model._rflat,
                                                       out={"z": ws.z, "kl": ws.kl}), 20, flush)
         ach = Bbig * bytes_fwd / (ms_f * 1e-3) / 1e9
+        traffic, traffic_src = ncu_traffic("pm_forward_kernel", sig, Bbig)
         line["roofline"] = {"kernel": "pm_forward_kernel", "bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"],
                             "unit": "GB/s", "frac": ach / peaks["hbm_gbs"],
-                            # dram__bytes_read.sum + dram__bytes_write.sum of this launch (same shape, 2^22 samples) from
-                            # the ncu --set full capture summarised in profiles/r01_ncu_prof_pm_d_pm2.md
-                            "traffic": (302.07e6 + 152.17e6) if (sig == "h2,s2,e2") else None,
+                            "traffic": traffic, "traffic_source": traffic_src,
+                            "regime": "asymptotic: 2^22 samples per launch, not a launch of the timed step (the step "
+                                      "runs the fused latent block / this kernel at the config batch: roofline_step)",
                             "algorithmic_bytes": Bbig * bytes_fwd,
                             "bytes_per_sample": bytes_fwd, "samples_per_launch": Bbig, "us_per_launch": ms_f * 1e3,
                             "us_at_config_batch": ms_f_cfg * 1e3, "peak_source": peaks["source"]}
         achb = Bbig * bytes_bwd / (ms_b * 1e-3) / 1e9
+        traffic_b, traffic_b_src = ncu_traffic("pm_backward_kernel", sig, Bbig)
         line["roofline_backward"] = {"kernel": "pm_backward_kernel", "bound": "hbm", "achieved": achb,
                                      "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achb / peaks["hbm_gbs"],
+                                     "traffic": traffic_b, "traffic_source": traffic_b_src,
                                      "bytes_per_sample": bytes_bwd, "samples_per_launch": Bbig,
                                      "us_per_launch": ms_b * 1e3}
         del ml, eps, z, kl, gz, gml
@@ -449,20 +576,24 @@ def run_ours(args):
                                  "us_per_launch": ms_g * 1e3,
                                  "note": "algorithmic fp32 flops; the kernel issues 3 bf16 MMAs per product (split planes)"}
 
-    # ---------------- CPU baseline (oracle port on the host cores), bounded sample ----------------
+        line["roofline_step"] = step_rooflines(model, opt, xs_dev[0], peaks, flush, C, Sn, Sd, P, H, B)
+
+    # ---------------- CPU baseline (oracle/cpu_baseline.py on the host cores), bounded sample ----------------
     if world == 1 and not args.skip_cpu:
         cores = os.cpu_count() or 1
         torch.set_num_threads(cores)
-        step = cpu_step_fn(args.workload, B)
+        step, threads = cpu_step_fn(args.workload, B)
         step()
-        n_cpu = 5
-        t0 = time.perf_counter()
-        for _ in range(n_cpu):
+        step()
+        n_cpu, t0 = 0, time.perf_counter()
+        while n_cpu < 200 and time.perf_counter() - t0 < 12.0:   # ~12 s of CPU work
             step()
+            n_cpu += 1
         dt = (time.perf_counter() - t0) / n_cpu
-        line["cpu_baseline"] = {"value": B / dt, "unit": UNIT, "cores": cores, "kind": "port",
-                                "sample": f"{n_cpu} full steps of batch {B}, float32, numpy BLAS + C/OpenMP oracle",
-                                "ms_per_step": dt * 1e3}
+        line["cpu_baseline"] = {"value": B / dt, "unit": UNIT, "cores": threads, "kind": "port",
+                                "sample": f"{n_cpu} full train steps of batch {B}, float32, ATen CPU dense layers + "
+                                          "C/OpenMP oracle for the latent chain (oracle/cpu_baseline.py)",
+                                "ms_per_step": dt * 1e3, "omp_num_threads": os.environ.get("OMP_NUM_THREADS")}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -481,6 +612,8 @@ def main():
     ap.add_argument("--float-inputs", action="store_true",
                     help="e2e with float32 host batches (4 bytes per pixel) instead of uint8 pixels binarised on the device")
     args = ap.parse_args()
+    if args.impl == "reference" or int(os.environ.get("WORLD_SIZE", "1")) == 1:
+        force_host_threads()  # the CPU legs use every host core (torchrun pre-sets OMP_NUM_THREADS=1)
     if args.impl == "reference":
         run_reference(args)
     else:

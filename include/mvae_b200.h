@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define MVAE_ABI_VERSION 2
+#define MVAE_ABI_VERSION 3
 #define MVAE_MAX_COMPONENTS 96
 
 /* ------------------------------------------------------------------------------------------------ status */
@@ -361,16 +361,22 @@ int mvae_opt_step_fused(int64_t n, float* param, const float* grad, float* exp_a
 /* ------------------------------------------------------------------- data-parallel step over peer memory */
 /* The reference has no distributed mode.  Data parallelism here shards the batch by rank; the
  * only exchange of a step is the SUM of the flat bucket [network grads (n_net) | radius grads (C) | ELBO statistics
- * (3 + C)] (the reference's ELBO is a sum over the batch, stats.py:200-202).  mvae_dp_adam_step does that exchange and
- * the optimizer update (Adam on the network parameters, SGD on the radii: train.py:327-360, utils.py:148-180) in ONE
- * kernel over NVLink peer memory: reduce-scatter of the gradients with peer loads, Adam on the rank's slice (its
- * moments are the only optimizer state the rank keeps current), all-gather of the new parameters with peer stores.
+ * (3 + C)] (the reference's ELBO is a sum over the batch, stats.py:200-202).  mvae_dp_step does that exchange and
+ * the optimizer update (Adam on the network parameters, SGD on the radii: train.py:327-360, utils.py:148-180, gradient
+ * clip of the "curvature" parameters: vae.py:161-163) for one RANGE of the parameter buffer in ONE kernel over NVLink
+ * peer memory: reduce-scatter of the gradients with peer loads, Adam on the rank's slice (its moments are the only
+ * optimizer state the rank keeps current), all-gather of the new parameters with peer stores.  A step is one or more
+ * launches over disjoint ranges (a range whose gradient is complete early can be exchanged on a side stream while
+ * the backward pass continues; concurrent launches use different channels); exactly one of them owns the tail.
  *
  * Every rank allocates one region with mvae_dp_alloc, exports it (mvae_dp_ipc_export), and opens its peers' regions
  * (mvae_dp_ipc_open) after exchanging the 64-byte handles out of band (e.g. torch.distributed.all_gather_object).
- * bucket[r] / flat[r] / flags[r] are rank r's gradient bucket, parameter buffer and flag slots (MVAE_DP_MAX_RANKS slots
- * of 128 bytes, zero-initialised) as mapped in THIS process. */
+ * bucket[r] / flat[r] / flags[r] are rank r's gradient bucket, parameter buffer and flag area (MVAE_DP_FLAG_BYTES,
+ * zero-initialised: [channel][phase][source rank] slots of 128 bytes) as mapped in THIS process. */
 #define MVAE_DP_MAX_RANKS 8
+#define MVAE_DP_CHANNELS 2
+#define MVAE_DP_FLAG_BYTES (MVAE_DP_CHANNELS * 2 * MVAE_DP_MAX_RANKS * 128)
+#define MVAE_DP_SYNC_WORDS 16
 #define MVAE_DP_HANDLE_BYTES 64
 typedef struct mvae_dp_comm {
   int32_t rank, world;
@@ -385,19 +391,39 @@ int mvae_dp_ipc_export(void* dev_ptr, uint8_t* handle_out /* [MVAE_DP_HANDLE_BYT
 int mvae_dp_ipc_open(const uint8_t* handle, void** peer_ptr);
 int mvae_dp_ipc_close(void* peer_ptr);
 
-/* One data-parallel optimizer step.  n_net (multiple of 4) network parameters, n_tail = C + 3 + C tail entries.
- * exp_avg / exp_avg_sq: full-size moment buffers of which this rank updates its slice only.  step_dev: device step
- * counter (incremented here).  radius [C] (may be NULL): raw radius parameters, stepped with radius_lr (0 = the
- * curvature optimizers do not step) on the summed gradient times radius_mask (NULL = ones).  tail_out [n_tail]: the
- * summed tail (radius grads, then bce, kl, elbo, kl_c sums).  sync_words: 4 zero-initialised device words private to
- * this rank ([3] != 0 afterwards = a peer did not arrive within ~2 s; results are then undefined).
- * targets: weight matrices whose split-bf16 planes are refreshed from the gathered parameters (as mvae_opt_step_fused).
- * Captured in a CUDA graph like any other launch; all ranks must launch it the same number of times. */
-int mvae_dp_adam_step(const mvae_dp_comm* comm, int64_t n_net, int32_t n_tail, int32_t C, float* exp_avg,
-                      float* exp_avg_sq, float lr, float beta1, float beta2, float eps, int32_t* step_dev,
-                      float* radius, float radius_lr, const float* radius_mask, float* tail_out, uint32_t* sync_words,
-                      int32_t n_targets, const int64_t* target_begin, const int32_t* target_rows,
-                      const mvae_planes* targets, void* stream);
+/* One launch of the data-parallel optimizer step over the float range [begin, end) (multiples of 4) of the n_net
+ * network parameters.  exp_avg / exp_avg_sq: full-size moment buffers of which this rank updates its slice only.
+ * step_dev: device step counter, read as "step - 1" by every launch and incremented by the launch with do_tail != 0
+ * (the LAST launch of a step).  That launch also sums the n_tail = C + 3 + C tail entries into tail_out [n_tail + 1]
+ * (radius grads, then bce, kl, elbo, kl_c sums; the extra entry is the error word below as a float), scales the
+ * radius gradients selected by clip_mask [C] (NULL = none) so that their 2-norm is at most clip_max_norm, and steps
+ * radius [C] (may be NULL) with radius_lr (0 = the curvature optimizers do not step) on the summed gradient times
+ * radius_mask (NULL = ones).
+ * sync_words: MVAE_DP_SYNC_WORDS zero-initialised device words private to this rank.  Word [8] is a STICKY error:
+ * non-zero = a peer did not arrive within MVAE_DP_TIMEOUT_S seconds (environment, default 30); the launch that saw it
+ * and every later launch write no parameter.  The host must check it (tail_out[n_tail] carries it with the statistics).
+ * targets: weight matrices inside [begin, end) whose split-bf16 planes are refreshed from the gathered parameters.
+ * max_ctas: 0 = size the grid for the range; a launch that overlaps other kernels should ask for a few CTAs.
+ * Captured in a CUDA graph like any other launch; all ranks must issue the same sequence of launches. */
+typedef struct mvae_dp_step_args {
+  int64_t n_net, begin, end;
+  int32_t channel, do_tail, n_tail, C;
+  float* exp_avg;
+  float* exp_avg_sq;
+  float lr, beta1, beta2, eps;
+  int32_t* step_dev;
+  float* radius;
+  const float* radius_mask;
+  const float* clip_mask;
+  float radius_lr, clip_max_norm;
+  float* tail_out;
+  uint32_t* sync_words;
+  int32_t max_ctas, n_targets;
+  const int64_t* target_begin;
+  const int32_t* target_rows;
+  const mvae_planes* targets;
+} mvae_dp_step_args;
+int mvae_dp_step(const mvae_dp_comm* comm, const mvae_dp_step_args* args, void* stream);
 
 /* Device attributes the host layer needs for grid sizing / reporting. */
 int mvae_device_info(int32_t* sm_count, int32_t* cc_major, int32_t* cc_minor);

@@ -11,7 +11,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libmvae_b200.so")
 
 MAX_COMPONENTS = 96
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 # mvae_manifold
 EUCLIDEAN, HYPERBOLOID, SPHERE, POINCARE, PROJ_SPHERE, UNIVERSAL = 0, 1, 2, 3, 4, 5
@@ -48,12 +48,25 @@ class GemmArgs(ctypes.Structure):
                 ("tile_n", ctypes.c_int32), ("ctas_per_sm", ctypes.c_int32), ("aux_rows", ctypes.c_int64)]
 
 
-DP_MAX_RANKS, DP_HANDLE_BYTES = 8, 64
+DP_MAX_RANKS, DP_HANDLE_BYTES, DP_CHANNELS, DP_SYNC_WORDS = 8, 64, 2, 16
+DP_FLAG_BYTES = DP_CHANNELS * 2 * DP_MAX_RANKS * 128
 
 
 class DpComm(ctypes.Structure):
     _fields_ = [("rank", ctypes.c_int32), ("world", ctypes.c_int32), ("bucket", ctypes.c_void_p * DP_MAX_RANKS),
                 ("flat", ctypes.c_void_p * DP_MAX_RANKS), ("flags", ctypes.c_void_p * DP_MAX_RANKS)]
+
+
+class DpStepArgs(ctypes.Structure):
+    _fields_ = [("n_net", ctypes.c_int64), ("begin", ctypes.c_int64), ("end", ctypes.c_int64),
+                ("channel", ctypes.c_int32), ("do_tail", ctypes.c_int32), ("n_tail", ctypes.c_int32),
+                ("C", ctypes.c_int32), ("exp_avg", ctypes.c_void_p), ("exp_avg_sq", ctypes.c_void_p),
+                ("lr", ctypes.c_float), ("beta1", ctypes.c_float), ("beta2", ctypes.c_float), ("eps", ctypes.c_float),
+                ("step_dev", ctypes.c_void_p), ("radius", ctypes.c_void_p), ("radius_mask", ctypes.c_void_p),
+                ("clip_mask", ctypes.c_void_p), ("radius_lr", ctypes.c_float), ("clip_max_norm", ctypes.c_float),
+                ("tail_out", ctypes.c_void_p), ("sync_words", ctypes.c_void_p), ("max_ctas", ctypes.c_int32),
+                ("n_targets", ctypes.c_int32), ("target_begin", ctypes.POINTER(ctypes.c_int64)),
+                ("target_rows", ctypes.POINTER(ctypes.c_int32)), ("targets", ctypes.POINTER(Planes))]
 
 
 _vp, _i32, _i64, _f32 = ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64, ctypes.c_float
@@ -100,9 +113,7 @@ PROTOTYPES = {
     "mvae_dp_ipc_export": (ctypes.c_int, [_vp, ctypes.c_char_p]),
     "mvae_dp_ipc_open": (ctypes.c_int, [ctypes.c_char_p, ctypes.POINTER(ctypes.c_void_p)]),
     "mvae_dp_ipc_close": (ctypes.c_int, [_vp]),
-    "mvae_dp_adam_step": (ctypes.c_int, [ctypes.POINTER(DpComm), _i64, _i32, _i32, _vp, _vp, _f32, _f32, _f32, _f32, _vp,
-                                         _vp, _f32, _vp, _vp, _vp, _i32, ctypes.POINTER(_i64), ctypes.POINTER(_i32),
-                                         ctypes.POINTER(Planes), _vp]),
+    "mvae_dp_step": (ctypes.c_int, [ctypes.POINTER(DpComm), ctypes.POINTER(DpStepArgs), _vp]),
     "mvae_device_info": (ctypes.c_int, [ctypes.POINTER(_i32), ctypes.POINTER(_i32), ctypes.POINTER(_i32)]),
 }
 

@@ -90,6 +90,12 @@ class Component(torch.nn.Module):
     def summary_name(self, comp_idx: int) -> str:
         return f"comp_{comp_idx:03d}_{self._shortcut()}"
 
+    def summaries(self, comp_idx: int, q_z, prefix: str = "train") -> dict:
+        """component.py:95-100: histograms Trainer logs under --train_statistics (train.py:204-206)."""
+        name = prefix + "/" + self.summary_name(comp_idx)
+        return {name + "/mean/norm": torch.norm(q_z.mean, p=2, dim=-1),
+                name + "/stddev/norm": torch.norm(q_z.stddev, p=2, dim=-1)}
+
     def create_manifold(self) -> Manifold:
         raise NotImplementedError
 

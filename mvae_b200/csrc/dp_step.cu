@@ -1,26 +1,36 @@
-// dp_step.cu — the data-parallel optimizer step as ONE kernel over NVLink peer memory (mvae_dp_adam_step).
+// dp_step.cu — the data-parallel optimizer step as kernels over NVLink peer memory (mvae_dp_step).
 //
 // The reference has no distributed mode; its ELBO is a SUM over the batch (stats.py:200-202), so N ranks holding B/N
 // samples each reproduce the single-GPU step at batch B when the gradient / statistics bucket is SUMMED across ranks
 // before the update (Trainer.build_optimizer's Adam + the curvature SGD, train.py:327-360, utils.py:148-180).
 // With NCCL that is all-reduce -> Adam -> weight refresh: three dependent launches whose latency (not bandwidth — the
-// bucket is 2.5 MB) is exposed at the end of every 0.3 ms step.  Here the collective and the update are one kernel:
+// bucket is 2.5 MB) is exposed at the end of every 0.2 ms step.  Here the collective and the update are one kernel
+// per RANGE of the flat parameter buffer, so that a range whose gradient is complete early (fc_logits: half of the
+// parameters, ready before the latent backward pass starts) is exchanged on a side branch UNDER the rest of the
+// backward pass, and only the last range (fc_e0, heads, fc_d0 + the statistics tail) sits at the end of the step:
 //
-//   barrier A   every rank has finished its backward pass                 (flags in peer memory, release/acquire.sys)
+//   phase A     "my gradients of this range are complete": one flag store per peer (release.sys), issued when the
+//               kernel starts (stream order already guarantees the local backward pass is done — no grid-wide arrival);
+//               every CTA polls the flags the peers stored into ITS rank's memory (local loads).
 //   reduce-scatter + Adam
-//               rank r owns the slice [r n/N, (r+1) n/N) of the parameters: it sums that slice of the gradient over
+//               rank r owns the slice [r n/N, (r+1) n/N) of the range: it sums that slice of the gradient over
 //               all ranks with 128-bit loads from the peers' buckets (NVSwitch gives every peer full bandwidth),
 //               applies Adam with ITS slice of the moments (the optimizer state is sharded N ways), and
 //   all-gather  stores the new parameter values straight into every peer's parameter buffer;
 //               the 3+2C statistics / radius-gradient tail is summed redundantly by every rank (same order, so the
-//               replicas stay bit-identical) and the radii take their SGD step locally
-//   barrier B   every rank has read my bucket and written my parameters
+//               replicas stay bit-identical), the "curvature" gradients are clipped (vae.py:161-163) and the radii take
+//               their SGD step locally
+//   phase B     the LAST CTA to finish (atomic ticket) tells every rank, itself included, "my slice is in your buffer
+//               and I am done reading your bucket"; every CTA polls those flags, then refreshes its share of the
+//               split-bf16 planes of the GEMM weights from the gathered parameters.
 //
-// Everything the kernel needs to know about the step (Adam step count, barrier epoch) lives on the device, so the launch
-// is captured once in the step's CUDA graph.  Spin loops are bounded (clock64) and raise an error word instead of
-// hanging the GPU if a peer never arrives.
+// Everything the kernel needs to know about the step (Adam step count, flag epoch) lives on the device, so the launches
+// are captured in the step's CUDA graph.  Waits are bounded (%globaltimer): a peer that never arrives makes the kernel
+// raise a STICKY error word, write no parameter, and turn every later launch into a no-op; the host checks the word
+// (it travels with the step's statistics) and raises.
 #include <cuda_bf16.h>
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "mvae_common.cuh"
@@ -29,6 +39,7 @@ namespace mvae {
 
 constexpr int kDpThreads = 512;
 constexpr int kDpFlagStride = 32;  // uint32 per flag slot (one 128-byte line each)
+constexpr int kDpErrWord = 8;      // index of the sticky error word in sync_words
 
 struct DpPlaneTarget {
   int64_t begin, end;  // float range of the flat parameter buffer holding a [rows, cols] matrix (both % 4 == 0)
@@ -39,8 +50,9 @@ struct DpPlaneTarget {
 
 struct DpParams {
   mvae_dp_comm comm;
-  int64_t n4;        // float4 elements of the network-parameter bucket
+  int64_t lo4, hi4;  // float4 range of this launch
   int64_t n_net;
+  int channel, do_tail;
   int n_tail, C;
   float* m;
   float* v;
@@ -49,9 +61,11 @@ struct DpParams {
   float* radius;
   float radius_lr;
   const float* radius_mask;
+  const float* clip_mask;
+  float clip_max_norm;
   float* tail_out;
-  uint32_t* sync;    // local: [0] epoch, [1] arrival counter, [2] release word, [3] error
-  long long spin_limit;
+  uint32_t* sync;    // local: [4 ch + 0] epoch, [4 ch + 1] arrival ticket, [8] sticky error
+  unsigned long long timeout_ns;
   int n_targets;     // weight matrices whose split-bf16 planes are refreshed after the all-gather
   DpPlaneTarget t[4];
 };
@@ -64,11 +78,6 @@ __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
   asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
-__device__ __forceinline__ uint32_t ld_acquire_gpu(const uint32_t* p) {
-  uint32_t v;
-  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
 __device__ __forceinline__ float4 ld_peer4(const float* p) {  // peer (or own) memory, never through a stale L1 line
   float4 r;
   asm volatile("ld.relaxed.sys.global.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p) : "memory");
@@ -79,67 +88,63 @@ __device__ __forceinline__ float ld_peer1(const float* p) {
   asm volatile("ld.relaxed.sys.global.f32 %0, [%1];" : "=f"(r) : "l"(p) : "memory");
   return r;
 }
-
-// Grid-wide barrier that also spans the ranks: every CTA arrives on a local counter; CTA 0 then publishes the barrier
-// index `b` in every peer's flag slot for this rank, waits until every peer has published >= b in ours, and releases
-// the other CTAs.  Counters are monotonic across launches (b grows by 2 per step).
-__device__ void dp_barrier(const DpParams& p, uint32_t b) {
-  __syncthreads();
-  uint32_t* sync = p.sync;
-  const int world = p.comm.world, rank = p.comm.rank;
-  if (threadIdx.x == 0) {
-    __threadfence_system();
-    atomicAdd(&sync[1], 1u);
-  }
-  if (blockIdx.x == 0) {
-    const long long t0 = clock64();
-    if (threadIdx.x == 0) {
-      const uint32_t target = b * gridDim.x;
-      while (ld_acquire_gpu(&sync[1]) < target)
-        if (clock64() - t0 > p.spin_limit) {
-          sync[3] = 1u;
-          break;
-        }
-    }
-    __syncthreads();
-    if ((int)threadIdx.x < world) {
-      const int r = threadIdx.x;
-      st_release_sys(p.comm.flags[r] + rank * kDpFlagStride, b);
-      while (ld_acquire_sys(p.comm.flags[rank] + r * kDpFlagStride) < b)
-        if (clock64() - t0 > p.spin_limit) {
-          sync[3] = 2u;
-          break;
-        }
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      __threadfence();
-      atomicExch(&sync[2], b);
-    }
-  } else if (threadIdx.x == 0) {
-    const long long t0 = clock64();
-    while (ld_acquire_gpu(&sync[2]) < b)
-      if (clock64() - t0 > p.spin_limit) {
-        sync[3] = 3u;
-        break;
-      }
-  }
-  __syncthreads();
+__device__ __forceinline__ unsigned long long global_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
 }
 
-__global__ void __launch_bounds__(kDpThreads) dp_adam_kernel(const __grid_constant__ DpParams p) {
-  const int world = p.comm.world, rank = p.comm.rank;
-  const uint32_t epoch = p.sync[0];  // completed steps; every CTA reads it before barrier A, CTA 0 bumps it after B
-  const int32_t step = *p.step_dev + 1;
-  dp_barrier(p, 2u * epoch + 1u);
+// flag slot of (channel, phase, source rank) inside a rank's flag area
+__device__ __forceinline__ int dp_slot(int channel, int phase, int src) {
+  return ((channel * 2 + phase) * MVAE_DP_MAX_RANKS + src) * kDpFlagStride;
+}
 
-  // ---- reduce-scatter + Adam + all-gather on my slice ----
+// Threads 0..world-1 wait until peer `tid` has stored >= e into this rank's slot; false (and the sticky error word set)
+// if one of them ran out of time.  All threads of the CTA get the same answer.
+__device__ bool dp_wait_peers(const DpParams& p, int phase, uint32_t e, int* s_err) {
+  const int world = p.comm.world, rank = p.comm.rank;
+  if ((int)threadIdx.x < world) {
+    const uint32_t* f = p.comm.flags[rank] + dp_slot(p.channel, phase, threadIdx.x);
+    const unsigned long long t0 = global_ns();
+    while (ld_acquire_sys(f) < e) {
+      if (global_ns() - t0 > p.timeout_ns) {
+        const uint32_t code = 1u + (uint32_t)phase;
+        atomicCAS(&p.sync[kDpErrWord], 0u, code);
+        p.tail_out[p.n_tail] = (float)code;  // the word the host reads with the step's statistics
+        *s_err = 1;
+        break;
+      }
+    }
+  }
+  __syncthreads();
+  return *s_err == 0;
+}
+
+__global__ void __launch_bounds__(kDpThreads) dp_step_kernel(const __grid_constant__ DpParams p) {
+  __shared__ int s_err, s_last, s_dead;
+  const int world = p.comm.world, rank = p.comm.rank;
+  uint32_t* sync = p.sync + 4 * p.channel;
+  if (threadIdx.x == 0) s_err = 0, s_last = 0, s_dead = (p.sync[kDpErrWord] != 0u);
+  __syncthreads();
+  if (s_dead) return;  // a peer timed out earlier: parameters stay frozen until the host raises
+  const uint32_t e = sync[0] + 1u;     // launches of this channel so far + 1; bumped by the last CTA after every CTA read it
+  const int32_t step = *p.step_dev + 1;  // bumped by the launch that owns the tail, the last one of a step
+  __syncthreads();
+
+  // ---- phase A: announce that my gradients are complete, wait for every peer's announcement ----
+  if (blockIdx.x == 0 && (int)threadIdx.x < world) {
+    __threadfence_system();
+    st_release_sys(p.comm.flags[threadIdx.x] + dp_slot(p.channel, 0, rank), e);
+  }
+  if (!dp_wait_peers(p, 0, e, &s_err)) return;  // nothing has been written yet
+
+  // ---- reduce-scatter + Adam + all-gather on my slice of the range ----
   const double st = (double)step;
   const float step_size = (float)((double)p.lr / (1.0 - pow((double)p.b1, st)));
   const float inv_bc2_sqrt = (float)(1.0 / sqrt(1.0 - pow((double)p.b2, st)));
   const float w1 = 1.f - p.b1, w2 = 1.f - p.b2;
-  const int64_t per = (p.n4 + world - 1) / world;
-  const int64_t lo = rank * per, hi = min(p.n4, lo + per);
+  const int64_t per = (p.hi4 - p.lo4 + world - 1) / world;
+  const int64_t lo = p.lo4 + rank * per, hi = min(p.hi4, lo + per);
   // Two float4 per thread and iteration: all 2 x world peer loads are in flight before the first is consumed (the
   // loop is latency bound: a peer load is a few microseconds over NVLink).
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
@@ -177,25 +182,62 @@ __global__ void __launch_bounds__(kDpThreads) dp_adam_kernel(const __grid_consta
       for (int r = 0; r < world; ++r) reinterpret_cast<float4*>(p.comm.flat[r])[i] = pi;
     }
   }
-  // ---- statistics / radius-gradient tail: every rank sums it (same order), radii step locally ----
-  if (blockIdx.x == gridDim.x - 1) {
+  // ---- statistics / radius-gradient tail: every rank sums it (same order), clips, and steps its radii locally ----
+  if (p.do_tail && blockIdx.x == gridDim.x - 1) {
+    __shared__ float s_clip;
     for (int t = threadIdx.x; t < p.n_tail; t += blockDim.x) {
       float s = 0.f;
       for (int r = 0; r < world; ++r) s += ld_peer1(p.comm.bucket[r] + p.n_net + t);
       p.tail_out[t] = s;
-      if (t < p.C && p.radius && p.radius_lr != 0.f) {
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      // torch.nn.utils.clip_grad_norm_(curvature parameters, max_norm) on the rank-summed gradient (vae.py:161-163)
+      float coef = 1.f;
+      if (p.clip_mask) {
+        float ss = 0.f;
+        for (int t = 0; t < p.C; ++t) ss += p.clip_mask[t] * p.tail_out[t] * p.tail_out[t];
+        coef = fminf(1.f, p.clip_max_norm / (sqrtf(ss) + 1e-6f));
+      }
+      s_clip = coef;
+    }
+    __syncthreads();
+    for (int t = threadIdx.x; t < p.C; t += blockDim.x) {
+      float s = p.tail_out[t];
+      if (p.clip_mask && p.clip_mask[t] != 0.f) p.tail_out[t] = s = s * s_clip;
+      if (p.radius && p.radius_lr != 0.f) {
         const float mk = p.radius_mask ? p.radius_mask[t] : 1.f;
         p.radius[t] = p.radius[t] - p.radius_lr * (s * mk);
       }
     }
   }
+
+  // ---- phase B: the last CTA to get here tells every rank (this one included) that my slice has been delivered ----
   __threadfence_system();
-  dp_barrier(p, 2u * epoch + 2u);
-  if (blockIdx.x == 0 && threadIdx.x == 0) {
-    p.sync[0] = epoch + 1u;
-    *p.step_dev = step;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const uint32_t ticket = atomicAdd(&sync[1], 1u);
+    __threadfence();
+    s_last = (ticket + 1u == gridDim.x);
   }
-  // ---- every slice of the parameters has arrived: refresh the split-bf16 planes of the GEMM weights locally ----
+  __syncthreads();
+  if (s_last) {
+    if ((int)threadIdx.x < world) {
+      __threadfence_system();
+      st_release_sys(p.comm.flags[threadIdx.x] + dp_slot(p.channel, 1, rank), e);
+    }
+    if (threadIdx.x == 0) {
+      sync[1] = 0u;  // ticket counter for the next launch of this channel
+      sync[0] = e;
+      if (p.do_tail) {
+        *p.step_dev = step;
+        p.tail_out[p.n_tail] = 0.f;
+      }
+    }
+  }
+  if (!dp_wait_peers(p, 1, e, &s_err)) return;
+
+  // ---- every slice of the range has arrived: refresh the split-bf16 planes of its GEMM weights locally ----
   for (int t = 0; t < p.n_targets; ++t) {
     const DpPlaneTarget& tg = p.t[t];
     const int64_t n4 = (tg.end - tg.begin) >> 2;
@@ -261,21 +303,19 @@ extern "C" int mvae_dp_ipc_close(void* peer_ptr) {
   return MVAE_OK;
 }
 
-extern "C" int mvae_dp_adam_step(const mvae_dp_comm* comm, int64_t n_net, int32_t n_tail, int32_t C, float* exp_avg,
-                                 float* exp_avg_sq, float lr, float beta1, float beta2, float eps, int32_t* step_dev,
-                                 float* radius, float radius_lr, const float* radius_mask, float* tail_out,
-                                 uint32_t* sync_words, int32_t n_targets, const int64_t* target_begin,
-                                 const int32_t* target_rows, const mvae_planes* targets, void* stream) {
-  if (!comm || comm->world < 1 || comm->world > MVAE_DP_MAX_RANKS || comm->rank < 0 || comm->rank >= comm->world ||
-      n_net < 0 || (n_net & 3) || n_tail < 0 || C < 0 || C > n_tail || !exp_avg || !exp_avg_sq || !step_dev ||
-      !tail_out || !sync_words)
+extern "C" int mvae_dp_step(const mvae_dp_comm* comm, const mvae_dp_step_args* a, void* stream) {
+  if (!comm || !a || comm->world < 1 || comm->world > MVAE_DP_MAX_RANKS || comm->rank < 0 ||
+      comm->rank >= comm->world || a->n_net < 0 || (a->n_net & 3) || a->begin < 0 || a->end < a->begin ||
+      a->end > a->n_net || (a->begin & 3) || (a->end & 3) || a->channel < 0 || a->channel >= MVAE_DP_CHANNELS ||
+      a->n_tail < 0 || a->C < 0 || a->C > a->n_tail || !a->exp_avg || !a->exp_avg_sq || !a->step_dev || !a->tail_out ||
+      !a->sync_words)
     return MVAE_ERR_INVALID_ARGUMENT;
   for (int r = 0; r < comm->world; ++r) {
     if (!comm->bucket[r] || !comm->flat[r] || !comm->flags[r]) return MVAE_ERR_INVALID_ARGUMENT;
     if ((reinterpret_cast<uintptr_t>(comm->bucket[r]) & 15) || (reinterpret_cast<uintptr_t>(comm->flat[r]) & 15))
       return MVAE_ERR_ALIGNMENT;
   }
-  if ((reinterpret_cast<uintptr_t>(exp_avg) & 15) || (reinterpret_cast<uintptr_t>(exp_avg_sq) & 15))
+  if ((reinterpret_cast<uintptr_t>(a->exp_avg) & 15) || (reinterpret_cast<uintptr_t>(a->exp_avg_sq) & 15))
     return MVAE_ERR_ALIGNMENT;
   DeviceInfo di;
   int rc = get_device_info(&di);
@@ -283,45 +323,66 @@ extern "C" int mvae_dp_adam_step(const mvae_dp_comm* comm, int64_t n_net, int32_
   DpParams p;
   memset(&p, 0, sizeof(p));
   p.comm = *comm;
-  p.n_net = n_net;
-  p.n4 = n_net / 4;
-  p.n_tail = n_tail;
-  p.C = C;
-  p.m = exp_avg;
-  p.v = exp_avg_sq;
-  p.lr = lr;
-  p.b1 = beta1;
-  p.b2 = beta2;
-  p.eps = eps;
-  p.step_dev = step_dev;
-  p.radius = radius;
-  p.radius_lr = radius_lr;
-  p.radius_mask = radius_mask;
-  p.tail_out = tail_out;
-  p.sync = sync_words;
-  if (n_targets < 0 || n_targets > 4 || (n_targets > 0 && (!target_begin || !target_rows || !targets)))
+  p.n_net = a->n_net;
+  p.lo4 = a->begin / 4;
+  p.hi4 = a->end / 4;
+  p.channel = a->channel;
+  p.do_tail = a->do_tail ? 1 : 0;
+  p.n_tail = a->n_tail;
+  p.C = a->C;
+  p.m = a->exp_avg;
+  p.v = a->exp_avg_sq;
+  p.lr = a->lr;
+  p.b1 = a->beta1;
+  p.b2 = a->beta2;
+  p.eps = a->eps;
+  p.step_dev = a->step_dev;
+  p.radius = a->radius;
+  p.radius_lr = a->radius_lr;
+  p.radius_mask = a->radius_mask;
+  p.clip_mask = a->clip_mask;
+  p.clip_max_norm = a->clip_max_norm;
+  p.tail_out = a->tail_out;
+  p.sync = a->sync_words;
+  if (a->n_targets < 0 || a->n_targets > 4 ||
+      (a->n_targets > 0 && (!a->target_begin || !a->target_rows || !a->targets)))
     return MVAE_ERR_INVALID_ARGUMENT;
-  p.n_targets = n_targets;
-  for (int t = 0; t < n_targets; ++t) {
-    const mvae_planes& pl = targets[t];
-    if (!pl.base || pl.planes < 1 || pl.planes > 3 || pl.rows != target_rows[t] || pl.ld < pl.cols)
+  p.n_targets = a->n_targets;
+  int64_t refresh4 = 0;
+  for (int t = 0; t < a->n_targets; ++t) {
+    const mvae_planes& pl = a->targets[t];
+    if (!pl.base || pl.planes < 1 || pl.planes > 3 || pl.rows != a->target_rows[t] || pl.ld < pl.cols)
       return MVAE_ERR_INVALID_ARGUMENT;
-    if ((target_begin[t] & 3) || (pl.cols & 3) || (pl.ld & 7) || (pl.plane_stride & 7) || target_begin[t] < 0 ||
-        target_begin[t] + (int64_t)target_rows[t] * pl.cols > n_net || (reinterpret_cast<uintptr_t>(pl.base) & 15))
+    const int64_t tb = a->target_begin[t], te = tb + (int64_t)a->target_rows[t] * pl.cols;
+    if ((tb & 3) || (pl.cols & 3) || (pl.ld & 7) || (pl.plane_stride & 7) || (reinterpret_cast<uintptr_t>(pl.base) & 15))
       return MVAE_ERR_ALIGNMENT;
-    p.t[t].begin = target_begin[t];
-    p.t[t].end = target_begin[t] + (int64_t)target_rows[t] * pl.cols;
+    if (tb < a->begin || te > a->end) return MVAE_ERR_INVALID_ARGUMENT;  // refreshed from THIS launch's range only
+    p.t[t].begin = tb;
+    p.t[t].end = te;
     p.t[t].cols = pl.cols;
     p.t[t].ld = pl.ld;
     p.t[t].planes = pl.planes;
     p.t[t].base = pl.base;
     p.t[t].plane_stride = pl.planes > 1 ? pl.plane_stride : 0;
+    refresh4 = refresh4 > (te - tb) / 4 ? refresh4 : (te - tb) / 4;
   }
-  p.spin_limit = 4000000000ll;  // ~2 s of SM clocks: a peer that has not arrived by then never will
-  // The CTAs spin on each other, so all of them must be resident at once: a FIXED grid of at most one CTA per SM
-  // (the barrier counters assume the same grid on every launch; 64 registers x 512 threads fit one SM).
-  const int grid = di.sm_count;
-  dp_adam_kernel<<<grid, kDpThreads, 0, as_stream(stream)>>>(p);
+  // a peer that has not arrived within this time never will (MVAE_DP_TIMEOUT_S, default 30 s: rank skew of an
+  // evaluation pass or a checkpoint between two steps is legitimate, a dead peer is not)
+  double timeout_s = 30.0;
+  if (const char* env = getenv("MVAE_DP_TIMEOUT_S")) {
+    const double v = atof(env);
+    if (v > 0.0) timeout_s = v;
+  }
+  p.timeout_ns = (unsigned long long)(timeout_s * 1e9);
+  // The CTAs wait for each other (ticket in phase B), so all of them must be resident at once: at most one CTA per SM.
+  // Enough CTAs for one pass over my slice (two float4 per thread) and over the largest matrix to re-split.
+  const int64_t per4 = (p.hi4 - p.lo4 + comm->world - 1) / comm->world;
+  int64_t want = (per4 + 2 * kDpThreads - 1) / (2 * kDpThreads);
+  const int64_t want_refresh = (refresh4 + 2 * kDpThreads - 1) / (2 * kDpThreads);
+  if (want_refresh > want) want = want_refresh;
+  int grid = (int)(want < 1 ? 1 : (want > di.sm_count ? di.sm_count : want));
+  if (a->max_ctas > 0 && grid > a->max_ctas) grid = a->max_ctas;
+  dp_step_kernel<<<grid, kDpThreads, 0, as_stream(stream)>>>(p);
   MVAE_LAUNCH_CHECK();
   return MVAE_OK;
 }

@@ -429,19 +429,25 @@ def skinny_wgrad(small, S: int, wide, Wd: int, out, out_stride_s: int, out_strid
     _LAUNCHES[0] += 1
 
 
-def dp_adam_step(comm: "L.DpComm", n_net: int, n_tail: int, C: int, exp_avg, exp_avg_sq, lr: float, beta1: float,
-                 beta2: float, eps: float, step_dev, radius, radius_lr: float, radius_mask, tail_out, sync_words,
-                 targets=()):
-    """Gradient reduce-scatter + Adam + parameter all-gather over peer memory + weight-plane refresh in one kernel
-    (mvae_dp_adam_step).  targets: list of (flat offset, rows, PlaneBuf)."""
+def dp_step(comm: "L.DpComm", n_net: int, begin: int, end: int, channel: int, do_tail: bool, n_tail: int, C: int,
+            exp_avg, exp_avg_sq, lr: float, beta1: float, beta2: float, eps: float, step_dev, radius, radius_lr: float,
+            radius_mask, clip_mask, clip_max_norm: float, tail_out, sync_words, targets=(), max_ctas: int = 0):
+    """Gradient reduce-scatter + Adam + parameter all-gather over peer memory + weight-plane refresh for the float
+    range [begin, end) of the parameter buffer, one kernel (mvae_dp_step).  targets: list of (flat offset, rows,
+    PlaneBuf) inside the range."""
     nt = len(targets)
     begins = (ctypes.c_int64 * max(nt, 1))(*[t[0] for t in targets])
     rows = (ctypes.c_int32 * max(nt, 1))(*[t[1] for t in targets])
     planes = (L.Planes * max(nt, 1))(*[t[2].struct() for t in targets])
-    rc = L.lib().mvae_dp_adam_step(ctypes.byref(comm), n_net, n_tail, C, _ptr(exp_avg), _ptr(exp_avg_sq), lr, beta1,
-                                   beta2, eps, _ptr(step_dev), _ptr(radius), radius_lr, _ptr(radius_mask),
-                                   _ptr(tail_out), _ptr(sync_words), nt, begins, rows, planes, _stream())
-    L.check(rc, "mvae_dp_adam_step")
+    vp = lambda t: None if t is None else t.data_ptr()  # noqa: E731
+    a = L.DpStepArgs(n_net=n_net, begin=begin, end=end, channel=channel, do_tail=int(bool(do_tail)), n_tail=n_tail, C=C,
+                     exp_avg=vp(exp_avg), exp_avg_sq=vp(exp_avg_sq), lr=lr, beta1=beta1, beta2=beta2, eps=eps,
+                     step_dev=vp(step_dev), radius=vp(radius), radius_mask=vp(radius_mask), clip_mask=vp(clip_mask),
+                     radius_lr=radius_lr, clip_max_norm=clip_max_norm, tail_out=vp(tail_out),
+                     sync_words=vp(sync_words), max_ctas=max_ctas, n_targets=nt, target_begin=begins, target_rows=rows,
+                     targets=planes)
+    rc = L.lib().mvae_dp_step(ctypes.byref(comm), ctypes.byref(a), _stream())
+    L.check(rc, "mvae_dp_step")
     _LAUNCHES[0] += 1
 
 

@@ -62,6 +62,8 @@ def allreduce_sum_(bucket: torch.Tensor, group=None) -> torch.Tensor:
 def attach(model, group=None) -> None:
     """Make `model.train_step` all-reduce its gradient/statistics bucket before the optimizer step."""
     model._grad_hook = lambda bucket: allreduce_sum_(bucket, group)
+    if dist.is_initialized():
+        model.binarize_seed = int(model.binarize_seed) + 0x9E3779B1 * (dist.get_rank(group) + 1)
 
 
 def broadcast_parameters(model, src: int = 0, group=None) -> None:
@@ -94,7 +96,7 @@ class _DeviceRegion:
 
 
 def attach_p2p(model, optimizer, group=None) -> bool:
-    """Data-parallel step over NVLink peer memory (mvae_dp_adam_step): the model's parameter buffer and gradient
+    """Data-parallel step over NVLink peer memory (mvae_dp_step): the model's parameter buffer and gradient
     bucket are re-homed into a cudaMalloc'ed region that every peer maps through CUDA IPC; the optimizer's step then
     does gradient reduce-scatter + Adam + parameter all-gather in ONE kernel instead of all-reduce -> Adam.
     Single node, world size <= 8.  Returns False (and leaves the model untouched) if the peers cannot be mapped."""
@@ -106,8 +108,6 @@ def attach_p2p(model, optimizer, group=None) -> bool:
     world, rank = dist.get_world_size(group), dist.get_rank(group)
     if world > L.DP_MAX_RANKS:
         return False
-    if getattr(model, "_clip_mask", None) is not None:
-        return False  # 'u' components: the gradient clip sits between the reduction and the update (NCCL path)
     lib = L.lib()
     dev = model.device
     n_flat, n_bucket = model.flat_sizes()
@@ -115,7 +115,7 @@ def attach_p2p(model, optimizer, group=None) -> bool:
     off_bucket = 0
     off_flat = off_bucket + al(4 * n_bucket)
     off_flags = off_flat + al(4 * n_flat)
-    nbytes = off_flags + L.DP_MAX_RANKS * 128
+    nbytes = off_flags + L.DP_FLAG_BYTES
     ptr = ctypes.c_void_p()
     ok = True
     try:
@@ -153,19 +153,38 @@ def attach_p2p(model, optimizer, group=None) -> bool:
         comm.flags[r] = bases[r] + off_flags
     C = model.desc.C
     optimizer._dp = comm
-    optimizer._dp_tail = torch.zeros(2 * C + 3, device=dev, dtype=torch.float32)
-    optimizer._dp_sync = torch.zeros(4, device=dev, dtype=torch.int32)
-    # moments follow the re-homed parameters (fresh optimizer state), statistics are read from the summed tail
+    optimizer._dp_tail = torch.zeros(2 * C + 3 + 1, device=dev, dtype=torch.float32)  # + the error word (as float)
+    optimizer._dp_sync = torch.zeros(L.DP_SYNC_WORDS, device=dev, dtype=torch.int32)
+    # moments follow the re-homed parameters (fresh optimizer state: moments AND step counter), statistics are read
+    # from the summed tail
     optimizer.exp_avg = torch.zeros_like(model._flat)
     optimizer.exp_avg_sq = torch.zeros_like(model._flat)
-    model._stats_report = optimizer._dp_tail[C:]
+    optimizer.step_count = 0
+    optimizer.step_dev.zero_()
+    model._stats_report = optimizer._dp_tail[C:2 * C + 3]
+    model._stats_wire = optimizer._dp_tail[C:]
     model._grad_hook = None
+    model._early_step = optimizer.step_early
     model._dp_region = region
+    # dynamic binarisation (uint8 batches): every rank draws its own uniforms
+    model.binarize_seed = int(model.binarize_seed) + 0x9E3779B1 * (rank + 1)
     torch.cuda.synchronize(dev)
     dist.barrier(group=group)  # every peer has mapped every region before the first step
     return True
 
 
 def dp_error_word(optimizer) -> int:
-    """0 unless a peer failed to arrive at a barrier of mvae_dp_adam_step within its time limit."""
-    return 0 if optimizer._dp_sync is None else int(optimizer._dp_sync[3].item())
+    """0 unless a peer failed to arrive at a flag wait of mvae_dp_step within its time limit (sticky: every later step
+    is a no-op).  train_step / train_epoch raise on it by themselves — it travels with the step's statistics."""
+    return 0 if optimizer._dp_sync is None else int(optimizer._dp_sync[8].item())
+
+
+def replicas_identical(model, group=None) -> bool:
+    """True when every rank holds bit-identical parameters and radii (collective call)."""
+    if not (dist.is_initialized() and dist.get_world_size(group) > 1):
+        return True
+    mine = torch.cat([model._flat.detach().reshape(-1), model._rflat.detach().reshape(-1)]).view(torch.int32)
+    lo, hi = mine.clone(), mine.clone()
+    dist.all_reduce(lo, op=dist.ReduceOp.MIN, group=group)
+    dist.all_reduce(hi, op=dist.ReduceOp.MAX, group=group)
+    return bool(torch.equal(lo, hi))

@@ -30,6 +30,48 @@ from . import ops
 from .components import Component
 from .distributions import EuclideanNormal, WrappedNormal
 
+# ---------------------------------------------------------------------------------------------- component adapters
+# The model accepts the mirror components of mvae_b200.components AND the reference's own Component objects
+# (mt/mvae/components/component.py:30-242, as built by mt.mvae.utils.parse_components): the reference's Trainer
+# singles components out with isinstance checks against ITS classes (radius warm-up, train.py:189-194), which only
+# hold for its own objects.  Everything the kernels need is read through these three functions.
+_KIND_OF_CLASS = {"HyperbolicComponent": L.HYPERBOLOID, "SphericalComponent": L.SPHERE,
+                  "PoincareComponent": L.POINCARE, "StereographicallyProjectedSphereComponent": L.PROJ_SPHERE,
+                  "EuclideanComponent": L.EUCLIDEAN, "UniversalComponent": L.UNIVERSAL}
+_SUPPORTED_PROCEDURES = ("WrappedNormalProcedure", "EuclideanNormalProcedure", "UniversalSamplingProcedure")
+
+
+def kind_of(c) -> int:
+    """Manifold kind (mvae_manifold) of a mirror or reference component."""
+    k = getattr(c, "kind", None)
+    if isinstance(k, int) and k >= 0:
+        return k
+    for cls in type(c).__mro__:
+        if cls.__name__ in _KIND_OF_CLASS:
+            proc = getattr(c, "_sampling_procedure_type", None)
+            if proc is not None and proc.__name__ not in _SUPPORTED_PROCEDURES:
+                raise NotImplementedError(f"sampling procedure {proc.__name__} is outside the fused hot path "
+                                          "(wrapped / Euclidean normal only, SURVEY.md §8)")
+            return _KIND_OF_CLASS[cls.__name__]
+    raise NotImplementedError(f"component type {type(c).__name__} is outside the fused hot path")
+
+
+def radius_parameter_of(c):
+    """(name, parameter) of the component's curvature parameter: a raw radius, or the raw curvature of 'u'."""
+    for name in ("_nradius", "_pradius", "_curvature"):
+        if hasattr(c, name):
+            return name, getattr(c, name)
+    return None, None
+
+
+def effective_kind_of(c) -> int:
+    """Manifold the component currently lives on (differs from kind_of only for 'u': universal.py:64-74)."""
+    k = kind_of(c)
+    if k != L.UNIVERSAL:
+        return k
+    kappa, eps = float(c._curvature.detach()), float(getattr(c, "_eps", 1e-6))
+    return L.POINCARE if kappa < -eps else (L.PROJ_SPHERE if kappa > eps else L.EUCLIDEAN)
+
 
 class Reparametrized:
     """mt/mvae/models/vae.py:29-35.  `data` (= (u, v) of rsample_with_parts) is recomputed on demand."""
@@ -44,13 +86,67 @@ class Reparametrized:
 
     @property
     def data(self):
-        if isinstance(self.q_z, EuclideanNormal):
+        if not hasattr(self.q_z, "manifold"):  # EuclideanNormal (mirror or reference): no parts
             return None
         if self._data is None:
             v = self._eps * self.q_z.scale
             _, (u, _) = self.q_z.manifold.sample_projection_mu0(v.contiguous(), self.q_z.loc)
             self._data = (u, v)
         return self._data
+
+
+class LazyTensor:
+    """A tensor computed on first use.  train_step returns the reference's Outputs triple (vae.py:166); the training
+    kernels never materialise the logits x_mb_ (the reconstruction loss is fused into the GEMM that would produce
+    them), so the third element is this proxy: touching it decodes the step's latent sample once."""
+
+    def __init__(self, fn) -> None:
+        object.__setattr__(self, "_fn", fn)
+        object.__setattr__(self, "_t", None)
+
+    def get(self) -> Tensor:
+        if self._t is None:
+            object.__setattr__(self, "_t", self._fn())
+        return self._t
+
+    def __getattr__(self, name):
+        return getattr(self.get(), name)
+
+    def __getitem__(self, idx):
+        return self.get()[idx]
+
+    def __len__(self) -> int:
+        return len(self.get())
+
+    def __repr__(self) -> str:
+        return "LazyTensor(" + ("pending" if self._t is None else repr(self._t)) + ")"
+
+    @classmethod
+    def __torch_function__(cls, func, types, args=(), kwargs=None):
+        unwrap = lambda a: a.get() if isinstance(a, LazyTensor) else a  # noqa: E731
+        return func(*[unwrap(a) for a in args], **{k: unwrap(v) for k, v in (kwargs or {}).items()})
+
+
+class LazyReparametrized:
+    """List[Reparametrized] of the last train step, built on first use (the training kernels keep q_z's loc / scale in
+    registers; Trainer._train_epoch reads them only under --train_statistics, train.py:200-206)."""
+
+    def __init__(self, fn) -> None:
+        self._fn, self._items = fn, None
+
+    def _get(self) -> List[Reparametrized]:
+        if self._items is None:
+            self._items = self._fn()
+        return self._items
+
+    def __iter__(self):
+        return iter(self._get())
+
+    def __len__(self) -> int:
+        return len(self._get())
+
+    def __getitem__(self, idx):
+        return self._get()[idx]
 
 
 class BatchStatsFloat:
@@ -142,7 +238,7 @@ class _Workspace:
         # u8 = the current batch arrived as uint8; bin_ctr = Philox step counter of the dynamic binarisation
         self.x8buf = None
         self._u8 = [False, False]  # per input slot (train_epoch stages batch i+1 while step i is being enqueued)
-        self.bin_ctr = torch.zeros(1, device=dev, dtype=torch.int64)
+        self.bin_ctr = m._bin_ctr  # one counter per model: no two steps (of any batch size) share uniforms
         self.eps = torch.zeros(B, Sn, **f)
         self.xp = ops.PlaneBuf(B, D, m.input_planes, dev, ones_col=True)
         self.hp = ops.PlaneBuf(B, H, 3, dev, ones_col=True)   # 3 planes: feeds the heads at fp32 accuracy
@@ -202,14 +298,14 @@ class FusedFeedForwardVAE(nn.Module):
         self.input_planes = input_planes or (1 if getattr(dataset, "binary_inputs", False) else 3)
         self.components = nn.ModuleList(components)
         self.total_z_dim = sum(c.dim for c in components)
+        self._kinds = [kind_of(c) for c in components]  # refuses components / procedures outside the hot path
         # construction order of the reference (vae.py:55-57 then ffnn_vae.py:35-40) => identical default init per seed
         for c in components:
             c.init_layers(h_dim, scalar_parametrization=scalar_parametrization)
         self.fc_e0 = nn.Linear(self.in_dim, h_dim)
         self.fc_d0 = nn.Linear(self.total_z_dim, h_dim)
         self.fc_logits = nn.Linear(h_dim, self.in_dim)
-        self.desc = L.make_desc([c.kind for c in components], [c.true_dim for c in components],
-                                scalar_parametrization)
+        self.desc = L.make_desc(self._kinds, [c.true_dim for c in components], scalar_parametrization)
         assert self.desc.ld_z == self.total_z_dim
         if self.desc.ld_ml > 64 or self.desc.ld_z > 64:
             raise NotImplementedError("product manifolds with more than 64 head outputs / latent coordinates")
@@ -219,8 +315,8 @@ class FusedFeedForwardVAE(nn.Module):
         self._eps_override: Optional[Tensor] = None
         self._flat = None
         self.check_finite = False
-        if self.device.type == "cuda":
-            self._flatten()
+        # (on a CPU device this is host-side bookkeeping only — every kernel entry point refuses non-CUDA tensors)
+        self._flatten()
 
     # ------------------------------------------------------------------------------------------ parameter storage
     def _net_params(self) -> List[Tuple[str, nn.Parameter]]:
@@ -274,7 +370,7 @@ class FusedFeedForwardVAE(nn.Module):
             self._slices[name] = (off, n)
         self._radius_mask = torch.zeros(C, device=dev, dtype=torch.float32)
         for i, c in enumerate(self.components):
-            _, rp = c.radius_parameter()
+            _, rp = radius_parameter_of(c)
             if rp is not None:
                 rflat[i] = rp.data.to(dev, torch.float32)
                 rp.data = rflat[i]
@@ -284,15 +380,18 @@ class FusedFeedForwardVAE(nn.Module):
         # universal components: the reference clips the 2-norm of their "curvature"-named gradients to 1 in every
         # train step (vae.py:161-163); _clip_mask selects them in the radius-gradient vector
         self._clip_mask = None
-        if any(c.kind == L.UNIVERSAL for c in self.components):
-            self._clip_mask = torch.tensor([1.0 if c.kind == L.UNIVERSAL else 0.0 for c in self.components], device=dev)
-        self._any_fixed_radius = any((c.radius_parameter()[1] is not None) and (not c.radius_parameter()[1].requires_grad)
-                                     for c in self.components)
+        if any(k == L.UNIVERSAL for k in self._kinds):
+            self._clip_mask = torch.tensor([1.0 if k == L.UNIVERSAL else 0.0 for k in self._kinds], device=dev)
+        self._radius_params = [radius_parameter_of(c)[1] for c in self.components]
+        self._any_fixed_radius = any((rp is not None) and (not rp.requires_grad) for rp in self._radius_params)
         self._flat, self._rflat, self._bucket, self._n_net = flat, rflat, bucket, n_net
         self._gnet = bucket[:n_net]
         self._gradius = bucket[n_net:n_net + C]
         self._stats = bucket[n_net + C:]
         self._stats_report = self._stats  # where the step's (rank-summed) statistics are read from
+        # what one device->host copy brings back per step: the statistics, followed (peer-memory data parallel) by the
+        # sticky error word of mvae_dp_step
+        self._stats_wire = self._stats_report
         H, D, P, Sd = self.h_dim, self.in_dim, self.desc.ld_ml, self.desc.ld_z
 
         def view(buf, name, shape):
@@ -318,6 +417,8 @@ class FusedFeedForwardVAE(nn.Module):
         self._ws = {}
         self._graphs = {}
         self._gemm_tiles = {}
+        self._bin_ctr = torch.zeros(1, device=dev, dtype=torch.int64)
+        self._radius_ptrs = [rflat.data_ptr() + 4 * i for i in range(C)]
         # heads + manifold chain + fc_d0 as one kernel per direction (mvae_latent_forward / _backward)
         self.fused_latent = (H % 8 == 0) and P <= 64 and Sd <= 64 and os.environ.get("MVAE_FUSED_LATENT", "1") != "0"
         # Wide products (cfg3: 60 head outputs, 34 latent coordinates): the per-CTA weight-gradient reductions of the
@@ -356,6 +457,16 @@ class FusedFeedForwardVAE(nn.Module):
             ops.split_planes(self.fc_d0.weight.data, self.Wd0p)
         self._planes_stale = False
 
+    def _sync_radii(self) -> None:
+        """Trainer._train_epoch REBINDS `c._pradius.data = ones_like(...) * (11 - epoch)` during its first ten epochs
+        (train.py:189-194): a fresh tensor the kernels — which read the flat radius vector — would never see.  A rebind
+        is detected by address; the value moves into the flat vector and the parameter is re-homed there.  In-place
+        writes (`fill_`, optimizers) land in the flat vector directly.  Called before every kernel sequence."""
+        for i, rp in enumerate(self._radius_params):
+            if rp is not None and rp.data_ptr() != self._radius_ptrs[i]:
+                self._rflat[i:i + 1].copy_(rp.data.detach().reshape(1).to(self._rflat.device, torch.float32))
+                rp.data = self._rflat[i]
+
     def mark_parameters_changed(self) -> None:
         """Call after modifying parameters outside of train_step (external optimizers are handled automatically)."""
         self._planes_stale = True
@@ -367,6 +478,12 @@ class FusedFeedForwardVAE(nn.Module):
         return ws
 
     # ------------------------------------------------------------------------------------------ kernel sequences
+    def _comm_stream(self) -> "torch.cuda.Stream":
+        st = getattr(self, "_comm", None)
+        if st is None:
+            st = self._comm = torch.cuda.Stream(device=self.device)
+        return st
+
     def _side_stream(self) -> "torch.cuda.Stream":
         st = getattr(self, "_side", None)
         if st is None:
@@ -390,16 +507,9 @@ class FusedFeedForwardVAE(nn.Module):
                 ws.ml.zero_()  # the heads GEMM accumulates its K slices into it
             if train:
                 self._bucket[:self._n_net + self.desc.C].zero_()
-        if ws.u8:
-            # uint8 pixels -> binarised fp32 targets + the bf16 operand plane of fc_e0 in one kernel
-            # (image_reconstruction.py:37-53: dynamic in training, threshold 0.5 in evaluation)
-            ops.binarize(ws.x8, x=ws.x, planes=ws.xp, seed=self.binarize_seed, offset_dev=ws.bin_ctr,
-                         dynamic=train or self.binarize_eval_dynamic, invert=self.binarize_invert)
-            if self.input_planes > 1:  # binarised values are exact in plane 0: the residual planes are zero
-                ws.xp.t[1:, :, :self.in_dim].zero_()
-        else:
-            ops.split_planes(ws.x, ws.xp)
+        self._input_planes(ws, train)
         fused = self.fused_latent and not want_mu_sigma
+        ws.has_mu_sigma = want_mu_sigma
         if fused:
             self._gemm("e0_fwd32", ws.xp, self.We0p, B, H, D, epilogue=L.EPI_BIAS_RELU, bias=self.fc_e0.bias.data,
                        out_f32=ws.h32)
@@ -438,7 +548,9 @@ class FusedFeedForwardVAE(nn.Module):
         if not train:  # training: the reduction runs beside the backward GEMMs (_backward_kernels)
             ops.elbo_reduce(ws.bce, ws.kl, beta, out=self._stats)
 
-    def _backward_kernels(self, ws: _Workspace, beta: float):
+    def _backward_kernels(self, ws: _Workspace, beta: float, early: bool = True):
+        """`early`: let a data-parallel optimizer exchange + update fc_logits on a third stream as soon as its gradient
+        is complete (FusedCurvatureOptimizer.step_early) — False for a backward pass that no optimizer step follows."""
         B, D, H, P, Sd, C = ws.B, self.in_dim, self.h_dim, self.desc.ld_ml, self.desc.ld_z, self.desc.C
         MN = L.MN_MAJOR
         # Fork: the ELBO reduction and the weight gradient of fc_logits depend only on the forward pass; they run as a
@@ -454,13 +566,23 @@ class FusedFeedForwardVAE(nn.Module):
             self._gemm("logits_wgrad", ws.gLp, ws.ddp, D, H + 1, B, a_major=MN, b_major=MN, split_k=0, out_f32=self.gWl,
                        out_col=self.gbl, col_split=H)
         # gdd = (gL W) * 1[dd > 0]
-        if self.fused_latent:
+        fused_latent = ws.fused  # what the forward pass of this step ran (train_statistics keeps mu / sigma: unfused)
+        if fused_latent:
             self._gemm("logits_dgrad32", ws.gLp, self.Wlp, B, H, D, b_major=MN, epilogue=L.EPI_RELU_MASK, mask=ws.ddp,
                        out_f32=ws.gdd32)
         else:
             self._gemm("logits_dgrad", ws.gLp, self.Wlp, B, H, D, b_major=MN, epilogue=L.EPI_RELU_MASK, mask=ws.ddp,
                        out_planes=ws.gddp)
-        if self.fused_latent:
+        early = early and self._early_step is not None
+        if early:
+            # fc_logits is final once its weight gradient (side branch) is in the bucket and the input-gradient GEMM
+            # (main branch: the last reader of its weight planes) is done
+            comm = self._comm_stream()
+            comm.wait_stream(side)
+            comm.wait_stream(main)
+            with torch.cuda.stream(comm):
+                self._early_step()
+        if fused_latent:
             # fc_d0 dgrad + wgrad, manifold reverse sweep (d(-ELBO)/d kl = beta), heads dgrad + wgrad: ONE kernel
             ops.latent_backward(self.desc, ws.gdd32, ws.h32, self.Wh, self.fc_d0.weight.data, ws.ml, ws.eps, self._rflat,
                                 ws.z, beta, ws.ghp, self.gWd0, self.gbd0, self.gWh, self.gbh, self._gradius)
@@ -499,6 +621,8 @@ class FusedFeedForwardVAE(nn.Module):
         self._gemm("e0_wgrad", ws.ghp, ws.xp, H, D + 1, B, a_major=MN, b_major=MN, split_k=0, out_f32=self.gWe0,
                  out_col=self.gbe0, col_split=D, b_planes=2)
         main.wait_stream(side)  # join
+        if early:
+            main.wait_stream(comm)
 
     # ------------------------------------------------------------------------------------------ GEMM tile policy
     # The five big GEMMs of a step are launch- and L2-bound at these shapes and their best tile (BLOCK_N, CTAs per SM,
@@ -553,6 +677,18 @@ class FusedFeedForwardVAE(nn.Module):
         ops.add_launches(n0 - ops.launch_count())  # tuning launches are not part of any step
         return best
 
+    def _input_planes(self, ws: _Workspace, train: bool) -> None:
+        """The staged batch -> fp32 targets ws.x + the bf16 operand planes of fc_e0."""
+        if ws.u8:
+            # uint8 pixels -> binarised fp32 targets + the bf16 operand plane of fc_e0 in one kernel
+            # (image_reconstruction.py:37-53: dynamic in training, threshold 0.5 in evaluation)
+            ops.binarize(ws.x8, x=ws.x, planes=ws.xp, seed=self.binarize_seed, offset_dev=ws.bin_ctr,
+                         dynamic=train or self.binarize_eval_dynamic, invert=self.binarize_invert)
+            if self.input_planes > 1:  # binarised values are exact in plane 0: the residual planes are zero
+                ws.xp.t[1:, :, :self.in_dim].zero_()
+        else:
+            ops.split_planes(ws.x, ws.xp)
+
     def _stage(self, ws: _Workspace, x: Tensor, eps: Optional[Tensor]) -> bool:
         """Input batch (and supplied noise) into the workspace.  Returns True when the noise has to be drawn: the
         forward kernels then do it on their side branch (inside the step's CUDA graph)."""
@@ -584,10 +720,10 @@ class FusedFeedForwardVAE(nn.Module):
     def encode(self, x: Tensor) -> Tensor:
         """ffnn_vae.py:42-50 -> relu(fc_e0(x)) as fp32."""
         ws = self._workspace(x.shape[0])
-        ws.x.copy_(x)
+        self._stage_x(ws, ws.slot, x)
         if self._planes_stale:
             self.refresh_weight_planes()
-        ops.split_planes(ws.x, ws.xp)
+        self._input_planes(ws, train=False)
         h = torch.empty(ws.B, self.h_dim, device=self.device)
         ops.gemm(ws.xp, self.We0p, ws.B, self.h_dim, self.in_dim, epilogue=L.EPI_BIAS_RELU,
                  bias=self.fc_e0.bias.data, out_planes=ws.hp, out_f32=h)
@@ -614,11 +750,15 @@ class FusedFeedForwardVAE(nn.Module):
             loc = ws.mu[:, d.z_off:d.z_off + d.d]
             scale = ws.sigma[:, d.eps_off:d.eps_off + d.n]
             z = ws.z[:, d.z_off:d.z_off + d.d]
-            if c.effective_kind() == L.EUCLIDEAN:
+            if hasattr(c, "sampling_procedure"):
+                # a reference component: its own procedure builds its own distribution types
+                # (sampling_procedures.py:93-99,147-151)
+                q_z, p_z = c.sampling_procedure.reparametrize(loc, scale)
+            elif effective_kind_of(c) == L.EUCLIDEAN:
                 q_z = EuclideanNormal(loc, scale)
                 p_z = EuclideanNormal(torch.zeros_like(loc), torch.ones_like(scale))
             else:
-                man = c.manifold.manifold if c.kind == L.UNIVERSAL else c.manifold
+                man = c.manifold.manifold if self._kinds[i] == L.UNIVERSAL else c.manifold
                 q_z = WrappedNormal(loc, scale, man)
                 p_z = WrappedNormal(man.mu_0(loc.shape, device=loc.device, dtype=loc.dtype), torch.ones_like(scale), man)
             res.append(Reparametrized(q_z, p_z, z, ws.kl[:, i], ws.eps[:, d.eps_off:d.eps_off + d.n]))
@@ -628,6 +768,7 @@ class FusedFeedForwardVAE(nn.Module):
     def forward(self, x: Tensor, eps: Optional[Tensor] = None, beta: float = 1.0):
         """vae.py:69-80 -> (List[Reparametrized], concat_z, x_).  Also leaves the ELBO statistics of this batch in
         the stats vector (see compute_batch_stats)."""
+        self._sync_radii()
         x = x.to(self.device, non_blocking=True)
         ws = self._workspace(x.shape[0])
         draw = self._stage(ws, x, eps)
@@ -641,6 +782,15 @@ class FusedFeedForwardVAE(nn.Module):
     def compute_batch_stats(self, x_mb: Tensor, x_mb_: Tensor, reparametrized: List[Reparametrized], beta: float,
                             likelihood_n: int = 0) -> BatchStats:
         """vae.py:125-147: bce row sums of the given logits + the per-component KL of `reparametrized` -> BatchStats."""
+        if x_mb.dtype == torch.uint8:
+            # raw pixels: the targets are the binarised batch (image_reconstruction.py:37-53) — the very one forward()
+            # produced when it ran on this batch just before (eval.py:95-96, train.py:236-238), else the 0.5 threshold
+            ws = self._ws.get(x_mb.shape[0])
+            if ws is not None and ws.u8 and x_mb_.data_ptr() == (ws.logits.data_ptr() if ws.logits is not None else 0):
+                x_mb = ws.x.clone()
+            else:
+                x_mb = ops.binarize(x_mb.to(self.device).reshape(x_mb.shape[0], -1).contiguous(), dynamic=False,
+                                    invert=self.binarize_invert)
         x_mb = x_mb.to(self.device).float().contiguous()
         bce, _ = ops.recon_loss(self.recon_kind, x_mb_.float().contiguous(), x_mb)
         kl = torch.stack([r.kl for r in reparametrized], dim=-1).contiguous()
@@ -663,17 +813,12 @@ class FusedFeedForwardVAE(nn.Module):
         x.repeat((n, 1, 1)), no [n, B, D] logits in HBM) ; then ONE streaming logsumexp over the sample axis for both
         estimates, and cov_norm from sum_s z (the sample mean commutes with the bilinear form of :119-121)."""
         B, D, H, P, Sd, Sn = x.shape[0], self.in_dim, self.h_dim, self.desc.ld_ml, self.desc.ld_z, self.desc.ld_eps
+        self._sync_radii()
         ws = self._workspace(B)
         self._stage_x(ws, ws.slot, x)
         if self._planes_stale:
             self.refresh_weight_planes()
-        if ws.u8:
-            ops.binarize(ws.x8, x=ws.x, planes=ws.xp, seed=self.binarize_seed, offset_dev=ws.bin_ctr,
-                         dynamic=self.binarize_eval_dynamic, invert=self.binarize_invert)
-            if self.input_planes > 1:
-                ws.xp.t[1:, :, :self.in_dim].zero_()
-        else:
-            ops.split_planes(ws.x, ws.xp)
+        self._input_planes(ws, train=False)
         self._gemm("e0_fwd", ws.xp, self.We0p, B, H, D, epilogue=L.EPI_BIAS_RELU, bias=self.fc_e0.bias.data,
                    out_planes=ws.hp)
         if self.latent_gemm:
@@ -730,23 +875,37 @@ class FusedFeedForwardVAE(nn.Module):
         ws = self._workspace(x_mb.shape[0])
         draw = self._stage(ws, x_mb, eps)
         self._step_kernels(optimizer, ws, beta, draw)
-        stats = BatchStats(self._stats_report.clone() if not sync_stats else self._stats_report, beta)
         self._last_ws = ws
-        out = (None, ws.z, None)
+        # Outputs of vae.py:166 = (reparametrized, concat_z, x_mb_); the first and the last are built on first use
+        # from this step's buffers (valid until the next step on the same batch size)
+        out = (LazyReparametrized(lambda: self._reparametrized_of(ws)), ws.z, LazyTensor(lambda: self.decode(ws.z)))
         if sync_stats:
+            h = self._stats_wire.cpu().tolist()  # ONE device->host copy (the reference: 3 + C .item() syncs)
             if self.check_finite and int(ws.flag.item()) != 0:
                 raise FloatingPointError("non-finite latent sample or KL term (device flag set by mvae_pm_forward)")
-            return stats.convert_to_float(), out
-        return stats, out
+            return self._floats_of(h, beta), out
+        return BatchStats(self._stats_report.clone(), beta), out
+
+    def _floats_of(self, h: List[float], beta: float) -> BatchStatsFloat:
+        """Host copy of the statistics wire -> BatchStatsFloat; raises if the data-parallel step reported a peer
+        that never arrived (the parameters are frozen from that step on: mvae_dp_step)."""
+        n = 3 + self.desc.C
+        if len(h) > n and h[n] != 0.0:
+            raise RuntimeError(f"data-parallel step failed: a peer did not arrive within the time limit (phase "
+                               f"{int(h[n])}); parameters have not been updated since — all ranks must run the same "
+                               "number of steps (MVAE_DP_TIMEOUT_S sets the limit)")
+        return BatchStatsFloat(h[0], h[1], h[2], h[3:n], beta)
 
     def _step_kernels(self, optimizer, ws: _Workspace, beta: float, draw_eps: bool = False) -> None:
+        self._sync_radii()
         fused = isinstance(optimizer, FusedCurvatureOptimizer)
         if fused and self.use_cuda_graph:
             self._graphed_step(optimizer, ws, beta, draw_eps)
         else:
             if not fused:
                 optimizer.zero_grad()
-            self._forward_kernels(ws, beta, train=True, want_mu_sigma=False, logits=None, draw_eps=draw_eps)
+            self._forward_kernels(ws, beta, train=True, want_mu_sigma=self.train_statistics, logits=None,
+                                     draw_eps=draw_eps)
             self._backward_kernels(ws, beta)
             if self._grad_hook is not None:
                 self._grad_hook(self._bucket)  # data-parallel: one SUM all-reduce over [grads | radius grads | stats]
@@ -775,8 +934,8 @@ class FusedFeedForwardVAE(nn.Module):
             self._slot_ready = [torch.cuda.Event(), torch.cuda.Event()]
             self._slot_free = [torch.cuda.Event(), torch.cuda.Event()]
         copy = self._copy_stream
-        ring_n, nst = 64, self._stats_report.numel()
-        if getattr(self, "_stats_ring", None) is None:
+        ring_n, nst = 64, self._stats_wire.numel()
+        if getattr(self, "_stats_ring", None) is None or self._stats_ring.shape[1] != nst:
             self._stats_ring = torch.zeros(ring_n, nst, dtype=torch.float32).pin_memory()
             self._ring_ev = [torch.cuda.Event() for _ in range(ring_n)]
         ring, ring_ev = self._stats_ring, self._ring_ev
@@ -797,8 +956,7 @@ class FusedFeedForwardVAE(nn.Module):
 
         def drain(i):
             ring_ev[i % ring_n].synchronize()
-            h = ring[i % ring_n].tolist()
-            results.append(BatchStatsFloat(h[0], h[1], h[2], h[3:], beta))
+            results.append(self._floats_of(ring[i % ring_n].tolist(), beta))
 
         it = iter(batches)
         eps_it = iter(eps_batches) if eps_batches is not None else None
@@ -825,7 +983,7 @@ class FusedFeedForwardVAE(nn.Module):
             self._slot_free[slot].record(main)
             if i >= ring_n:
                 drain(i - ring_n)
-            ring[i % ring_n].copy_(self._stats_report, non_blocking=True)
+            ring[i % ring_n].copy_(self._stats_wire, non_blocking=True)
             ring_ev[i % ring_n].record(main)
             i += 1
             if x_next is not None and x_next.shape[0] != B:  # ragged last batch: its own workspace, no overlap
@@ -843,8 +1001,10 @@ class FusedFeedForwardVAE(nn.Module):
         return results
 
     _grad_hook = None
+    _early_step = None  # data parallel over peer memory: FusedCurvatureOptimizer.step_early (parallel.attach_p2p)
     use_cuda_graph = False
     latent_gemm = False
+    train_statistics = False  # True: train_step keeps q_z's loc / scale (Trainer --train_statistics, train.py:200-206)
 
     def _graphed_step(self, optimizer: "FusedCurvatureOptimizer", ws: _Workspace, beta: float,
                       draw_eps: bool = False) -> None:
@@ -852,18 +1012,23 @@ class FusedFeedForwardVAE(nn.Module):
         One graph holds forward + backward + optimizer step (+ refresh of the weight planes); with a gradient hook
         (the NCCL data-parallel path) it is split in two and the all-reduce runs between them, eagerly.  Keyed by everything baked into launch
         parameters: batch size, beta, and whether the curvature optimizers step."""
+        # ... and every other value a launch bakes into its parameters (a changed learning rate must not replay the old one)
         key = (ws.B, ws.slot, float(beta), optimizer.curvature_step_enabled(), id(optimizer), bool(draw_eps), ws.u8,
-               self._grad_hook is None)
+               self._grad_hook is None, optimizer.hyper_parameters(), self.binarize_seed, self.binarize_invert,
+               self.check_finite, self.train_statistics, self.fused_latent, self.latent_gemm)
         entry = self._graphs.get(key)
+        # Parameters changed outside the fused optimizer (load_state_dict, broadcast_parameters, an interleaved torch
+        # optimizer): the graph's GEMMs read the weight PLANES, so they are rebuilt eagerly before any replay.
+        if self._planes_stale:
+            self.refresh_weight_planes()
         if entry is None:
-            if self._planes_stale:
-                self.refresh_weight_planes()
             # warm-up on a side stream (lazy func attributes / module loading must not happen during capture)
             side = torch.cuda.Stream(device=self.device)
             side.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(side):
-                self._forward_kernels(ws, beta, train=True, want_mu_sigma=False, logits=None, draw_eps=draw_eps)
-                self._backward_kernels(ws, beta)
+                self._forward_kernels(ws, beta, train=True, want_mu_sigma=self.train_statistics, logits=None,
+                                     draw_eps=draw_eps)
+                self._backward_kernels(ws, beta, early=False)  # no optimizer step follows: nothing is exchanged
             torch.cuda.current_stream().wait_stream(side)
             n0 = ops.launch_count()
             one_graph = self._grad_hook is None  # nothing eager between backward and optimizer: ONE graph, one replay
@@ -876,7 +1041,8 @@ class FusedFeedForwardVAE(nn.Module):
 
             ga = torch.cuda.CUDAGraph()
             with torch.cuda.graph(ga):
-                self._forward_kernels(ws, beta, train=True, want_mu_sigma=False, logits=None, draw_eps=draw_eps)
+                self._forward_kernels(ws, beta, train=True, want_mu_sigma=self.train_statistics, logits=None,
+                                     draw_eps=draw_eps)
                 self._backward_kernels(ws, beta)
                 if one_graph:
                     capture_opt()
@@ -904,13 +1070,22 @@ class FusedFeedForwardVAE(nn.Module):
         for name, p in self._net_params():
             o, n = self._slices[name]
             p.grad = self._bucket[o:o + n].view(p.shape)
-        for i, c in enumerate(self.components):
-            _, rp = c.radius_parameter()
+        for i, rp in enumerate(self._radius_params):
             if rp is not None and rp.requires_grad:
                 rp.grad = self._bucket[self._n_net + i]
 
+    def _reparametrized_of(self, ws: _Workspace) -> List[Reparametrized]:
+        """q_z / p_z / z / kl of the step that last ran on `ws`.  With train_statistics the step wrote loc and scale
+        itself; otherwise they are recomputed here from the head pre-activations and the noise the step kept (with the
+        radii as they are NOW: after a curvature step they differ from the step's own by lr * gradient)."""
+        if not getattr(ws, "has_mu_sigma", False):
+            ops.pm_forward(self.desc, ws.ml, ws.eps, self._rflat, want_mu_sigma=True,
+                           out={"z": ws.z, "kl": ws.kl, "mu": ws.mu, "sigma": ws.sigma})
+            ws.has_mu_sigma = True
+        return self._reparametrized(ws)
+
     def reparametrized_of_last_step(self) -> List[Reparametrized]:
-        return self._reparametrized(self._last_ws)
+        return self._reparametrized_of(self._last_ws)
 
 
 class FusedCurvatureOptimizer:
@@ -932,6 +1107,9 @@ class FusedCurvatureOptimizer:
         self.step_dev = torch.zeros(1, device=model._flat.device, dtype=torch.int32)  # 1-based after the first step
         self.param_groups = [{"params": [p for _, p in model._net_params()], "lr": learning_rate}]
         self._dp = self._dp_tail = self._dp_sync = None  # set by parallel.attach_p2p
+        self._early_done = False
+        self.dp_overlap = os.environ.get("MVAE_DP_OVERLAP", "1") != "0"
+        self.dp_early_ctas = int(os.environ.get("MVAE_DP_EARLY_CTAS", "24"))
         self._done = torch.zeros(1, device=model._flat.device, dtype=torch.int32)
         self.planes_fresh = False  # True after a step that also refreshed the model's weight planes
 
@@ -941,36 +1119,69 @@ class FusedCurvatureOptimizer:
     def curvature_step_enabled(self) -> bool:
         return (not self.fixed_curvature) and bool(self.curv_condition())
 
+    def hyper_parameters(self) -> tuple:
+        """Everything step() bakes into launch parameters (part of the key of the model's CUDA graphs)."""
+        return (float(self.lr), float(self.betas[0]), float(self.betas[1]), float(self.eps), float(self.curvature_lr))
+
+    def _plane_targets(self):
+        """(targets the fused kernels refresh in place, [(weight, planes)] that need their own plane-split launch).
+        The fused kernels refresh a weight's planes with 128-bit accesses: rows must be a multiple of 4 floats wide
+        (in_dim = 50 of the BDP data is not); such a matrix gets its own launch after the update."""
+        m = self.model
+        targets = [(m._slices["fc_e0.weight"][0], m.h_dim, m.We0p, m.fc_e0.weight),
+                   (m._slices["fc_logits.weight"][0], m.in_dim, m.Wlp, m.fc_logits.weight)]
+        if m.latent_gemm:
+            targets += [(m._slices["components.0.fc_mean.weight"][0], m.desc.ld_ml, m.Whp, None),
+                        (m._slices["fc_d0.weight"][0], m.h_dim, m.Wd0p, m.fc_d0.weight)]
+        late = [(t[3].data if t[3] is not None else m.Wh, t[2]) for t in targets if t[2].cols % 4]
+        return [t[:3] for t in targets if t[2].cols % 4 == 0], late
+
+    def _dp_launch(self, begin: int, end: int, channel: int, do_tail: bool, max_ctas: int = 0) -> None:
+        m = self.model
+        targets, late = self._plane_targets()
+        inside = lambda off: begin <= off < end  # noqa: E731
+        ops.dp_step(self._dp, m._n_net, begin, end, channel, do_tail, 2 * m.desc.C + 3, m.desc.C, self.exp_avg,
+                    self.exp_avg_sq, self.lr, self.betas[0], self.betas[1], self.eps, self.step_dev, m._rflat,
+                    self.curvature_lr if self.curvature_step_enabled() else 0.0, m._radius_mask, m._clip_mask, 1.0,
+                    self._dp_tail, self._dp_sync, [t for t in targets if inside(t[0])], max_ctas=max_ctas)
+        for w, buf in late:
+            if inside(w.data_ptr() - m._flat.data_ptr() >> 2):
+                ops.split_planes(w, buf)
+
+    def _dp_ranges(self):
+        """Float ranges of the parameter buffer exchanged by the launches of one data-parallel step."""
+        m = self.model
+        o = m._slices["fc_logits.weight"][0]
+        return [(o, m._n_net), (0, o)] if self.dp_overlap else [(0, m._n_net)]
+
+    def step_early(self) -> None:
+        """Data parallel only: exchange + update of fc_logits (half of the parameters), whose gradient is complete as
+        soon as the logits weight-gradient and input-gradient GEMMs are: the model calls this on a side stream so that
+        it runs UNDER the latent backward pass and the fc_e0 weight gradient (mvae_dp_step, channel 0, a few CTAs)."""
+        if self._dp is None or not self.dp_overlap:
+            return
+        begin, end = self._dp_ranges()[0]
+        self._dp_launch(begin, end, 0, False, max_ctas=self.dp_early_ctas)
+        self._early_done = True
+
     def step(self, closure=None) -> None:
         """The Adam step counter lives on the device (mvae_adam_step_dev), so this call can be captured in a CUDA
         graph and replayed."""
         m = self.model
         self.step_count += 1
-        if m._clip_mask is not None:
-            ops.clip_grad_norm(m._gradius, m._clip_mask, 1.0)  # vae.py:161-163, on the (rank-summed) gradient
-        targets = [(m._slices["fc_e0.weight"][0], m.h_dim, m.We0p), (m._slices["fc_logits.weight"][0], m.in_dim, m.Wlp)]
-        if m.latent_gemm:
-            targets += [(m._slices["components.0.fc_mean.weight"][0], m.desc.ld_ml, m.Whp),
-                        (m._slices["fc_d0.weight"][0], m.h_dim, m.Wd0p)]
-        # the fused kernels refresh a weight's planes with 128-bit accesses: rows must be a multiple of 4 floats wide
-        # (in_dim = 50 of the BDP data is not); such a matrix gets its own plane-split launch after the update
-        src_of = {id(m.We0p): lambda: m.fc_e0.weight.data, id(m.Wlp): lambda: m.fc_logits.weight.data}
-        if m.latent_gemm:
-            src_of.update({id(m.Whp): lambda: m.Wh, id(m.Wd0p): lambda: m.fc_d0.weight.data})
-        late = [(src_of[id(t[2])](), t[2]) for t in targets if t[2].cols % 4]
-        targets = [t for t in targets if t[2].cols % 4 == 0]
         if self._dp is not None:
             # data parallel over NVLink peer memory: gradient reduce-scatter + Adam on this rank's slice + parameter
-            # all-gather + the radii's SGD step, one kernel (mvae_dp_adam_step)
-            ops.dp_adam_step(self._dp, m._n_net, 2 * m.desc.C + 3, m.desc.C, self.exp_avg, self.exp_avg_sq, self.lr,
-                             self.betas[0], self.betas[1], self.eps, self.step_dev, m._rflat,
-                             self.curvature_lr if self.curvature_step_enabled() else 0.0, m._radius_mask,
-                             self._dp_tail, self._dp_sync, targets)
-            for w, buf in late:
-                ops.split_planes(w, buf)
+            # all-gather + the clip of the curvature gradients + the radii's SGD step, one kernel (mvae_dp_step) over
+            # whatever step_early() has not taken already
+            end = self._dp_ranges()[-1][1] if self._early_done else m._n_net
+            self._early_done = False
+            self._dp_launch(0, end, 1, True)
             m._planes_stale = False
             self.planes_fresh = True
             return
+        if m._clip_mask is not None:
+            ops.clip_grad_norm(m._gradius, m._clip_mask, 1.0)  # vae.py:161-163
+        targets, late = self._plane_targets()
         # Adam + the radii's SGD step + the refresh of the GEMM weight planes + the step counter: one launch
         # (fixed radii receive no gradient: radius_mask)
         ops.opt_step_fused(m._flat, m._gnet, self.exp_avg, self.exp_avg_sq, self.lr, self.betas[0], self.betas[1],
@@ -982,7 +1193,21 @@ class FusedCurvatureOptimizer:
         self.planes_fresh = True
 
     def state_dict(self):
-        return {"exp_avg": self.exp_avg, "exp_avg_sq": self.exp_avg_sq, "step": int(self.step_dev.item())}
+        """Under the peer-memory data-parallel step every rank keeps only ITS 1/N slice of the moments current
+        (mvae_dp_step): the slices are gathered here, so the dict is complete on every rank (collective call)."""
+        m, v = self.exp_avg, self.exp_avg_sq
+        if self._dp is not None:
+            import torch.distributed as dist
+            world, rank = int(self._dp.world), int(self._dp.rank)
+            m, v = torch.zeros_like(m), torch.zeros_like(v)
+            for begin, end in self._dp_ranges():
+                n4 = (end - begin) // 4
+                per = (n4 + world - 1) // world
+                lo, hi = begin + 4 * min(n4, rank * per), begin + 4 * min(n4, (rank + 1) * per)
+                m[lo:hi], v[lo:hi] = self.exp_avg[lo:hi], self.exp_avg_sq[lo:hi]
+            dist.all_reduce(m)
+            dist.all_reduce(v)
+        return {"exp_avg": m, "exp_avg_sq": v, "step": int(self.step_dev.item())}
 
     def load_state_dict(self, sd) -> None:
         self.exp_avg.copy_(sd["exp_avg"])

@@ -299,3 +299,47 @@ class OracleVAE:
         out["gz"] = gz
         out["gml"] = gml
         return out
+
+
+class OracleTrainer:
+    """k train steps of the reference on the CPU: OracleVAE.step (vae.py:149-160) followed by the update of
+    Trainer.build_optimizer + CurvatureOptimizer.step (train.py:327-360, utils.py:174-180): torch.optim.Adam(lr) on
+    every network parameter, the 2-norm clip of the "curvature"-named gradients (vae.py:161-163), SGD(lr=1e-4) on
+    `_nradius` / `_pradius` / `_curvature` when the curvature optimizers step.  All arithmetic in the dtype of `params`
+    (float64 for the parity tests).  Under data parallelism the global batch is simply passed as one batch (the ELBO
+    and its gradients are sums over samples)."""
+
+    def __init__(self, ovae: OracleVAE, params: dict, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, curvature_lr=1e-4,
+                 curvature_step=True, fixed_curvature=False):
+        self.ovae = ovae
+        self.params = {k: np.array(v, copy=True) for k, v in params.items()}
+        self.lr, self.betas, self.eps = lr, betas, eps
+        self.curvature_lr = curvature_lr if (curvature_step and not fixed_curvature) else 0.0
+        self.net_keys = [k for k in self.params if not any(s in k for s in ("radius", "curvature"))]
+        self.curv_keys = [k for k in self.params if any(s in k for s in ("radius", "curvature"))]
+        self.m = {k: np.zeros_like(self.params[k]) for k in self.net_keys}
+        self.v = {k: np.zeros_like(self.params[k]) for k in self.net_keys}
+        self.t = 0
+
+    def step(self, x, eps, beta=1.0, relu_decisions=None):
+        out = self.ovae.step(self.params, x, eps, beta=beta, relu_decisions=relu_decisions)
+        g = out["grads"]
+        clip_keys = [k for k in self.curv_keys if "curvature" in k and k in g]
+        if clip_keys:
+            total = float(np.sqrt(sum(float(g[k]) ** 2 for k in clip_keys)))
+            coef = min(1.0, 1.0 / (total + 1e-6))
+            for k in clip_keys:
+                g[k] = np.asarray(g[k]) * coef
+        self.t += 1
+        b1, b2 = self.betas
+        bc1, bc2 = 1.0 - b1 ** self.t, 1.0 - b2 ** self.t
+        for k in self.net_keys:
+            gk = np.asarray(g[k], dtype=self.params[k].dtype)
+            self.m[k] = b1 * self.m[k] + (1.0 - b1) * gk
+            self.v[k] = b2 * self.v[k] + (1.0 - b2) * gk * gk
+            self.params[k] = self.params[k] - (self.lr / bc1) * self.m[k] / (np.sqrt(self.v[k]) / np.sqrt(bc2) + self.eps)
+        if self.curvature_lr:
+            for k in self.curv_keys:
+                if k in g:
+                    self.params[k] = self.params[k] - self.curvature_lr * np.asarray(g[k], dtype=self.params[k].dtype)
+        return out

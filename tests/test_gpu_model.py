@@ -222,21 +222,6 @@ def test_training_reduces_loss(dev):
     assert last > first + 0.2 * abs(first)  # ELBO is a sum over the batch; it must rise markedly when overfitting one batch
 
 
-def test_peer_memory_data_parallel_step_two_gpus():
-    """mvae_dp_adam_step (gradient reduce-scatter + Adam + parameter all-gather over NVLink peer memory, one kernel)
-    against the NCCL all-reduce path on 2 GPUs: scripts/dp_check.py under torchrun.  Skipped on a single-GPU box."""
-    import os
-    import subprocess
-    import sys
-    if torch.cuda.device_count() < 2:
-        pytest.skip("needs 2 GPUs")
-    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
-                        "--master-addr", "127.0.0.1", "--master-port", "29541", os.path.join(root, "scripts", "dp_check.py")],
-                       capture_output=True, text=True, timeout=600)
-    assert r.returncode == 0 and "dp_check ok" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
-
-
 def test_uint8_batches_binarised_on_device(dev, oracle):
     """mvae_binarize (ImageDynamicBinarization, image_reconstruction.py:37-53, moved to the device): bit-exact against
     the reference's comparison `ToTensor(x) > U` for supplied draws and against `> 0.5` in evaluation mode; the Philox

@@ -143,3 +143,81 @@ def test_log_likelihood_vs_reference(oracle, name):
     for k in ("log_p_x", "mi"):
         assert normwise(r32[k], g[k]) < max(F32_TOL, 3 * normwise(g[k + "_f32"], g[k])), k
     assert abs(r32["cov_norm"] - float(g["cov_norm"])) < 1e-4 * float(g["cov_norm"])
+
+
+def test_oracle_trainer_update_is_torch_adam_and_sgd(oracle):
+    """oracle.OracleTrainer (the k-step reference of tests/test_gpu_timed_path.py and scripts/dp_check.py) applies
+    exactly torch.optim.Adam + SGD(1e-4) on the radii (Trainer.build_optimizer, train.py:327-360) to the oracle's
+    gradients."""
+    import torch
+    sig, B, D, H = "h2,s2,e2", 64, 20, 16
+    rng = np.random.default_rng(0)
+    ov = oracle.OracleVAE(sig, D, H, "bce", False)
+    params = {}
+    for i in range(3):
+        params[f"components.{i}.fc_mean.weight"] = rng.standard_normal((2, H)) * 0.3
+        params[f"components.{i}.fc_mean.bias"] = rng.standard_normal(2) * 0.1
+        params[f"components.{i}.fc_logvar.weight"] = rng.standard_normal((2, H)) * 0.3
+        params[f"components.{i}.fc_logvar.bias"] = rng.standard_normal(2) * 0.1
+    params["components.0._nradius"] = np.asarray(1.0)
+    params["components.1._pradius"] = np.asarray(1.0)
+    for nm, shp in (("fc_e0", (H, D)), ("fc_d0", (H, 8)), ("fc_logits", (D, H))):
+        params[nm + ".weight"] = rng.standard_normal(shp) * 0.3
+        params[nm + ".bias"] = rng.standard_normal(shp[0]) * 0.1
+    tr = oracle.OracleTrainer(ov, params)
+    tp = {k: torch.tensor(np.asarray(v), dtype=torch.float64, requires_grad=True) for k, v in params.items()}
+    adam = torch.optim.Adam([v for k, v in tp.items() if "radius" not in k], lr=1e-3)
+    sgd = torch.optim.SGD([v for k, v in tp.items() if "radius" in k], lr=1e-4)
+    for _ in range(4):
+        x = (rng.random((B, D)) < 0.3).astype(np.float64)
+        eps = rng.standard_normal((B, 6))
+        cur = {k: v.detach().numpy().copy() for k, v in tp.items()}
+        g = ov.step(cur, x, eps, beta=0.7)["grads"]
+        for k, v in tp.items():
+            v.grad = torch.tensor(np.asarray(g[k], dtype=np.float64)).reshape(v.shape)
+        adam.step()
+        sgd.step()
+        tr.step(x, eps, beta=0.7)
+    for k, v in tp.items():
+        assert np.allclose(v.detach().numpy(), tr.params[k], rtol=1e-10, atol=1e-12), k
+
+
+def test_cpu_baseline_step_matches_oracle(oracle):
+    """oracle/cpu_baseline.py — what bench.py's CPU arm times — computes the same step as OracleVAE.step (float32)."""
+    import torch
+    import cpu_baseline
+    sig, B, D, H = "h2,s2,p2,e2", 256, 40, 32
+    rng = np.random.default_rng(1)
+    ov = oracle.OracleVAE(sig, D, H, "bce", False)
+    params = {}
+    for i in range(4):
+        params[f"components.{i}.fc_mean.weight"] = (rng.standard_normal((2, H)) * 0.05).astype(np.float32)
+        params[f"components.{i}.fc_mean.bias"] = (rng.standard_normal(2) * 0.1).astype(np.float32)
+        params[f"components.{i}.fc_logvar.weight"] = (rng.standard_normal((2, H)) * 0.05).astype(np.float32)
+        params[f"components.{i}.fc_logvar.bias"] = (rng.standard_normal(2) * 0.1).astype(np.float32)
+    params["components.0._nradius"] = np.asarray(1.3, dtype=np.float32)
+    params["components.1._pradius"] = np.asarray(0.8, dtype=np.float32)
+    params["components.2._nradius"] = np.asarray(1.1, dtype=np.float32)
+    for nm, shp in (("fc_e0", (H, D)), ("fc_d0", (H, 10)), ("fc_logits", (D, H))):
+        params[nm + ".weight"] = (rng.standard_normal(shp) * 0.1).astype(np.float32)
+        params[nm + ".bias"] = (rng.standard_normal(shp[0]) * 0.1).astype(np.float32)
+    x = (rng.random((B, D)) < 0.3).astype(np.float32)
+    eps = rng.standard_normal((B, 8)).astype(np.float32)
+    ref = ov.step({k: v.astype(np.float64) for k, v in params.items()}, x.astype(np.float64), eps.astype(np.float64),
+                  beta=0.9)
+    cpu = cpu_baseline.CpuTrainStep(sig, D, H, "bce", params)
+    out = cpu.step(torch.from_numpy(x), torch.from_numpy(eps), beta=0.9, update=False)
+    assert abs(out["elbo"] - ref["elbo"]) < 1e-4 * abs(ref["elbo"])   # float32 oracle (reference-order arithmetic)
+    assert abs(out["kl_sum"] - ref["kl_sum"]) < 2e-3 * abs(ref["kl_sum"])
+    for k_cpu, k_ref in (("fc_e0.W", "fc_e0.weight"), ("fc_e0.b", "fc_e0.bias"), ("fc_d0.W", "fc_d0.weight"),
+                         ("fc_logits.W", "fc_logits.weight"), ("fc_logits.b", "fc_logits.bias")):
+        assert normwise(out["grads"][k_cpu].numpy(), ref["grads"][k_ref]) < 2e-4, k_cpu
+    gWh = np.concatenate([np.concatenate([ref["grads"][f"components.{i}.fc_mean.weight"],
+                                          ref["grads"][f"components.{i}.fc_logvar.weight"]]) for i in range(4)])
+    assert normwise(out["grads"]["Wh"].numpy(), gWh) < 2e-4
+    gR = [float(ref["grads"].get(f"components.{i}.{nm}", 0.0)) for i, nm in enumerate(("_nradius", "_pradius", "_nradius"))]
+    assert np.allclose(out["gR"][:3], gR, rtol=2e-3, atol=1e-3)
+    # and the update moves the parameters (Adam: about lr per step) and the radii
+    w0 = cpu.p["fc_e0.W"].clone()
+    cpu.step(torch.from_numpy(x), torch.from_numpy(eps), beta=0.9)
+    assert 1e-4 < float((cpu.p["fc_e0.W"] - w0).abs().max()) < 2e-3 and cpu.R[0] != np.float32(1.3)
