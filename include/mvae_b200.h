@@ -302,6 +302,16 @@ int mvae_binarize(const uint8_t* src, int64_t ld_src, int64_t B, int32_t D, int3
                   uint64_t seed, const uint64_t* offset_dev, float* x, int64_t ld_x, const mvae_planes* x_planes,
                   void* stream);
 
+/* Head of a train step, ONE launch: (a) eps [n_eps] ~ N(0, 1) — the draw of Normal.rsample behind every Wrapped-Normal
+ * / Euclidean-Normal sample (wrapped_normal.py:72, wrapped_distributions.py:25-27; torch's generator there, Philox4x32-10
+ * + Box-Muller here: key `seed`, offset 4 * *counter_dev, which is read, not advanced — graph replayable); eps NULL or
+ * n_eps 0 = the caller supplies the noise; (b) zero fill of up to 6 float buffers (the step's accumulating outputs:
+ * gradient bucket, reconstruction row sums, split-K targets), replacing optimizer.zero_grad() (vae.py:151). */
+int mvae_step_prologue(float* eps, int64_t n_eps, uint64_t seed, const uint64_t* counter_dev, int32_t n_zero,
+                       float* const* zero_ptr, const int64_t* zero_n, void* stream);
+/* *counter_dev += inc (the per-model step counter behind the Philox offsets above; one launch per step). */
+int mvae_counter_add(uint64_t* counter_dev, uint64_t inc, void* stream);
+
 /* ------------------------------------------------------ importance-weighted log-likelihood (evaluation) */
 /* ModelVAE.log_likelihood (vae.py:82-123) draws n samples per input row.  The encoder runs once; per chunk of `ns`
  * samples mvae_iwae_latent does Component.encode's manifold part + rsample_log_probs of EVERY component

@@ -108,6 +108,9 @@ PROTOTYPES = {
     "mvae_opt_step_fused": (ctypes.c_int, [_i64, _vp, _vp, _vp, _vp, _f32, _f32, _f32, _f32, _vp, _vp, _vp, _vp, _vp,
                                            _f32, _i32, _i32, ctypes.POINTER(_i64), ctypes.POINTER(_i32),
                                            ctypes.POINTER(Planes), _vp]),
+    "mvae_step_prologue": (ctypes.c_int, [_vp, _i64, ctypes.c_uint64, _vp, _i32, ctypes.POINTER(ctypes.c_void_p),
+                                          ctypes.POINTER(_i64), _vp]),
+    "mvae_counter_add": (ctypes.c_int, [_vp, ctypes.c_uint64, _vp]),
     "mvae_dp_alloc": (ctypes.c_int, [ctypes.c_size_t, ctypes.POINTER(ctypes.c_void_p)]),
     "mvae_dp_free": (ctypes.c_int, [_vp]),
     "mvae_dp_ipc_export": (ctypes.c_int, [_vp, ctypes.c_char_p]),

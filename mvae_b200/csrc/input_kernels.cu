@@ -110,9 +110,99 @@ __global__ void __launch_bounds__(256) binarize1_kernel(const BinParams p) {
   }
 }
 
+// ---- step prologue: the noise of the step's Wrapped-Normal samples + zero fill of its accumulating outputs ----
+constexpr int kMaxZeroSpans = 6;
+struct PrologueParams {
+  float* eps;
+  int64_t n_eps;
+  unsigned long long seed;
+  const unsigned long long* counter_dev;
+  int n_zero;
+  float* zptr[kMaxZeroSpans];
+  int64_t zn[kMaxZeroSpans];
+};
+
+__global__ void __launch_bounds__(256) step_prologue_kernel(const PrologueParams p) {
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, nth = (int64_t)gridDim.x * blockDim.x;
+  if (p.eps) {
+    // Normal.rsample draws eps ~ N(0, I) per step (wrapped_normal.py:72, torch.distributions.Normal): Philox4x32-10,
+    // one counter block (4 normals, Box-Muller) per group of 4 consecutive elements, offset = 4 x the step counter
+    const unsigned long long step = p.counter_dev ? *p.counter_dev : 0ull;
+    const int64_t groups = (p.n_eps + 3) >> 2;
+    const bool vec = (reinterpret_cast<uintptr_t>(p.eps) & 15) == 0;
+    for (int64_t i = tid; i < groups; i += nth) {
+      curandStatePhilox4_32_10_t st;
+      curand_init(p.seed, (unsigned long long)i, step * 4ull, &st);
+      const float4 v = curand_normal4(&st);
+      if (vec && 4 * i + 4 <= p.n_eps) {
+        reinterpret_cast<float4*>(p.eps)[i] = v;
+      } else {
+        const float t[4] = {v.x, v.y, v.z, v.w};
+        for (int j = 0; j < 4; ++j)
+          if (4 * i + j < p.n_eps) p.eps[4 * i + j] = t[j];
+      }
+    }
+  }
+  for (int s = 0; s < p.n_zero; ++s) {
+    float* q = p.zptr[s];
+    const int64_t n = p.zn[s];
+    if ((reinterpret_cast<uintptr_t>(q) & 15) == 0) {
+      const int64_t n4 = n >> 2;
+      for (int64_t i = tid; i < n4; i += nth) reinterpret_cast<float4*>(q)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int64_t i = 4 * n4 + tid; i < n; i += nth) q[i] = 0.f;
+    } else {
+      for (int64_t i = tid; i < n; i += nth) q[i] = 0.f;
+    }
+  }
+}
+
+__global__ void counter_add_kernel(unsigned long long* ctr, unsigned long long inc) { *ctr += inc; }
+
 }  // namespace mvae
 
 using namespace mvae;
+
+extern "C" int mvae_step_prologue(float* eps, int64_t n_eps, uint64_t seed, const uint64_t* counter_dev, int32_t n_zero,
+                                  float* const* zero_ptr, const int64_t* zero_n, void* stream) {
+  if (n_eps < 0 || n_zero < 0 || n_zero > kMaxZeroSpans || (n_zero > 0 && (!zero_ptr || !zero_n)))
+    return MVAE_ERR_INVALID_ARGUMENT;
+  DeviceInfo di;
+  int rc = get_device_info(&di);
+  if (rc != MVAE_OK) return rc;
+  PrologueParams p;
+  memset(&p, 0, sizeof(p));
+  p.eps = n_eps > 0 ? eps : nullptr;
+  p.n_eps = n_eps;
+  p.seed = (unsigned long long)seed;
+  p.counter_dev = reinterpret_cast<const unsigned long long*>(counter_dev);
+  int64_t work = (n_eps + 3) / 4;
+  for (int s = 0; s < n_zero; ++s) {
+    if (zero_n[s] < 0 || (zero_n[s] > 0 && !zero_ptr[s])) return MVAE_ERR_INVALID_ARGUMENT;
+    if (zero_n[s] == 0) continue;
+    p.zptr[p.n_zero] = zero_ptr[s];
+    p.zn[p.n_zero] = zero_n[s];
+    ++p.n_zero;
+    if (zero_n[s] / 4 > work) work = zero_n[s] / 4;
+  }
+  if (work == 0) return MVAE_OK;
+  int64_t blocks = (work + 255) / 256;
+  const int64_t cap = (int64_t)di.sm_count * 8;
+  if (blocks > cap) blocks = cap;
+  step_prologue_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(p);
+  MVAE_LAUNCH_CHECK();
+  return MVAE_OK;
+}
+
+extern "C" int mvae_counter_add(uint64_t* counter_dev, uint64_t inc, void* stream) {
+  if (!counter_dev) return MVAE_ERR_INVALID_ARGUMENT;
+  DeviceInfo di;
+  int rc = get_device_info(&di);
+  if (rc != MVAE_OK) return rc;
+  counter_add_kernel<<<1, 1, 0, as_stream(stream)>>>(reinterpret_cast<unsigned long long*>(counter_dev),
+                                                     (unsigned long long)inc);
+  MVAE_LAUNCH_CHECK();
+  return MVAE_OK;
+}
 
 extern "C" int mvae_binarize(const uint8_t* src, int64_t ld_src, int64_t B, int32_t D, int32_t mode, int32_t invert,
                              const float* u, uint64_t seed, const uint64_t* offset_dev, float* x, int64_t ld_x,

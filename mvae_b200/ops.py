@@ -207,6 +207,30 @@ def binarize(src_u8: torch.Tensor, x: Optional[torch.Tensor] = None, planes: Opt
     return x
 
 
+def step_prologue(eps: Optional[torch.Tensor], seed: int, counter_dev: Optional[torch.Tensor], zero=()):
+    """Head of a train step in one launch (mvae_step_prologue): standard-normal noise into `eps` (None: the caller
+    supplies it) drawn with Philox at offset *counter_dev, and zero fill of the float tensors in `zero`."""
+    zero = [t for t in zero if t is not None and t.numel() > 0]
+    for t in zero:
+        if not (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()):
+            raise L.MvaeError("step_prologue: zero targets must be contiguous float32 CUDA tensors")
+    n = len(zero)
+    ptrs = (ctypes.c_void_p * max(n, 1))(*[t.data_ptr() for t in zero])
+    counts = (ctypes.c_int64 * max(n, 1))(*[t.numel() for t in zero])
+    if eps is not None:
+        eps = _f32(eps, "eps")
+    rc = L.lib().mvae_step_prologue(_ptr(eps), eps.numel() if eps is not None else 0, int(seed) & (2**64 - 1),
+                                    _ptr(counter_dev), n, ptrs, counts, _stream())
+    L.check(rc, "mvae_step_prologue")
+    _LAUNCHES[0] += 1
+
+
+def counter_add(counter_dev: torch.Tensor, inc: int = 1):
+    rc = L.lib().mvae_counter_add(_ptr(counter_dev), int(inc), _stream())
+    L.check(rc, "mvae_counter_add")
+    _LAUNCHES[0] += 1
+
+
 # ------------------------------------------------------------------------------------------ IWAE log-likelihood
 def iwae_latent(desc: L.PmDesc, ml, eps, radius, z, diff, zsum: Optional[torch.Tensor] = None):
     """z [ns, B, ld_z] and diff [ns, B] = sum_c (log q_c - log p_c) for ns samples per row of ml [B, ld_ml]

@@ -64,6 +64,7 @@ def attach(model, group=None) -> None:
     model._grad_hook = lambda bucket: allreduce_sum_(bucket, group)
     if dist.is_initialized():
         model.binarize_seed = int(model.binarize_seed) + 0x9E3779B1 * (dist.get_rank(group) + 1)
+        model.noise_seed = (int(model.noise_seed) + 0x85EBCA6B * (dist.get_rank(group) + 1)) & (2**62 - 1)
 
 
 def broadcast_parameters(model, src: int = 0, group=None) -> None:
@@ -168,6 +169,7 @@ def attach_p2p(model, optimizer, group=None) -> bool:
     model._dp_region = region
     # dynamic binarisation (uint8 batches): every rank draws its own uniforms
     model.binarize_seed = int(model.binarize_seed) + 0x9E3779B1 * (rank + 1)
+    model.noise_seed = (int(model.noise_seed) + 0x85EBCA6B * (rank + 1)) & (2**62 - 1)  # rank-offset seeds for eps
     torch.cuda.synchronize(dev)
     dist.barrier(group=group)  # every peer has mapped every region before the first step
     return True

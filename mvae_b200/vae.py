@@ -315,6 +315,10 @@ class FusedFeedForwardVAE(nn.Module):
         self._eps_override: Optional[Tensor] = None
         self._flat = None
         self.check_finite = False
+        # Philox key of the step's noise: taken from torch's global generator AFTER every layer has been initialised
+        # (torch.manual_seed governs the noise like it does for the reference's Normal.rsample, without disturbing the
+        # default initialisation, which must match the reference's per seed)
+        self.noise_seed = int(torch.randint(0, 2**62, (1,)).item())
         # (on a CPU device this is host-side bookkeeping only — every kernel entry point refuses non-CUDA tensors)
         self._flatten()
 
@@ -500,13 +504,13 @@ class FusedFeedForwardVAE(nn.Module):
         main, side = torch.cuda.current_stream(self.device), self._side_stream()
         side.wait_stream(main)
         with torch.cuda.stream(side):
-            if draw_eps:
-                ws.eps.normal_()
-            ws.bce.zero_()
-            if self.latent_gemm:
-                ws.ml.zero_()  # the heads GEMM accumulates its K slices into it
-            if train:
-                self._bucket[:self._n_net + self.desc.C].zero_()
+            # ONE launch: eps ~ N(0, I) (Philox, offset = the model's device step counter) + zero fill of the
+            # reconstruction row sums, of ml (the heads GEMM accumulates its K slices into it) and of the gradient
+            # bucket (optimizer.zero_grad(), vae.py:151)
+            ops.step_prologue(ws.eps if draw_eps else None, self.noise_seed, self._bin_ctr,
+                              [ws.bce, ws.ml if self.latent_gemm else None,
+                               self._bucket[:self._n_net + self.desc.C] if train else None])
+        ws.drew_eps = draw_eps
         self._input_planes(ws, train)
         fused = self.fused_latent and not want_mu_sigma
         ws.has_mu_sigma = want_mu_sigma
@@ -550,7 +554,10 @@ class FusedFeedForwardVAE(nn.Module):
 
     def _backward_kernels(self, ws: _Workspace, beta: float, early: bool = True):
         """`early`: let a data-parallel optimizer exchange + update fc_logits on a third stream as soon as its gradient
-        is complete (FusedCurvatureOptimizer.step_early) — False for a backward pass that no optimizer step follows."""
+        is complete (FusedCurvatureOptimizer.step_early), and advance the step counter behind the Philox draws —
+        False for the warm-up pass ahead of a graph capture, which no optimizer step follows and which must leave the
+        model's state (counters, exchanged parameters) untouched."""
+        advance = early
         B, D, H, P, Sd, C = ws.B, self.in_dim, self.h_dim, self.desc.ld_ml, self.desc.ld_z, self.desc.C
         MN = L.MN_MAJOR
         # Fork: the ELBO reduction and the weight gradient of fc_logits depend only on the forward pass; they run as a
@@ -559,8 +566,8 @@ class FusedFeedForwardVAE(nn.Module):
         main, side = torch.cuda.current_stream(self.device), self._side_stream()
         side.wait_stream(main)
         with torch.cuda.stream(side):
-            if ws.u8:
-                ws.bin_ctr.add_(1)  # next step's binarisation draws fresh uniforms
+            if advance and (ws.u8 or ws.drew_eps):
+                ops.counter_add(self._bin_ctr)  # the next step's noise / binarisation draws are fresh
             ops.elbo_reduce(ws.bce, ws.kl, beta, out=self._stats)
             # fc_logits: gW = gL^T dd (+ bias from the ones column of dd)
             self._gemm("logits_wgrad", ws.gLp, ws.ddp, D, H + 1, B, a_major=MN, b_major=MN, split_k=0, out_f32=self.gWl,
@@ -700,6 +707,7 @@ class FusedFeedForwardVAE(nn.Module):
         ws.eps.copy_(eps, non_blocking=True)
         return False
 
+    noise_seed = 0x5EED            # Philox key of the in-kernel N(0, I) draws (set per model from torch's generator)
     binarize_seed = 0              # Philox key of the on-device dynamic binarisation
     binarize_invert = False        # ImageDynamicBinarization(invert=...) (Omniglot)
     binarize_eval_dynamic = False  # forward() / log_likelihood() use the fixed 0.5 threshold like the reference's test loader
@@ -775,6 +783,8 @@ class FusedFeedForwardVAE(nn.Module):
         if ws.logits is None:
             ws.logits = torch.empty(ws.B, self.in_dim, device=self.device)
         self._forward_kernels(ws, beta, train=False, want_mu_sigma=True, logits=ws.logits, draw_eps=draw)
+        if draw:
+            ops.counter_add(self._bin_ctr)  # the next call draws fresh noise
         self._last_ws = ws
         return self._reparametrized(ws), ws.z, ws.logits
 
@@ -1014,7 +1024,8 @@ class FusedFeedForwardVAE(nn.Module):
         parameters: batch size, beta, and whether the curvature optimizers step."""
         # ... and every other value a launch bakes into its parameters (a changed learning rate must not replay the old one)
         key = (ws.B, ws.slot, float(beta), optimizer.curvature_step_enabled(), id(optimizer), bool(draw_eps), ws.u8,
-               self._grad_hook is None, optimizer.hyper_parameters(), self.binarize_seed, self.binarize_invert,
+               self._grad_hook is None, optimizer.hyper_parameters(), self.binarize_seed, self.noise_seed,
+               self.binarize_invert,
                self.check_finite, self.train_statistics, self.fused_latent, self.latent_gemm)
         entry = self._graphs.get(key)
         # Parameters changed outside the fused optimizer (load_state_dict, broadcast_parameters, an interleaved torch

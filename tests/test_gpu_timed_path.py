@@ -279,3 +279,62 @@ def test_data_parallel_steps_vs_oracle_on_the_global_batch():
                         "--master-addr", "127.0.0.1", "--master-port", "29541", os.path.join(ROOT, "scripts", "dp_check.py")],
                        capture_output=True, text=True, timeout=900)
     assert r.returncode == 0 and "dp_check ok" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
+
+
+def test_step_prologue_noise_and_zero_fill(dev):
+    """mvae_step_prologue: the N(0, I) draw behind Normal.rsample (wrapped_normal.py:72) as Philox4x32 + Box-Muller —
+    deterministic per (seed, step counter), fresh per step, standard normal to 5 sigma on 4 M draws — and the zero
+    fill that stands in for optimizer.zero_grad() (vae.py:151), for aligned and unaligned spans."""
+    from mvae_b200 import ops
+    n = 1 << 22
+    ctr = torch.zeros(1, dtype=torch.int64, device=dev)
+    a, b, c = (torch.empty(n, device=dev) for _ in range(3))
+    ops.step_prologue(a, 7, ctr)
+    ops.step_prologue(b, 7, ctr)
+    assert torch.equal(a, b)
+    ops.counter_add(ctr)
+    assert int(ctr.item()) == 1
+    ops.step_prologue(c, 7, ctr)
+    assert not torch.equal(a, c)
+    ops.step_prologue(b, 8, ctr)
+    assert not torch.equal(b, c)
+    x = a.double()
+    se = 1.0 / np.sqrt(n)
+    assert abs(float(x.mean())) < 5 * se
+    assert abs(float(x.var()) - 1.0) < 5 * np.sqrt(2.0) * se
+    assert abs(float((x ** 4).mean()) - 3.0) < 5 * np.sqrt(96.0) * se
+    assert abs(float((a * c).double().mean())) < 5 * se            # consecutive steps are uncorrelated
+    assert abs(float((a[:-1] * a[1:]).double().mean())) < 5 * se   # neighbours within a step too
+    assert float(a.abs().max()) < 7.0 and torch.isfinite(a).all()
+    # ragged length + unaligned zero spans
+    e = torch.full((1003,), 9.0, device=dev)
+    buf = torch.full((4099,), 5.0, device=dev)
+    z1, z2 = buf[1:1030], buf[2048:4099]
+    ops.step_prologue(e[:1001], 3, ctr, [z1, z2])
+    assert float(e[1001]) == 9.0 and float(e[1002]) == 9.0 and float(e[:1001].abs().max()) < 6.0
+    assert float(buf[0]) == 5.0 and float(buf[1030]) == 5.0 and float(buf[2047]) == 5.0
+    assert float(z1.abs().sum()) == 0.0 and float(z2.abs().sum()) == 0.0
+    ops.step_prologue(None, 0, None, [buf])
+    assert float(buf.abs().sum()) == 0.0
+
+
+def test_train_step_draws_its_own_noise(dev):
+    """Without supplied eps the step draws N(0, I) itself (inside the graph), fresh every step, also through
+    train_epoch and forward()."""
+    model, opt = _build("h2,s2,e2", 2048, 784, 400, dev)
+    xs, _ = _batches(2048, 784, 6, seed=11)
+    seen = []
+    for i in range(3):
+        model.train_step(opt, xs[i].to(dev), 1.0)
+        seen.append(model._last_ws.eps.clone())
+    model.train_epoch(opt, [x.pin_memory() for x in xs[:2]], 1.0)
+    seen.append(model._last_ws.eps.clone())
+    model.forward(xs[0].to(dev))
+    seen.append(model._last_ws.eps.clone())
+    model.forward(xs[0].to(dev))
+    seen.append(model._last_ws.eps.clone())
+    for i in range(len(seen)):
+        e = seen[i].double()
+        assert abs(float(e.mean())) < 0.05 and abs(float(e.var()) - 1.0) < 0.05
+        for j in range(i):
+            assert not torch.equal(seen[i], seen[j]), (i, j)
