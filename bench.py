@@ -217,7 +217,7 @@ def cpu_step_fn(workload, B, seed=0):
             params[f"components.{i}.{nm}.bias"] = getattr(c, nm).bias.detach().numpy().copy()
         name, rp = c.radius_parameter()
         if rp is not None and not fixed:
-            params[f"components.{i}.{name}"] = np.asarray(1.0, dtype=np.float32)
+            params[f"components.{i}.{name}"] = np.asarray(10.0, dtype=np.float32)  # as the GPU arm (--radius)
     tz = sum(c.dim for c in comps)
     for nm, (o, i_) in (("fc_e0", (H, D)), ("fc_d0", (H, tz)), ("fc_logits", (D, H))):
         lin = torch.nn.Linear(i_, o)
@@ -370,12 +370,20 @@ def run_ours(args):
     model = vae.FusedFeedForwardVAE(H, comps, data.GenericDataset(B, D, recon, binary_inputs=(recon == "bce")), False,
                                     device=dev)  # MNIST-shaped batches are binarised (0/1): one exact bf16 plane
     model.use_cuda_graph = not args.no_graph
+    # Learnable radii start at R = 10, the value the reference's own schedule gives them in its first training epoch
+    # (Trainer._train_epoch: R = 11 - epoch for epoch < 10, train.py:189-194).  The ELBO is a SUM over the batch, so at
+    # R = 1 the radius gradient of a 4096 x N batch times the reference's SGD step (1e-4) moves R by O(1) per step: with
+    # N >= 2 it reaches the clamp at 1e-8 within a few hundred steps and the run trains on NaNs (seen at N = 2).
+    with torch.no_grad():
+        for rp in model._radius_params:
+            if rp is not None and rp.requires_grad:
+                rp.fill_(args.radius)
     opt = vae.FusedCurvatureOptimizer(model, 1e-3, fixed_curvature=fixed, should_do_curvature_step=lambda: True)
     collective = "none"
     if world > 1:
         # one exchange per step: fused into the optimizer kernel over NVLink peer memory (default), or NCCL all-reduce
         if os.environ.get("MVAE_DP", "p2p") != "nccl" and parallel.attach_p2p(model, opt):
-            collective = "peer-memory kernel: gradient reduce-scatter + Adam + parameter all-gather (mvae_dp_adam_step)"
+            collective = "peer-memory kernel: gradient reduce-scatter + Adam + parameter all-gather (mvae_dp_step)"
         else:
             parallel.attach(model)
             collective = "NCCL all-reduce(SUM) of the gradient/statistics bucket, then Adam"
@@ -491,7 +499,14 @@ def run_ours(args):
         if local is not None:
             dist.all_reduce(local, op=dist.ReduceOp.SUM)
             rel = abs(bs_chk.elbo - float(local[2].item())) / abs(float(local[2].item()))
+        phases = parallel.dp_phase_times(opt) if not collective.startswith("NCCL") else {}
+        if phases:  # of the last step, on the slowest rank per phase
+            keys = sorted(phases)
+            t = torch.tensor([phases[k] for k in keys], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            phases = {k: round(float(v), 2) for k, v in zip(keys, t.tolist())}
         dp_check = {"replicas_identical": bool(identical and parallel.replicas_identical(model)),
+                    "phases_us_max_over_ranks": phases,
                     "elbo_vs_nccl_rel": rel, "dp_error_word": parallel.dp_error_word(opt),
                     "overlap": bool(getattr(opt, "dp_overlap", False) and opt._dp is not None)}
     e2e_ms = e2e_s / args.steps * 1e3
@@ -510,6 +525,7 @@ def run_ours(args):
             "config": {"workload": desc, "signature": sig, "batch_per_gpu": B, "global_batch": gb, "in_dim": D,
                        "h_dim": H, "parallelism": f"dp{world}", "l2": "flushed between timed steps (256 MiB memset)",
                        "cuda_graph": bool(model.use_cuda_graph), "optimizer": "Adam(1e-3) + SGD(1e-4) on radii",
+                       "initial_radius": args.radius,
                        "collective": collective, "numa_bound": bool(numa_bound)},
             "e2e": {"value": gb / (e2e_ms / 1e3), "unit": UNIT, "ms_per_step": e2e_ms,
                     "h2d_bytes_per_step": B * D * (1 if u8_inputs else 4), "d2h_bytes_per_step": (3 + C) * 4,
@@ -525,6 +541,7 @@ def run_ours(args):
                                "api": "the reference's literal call pattern: model.train_step(optimizer, float32 host "
                                       "batch, beta), blocking on the statistics every step (train.py:197-198)"}},
             "gpu_launches": int(launches), "clocks": clocks, "elbo_per_sample": float(bs.elbo) / gb,
+            "elbo_finite": bool(all(s.elbo == s.elbo and abs(s.elbo) < float("inf") for s in stats_list)),
             "peaks": peaks["source"]}
     if dp_check is not None:
         line["dp_check"] = dp_check
@@ -607,6 +624,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly instead of replaying CUDA graphs")
+    ap.add_argument("--radius", type=float, default=10.0, help="initial value of the learnable radii")
     ap.add_argument("--skip-roofline", action="store_true")
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--float-inputs", action="store_true",

@@ -131,12 +131,18 @@ __global__ void __launch_bounds__(kDpThreads) dp_step_kernel(const __grid_consta
   const int32_t step = *p.step_dev + 1;  // bumped by the launch that owns the tail, the last one of a step
   __syncthreads();
 
+  // time stamps of the phases (low 32 bits of %globaltimer, ns) for the host to read after a run: channel 1 (the launch
+  // at the end of the step) -> sync[9..13] = start, A passed, slice delivered, B passed, planes refreshed;
+  // channel 0 -> sync[2], sync[3] = start, end
+  const bool stamp = blockIdx.x == 0 && threadIdx.x == 0;
+  if (stamp) p.sync[p.channel ? 9 : 2] = (uint32_t)global_ns();
   // ---- phase A: announce that my gradients are complete, wait for every peer's announcement ----
   if (blockIdx.x == 0 && (int)threadIdx.x < world) {
     __threadfence_system();
     st_release_sys(p.comm.flags[threadIdx.x] + dp_slot(p.channel, 0, rank), e);
   }
   if (!dp_wait_peers(p, 0, e, &s_err)) return;  // nothing has been written yet
+  if (stamp && p.channel) p.sync[10] = (uint32_t)global_ns();
 
   // ---- reduce-scatter + Adam + all-gather on my slice of the range ----
   const double st = (double)step;
@@ -227,6 +233,7 @@ __global__ void __launch_bounds__(kDpThreads) dp_step_kernel(const __grid_consta
       st_release_sys(p.comm.flags[threadIdx.x] + dp_slot(p.channel, 1, rank), e);
     }
     if (threadIdx.x == 0) {
+      if (p.channel) p.sync[11] = (uint32_t)global_ns();
       sync[1] = 0u;  // ticket counter for the next launch of this channel
       sync[0] = e;
       if (p.do_tail) {
@@ -236,6 +243,7 @@ __global__ void __launch_bounds__(kDpThreads) dp_step_kernel(const __grid_consta
     }
   }
   if (!dp_wait_peers(p, 1, e, &s_err)) return;
+  if (stamp && p.channel) p.sync[12] = (uint32_t)global_ns();
 
   // ---- every slice of the range has arrived: refresh the split-bf16 planes of its GEMM weights locally ----
   for (int t = 0; t < p.n_targets; ++t) {
@@ -258,6 +266,7 @@ __global__ void __launch_bounds__(kDpThreads) dp_step_kernel(const __grid_consta
       }
     }
   }
+  if (stamp) p.sync[p.channel ? 13 : 3] = (uint32_t)global_ns();
 }
 
 }  // namespace mvae

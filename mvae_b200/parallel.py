@@ -181,6 +181,19 @@ def dp_error_word(optimizer) -> int:
     return 0 if optimizer._dp_sync is None else int(optimizer._dp_sync[8].item())
 
 
+def dp_phase_times(optimizer) -> dict:
+    """Durations (microseconds) of the phases of the LAST mvae_dp_step launches on this rank, from the %globaltimer
+    stamps the kernel leaves in its sync words: the launch at the end of the step (wait for the peers' gradients,
+    reduce-scatter + Adam + all-gather, wait for the peers' slices, weight-plane refresh) and the early launch."""
+    if optimizer._dp_sync is None:
+        return {}
+    w = [int(v) & 0xFFFFFFFF for v in optimizer._dp_sync.tolist()]
+    d = lambda a, b: ((w[b] - w[a]) & 0xFFFFFFFF) / 1e3  # noqa: E731
+    return {"late_wait_grads": d(9, 10), "late_reduce_adam_gather": d(10, 11), "late_wait_slices": d(11, 12),
+            "late_plane_refresh": d(12, 13), "late_total": d(9, 13), "early_total": d(2, 3),
+            "early_start_to_late_start": d(2, 9)}
+
+
 def replicas_identical(model, group=None) -> bool:
     """True when every rank holds bit-identical parameters and radii (collective call)."""
     if not (dist.is_initialized() and dist.get_world_size(group) > 1):

@@ -343,3 +343,138 @@ class OracleTrainer:
                 if k in g:
                     self.params[k] = self.params[k] - self.curvature_lr * np.asarray(g[k], dtype=self.params[k].dtype)
         return out
+
+
+# ------------------------------------------------------------------------------------------ convolutional VAE
+# ConvolutionalVAE (mt/mvae/models/conv_vae.py:28-79): three nn.Conv2d(k=4, s=2, p=1) + relu -> flatten (8192) ->
+# components -> nn.Linear(z, 2048) + relu -> view(128, 4, 4) -> three nn.ConvTranspose2d(k=4, s=2, p=1) (relu between).
+# The layer arithmetic is torch's (a dependency of the reference, not code under /root/reference): restated here from
+# its documented definition and pinned by tests/golden/conv_*.npz, which the reference's own model produced.
+def _im2col_k4s2p1(x):
+    """x [B, C, H, W] -> cols [B, H/2, W/2, C, 4, 4]: cols[b,oy,ox,c,ky,kx] = xpad[b,c,2oy+ky,2ox+kx] (pad 1)."""
+    B, C, H, W = x.shape
+    OH, OW = H // 2, W // 2
+    xp = np.zeros((B, C, H + 2, W + 2), dtype=x.dtype)
+    xp[:, :, 1:-1, 1:-1] = x
+    cols = np.empty((B, OH, OW, C, 4, 4), dtype=x.dtype)
+    for ky in range(4):
+        for kx in range(4):
+            cols[:, :, :, :, ky, kx] = xp[:, :, ky:ky + 2 * OH:2, kx:kx + 2 * OW:2].transpose(0, 2, 3, 1)
+    return cols
+
+
+def _col2im_k4s2p1(cols):
+    """Adjoint of _im2col_k4s2p1: cols [B, OH, OW, C, 4, 4] -> x [B, C, 2 OH, 2 OW] (scatter-add)."""
+    B, OH, OW, C = cols.shape[:4]
+    xp = np.zeros((B, C, 2 * OH + 2, 2 * OW + 2), dtype=cols.dtype)
+    for ky in range(4):
+        for kx in range(4):
+            xp[:, :, ky:ky + 2 * OH:2, kx:kx + 2 * OW:2] += cols[:, :, :, :, ky, kx].transpose(0, 3, 1, 2)
+    return xp[:, :, 1:-1, 1:-1]
+
+
+def conv2d_k4s2p1(x, w, b):
+    """torch.nn.Conv2d(Ci, Co, 4, 2, 1): x [B,Ci,H,W], w [Co,Ci,4,4] -> [B,Co,H/2,W/2]."""
+    B, Ci, H, W = x.shape
+    Co = w.shape[0]
+    cols = _im2col_k4s2p1(x).reshape(B * (H // 2) * (W // 2), Ci * 16)
+    y = cols @ w.reshape(Co, Ci * 16).T + b
+    return y.reshape(B, H // 2, W // 2, Co).transpose(0, 3, 1, 2)
+
+
+def conv2d_k4s2p1_bwd(x, w, gy):
+    B, Ci, H, W = x.shape
+    Co = w.shape[0]
+    OH, OW = H // 2, W // 2
+    cols = _im2col_k4s2p1(x).reshape(B * OH * OW, Ci * 16)
+    g = gy.transpose(0, 2, 3, 1).reshape(B * OH * OW, Co)
+    gw = (g.T @ cols).reshape(w.shape)
+    gx = _col2im_k4s2p1((g @ w.reshape(Co, Ci * 16)).reshape(B, OH, OW, Ci, 4, 4))
+    return gx, gw, g.sum(0)
+
+
+def convT2d_k4s2p1(x, w, b):
+    """torch.nn.ConvTranspose2d(Ci, Co, 4, 2, 1): x [B,Ci,H,W], w [Ci,Co,4,4] -> [B,Co,2H,2W]:
+    out[b,co,2iy-1+ky,2ix-1+kx] += x[b,ci,iy,ix] w[ci,co,ky,kx]."""
+    B, Ci, H, W = x.shape
+    Co = w.shape[1]
+    xm = x.transpose(0, 2, 3, 1).reshape(B * H * W, Ci)
+    cols = (xm @ w.reshape(Ci, Co * 16)).reshape(B, H, W, Co, 4, 4)
+    return _col2im_k4s2p1(cols) + b[None, :, None, None]
+
+
+def convT2d_k4s2p1_bwd(x, w, gy):
+    B, Ci, H, W = x.shape
+    Co = w.shape[1]
+    xm = x.transpose(0, 2, 3, 1).reshape(B * H * W, Ci)
+    gcols = _im2col_k4s2p1(gy).reshape(B * H * W, Co * 16)
+    gx = (gcols @ w.reshape(Ci, Co * 16).T).reshape(B, H, W, Ci).transpose(0, 3, 1, 2)
+    gw = (xm.T @ gcols).reshape(w.shape)
+    return gx, gw, gy.sum((0, 2, 3))
+
+
+class OracleConvVAE(OracleVAE):
+    """ConvolutionalVAE (conv_vae.py:28-79) + the same latent path / ELBO / backward as OracleVAE.  Inputs are
+    [B, 3072] rows in (c, y, x) order (conv_vae.py:61), h_dim = 8192 (the flattened 512 x 4 x 4 encoder output)."""
+
+    IMG = (3, 32, 32)
+
+    def __init__(self, sig, recon_kind="bce", scalar_parametrization=False):
+        super().__init__(sig, 3072, 8192, recon_kind, scalar_parametrization)
+
+    def step(self, params, x, eps, beta=1.0, backward=True):
+        p = params
+        B = x.shape[0]
+        R = self.radii(p, x.dtype)
+        Wh, bh = self.heads_matrix(p)
+        a0 = x.reshape((B,) + self.IMG)
+        pre, act = [], [a0]
+        for nm in ("e0", "e1", "e2"):                                            # conv_vae.py:62-64
+            pre.append(conv2d_k4s2p1(act[-1], p[nm + ".weight"], p[nm + ".bias"]))
+            act.append(np.maximum(pre[-1], 0))
+        h = act[-1].reshape(B, -1)                                               # :65 flatten (c, y, x)
+        ml = linear(h, Wh, bh)
+        f = pm_forward(self.desc, ml, eps, R, want=("z", "kl", "mu", "sigma"))
+        dd_pre = linear(f["z"], p["d0.weight"], p["d0.bias"])                    # :72
+        dact = [np.maximum(dd_pre, 0).reshape(B, 128, 4, 4)]                     # :73
+        dpre = []
+        for nm in ("d1", "d2"):                                                  # :74-75
+            dpre.append(convT2d_k4s2p1(dact[-1], p[nm + ".weight"], p[nm + ".bias"]))
+            dact.append(np.maximum(dpre[-1], 0))
+        logits = convT2d_k4s2p1(dact[-1], p["d3.weight"], p["d3.bias"]).reshape(B, -1)   # :76-78
+        bce, glogits = recon(self.recon_kind, logits, x, want_grad=backward)
+        stats = elbo(bce, f["kl"], beta)
+        out = {"h": h, "ml": ml, "z": f["z"], "kl": f["kl"], "mu": f["mu"], "sigma": f["sigma"], "logits": logits,
+               "bce": bce, "bce_sum": stats[0], "kl_sum": stats[1], "elbo": stats[2], "kl_comp": stats[3:]}
+        if not backward:
+            return out
+        g = {}
+        gy = glogits.reshape((B,) + self.IMG)
+        gy, g["d3.weight"], g["d3.bias"] = convT2d_k4s2p1_bwd(dact[2], p["d3.weight"], gy)
+        for i, nm in ((1, "d2"), (0, "d1")):
+            gy = gy * (dact[i + 1] > 0)
+            gy, g[nm + ".weight"], g[nm + ".bias"] = convT2d_k4s2p1_bwd(dact[i], p[nm + ".weight"], gy)
+        gdd = gy.reshape(B, -1) * (dd_pre > 0)
+        g["d0.weight"], g["d0.bias"] = gdd.T @ f["z"], gdd.sum(0)
+        gz = gdd @ p["d0.weight"]
+        gml, gR = pm_backward(self.desc, ml, eps, R, gz, None, beta)
+        gWh, gbh = gml.T @ h, gml.sum(0)
+        row = 0
+        for i in range(self.C):
+            c = self.desc.comp[i]
+            g[f"components.{i}.fc_mean.weight"], g[f"components.{i}.fc_mean.bias"] = gWh[row:row + c.n], gbh[row:row + c.n]
+            row += c.n
+            g[f"components.{i}.fc_logvar.weight"] = gWh[row:row + c.l_n]
+            g[f"components.{i}.fc_logvar.bias"] = gbh[row:row + c.l_n]
+            row += c.l_n
+            for nm in ("_nradius", "_pradius", "_curvature"):
+                if f"components.{i}.{nm}" in p:
+                    g[f"components.{i}.{nm}"] = np.asarray(gR[i])
+        gy = ((gml @ Wh) * (h > 0)).reshape(B, 512, 4, 4)
+        for i, nm in ((2, "e2"), (1, "e1"), (0, "e0")):
+            gy, g[nm + ".weight"], g[nm + ".bias"] = conv2d_k4s2p1_bwd(act[i], p[nm + ".weight"], gy)
+            if i > 0:
+                gy = gy * (act[i] > 0)
+        out["grads"] = g
+        out["gz"], out["gml"] = gz, gml
+        return out

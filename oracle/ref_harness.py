@@ -100,14 +100,18 @@ class _Dataset:
         self.ds = BCE() if kind == "bce" else NLL()
 
 
-def build_model(model_sig, in_dim, h_dim, fixed_curvature, scalar_parametrization, recon, seed, dtype):
+def build_model(model_sig, in_dim, h_dim, fixed_curvature, scalar_parametrization, recon, seed, dtype,
+                architecture="ff"):
+    """architecture "ff": FeedForwardVAE (ffnn_vae.py:27-60); "conv": ConvolutionalVAE (conv_vae.py:28-79; in_dim 3072,
+    h_dim 8192 are fixed by its layers)."""
     mt = load_reference()
     from mt.mvae import utils
-    from mt.mvae.models import FeedForwardVAE
+    from mt.mvae.models import ConvolutionalVAE, FeedForwardVAE
     with default_dtype(dtype):
         torch.manual_seed(seed)
         comps = utils.parse_components(model_sig, fixed_curvature)
-        model = FeedForwardVAE(h_dim, comps, _Dataset(mt, recon, in_dim).ds, scalar_parametrization)
+        cls = ConvolutionalVAE if architecture == "conv" else FeedForwardVAE
+        model = cls(h_dim, comps, _Dataset(mt, recon, in_dim).ds, scalar_parametrization)
         return model.to(torch.device("cpu")).to(dtype)
 
 

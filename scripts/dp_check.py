@@ -34,7 +34,7 @@ def gather_rows(t):
     return torch.cat(out, 0)
 
 
-def run_case(sig, B, D, H, mode):
+def run_case(sig, B, D, H, mode, radius=1.0):
     os.environ["MVAE_DP_OVERLAP"] = "1" if mode in ("p2p_overlap", "p2p_overlap_graph") else "0"
     torch.manual_seed(0)
     model = vae.FusedFeedForwardVAE(H, components.parse_components(sig, False),
@@ -45,6 +45,11 @@ def run_case(sig, B, D, H, mode):
         parallel.attach(model)
     else:
         assert parallel.attach_p2p(model, opt), "peer mapping failed"
+    with torch.no_grad():
+        for c in model.components:   # wide spheres start at R = 10 like the reference's schedule (train.py:189-194):
+            for nm in ("_nradius", "_pradius"):   # see tests/test_gpu_timed_path.py on conditioning at R = 1
+                if hasattr(c, nm):
+                    getattr(c, nm).fill_(radius)
     parallel.broadcast_parameters(model)
     if any(hasattr(c, "_curvature") for c in model.components):  # 'u': curvatures on both sides of zero
         with torch.no_grad():
@@ -101,9 +106,9 @@ def run_case(sig, B, D, H, mode):
 
 
 for mode in ("nccl", "p2p", "p2p_overlap", "p2p_overlap_graph"):
-    run_case("h2,s2,e2", 1024, 784, 400, mode)
-run_case("h6,h6,s6,s6,e6", 512, 784, 400, "p2p_overlap_graph")   # wide product: latent dense layers on the tensor cores
-run_case("u2,u2,u2,e2", 512, 784, 64, "p2p_overlap_graph")      # clip of the curvature gradients inside the kernel
+    run_case("h2,s2,e2", 2048, 784, 400, mode)
+run_case("h6,h6,s6,s6,e6", 2048, 784, 400, "p2p_overlap_graph", radius=10.0)   # wide product: latent dense layers on the tensor cores
+run_case("u2,u2,u2,e2", 2048, 784, 64, "p2p_overlap_graph")      # clip of the curvature gradients inside the kernel
 if rank == 0:
     print("dp_check ok", flush=True)
 dist.destroy_process_group()

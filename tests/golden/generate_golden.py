@@ -84,6 +84,47 @@ def gen_model(name, sig, in_dim, h_dim, B, recon, fixed_curvature, radius, scala
     print("model", name, sig, "elbo", float(out["elbo"]))
 
 
+CONV_SUBSAMPLE = 1024  # gradient entries kept per parameter tensor of the conv fixture (evenly strided)
+
+
+def conv_stride(numel):
+    return max(1, numel // CONV_SUBSAMPLE)
+
+
+def gen_conv(name, sig, B, radius, seed=41, beta=1.0):
+    """ConvolutionalVAE (conv_vae.py:28-79; BASELINE cfg5: CIFAR-shaped 3 x 32 x 32 inputs, BCE on real-valued targets,
+    image_reconstruction.py:142-143).  The model has 2.1 M parameters: they are NOT stored — the fixture keeps the seed
+    (torch's default initialisation is a deterministic function of it; tests rebuild the same parameters and check a
+    digest) — and of every gradient tensor an evenly strided subsample plus its norms."""
+    model = rh.build_model(sig, 3072, 8192, False, False, "bce", seed, torch.float64, architecture="conv")
+    for c in model.components:
+        for pn in ("_nradius", "_pradius"):
+            if hasattr(c, pn):
+                getattr(c, pn).data.fill_(radius)
+    g = torch.Generator().manual_seed(seed + 1)
+    x = torch.rand(B, 3072, generator=g, dtype=torch.float64)
+    eps = rh.draw_eps(model, B, seed + 2, torch.float64)
+    res = rh.ref_model_step(model, x, eps, beta)
+    out = {k: v for k, v in res.items() if not k.startswith(("param.", "grad.")) and k not in ("h", "m", "l")}
+    for k, v in res.items():
+        if k.startswith("param."):
+            flat = v.reshape(-1)
+            out["pdigest." + k[6:]] = np.asarray([flat.sum(), np.abs(flat).sum(), flat[0], flat[-1]])
+        if k.startswith("grad."):
+            flat = v.reshape(-1)
+            out["gsub." + k[5:]] = flat[::conv_stride(flat.size)].copy()
+            out["gnorm." + k[5:]] = np.asarray([np.linalg.norm(flat), np.abs(flat).max()])
+    meta = {"sig": sig, "in_dim": 3072, "h_dim": 8192, "recon": "bce", "fixed_curvature": False, "seed": seed,
+            "scalar_parametrization": False, "beta": beta, "radius": radius, "subsample": CONV_SUBSAMPLE}
+    np.savez_compressed(os.path.join(HERE, f"conv_{name}.npz"), meta=json.dumps(meta), **out)
+    print("conv", name, sig, "elbo", float(out["elbo"]), "bytes", os.path.getsize(os.path.join(HERE, f"conv_{name}.npz")))
+
+
+def gen_convs():
+    gen_conv("h2_s2_e2", "h2,s2,e2", B=6, radius=1.0)
+    gen_conv("p2_d2_h3", "p2,d2,h3", B=4, radius=1.5, seed=43, beta=0.7)
+
+
 def gen_loglik(name, sig, in_dim, h_dim, B, n, recon, radius, scalar=False, seed=11):
     out = {}
     for dtype, sfx in ((torch.float64, ""), (torch.float32, "_f32")):
@@ -252,6 +293,9 @@ if __name__ == "__main__":
     if "--only-d" in sys.argv:
         gen_ds()
         sys.exit(0)
+    if "--only-conv" in sys.argv:  # added later: leaves the other committed fixtures byte-identical
+        gen_convs()
+        sys.exit(0)
     if "--only-loglik" in sys.argv:  # added later: leaves the other committed fixtures byte-identical
         gen_logliks()
         sys.exit(0)
@@ -259,6 +303,7 @@ if __name__ == "__main__":
     gen_logliks()
     gen_ds()
     gen_us()
+    gen_convs()
     gen_pm("h2_s2_e2_R1", "h2,s2,e2", [1.0, 1.0, 0.0])
     gen_pm("cfg3_R10", "h6,h6,s6,s6,e6", [10.0, 10.0, 10.0, 10.0, 0.0], seed=1)
     gen_pm("cfg3_Rmixed", "h6,h6,s6,s6,e6", [1.5, 0.7, 2.0, 1.0, 0.0], seed=2, scale_m=0.6)

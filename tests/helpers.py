@@ -57,3 +57,50 @@ def normwise(a, b):
 
 def radii_array(radii, dtype):
     return np.asarray([r if r else 1.0 for r in radii], dtype=dtype)
+
+
+def conv_golden_names():
+    return sorted(f[:-4] for f in os.listdir(GOLDEN) if f.startswith("conv_") and f.endswith(".npz"))
+
+
+def conv_params_from_seed(sig, seed, radius, fixed_curvature=False):
+    """The parameters the reference's ConvolutionalVAE(8192, parse_components(sig), ...) gets under
+    torch.manual_seed(seed) with float64 as default dtype (how tests/golden/generate_golden.py::gen_conv built it):
+    construction order of vae.py:55-57 (components) then conv_vae.py:47-55 (e0 e1 e2 d0 d1 d2 d3).  The conv fixtures
+    keep only a digest of the 2.1 M parameters; callers check it (pdigest.*)."""
+    import torch
+    from mvae_b200 import components
+    old = torch.get_default_dtype()
+    torch.set_default_dtype(torch.float64)
+    try:
+        torch.manual_seed(seed)
+        comps = components.parse_components(sig, fixed_curvature)
+        params = {}
+        for i, c in enumerate(comps):
+            c.init_layers(8192, scalar_parametrization=False)
+        total_z = sum(c.dim for c in comps)
+        layers = [("e0", torch.nn.Conv2d(3, 64, 4, 2, 1)), ("e1", torch.nn.Conv2d(64, 128, 4, 2, 1)),
+                  ("e2", torch.nn.Conv2d(128, 512, 4, 2, 1)), ("d0", torch.nn.Linear(total_z, 2048)),
+                  ("d1", torch.nn.ConvTranspose2d(128, 256, 4, 2, 1)), ("d2", torch.nn.ConvTranspose2d(256, 64, 4, 2, 1)),
+                  ("d3", torch.nn.ConvTranspose2d(64, 3, 4, 2, 1))]
+        for i, c in enumerate(comps):
+            name, rp = c.radius_parameter()
+            if rp is not None:
+                params[f"components.{i}.{name}"] = np.asarray(radius if name != "_curvature" else float(rp.detach()))
+            for nm in ("fc_mean", "fc_logvar"):
+                params[f"components.{i}.{nm}.weight"] = getattr(c, nm).weight.detach().numpy().copy()
+                params[f"components.{i}.{nm}.bias"] = getattr(c, nm).bias.detach().numpy().copy()
+        for nm, layer in layers:
+            params[nm + ".weight"] = layer.weight.detach().numpy().copy()
+            params[nm + ".bias"] = layer.bias.detach().numpy().copy()
+        return params
+    finally:
+        torch.set_default_dtype(old)
+
+
+def check_conv_digest(params, golden):
+    for k, v in params.items():
+        flat = np.asarray(v, dtype=np.float64).reshape(-1)
+        want = golden["pdigest." + k]
+        got = np.asarray([flat.sum(), np.abs(flat).sum(), flat[0], flat[-1]])
+        assert np.allclose(got, want, rtol=1e-12, atol=1e-12), (k, got, want)

@@ -221,3 +221,22 @@ def test_cpu_baseline_step_matches_oracle(oracle):
     w0 = cpu.p["fc_e0.W"].clone()
     cpu.step(torch.from_numpy(x), torch.from_numpy(eps), beta=0.9)
     assert 1e-4 < float((cpu.p["fc_e0.W"] - w0).abs().max()) < 2e-3 and cpu.R[0] != np.float32(1.3)
+
+
+@pytest.mark.parametrize("name", __import__("helpers").conv_golden_names())
+def test_conv_oracle_matches_reference_golden(oracle, name):
+    """oracle.OracleConvVAE (numpy restatement of ConvolutionalVAE, conv_vae.py:28-79, + the latent path) against the
+    run of the reference's own model: forward tensors, statistics and (subsampled) autograd gradients at 1e-9."""
+    from helpers import check_conv_digest, conv_params_from_seed
+    g, meta = load_golden(name)
+    params = conv_params_from_seed(meta["sig"], meta["seed"], meta["radius"])
+    check_conv_digest(params, g)
+    out = oracle.OracleConvVAE(meta["sig"]).step(params, g["x"], g["eps"], beta=meta["beta"])
+    for k in ("z", "mu", "sigma", "kl", "logits", "bce"):
+        assert normwise(out[k], g[k]) < 1e-9, k
+    assert abs(out["elbo"] - g["elbo"]) < 1e-10 * abs(g["elbo"])
+    stride = lambda n: max(1, n // meta["subsample"])  # noqa: E731
+    for k in params:
+        got = np.asarray(out["grads"][k], dtype=np.float64).reshape(-1)
+        assert normwise(got[::stride(got.size)], g["gsub." + k]) < 1e-8, k
+        assert abs(np.linalg.norm(got) - g["gnorm." + k][0]) < 1e-8 * max(g["gnorm." + k][0], 1e-30), k
