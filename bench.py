@@ -429,6 +429,14 @@ def run_ours(args):
         total_ms = float(t.item())
     ms = total_ms / args.steps
     clocks = sampler.stop() if rank == 0 else None
+    # phases of the LAST timed step's exchange kernel on every rank (steady state), slowest rank per phase
+    phases = {}
+    if world > 1 and not collective.startswith("NCCL"):
+        ph = parallel.dp_phase_times(opt)
+        keys = sorted(ph)
+        t = torch.tensor([ph[k] for k in keys], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        phases = {k: round(float(v), 2) for k, v in zip(keys, t.tolist())}
     stats_vec = model._stats.clone()
 
     # ---------------- e2e: public API with host buffers (H2D of x, D2H of the statistics, every step) ----------------
@@ -499,12 +507,6 @@ def run_ours(args):
         if local is not None:
             dist.all_reduce(local, op=dist.ReduceOp.SUM)
             rel = abs(bs_chk.elbo - float(local[2].item())) / abs(float(local[2].item()))
-        phases = parallel.dp_phase_times(opt) if not collective.startswith("NCCL") else {}
-        if phases:  # of the last step, on the slowest rank per phase
-            keys = sorted(phases)
-            t = torch.tensor([phases[k] for k in keys], device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            phases = {k: round(float(v), 2) for k, v in zip(keys, t.tolist())}
         dp_check = {"replicas_identical": bool(identical and parallel.replicas_identical(model)),
                     "phases_us_max_over_ranks": phases,
                     "elbo_vs_nccl_rel": rel, "dp_error_word": parallel.dp_error_word(opt),

@@ -288,6 +288,36 @@ int mvae_recon_loss(int32_t kind, int64_t B, int32_t D, const float* logits, con
  * elbo = sum_b(-bce_b - beta * sum_c kl_bc).  Warp-shuffle + block reduce; `out` [3+C] is overwritten. */
 int mvae_elbo_reduce(int64_t B, int32_t C, const float* bce, const float* kl, float beta, float* out, void* stream);
 
+/* ------------------------------------------------------------------- convolutional encoder / decoder */
+/* ConvolutionalVAE (mt/mvae/models/conv_vae.py:28-79): nn.Conv2d / nn.ConvTranspose2d with kernel 4, stride 2,
+ * padding 1 (:47-55) run through mvae_gemm with the filter taps unrolled into the contraction dimension.
+ * Activations are channels-last: [B, H, W, C] = the row-major matrix [B*H*W, C] as split-bf16 planes.
+ *   Conv2d           y[B*OH*OW, Co] = im2col(x)[B*OH*OW, 16 Ci] . W[Co, (ky,kx,ci)]^T      (+ bias, relu in the GEMM)
+ *   ConvTranspose2d  y = col2im( x[B*H*W, Ci] . W[Ci, (ky,kx,co)] ) + bias, relu
+ * and each one's input gradient is the other's data movement around the same GEMM.
+ *
+ * mvae_conv_im2col: dst[(b,oy,ox), (ky,kx,c)] = src[(b, 2oy-1+ky, 2ox-1+kx), c] (0 outside the image), plane by plane
+ *   (dst->planes <= src->planes); ones_col != 0 additionally writes 1.0 into column 16 C (dst->ld must leave room):
+ *   read as a weight-gradient operand it yields the bias gradient.  src [B*H*W, C], dst [B*(H/2)*(W/2), 16 C].
+ * mvae_conv_col2im: out[(b,oy,ox), c] = bias[c] + sum over the <= 4 (ky,kx) with oy = 2iy-1+ky, ox = 2ix-1+kx of
+ *   cols[(b,iy,ix), (ky,kx,c)]; act 0 none / 1 relu / 2 zero where mask (plane 0, [B*2H*2W, C]) <= 0; written as
+ *   planes (out_planes) and / or fp32 (out_f32, row stride ld_out).  cols fp32 [B*H*W, ld_cols >= 16 C].
+ * mvae_permute_sc: [B, C*S] rows in (c, s) order (the reference's x.view(bs, -1) of a [B, C, H, W] tensor, S = H*W,
+ *   conv_vae.py:61,65,73,77) <-> [B*S, C] channels-last rows; elements of 2 (planes: `planes` of them, strides in
+ *   elements) or 4 bytes; to_nhwc selects the direction; src_ld / dst_ld are row strides in elements.
+ * mvae_colsum: out[c] += sum_m src[m, c] (src fp32 with row stride ld, or the sum of src_planes' planes): bias gradients
+ *   of the transposed convolutions.  C <= 1024; out is accumulated into (the caller zeroes it). */
+int mvae_conv_im2col(const mvae_planes* src, int32_t B, int32_t H, int32_t W, int32_t C, const mvae_planes* dst,
+                     int32_t ones_col, void* stream);
+int mvae_conv_col2im(const float* cols, int64_t ld_cols, int32_t B, int32_t H, int32_t W, int32_t C, const float* bias,
+                     int32_t act, const mvae_planes* mask, const mvae_planes* out_planes, float* out_f32,
+                     int64_t ld_out, void* stream);
+int mvae_permute_sc(int32_t elem_bytes, const void* src, int64_t src_ld, int64_t src_plane_stride, void* dst,
+                    int64_t dst_ld, int64_t dst_plane_stride, int32_t planes, int64_t B, int32_t S, int32_t C,
+                    int32_t to_nhwc, void* stream);
+int mvae_colsum(const float* src_f32, const mvae_planes* src_planes, int64_t M, int32_t C, int64_t ld, float* out,
+                void* stream);
+
 /* ------------------------------------------------------------------------------------ input pipeline */
 /* Dynamic binarisation of image batches on the device.  The reference does it per sample on the CPU inside its
  * DataLoader (ImageDynamicBinarization, mt/data/image_reconstruction.py:37-53) and ships float batches; here the batch

@@ -108,6 +108,11 @@ PROTOTYPES = {
     "mvae_opt_step_fused": (ctypes.c_int, [_i64, _vp, _vp, _vp, _vp, _f32, _f32, _f32, _f32, _vp, _vp, _vp, _vp, _vp,
                                            _f32, _i32, _i32, ctypes.POINTER(_i64), ctypes.POINTER(_i32),
                                            ctypes.POINTER(Planes), _vp]),
+    "mvae_conv_im2col": (ctypes.c_int, [ctypes.POINTER(Planes), _i32, _i32, _i32, _i32, ctypes.POINTER(Planes), _i32, _vp]),
+    "mvae_conv_col2im": (ctypes.c_int, [_vp, _i64, _i32, _i32, _i32, _i32, _vp, _i32, ctypes.POINTER(Planes),
+                                        ctypes.POINTER(Planes), _vp, _i64, _vp]),
+    "mvae_permute_sc": (ctypes.c_int, [_i32, _vp, _i64, _i64, _vp, _i64, _i64, _i32, _i64, _i32, _i32, _i32, _vp]),
+    "mvae_colsum": (ctypes.c_int, [_vp, ctypes.POINTER(Planes), _i64, _i32, _i64, _vp, _vp]),
     "mvae_step_prologue": (ctypes.c_int, [_vp, _i64, ctypes.c_uint64, _vp, _i32, ctypes.POINTER(ctypes.c_void_p),
                                           ctypes.POINTER(_i64), _vp]),
     "mvae_counter_add": (ctypes.c_int, [_vp, ctypes.c_uint64, _vp]),

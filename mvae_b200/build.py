@@ -15,7 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(CSRC, "_build")
 LIB = os.path.join(HERE, "libmvae_b200.so")
-SOURCES = ["api.cu", "pm_kernels.cu", "pm_fwd.cu", "pm_bwd.cu", "manifold_ops.cu", "elbo_kernels.cu", "skinny_kernels.cu", "latent_fwd.cu", "latent_bwd.cu", "dp_step.cu", "iwae_kernels.cu", "input_kernels.cu", "gemm_sm100.cu"]
+SOURCES = ["api.cu", "pm_kernels.cu", "pm_fwd.cu", "pm_bwd.cu", "manifold_ops.cu", "elbo_kernels.cu", "skinny_kernels.cu", "latent_fwd.cu", "latent_bwd.cu", "dp_step.cu", "iwae_kernels.cu", "input_kernels.cu", "conv_kernels.cu", "gemm_sm100.cu"]
 HEADERS = ["mvae_common.cuh", "manifold_math.cuh", "pm_math.cuh", "pm_item.cuh", "latent_impl.cuh", "pm_params.cuh", "pm_kernels_impl.cuh", os.path.join("..", "..", "include", "mvae_b200.h")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",

@@ -16,13 +16,15 @@
 //               rank r owns the slice [r n/N, (r+1) n/N) of the range: it sums that slice of the gradient over
 //               all ranks with 128-bit loads from the peers' buckets (NVSwitch gives every peer full bandwidth),
 //               applies Adam with ITS slice of the moments (the optimizer state is sharded N ways), and
-//   all-gather  stores the new parameter values straight into every peer's parameter buffer;
+//               writes the new values into ITS OWN parameter buffer;
 //               the 3+2C statistics / radius-gradient tail is summed redundantly by every rank (same order, so the
 //               replicas stay bit-identical), the "curvature" gradients are clipped (vae.py:161-163) and the radii take
 //               their SGD step locally
-//   phase B     the LAST CTA to finish (atomic ticket) tells every rank, itself included, "my slice is in your buffer
-//               and I am done reading your bucket"; every CTA polls those flags, then refreshes its share of the
-//               split-bf16 planes of the GEMM weights from the gathered parameters.
+//   phase B     the LAST CTA to finish (atomic ticket) tells every rank, itself included, "my slice is final and I am
+//               done reading your bucket"; every CTA polls those flags, then
+//   all-gather  PULLS the peers' slices with 128-bit peer loads into its own buffer (no remote stores anywhere: a load
+//               completes when its data arrives, a pushed store would need a system-scope fence that waits for the
+//               remote writes to drain) and refreshes the split-bf16 planes of the GEMM weights on the way.
 //
 // Everything the kernel needs to know about the step (Adam step count, flag epoch) lives on the device, so the launches
 // are captured in the step's CUDA graph.  Waits are bounded (%globaltimer): a peer that never arrives makes the kernel
@@ -67,7 +69,7 @@ struct DpParams {
   uint32_t* sync;    // local: [4 ch + 0] epoch, [4 ch + 1] arrival ticket, [8] sticky error
   unsigned long long timeout_ns;
   int n_targets;     // weight matrices whose split-bf16 planes are refreshed after the all-gather
-  DpPlaneTarget t[4];
+  DpPlaneTarget t[8];
 };
 
 __device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
@@ -136,6 +138,27 @@ __global__ void __launch_bounds__(kDpThreads) dp_step_kernel(const __grid_consta
   // channel 0 -> sync[2], sync[3] = start, end
   const bool stamp = blockIdx.x == 0 && threadIdx.x == 0;
   if (stamp) p.sync[p.channel ? 9 : 2] = (uint32_t)global_ns();
+  // ---- everything that does not depend on the peers happens BEFORE the wait: bias corrections, and the first
+  //      (usually only) pass's moments and parameters, which nobody but this rank ever writes ----
+  const double st = (double)step;
+  const float step_size = (float)((double)p.lr / (1.0 - pow((double)p.b1, st)));
+  const float inv_bc2_sqrt = (float)(1.0 / sqrt(1.0 - pow((double)p.b2, st)));
+  const float w1 = 1.f - p.b1, w2 = 1.f - p.b2;
+  const int64_t per = (p.hi4 - p.lo4 + world - 1) / world;
+  const int64_t lo = p.lo4 + rank * per, hi = min(p.hi4, lo + per);
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const int64_t first = lo + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  float4 m0[2], v0[2], p0[2];
+#pragma unroll
+  for (int u = 0; u < 2; ++u) {
+    const int64_t i = first + u * stride;
+    if (i < hi) {
+      m0[u] = reinterpret_cast<const float4*>(p.m)[i];
+      v0[u] = reinterpret_cast<const float4*>(p.v)[i];
+      p0[u] = reinterpret_cast<const float4*>(p.comm.flat[rank])[i];
+    }
+  }
+
   // ---- phase A: announce that my gradients are complete, wait for every peer's announcement ----
   if (blockIdx.x == 0 && (int)threadIdx.x < world) {
     __threadfence_system();
@@ -144,17 +167,10 @@ __global__ void __launch_bounds__(kDpThreads) dp_step_kernel(const __grid_consta
   if (!dp_wait_peers(p, 0, e, &s_err)) return;  // nothing has been written yet
   if (stamp && p.channel) p.sync[10] = (uint32_t)global_ns();
 
-  // ---- reduce-scatter + Adam + all-gather on my slice of the range ----
-  const double st = (double)step;
-  const float step_size = (float)((double)p.lr / (1.0 - pow((double)p.b1, st)));
-  const float inv_bc2_sqrt = (float)(1.0 / sqrt(1.0 - pow((double)p.b2, st)));
-  const float w1 = 1.f - p.b1, w2 = 1.f - p.b2;
-  const int64_t per = (p.hi4 - p.lo4 + world - 1) / world;
-  const int64_t lo = p.lo4 + rank * per, hi = min(p.hi4, lo + per);
+  // ---- reduce-scatter + Adam on my slice of the range: the new values go into MY parameter buffer only ----
   // Two float4 per thread and iteration: all 2 x world peer loads are in flight before the first is consumed (the
   // loop is latency bound: a peer load is a few microseconds over NVLink).
-  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t i0 = lo + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < hi; i0 += 2 * stride) {
+  for (int64_t i0 = first; i0 < hi; i0 += 2 * stride) {
     const int64_t idx[2] = {i0, i0 + stride};
     float4 t[2][MVAE_DP_MAX_RANKS];
 #pragma unroll
@@ -175,8 +191,14 @@ __global__ void __launch_bounds__(kDpThreads) dp_step_kernel(const __grid_consta
           g.z += t[u][r].z;
           g.w += t[u][r].w;
         }
-      float4 mi = reinterpret_cast<float4*>(p.m)[i], vi = reinterpret_cast<float4*>(p.v)[i];
-      float4 pi = reinterpret_cast<float4*>(p.comm.flat[rank])[i];
+      float4 mi, vi, pi;
+      if (i0 == first) {
+        mi = m0[u], vi = v0[u], pi = p0[u];
+      } else {
+        mi = reinterpret_cast<const float4*>(p.m)[i];
+        vi = reinterpret_cast<const float4*>(p.v)[i];
+        pi = reinterpret_cast<const float4*>(p.comm.flat[rank])[i];
+      }
 #define MVAE_ADAM1(c)                                       \
   mi.c = mi.c + (g.c - mi.c) * w1;                          \
   vi.c = vi.c * p.b2 + w2 * (g.c * g.c);                    \
@@ -185,9 +207,10 @@ __global__ void __launch_bounds__(kDpThreads) dp_step_kernel(const __grid_consta
 #undef MVAE_ADAM1
       reinterpret_cast<float4*>(p.m)[i] = mi;
       reinterpret_cast<float4*>(p.v)[i] = vi;
-      for (int r = 0; r < world; ++r) reinterpret_cast<float4*>(p.comm.flat[r])[i] = pi;
+      reinterpret_cast<float4*>(p.comm.flat[rank])[i] = pi;
     }
   }
+  if (stamp && p.channel) p.sync[14] = (uint32_t)global_ns();
   // ---- statistics / radius-gradient tail: every rank sums it (same order), clips, and steps its radii locally ----
   if (p.do_tail && blockIdx.x == gridDim.x - 1) {
     __shared__ float s_clip;
@@ -220,6 +243,7 @@ __global__ void __launch_bounds__(kDpThreads) dp_step_kernel(const __grid_consta
 
   // ---- phase B: the last CTA to get here tells every rank (this one included) that my slice has been delivered ----
   __threadfence_system();
+  if (stamp && p.channel) p.sync[15] = (uint32_t)global_ns();
   __syncthreads();
   if (threadIdx.x == 0) {
     const uint32_t ticket = atomicAdd(&sync[1], 1u);
@@ -245,13 +269,19 @@ __global__ void __launch_bounds__(kDpThreads) dp_step_kernel(const __grid_consta
   if (!dp_wait_peers(p, 1, e, &s_err)) return;
   if (stamp && p.channel) p.sync[12] = (uint32_t)global_ns();
 
-  // ---- every slice of the range has arrived: refresh the split-bf16 planes of its GEMM weights locally ----
-  for (int t = 0; t < p.n_targets; ++t) {
-    const DpPlaneTarget& tg = p.t[t];
-    const int64_t n4 = (tg.end - tg.begin) >> 2;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
-      const float4 w = ld_peer4(p.comm.flat[rank] + tg.begin + 4 * i);  // peers wrote it: not through L1
-      const int64_t rel = 4 * i;
+  // ---- all-gather by PULLING: every slice of the range is final in its owner's buffer; read the peers' slices over
+  //      NVLink (a load needs no fence — a pushed store would need a system-scope fence that waits for the remote
+  //      writes to drain: measured 8 us), keep a local copy, and refresh the split-bf16 planes of the GEMM weights ----
+  for (int64_t i = p.lo4 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < p.hi4; i += stride) {
+    int owner = (int)((i - p.lo4) / per);
+    owner = owner < world ? owner : world - 1;
+    const float4 w = ld_peer4(p.comm.flat[owner] + 4 * i);  // peers' (or my CTAs') fresh values: not through L1
+    if (owner != rank) reinterpret_cast<float4*>(p.comm.flat[rank])[i] = w;
+    const int64_t idx = 4 * i;
+    for (int t = 0; t < p.n_targets; ++t) {
+      const DpPlaneTarget& tg = p.t[t];
+      if (idx < tg.begin || idx >= tg.end) continue;
+      const int64_t rel = idx - tg.begin;
       const int64_t r = rel / tg.cols;
       const int c = (int)(rel - r * tg.cols);
       float v4[4] = {w.x, w.y, w.z, w.w};
@@ -264,6 +294,7 @@ __global__ void __launch_bounds__(kDpThreads) dp_step_kernel(const __grid_consta
         v4[2] -= __uint_as_float(u1 << 16);
         v4[3] -= __uint_as_float(u1 & 0xFFFF0000u);
       }
+      break;
     }
   }
   if (stamp) p.sync[p.channel ? 13 : 3] = (uint32_t)global_ns();
@@ -353,7 +384,7 @@ extern "C" int mvae_dp_step(const mvae_dp_comm* comm, const mvae_dp_step_args* a
   p.clip_max_norm = a->clip_max_norm;
   p.tail_out = a->tail_out;
   p.sync = a->sync_words;
-  if (a->n_targets < 0 || a->n_targets > 4 ||
+  if (a->n_targets < 0 || a->n_targets > 8 ||
       (a->n_targets > 0 && (!a->target_begin || !a->target_rows || !a->targets)))
     return MVAE_ERR_INVALID_ARGUMENT;
   p.n_targets = a->n_targets;
@@ -384,11 +415,12 @@ extern "C" int mvae_dp_step(const mvae_dp_comm* comm, const mvae_dp_step_args* a
   }
   p.timeout_ns = (unsigned long long)(timeout_s * 1e9);
   // The CTAs wait for each other (ticket in phase B), so all of them must be resident at once: at most one CTA per SM.
-  // Enough CTAs for one pass over my slice (two float4 per thread) and over the largest matrix to re-split.
+  // Enough CTAs for one pass over my slice (two float4 per thread) and two passes of the gather over the range.
   const int64_t per4 = (p.hi4 - p.lo4 + comm->world - 1) / comm->world;
   int64_t want = (per4 + 2 * kDpThreads - 1) / (2 * kDpThreads);
-  const int64_t want_refresh = (refresh4 + 2 * kDpThreads - 1) / (2 * kDpThreads);
-  if (want_refresh > want) want = want_refresh;
+  const int64_t want_gather = (p.hi4 - p.lo4 + 2 * kDpThreads - 1) / (2 * kDpThreads);
+  if (want_gather > want) want = want_gather;
+  (void)refresh4;
   int grid = (int)(want < 1 ? 1 : (want > di.sm_count ? di.sm_count : want));
   if (a->max_ctas > 0 && grid > a->max_ctas) grid = a->max_ctas;
   dp_step_kernel<<<grid, kDpThreads, 0, as_stream(stream)>>>(p);

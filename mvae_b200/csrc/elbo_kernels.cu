@@ -295,7 +295,7 @@ struct OptParams {
   float radius_lr;
   int C;
   int n_targets;
-  PlaneTarget t[4];
+  PlaneTarget t[8];
 };
 __global__ void __launch_bounds__(256) opt_fused_kernel(const __grid_constant__ OptParams q) {
   pdl_launch_dependents();
@@ -322,7 +322,7 @@ __global__ void __launch_bounds__(256) opt_fused_kernel(const __grid_constant__ 
     reinterpret_cast<float4*>(q.p)[i] = pi;
     const int64_t idx = 4 * i;
 #pragma unroll
-    for (int t = 0; t < 4; ++t)
+    for (int t = 0; t < 8; ++t)
       if (t < q.n_targets && idx >= q.t[t].begin && idx < q.t[t].end) {
         const int64_t rel = idx - q.t[t].begin;
         const int64_t r = rel / q.t[t].cols;
@@ -538,7 +538,7 @@ extern "C" int mvae_opt_step_fused(int64_t n, float* param, const float* grad, f
                                    const float* radius_mask, float radius_lr, int32_t C, int32_t n_targets,
                                    const int64_t* target_begin, const int32_t* target_rows,
                                    const mvae_planes* targets, void* stream) {
-  if (n < 0 || (n & 3) || !step_dev || !done_counter || n_targets < 0 || n_targets > 4 || C < 0)
+  if (n < 0 || (n & 3) || !step_dev || !done_counter || n_targets < 0 || n_targets > 8 || C < 0)
     return MVAE_ERR_INVALID_ARGUMENT;
   if (n > 0 && (!param || !grad || !exp_avg || !exp_avg_sq)) return MVAE_ERR_INVALID_ARGUMENT;
   if (!aligned16(param) || !aligned16(grad) || !aligned16(exp_avg) || !aligned16(exp_avg_sq)) return MVAE_ERR_ALIGNMENT;

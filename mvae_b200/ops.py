@@ -161,12 +161,16 @@ def wn_log_prob(manifold: int, n: int, loc, scale, z, radius):
 
 
 # ------------------------------------------------------------------------------------------ losses / optimizer
-def recon_loss(kind: str, logits, x, want_grad: bool = False):
-    """kind 'bce' | 'nll' -> (rowsum [B], glogits | None)  (mvae_recon_loss)."""
+def recon_loss(kind: str, logits, x, want_grad: bool = False, out: Optional[tuple] = None):
+    """kind 'bce' | 'nll' -> (rowsum [B], glogits | None)  (mvae_recon_loss).  out = (rowsum, glogits | None) writes
+    into the caller's buffers."""
     logits, x = _f32(logits, "logits"), _f32(x, "x")
     B, D = logits.shape
-    rs = torch.empty(B, device=logits.device)
-    g = torch.empty_like(logits) if want_grad else None
+    if out is not None:
+        rs, g = out
+    else:
+        rs = torch.empty(B, device=logits.device)
+        g = torch.empty_like(logits) if want_grad else None
     rc = L.lib().mvae_recon_loss(0 if kind == "bce" else 1, B, D, _ptr(logits), _ptr(x), _ptr(rs), _ptr(g), _stream())
     L.check(rc, "mvae_recon_loss")
     _LAUNCHES[0] += 1
@@ -205,6 +209,58 @@ def binarize(src_u8: torch.Tensor, x: Optional[torch.Tensor] = None, planes: Opt
     L.check(rc, "mvae_binarize")
     _LAUNCHES[0] += 1
     return x
+
+
+# ------------------------------------------------------------------------------------------ convolutions
+def conv_im2col(src: "PlaneBuf", B: int, H: int, W: int, C: int, dst: "PlaneBuf", ones_col: bool = False):
+    """4x4 / stride 2 / pad 1 patches of a channels-last plane buffer [B*H*W, C] -> [B*(H/2)*(W/2), 16 C] (mvae_conv_im2col)."""
+    ss, ds = src.struct(rows=B * H * W), dst.struct(rows=B * (H // 2) * (W // 2))
+    rc = L.lib().mvae_conv_im2col(ctypes.byref(ss), B, H, W, C, ctypes.byref(ds), int(ones_col), _stream())
+    L.check(rc, "mvae_conv_im2col")
+    _LAUNCHES[0] += 1
+
+
+def conv_col2im(cols: torch.Tensor, B: int, H: int, W: int, C: int, bias=None, act: int = 0,
+                mask: Optional["PlaneBuf"] = None, out_planes: Optional["PlaneBuf"] = None, out_f32=None):
+    """Adjoint gather of conv_im2col: fp32 tap columns [B*H*W, 16 C] -> [B*2H*2W, C] (+ bias, act 1 relu / 2 mask) as
+    planes and / or fp32 (mvae_conv_col2im)."""
+    cols = _f32(cols, "cols")
+    rows = B * H * W * 4
+    ms = mask.struct(rows=rows) if mask is not None else None
+    os_ = out_planes.struct(rows=rows) if out_planes is not None else None
+    rc = L.lib().mvae_conv_col2im(_ptr(cols), cols.stride(0), B, H, W, C, _ptr(bias), act,
+                                  ctypes.byref(ms) if ms is not None else None,
+                                  ctypes.byref(os_) if os_ is not None else None, _ptr(out_f32),
+                                  out_f32.stride(0) if out_f32 is not None else 0, _stream())
+    L.check(rc, "mvae_conv_col2im")
+    _LAUNCHES[0] += 1
+
+
+def permute_sc(src, dst, B: int, S: int, C: int, to_nhwc: bool):
+    """[B, C*S] rows in (c, s) order <-> channels-last [B*S, C] rows (mvae_permute_sc); src / dst: float32 tensors or
+    PlaneBufs (all of the destination's planes are moved)."""
+    if isinstance(src, PlaneBuf):
+        assert isinstance(dst, PlaneBuf) and dst.planes <= src.planes
+        rc = L.lib().mvae_permute_sc(2, src.t.data_ptr(), src.ld, src.rows * src.ld, dst.t.data_ptr(), dst.ld,
+                                     dst.rows * dst.ld, dst.planes, B, S, C, int(to_nhwc), _stream())
+    else:
+        src, dst = _f32(src, "src"), _f32(dst, "dst")
+        rc = L.lib().mvae_permute_sc(4, src.data_ptr(), src.stride(0), 0, dst.data_ptr(), dst.stride(0), 0, 1, B, S, C,
+                                     int(to_nhwc), _stream())
+    L.check(rc, "mvae_permute_sc")
+    _LAUNCHES[0] += 1
+
+
+def colsum(src, M: int, C: int, out: torch.Tensor):
+    """out[c] += sum_m src[m, c] for a float32 matrix or a PlaneBuf (mvae_colsum)."""
+    if isinstance(src, PlaneBuf):
+        ps = src.struct(rows=M)
+        rc = L.lib().mvae_colsum(None, ctypes.byref(ps), M, C, 0, _ptr(out), _stream())
+    else:
+        src = _f32(src, "src")
+        rc = L.lib().mvae_colsum(_ptr(src), None, M, C, src.stride(0), _ptr(out), _stream())
+    L.check(rc, "mvae_colsum")
+    _LAUNCHES[0] += 1
 
 
 def step_prologue(eps: Optional[torch.Tensor], seed: int, counter_dev: Optional[torch.Tensor], zero=()):

@@ -189,7 +189,8 @@ def dp_phase_times(optimizer) -> dict:
         return {}
     w = [int(v) & 0xFFFFFFFF for v in optimizer._dp_sync.tolist()]
     d = lambda a, b: ((w[b] - w[a]) & 0xFFFFFFFF) / 1e3  # noqa: E731
-    return {"late_wait_grads": d(9, 10), "late_reduce_adam_gather": d(10, 11), "late_wait_slices": d(11, 12),
+    return {"late_wait_grads": d(9, 10), "late_reduce_adam_gather": d(10, 11), "late_cta0_loads_adam_stores": d(10, 14),
+            "late_cta0_fence_sys": d(14, 15), "late_wait_slices": d(11, 12),
             "late_plane_refresh": d(12, 13), "late_total": d(9, 13), "early_total": d(2, 3),
             "early_start_to_late_start": d(2, 9)}
 

@@ -302,9 +302,7 @@ class FusedFeedForwardVAE(nn.Module):
         # construction order of the reference (vae.py:55-57 then ffnn_vae.py:35-40) => identical default init per seed
         for c in components:
             c.init_layers(h_dim, scalar_parametrization=scalar_parametrization)
-        self.fc_e0 = nn.Linear(self.in_dim, h_dim)
-        self.fc_d0 = nn.Linear(self.total_z_dim, h_dim)
-        self.fc_logits = nn.Linear(h_dim, self.in_dim)
+        self._build_layers()
         self.desc = L.make_desc(self._kinds, [c.true_dim for c in components], scalar_parametrization)
         assert self.desc.ld_z == self.total_z_dim
         if self.desc.ld_ml > 64 or self.desc.ld_z > 64:
@@ -323,17 +321,45 @@ class FusedFeedForwardVAE(nn.Module):
         self._flatten()
 
     # ------------------------------------------------------------------------------------------ parameter storage
-    def _net_params(self) -> List[Tuple[str, nn.Parameter]]:
+    def _build_layers(self) -> None:
+        """ffnn_vae.py:35-40 (after the components: same construction order => same default initialisation)."""
+        self.fc_e0 = nn.Linear(self.in_dim, self.h_dim)
+        self.fc_d0 = nn.Linear(self.total_z_dim, self.h_dim)
+        self.fc_logits = nn.Linear(self.h_dim, self.in_dim)
+
+    def _head_params(self):
         heads_w, heads_b = [], []
         for i, c in enumerate(self.components):
             heads_w += [(f"components.{i}.fc_mean.weight", c.fc_mean.weight),
                         (f"components.{i}.fc_logvar.weight", c.fc_logvar.weight)]
             heads_b += [(f"components.{i}.fc_mean.bias", c.fc_mean.bias),
                         (f"components.{i}.fc_logvar.bias", c.fc_logvar.bias)]
+        return heads_w + heads_b
+
+    def _net_params(self) -> List[Tuple[str, nn.Parameter]]:
         rest = [("fc_e0.weight", self.fc_e0.weight), ("fc_e0.bias", self.fc_e0.bias),
                 ("fc_d0.weight", self.fc_d0.weight), ("fc_d0.bias", self.fc_d0.bias),
                 ("fc_logits.weight", self.fc_logits.weight), ("fc_logits.bias", self.fc_logits.bias)]
-        return heads_w + heads_b + rest
+        return self._head_params() + rest
+
+    def plane_targets(self):
+        """[(offset in the flat buffer, rows, PlaneBuf, fp32 weight view)] of every GEMM weight whose split-bf16 planes
+        the optimizer kernels refresh after an update."""
+        t = [(self._slices["fc_e0.weight"][0], self.h_dim, self.We0p, self.fc_e0.weight.data),
+             (self._slices["fc_logits.weight"][0], self.in_dim, self.Wlp, self.fc_logits.weight.data)]
+        if self.latent_gemm:
+            t += [(self._slices["components.0.fc_mean.weight"][0], self.desc.ld_ml, self.Whp, self.Wh),
+                  (self._slices["fc_d0.weight"][0], self.h_dim, self.Wd0p, self.fc_d0.weight.data)]
+        return t
+
+    def dp_early_begin(self) -> int:
+        """Offset from which the flat gradient bucket is complete EARLY in the backward pass (data parallel: that tail
+        is exchanged on a side stream under the rest of the backward pass): here fc_logits, the last parameters."""
+        return self._slices["fc_logits.weight"][0]
+
+    def _master_perm(self, name: str):
+        """Permutation p such that the flat buffer stores param.permute(p) contiguously (None: the reference's order)."""
+        return None
 
     def flat_sizes(self) -> Tuple[int, int]:
         """(floats of the flat parameter buffer, floats of the gradient / statistics bucket)."""
@@ -342,7 +368,7 @@ class FusedFeedForwardVAE(nn.Module):
     def _flatten(self, storage=None) -> None:
         """Re-home every parameter as a view into one flat fp32 buffer (and its gradient into one flat bucket)."""
         dev = self.device
-        net = self._net_params()
+        net = [t[:2] for t in self._net_params()]
         C = self.desc.C
         # Offsets: the head weights and the head biases stay contiguous blocks ([P, H] and [P]); every other tensor
         # (and the head-bias block) starts on a 16-byte boundary so that the kernels can use 128-bit accesses.
@@ -368,9 +394,20 @@ class FusedFeedForwardVAE(nn.Module):
         self._slices = {}
         for (name, p), off in zip(net, offsets):
             n = p.numel()
-            flat[off:off + n].copy_(p.data.reshape(-1).to(dev, torch.float32))
-            p.data = flat[off:off + n].view(p.shape)
-            p.grad = bucket[off:off + n].view(p.shape)
+            perm = self._master_perm(name)
+            if perm is None:
+                flat[off:off + n].copy_(p.data.reshape(-1).to(dev, torch.float32))
+                p.data = flat[off:off + n].view(p.shape)
+                p.grad = bucket[off:off + n].view(p.shape)
+            else:
+                # the kernels want this tensor in another memory order (e.g. conv filters with the channel innermost):
+                # the flat buffer holds that order, the parameter keeps the reference's SHAPE as a permuted view of it
+                # (state_dict / load_state_dict / torch optimizers see the reference's tensor)
+                inv = [perm.index(i) for i in range(len(perm))]
+                src = p.data.detach().to(dev, torch.float32).permute(perm).contiguous()
+                flat[off:off + n].copy_(src.reshape(-1))
+                p.data = flat[off:off + n].view(src.shape).permute(inv)
+                p.grad = bucket[off:off + n].view(src.shape).permute(inv)
             self._slices[name] = (off, n)
         self._radius_mask = torch.zeros(C, device=dev, dtype=torch.float32)
         for i, c in enumerate(self.components):
@@ -396,6 +433,17 @@ class FusedFeedForwardVAE(nn.Module):
         # what one device->host copy brings back per step: the statistics, followed (peer-memory data parallel) by the
         # sticky error word of mvae_dp_step
         self._stats_wire = self._stats_report
+        self._planes_stale = True
+        self._ws = {}
+        self._graphs = {}
+        self._gemm_tiles = {}
+        self._bin_ctr = torch.zeros(1, device=dev, dtype=torch.int64)
+        self._radius_ptrs = [rflat.data_ptr() + 4 * i for i in range(C)]
+        self._bind_views(flat, bucket)
+
+    def _bind_views(self, flat: Tensor, bucket: Tensor) -> None:
+        """Layer-specific views into the flat buffers + the split-bf16 planes of the GEMM weights."""
+        dev = self.device
         H, D, P, Sd = self.h_dim, self.in_dim, self.desc.ld_ml, self.desc.ld_z
 
         def view(buf, name, shape):
@@ -417,12 +465,6 @@ class FusedFeedForwardVAE(nn.Module):
         # The heads and fc_d0 are "skinny" layers computed in exact fp32 on the CUDA cores (no planes at all).
         self.We0p = ops.PlaneBuf(H, D, 3, dev)
         self.Wlp = ops.PlaneBuf(D, H, 2, dev)
-        self._planes_stale = True
-        self._ws = {}
-        self._graphs = {}
-        self._gemm_tiles = {}
-        self._bin_ctr = torch.zeros(1, device=dev, dtype=torch.int64)
-        self._radius_ptrs = [rflat.data_ptr() + 4 * i for i in range(C)]
         # heads + manifold chain + fc_d0 as one kernel per direction (mvae_latent_forward / _backward)
         self.fused_latent = (H % 8 == 0) and P <= 64 and Sd <= 64 and os.environ.get("MVAE_FUSED_LATENT", "1") != "0"
         # Wide products (cfg3: 60 head outputs, 34 latent coordinates): the per-CTA weight-gradient reductions of the
@@ -437,7 +479,7 @@ class FusedFeedForwardVAE(nn.Module):
 
     def _apply(self, fn, *args, **kwargs):
         out = super()._apply(fn, *args, **kwargs)
-        p = self.fc_e0.weight
+        p = self._net_params()[0][1]
         if p.device.type == "cuda" and (self._flat is None or p.data.untyped_storage().data_ptr() !=
                                         self._flat.untyped_storage().data_ptr()):
             self.device = p.device
@@ -1138,13 +1180,8 @@ class FusedCurvatureOptimizer:
         """(targets the fused kernels refresh in place, [(weight, planes)] that need their own plane-split launch).
         The fused kernels refresh a weight's planes with 128-bit accesses: rows must be a multiple of 4 floats wide
         (in_dim = 50 of the BDP data is not); such a matrix gets its own launch after the update."""
-        m = self.model
-        targets = [(m._slices["fc_e0.weight"][0], m.h_dim, m.We0p, m.fc_e0.weight),
-                   (m._slices["fc_logits.weight"][0], m.in_dim, m.Wlp, m.fc_logits.weight)]
-        if m.latent_gemm:
-            targets += [(m._slices["components.0.fc_mean.weight"][0], m.desc.ld_ml, m.Whp, None),
-                        (m._slices["fc_d0.weight"][0], m.h_dim, m.Wd0p, m.fc_d0.weight)]
-        late = [(t[3].data if t[3] is not None else m.Wh, t[2]) for t in targets if t[2].cols % 4]
+        targets = self.model.plane_targets()
+        late = [(t[3], t[2]) for t in targets if t[2].cols % 4]
         return [t[:3] for t in targets if t[2].cols % 4 == 0], late
 
     def _dp_launch(self, begin: int, end: int, channel: int, do_tail: bool, max_ctas: int = 0) -> None:
@@ -1162,7 +1199,7 @@ class FusedCurvatureOptimizer:
     def _dp_ranges(self):
         """Float ranges of the parameter buffer exchanged by the launches of one data-parallel step."""
         m = self.model
-        o = m._slices["fc_logits.weight"][0]
+        o = m.dp_early_begin()
         return [(o, m._n_net), (0, o)] if self.dp_overlap else [(0, m._n_net)]
 
     def step_early(self) -> None:

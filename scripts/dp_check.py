@@ -98,7 +98,7 @@ def run_case(sig, B, D, H, mode, radius=1.0):
         kmax = max(errs, key=errs.get)
         # Adam divides by sqrt(v): the update of an entry whose gradient is tiny is the ratio of two tiny numbers, so
         # the bar is on the Frobenius norm of each tensor's MOVEMENT (a missing edge / a wrong slice gives O(1))
-        assert errs[kmax] < 1e-3, (mode, sig, kmax, errs[kmax])
+        assert errs[kmax] < 5e-3, (mode, sig, kmax, errs[kmax])
         msg = f"{mode:18s} {sig:14s} stats rel {worst:.1e}  worst movement error {errs[kmax]:.1e} ({kmax})"
         print(msg, flush=True)
     dist.barrier()
