@@ -33,7 +33,10 @@ WORKLOADS = {
     "cfg3": ("h6,h6,s6,s6,e6", 8192, 784, 400, "bce", False, "MNIST h6,h6,s6,s6,e6 batch 8192 per GPU"),
     "cfg4a": ("h2", 16384, 50, 400, "nll", False, "BDP-shaped h2 (hyperboloid) batch 16384"),
     "cfg4b": ("p2", 16384, 50, 400, "nll", False, "BDP-shaped p2 (Poincare ball) batch 16384"),
+    "cfg5": ("h2,s2,e2", 256, 3072, 8192, "bce", False,
+             "CIFAR-shaped conv VAE (h_dim 8192) h2,s2,e2, batch 2048 over 8 GPUs = 256 per GPU"),
 }
+CONV_WORKLOADS = ("cfg5",)   # ConvolutionalVAE (conv_vae.py:28-79); the others are FeedForwardVAE
 METRIC = "ELBO train throughput (steps/sec x global batch)"
 UNIT = "samples/s"
 
@@ -84,6 +87,8 @@ def ncu_traffic(kernel, signature, samples):
 def synthetic_x(recon, B, D, seed):
     import torch
     g = torch.Generator().manual_seed(seed)
+    if D == 3072:   # CIFAR-shaped: real-valued pixels in [0, 1] (ToTensor), BCE on real-valued targets
+        return torch.rand(B, D, generator=g)
     if recon == "bce":
         return (torch.rand(B, D, generator=g) < 0.1307).float()
     return torch.randn(B, D, generator=g)
@@ -206,6 +211,25 @@ def cpu_step_fn(workload, B, seed=0):
     import cpu_baseline
     sig, _, D, H, recon, fixed, _ = WORKLOADS[workload]
     from mvae_b200 import components
+    if workload in CONV_WORKLOADS:
+        # convolutional model: ATen / oneDNN CPU convolutions under autograd + the C oracle for the latent chain
+        from mvae_b200 import conv_vae, data
+        torch.manual_seed(seed)
+        m = conv_vae.FusedConvolutionalVAE(H, components.parse_components(sig, fixed), data.GenericDataset(B, D, recon),
+                                           False, device="cpu")   # host-side construction only: default initialisation
+        params = {k: v.detach().numpy().astype(np.float32).copy() for k, v in m.state_dict().items()}
+        for k in params:
+            if "radius" in k:
+                params[k] = np.asarray(10.0, dtype=np.float32)
+        cpu = cpu_baseline.CpuConvTrainStep(sig, params)
+        x = synthetic_x(recon, B, D, seed)
+        g = torch.Generator().manual_seed(seed)
+
+        def conv_step():
+            eps = torch.randn(B, cpu.desc.ld_eps, generator=g)
+            return cpu.step(x, eps, beta=1.0)["elbo"]
+
+        return conv_step, torch.get_num_threads()
     torch.manual_seed(seed)
     comps = components.parse_components(sig, fixed)
     # reference-shaped parameters with nn.Linear default init (CPU only; no kernels involved)
@@ -367,8 +391,13 @@ def run_ours(args):
     peaks = measured_peaks()
     torch.manual_seed(0)
     comps = components.parse_components(sig, fixed)
-    model = vae.FusedFeedForwardVAE(H, comps, data.GenericDataset(B, D, recon, binary_inputs=(recon == "bce")), False,
-                                    device=dev)  # MNIST-shaped batches are binarised (0/1): one exact bf16 plane
+    conv = args.workload in CONV_WORKLOADS
+    if conv:
+        from mvae_b200 import conv_vae
+        model = conv_vae.FusedConvolutionalVAE(H, comps, data.GenericDataset(B, D, recon), False, device=dev)
+    else:
+        model = vae.FusedFeedForwardVAE(H, comps, data.GenericDataset(B, D, recon, binary_inputs=(recon == "bce")),
+                                        False, device=dev)  # MNIST-shaped batches are binarised: one exact bf16 plane
     model.use_cuda_graph = not args.no_graph
     # Learnable radii start at R = 10, the value the reference's own schedule gives them in its first training epoch
     # (Trainer._train_epoch: R = 11 - epoch for epoch < 10, train.py:189-194).  The ELBO is a SUM over the batch, so at
@@ -447,7 +476,7 @@ def run_ours(args):
     # Image workloads ship the batch as the dataset stores it — uint8 grayscale pixels, 1 byte per pixel — and binarise
     # it on the device (mvae_binarize: the reference's ImageDynamicBinarization, which runs per sample on the CPU in its
     # DataLoader); float32 host batches (the reference's loader output, 4 bytes per pixel) are timed as well.
-    u8_inputs = recon == "bce" and not args.float_inputs
+    u8_inputs = recon == "bce" and not args.float_inputs and not conv
     xs_e2e = [synthetic_pixels(B, D, 1000 * rank + i).pin_memory() for i in range(n_rot)] if u8_inputs else xs_host
 
     def host_batches(n, src):
@@ -587,13 +616,19 @@ def run_ours(args):
                                      "us_per_launch": ms_b * 1e3}
         del ml, eps, z, kl, gz, gml
         # tcgen05 GEMM (tensor bound): encoder layer of the workload, algorithmic flops 2*B*D*H
-        ms_g = time_kernel(lambda: ops.gemm(ws.xp, model.We0p, B, H, D, epilogue=1, bias=model.fc_e0.bias.data,
-                                            out_planes=ws.hp), 20, flush)
-        tf = 2.0 * B * D * H / (ms_g * 1e-3) / 1e12
-        line["roofline_gemm"] = {"kernel": "gemm_tcgen05_kernel (fc_e0 forward)", "bound": "tensor", "achieved": tf,
-                                 "peak": peaks["bf16_tflops"], "unit": "TFLOP/s", "frac": tf / peaks["bf16_tflops"],
-                                 "us_per_launch": ms_g * 1e3,
-                                 "note": "algorithmic fp32 flops; the kernel issues 3 bf16 MMAs per product (split planes)"}
+        if conv:   # the largest forward GEMM of the convolutional stack: e2 as [B*16, 2048] x [512, 2048]^T
+            gm, gn, gk, what = B * 16, 512, 2048, "e2 forward: im2col(a1) . W^T, 3 + 3 planes = 6 bf16 MMAs per product"
+            ms_g = time_kernel(lambda: ops.gemm(ws.A[2], model._Wp["e2"], gm, gn, gk, epilogue=1,
+                                                bias=model._bias["e2"], out_planes=ws.a[2], tile=(128, 1)), 20, flush)
+        else:
+            gm, gn, gk, what = B, H, D, "fc_e0 forward; 3 bf16 MMAs per product (split planes)"
+            ms_g = time_kernel(lambda: ops.gemm(ws.xp, model.We0p, B, H, D, epilogue=1, bias=model.fc_e0.bias.data,
+                                                out_planes=ws.hp), 20, flush)
+        tf = 2.0 * gm * gn * gk / (ms_g * 1e-3) / 1e12
+        line["roofline_gemm"] = {"kernel": "gemm_tcgen05_kernel", "shape": [gm, gn, gk], "bound": "tensor",
+                                 "achieved": tf, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
+                                 "frac": tf / peaks["bf16_tflops"], "us_per_launch": ms_g * 1e3,
+                                 "note": "algorithmic fp32 flops; " + what}
 
         line["roofline_step"] = step_rooflines(model, opt, xs_dev[0], peaks, flush, C, Sn, Sd, P, H, B)
 

@@ -160,13 +160,21 @@ __global__ void __launch_bounds__(kDpThreads) dp_step_kernel(const __grid_consta
   }
 
   // ---- phase A: announce that my gradients are complete, wait for every peer's announcement ----
-  if (blockIdx.x == 0 && (int)threadIdx.x < world) {
-    __threadfence_system();
+  // (st.release.sys is cumulative: it covers the gradient writes of the preceding kernels, which happen before this
+  // thread by stream order — no separate system-scope fence, which costs microseconds)
+  if (blockIdx.x == 0 && (int)threadIdx.x < world)
     st_release_sys(p.comm.flags[threadIdx.x] + dp_slot(p.channel, 0, rank), e);
-  }
   if (!dp_wait_peers(p, 0, e, &s_err)) return;  // nothing has been written yet
   if (stamp && p.channel) p.sync[10] = (uint32_t)global_ns();
 
+  // the CTA that owns the tail puts its peer loads in flight first (they complete under the slice work below)
+  const bool tail_cta = p.do_tail && blockIdx.x == gridDim.x - 1;
+  float tail_v[MVAE_DP_MAX_RANKS];
+  if (tail_cta && (int)threadIdx.x < p.n_tail) {
+#pragma unroll
+    for (int r = 0; r < MVAE_DP_MAX_RANKS; ++r)
+      if (r < world) tail_v[r] = ld_peer1(p.comm.bucket[r] + p.n_net + threadIdx.x);
+  }
   // ---- reduce-scatter + Adam on my slice of the range: the new values go into MY parameter buffer only ----
   // Two float4 per thread and iteration: all 2 x world peer loads are in flight before the first is consumed (the
   // loop is latency bound: a peer load is a few microseconds over NVLink).
@@ -212,12 +220,14 @@ __global__ void __launch_bounds__(kDpThreads) dp_step_kernel(const __grid_consta
   }
   if (stamp && p.channel) p.sync[14] = (uint32_t)global_ns();
   // ---- statistics / radius-gradient tail: every rank sums it (same order), clips, and steps its radii locally ----
-  if (p.do_tail && blockIdx.x == gridDim.x - 1) {
+  if (tail_cta) {
     __shared__ float s_clip;
-    for (int t = threadIdx.x; t < p.n_tail; t += blockDim.x) {
+    if ((int)threadIdx.x < p.n_tail) {  // n_tail = 2 C + 3 <= 195 < blockDim.x
       float s = 0.f;
-      for (int r = 0; r < world; ++r) s += ld_peer1(p.comm.bucket[r] + p.n_net + t);
-      p.tail_out[t] = s;
+#pragma unroll
+      for (int r = 0; r < MVAE_DP_MAX_RANKS; ++r)  // fixed rank order on every rank: replicas stay bit-identical
+        if (r < world) s += tail_v[r];
+      p.tail_out[threadIdx.x] = s;
     }
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -241,8 +251,11 @@ __global__ void __launch_bounds__(kDpThreads) dp_step_kernel(const __grid_consta
     }
   }
 
-  // ---- phase B: the last CTA to get here tells every rank (this one included) that my slice has been delivered ----
-  __threadfence_system();
+  // ---- phase B: the last CTA to get here tells every rank (this one included) that my slice is final ----
+  // Device-scope fence per thread; the system-scope fence is the publishing threads' (below): the release is cumulative
+  // over everything those threads have observed through the ticket.  (A system-scope fence in every thread costs
+  // 7 us here — measured — even though nothing but local memory was written.)
+  __threadfence();
   if (stamp && p.channel) p.sync[15] = (uint32_t)global_ns();
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -252,10 +265,8 @@ __global__ void __launch_bounds__(kDpThreads) dp_step_kernel(const __grid_consta
   }
   __syncthreads();
   if (s_last) {
-    if ((int)threadIdx.x < world) {
-      __threadfence_system();
+    if ((int)threadIdx.x < world)  // cumulative release: everything observed through the ticket is covered
       st_release_sys(p.comm.flags[threadIdx.x] + dp_slot(p.channel, 1, rank), e);
-    }
     if (threadIdx.x == 0) {
       if (p.channel) p.sync[11] = (uint32_t)global_ns();
       sync[1] = 0u;  // ticket counter for the next launch of this channel
@@ -347,7 +358,7 @@ extern "C" int mvae_dp_step(const mvae_dp_comm* comm, const mvae_dp_step_args* a
   if (!comm || !a || comm->world < 1 || comm->world > MVAE_DP_MAX_RANKS || comm->rank < 0 ||
       comm->rank >= comm->world || a->n_net < 0 || (a->n_net & 3) || a->begin < 0 || a->end < a->begin ||
       a->end > a->n_net || (a->begin & 3) || (a->end & 3) || a->channel < 0 || a->channel >= MVAE_DP_CHANNELS ||
-      a->n_tail < 0 || a->C < 0 || a->C > a->n_tail || !a->exp_avg || !a->exp_avg_sq || !a->step_dev || !a->tail_out ||
+      a->n_tail < 0 || a->n_tail > 512 || a->C < 0 || a->C > a->n_tail || !a->exp_avg || !a->exp_avg_sq || !a->step_dev || !a->tail_out ||
       !a->sync_words)
     return MVAE_ERR_INVALID_ARGUMENT;
   for (int r = 0; r < comm->world; ++r) {

@@ -392,6 +392,7 @@ class FusedFeedForwardVAE(nn.Module):
             bucket.zero_()
         rflat = torch.ones(C, device=dev, dtype=torch.float32)
         self._slices = {}
+        self._grad_views = {}
         for (name, p), off in zip(net, offsets):
             n = p.numel()
             perm = self._master_perm(name)
@@ -409,6 +410,7 @@ class FusedFeedForwardVAE(nn.Module):
                 p.data = flat[off:off + n].view(src.shape).permute(inv)
                 p.grad = bucket[off:off + n].view(src.shape).permute(inv)
             self._slices[name] = (off, n)
+            self._grad_views[name] = p.grad
         self._radius_mask = torch.zeros(C, device=dev, dtype=torch.float32)
         for i, c in enumerate(self.components):
             _, rp = radius_parameter_of(c)
@@ -1120,9 +1122,8 @@ class FusedFeedForwardVAE(nn.Module):
 
     def _attach_grads(self) -> None:
         """torch optimizers' zero_grad(set_to_none=True) drops .grad; re-attach the bucket views."""
-        for name, p in self._net_params():
-            o, n = self._slices[name]
-            p.grad = self._bucket[o:o + n].view(p.shape)
+        for name, p in [t[:2] for t in self._net_params()]:
+            p.grad = self._grad_views[name]   # (a permuted view for tensors the flat buffer stores in another order)
         for i, rp in enumerate(self._radius_params):
             if rp is not None and rp.requires_grad:
                 rp.grad = self._bucket[self._n_net + i]

@@ -422,7 +422,8 @@ class OracleConvVAE(OracleVAE):
     def __init__(self, sig, recon_kind="bce", scalar_parametrization=False):
         super().__init__(sig, 3072, 8192, recon_kind, scalar_parametrization)
 
-    def step(self, params, x, eps, beta=1.0, backward=True):
+    def step(self, params, x, eps, beta=1.0, backward=True, relu_decisions=None):
+        assert relu_decisions is None, "the convolutional oracle takes its own relu decisions"
         p = params
         B = x.shape[0]
         R = self.radii(p, x.dtype)

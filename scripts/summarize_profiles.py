@@ -66,7 +66,46 @@ def full(rep):
             fh.write("\n")
 
 
+def traffic():
+    """profiles/ncu_traffic.json: DRAM bytes per launch of the product-manifold kernels from the `ncu --set full`
+    captures of scripts/prof_driver.py pm <signature> (2^22 samples), with a hash of the kernels' sources so that
+    bench.py can tell whether a capture still describes the code it runs."""
+    import json
+    sys.path.insert(0, ROOT)
+    import bench
+    table = {}
+    for rep, sig in (("prof_pm.ncu-rep", "h2,s2,e2"), ("prof_pm_cfg3.ncu-rep", "h6,h6,s6,s6,e6")):
+        path = os.path.join(OUT, rep)
+        if not os.path.exists(path):
+            continue
+        raw = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+        rows = list(csv.reader(raw.splitlines()))
+        hdr, units = rows[0], rows[1]
+        scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+
+        def val(r, m):
+            i = hdr.index(m)
+            return float(r[i].replace(",", "")) * scale.get(units[i], 1.0)
+
+        for r in rows[2:]:
+            name = r[hdr.index("Kernel Name")]
+            kern = "pm_forward_kernel" if "pm_forward" in name else "pm_backward_kernel" if "pm_backward" in name else None
+            if kern is None:
+                continue
+            entry = {"signature": sig, "samples": 1 << 22,
+                     "dram_bytes": val(r, "dram__bytes_read.sum") + val(r, "dram__bytes_write.sum"),
+                     "us": val(r, "gpu__time_duration.sum") / 1e3 if units[hdr.index("gpu__time_duration.sum")] in ("ns", "nsecond") else None,
+                     "capture": f"profiles/r{rnd}_ncu_{rep.replace('.ncu-rep', '')}_{tag}.md",
+                     "source_hash": bench.source_hash(kern)}
+            table.setdefault(kern, [])
+            table[kern] = [e for e in table[kern] if e["signature"] != sig] + [entry]   # last launch of each wins
+    if table:
+        with open(os.path.join(PROF, "ncu_traffic.json"), "w") as fh:
+            json.dump(table, fh, indent=1)
+
+
 launches()
+traffic()
 for rep in sorted(os.listdir(OUT)):
     if rep.endswith(".ncu-rep"):
         full(rep)
