@@ -416,7 +416,7 @@ int mvae_opt_step_fused(int64_t n, float* param, const float* grad, float* exp_a
 #define MVAE_DP_MAX_RANKS 8
 #define MVAE_DP_CHANNELS 2
 #define MVAE_DP_FLAG_BYTES (MVAE_DP_CHANNELS * 2 * MVAE_DP_MAX_RANKS * 128)
-#define MVAE_DP_SYNC_WORDS 16
+#define MVAE_DP_SYNC_WORDS 528
 #define MVAE_DP_HANDLE_BYTES 64
 typedef struct mvae_dp_comm {
   int32_t rank, world;
@@ -439,7 +439,8 @@ int mvae_dp_ipc_close(void* peer_ptr);
  * radius gradients selected by clip_mask [C] (NULL = none) so that their 2-norm is at most clip_max_norm, and steps
  * radius [C] (may be NULL) with radius_lr (0 = the curvature optimizers do not step) on the summed gradient times
  * radius_mask (NULL = ones).
- * sync_words: MVAE_DP_SYNC_WORDS zero-initialised device words private to this rank.  Word [8] is a STICKY error:
+ * sync_words: MVAE_DP_SYNC_WORDS zero-initialised device words private to this rank (epochs and tickets, the error
+ * word, and %globaltimer stamps of the last launch's phases for diagnosis).  Word [8] is a STICKY error:
  * non-zero = a peer did not arrive within MVAE_DP_TIMEOUT_S seconds (environment, default 30); the launch that saw it
  * and every later launch write no parameter.  The host must check it (tail_out[n_tail] carries it with the statistics).
  * targets: weight matrices inside [begin, end) whose split-bf16 planes are refreshed from the gathered parameters.

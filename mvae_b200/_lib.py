@@ -48,7 +48,7 @@ class GemmArgs(ctypes.Structure):
                 ("tile_n", ctypes.c_int32), ("ctas_per_sm", ctypes.c_int32), ("aux_rows", ctypes.c_int64)]
 
 
-DP_MAX_RANKS, DP_HANDLE_BYTES, DP_CHANNELS, DP_SYNC_WORDS = 8, 64, 2, 16
+DP_MAX_RANKS, DP_HANDLE_BYTES, DP_CHANNELS, DP_SYNC_WORDS = 8, 64, 2, 528
 DP_FLAG_BYTES = DP_CHANNELS * 2 * DP_MAX_RANKS * 128
 
 

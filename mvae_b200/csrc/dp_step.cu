@@ -166,6 +166,10 @@ __global__ void __launch_bounds__(kDpThreads) dp_step_kernel(const __grid_consta
     st_release_sys(p.comm.flags[threadIdx.x] + dp_slot(p.channel, 0, rank), e);
   if (!dp_wait_peers(p, 0, e, &s_err)) return;  // nothing has been written yet
   if (stamp && p.channel) p.sync[10] = (uint32_t)global_ns();
+  // per-CTA stamps of the launch at the end of the step: sync[16 + 2 b] = CTA b passed phase A, [17 + 2 b] = it has
+  // finished its slice (MVAE_DP_SYNC_WORDS leaves room for 256 CTAs)
+  const bool cta_stamp = p.channel && threadIdx.x == 0 && blockIdx.x < 256;
+  if (cta_stamp) p.sync[16 + 2 * blockIdx.x] = (uint32_t)global_ns();
 
   // the CTA that owns the tail puts its peer loads in flight first (they complete under the slice work below)
   const bool tail_cta = p.do_tail && blockIdx.x == gridDim.x - 1;
@@ -257,6 +261,7 @@ __global__ void __launch_bounds__(kDpThreads) dp_step_kernel(const __grid_consta
   // 7 us here — measured — even though nothing but local memory was written.)
   __threadfence();
   if (stamp && p.channel) p.sync[15] = (uint32_t)global_ns();
+  if (cta_stamp) p.sync[17 + 2 * blockIdx.x] = (uint32_t)global_ns();
   __syncthreads();
   if (threadIdx.x == 0) {
     const uint32_t ticket = atomicAdd(&sync[1], 1u);

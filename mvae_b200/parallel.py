@@ -189,7 +189,15 @@ def dp_phase_times(optimizer) -> dict:
         return {}
     w = [int(v) & 0xFFFFFFFF for v in optimizer._dp_sync.tolist()]
     d = lambda a, b: ((w[b] - w[a]) & 0xFFFFFFFF) / 1e3  # noqa: E731
-    return {"late_wait_grads": d(9, 10), "late_reduce_adam_gather": d(10, 11), "late_cta0_loads_adam_stores": d(10, 14),
+    # per-CTA stamps: when the slowest CTA passed phase A / finished its slice, relative to CTA 0 passing phase A
+    ctas = [(w[16 + 2 * b], w[17 + 2 * b]) for b in range(256) if w[17 + 2 * b] != 0]
+    rel = lambda x: ((x - w[10]) & 0xFFFFFFFF) / 1e3 if ((x - w[10]) & 0xFFFFFFFF) < (1 << 31) else -(((w[10] - x) & 0xFFFFFFFF) / 1e3)  # noqa: E731
+    extra = {}
+    if ctas:
+        extra = {"late_ctas": len(ctas), "late_last_cta_passes_A": max(rel(a) for a, _ in ctas),
+                 "late_last_cta_done": max(rel(b) for _, b in ctas),
+                 "late_median_cta_done": sorted(rel(b) for _, b in ctas)[len(ctas) // 2]}
+    return {**extra, "late_wait_grads": d(9, 10), "late_reduce_adam_gather": d(10, 11), "late_cta0_loads_adam_stores": d(10, 14),
             "late_cta0_fence_sys": d(14, 15), "late_wait_slices": d(11, 12),
             "late_plane_refresh": d(12, 13), "late_total": d(9, 13), "early_total": d(2, 3),
             "early_start_to_late_start": d(2, 9)}

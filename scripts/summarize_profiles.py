@@ -12,7 +12,7 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 OUT = os.path.join(ROOT, "gpurun_out")
-PROF = os.path.join(ROOT, "profiles")
+PROF = os.environ.get("MVAE_PROF_DIR", os.path.join(ROOT, "profiles"))  # on the GPU box: under gpurun_out/
 rnd, tag = sys.argv[1], sys.argv[2]
 os.makedirs(PROF, exist_ok=True)
 
