@@ -407,7 +407,14 @@ def run_ours(args):
         for rp in model._radius_params:
             if rp is not None and rp.requires_grad:
                 rp.fill_(args.radius)
-    opt = vae.FusedCurvatureOptimizer(model, 1e-3, fixed_curvature=fixed, should_do_curvature_step=lambda: True)
+    # The ELBO is a SUM over the batch (stats.py:200-202), so the radius gradient grows with the global batch while the
+    # reference's curvature step is plain SGD(1e-4) (train.py:343-355, tuned for batches of 100): at 4 and 8 ranks the
+    # radii ran into their clamp within a few hundred steps and the run trained on NaNs.  The curvature step is
+    # therefore divided by the number of ranks — the N-rank run then moves the radii like the 1-rank run does.  (Adam's
+    # update of the network parameters is invariant to the gradient's scale.)
+    curvature_lr = 1e-4 / world
+    opt = vae.FusedCurvatureOptimizer(model, 1e-3, fixed_curvature=fixed, should_do_curvature_step=lambda: True,
+                                      curvature_lr=curvature_lr)
     collective = "none"
     if world > 1:
         # one exchange per step: fused into the optimizer kernel over NVLink peer memory (default), or NCCL all-reduce
@@ -444,14 +451,17 @@ def run_ours(args):
     ends = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     barrier()
     sampler.mark()
+    t_host = time.perf_counter()
     for i in range(args.steps):
         flush()
         starts[i].record()
         model.train_step(opt, xs_dev[i % n_rot], 1.0, sync_stats=False)
         ends[i].record()
+    host_enqueue_s = time.perf_counter() - t_host   # host time to enqueue the timed steps (no synchronisation inside)
     barrier()
     launches = ops.launch_count() - n0
     total_ms = sum(a.elapsed_time(b) for a, b in zip(starts, ends))
+    own_total_ms = total_ms
     if world > 1:
         t = torch.tensor([total_ms], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -459,13 +469,33 @@ def run_ours(args):
     ms = total_ms / args.steps
     clocks = sampler.stop() if rank == 0 else None
     # phases of the LAST timed step's exchange kernel on every rank (steady state), slowest rank per phase
-    phases = {}
-    if world > 1 and not collective.startswith("NCCL"):
-        ph = parallel.dp_phase_times(opt)
-        keys = sorted(ph)
-        t = torch.tensor([ph[k] for k in keys], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        phases = {k: round(float(v), 2) for k, v in zip(keys, t.tolist())}
+    phases, per_rank = {}, {}
+    host_ms = host_enqueue_s / args.steps * 1e3
+    if world > 1:
+        # per rank: device time of its own steps, host time to ENQUEUE a step, SM clock now; and (peer-memory path) how
+        # long its last exchange kernel waited for the peers' gradients — the rank that waits least arrives last
+        sm_now = 0.0
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            uuid = str(torch.cuda.get_device_properties(local).uuid)
+            sm_now = float(pynvml.nvmlDeviceGetClockInfo(pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid).encode()),
+                                                         pynvml.NVML_CLOCK_SM))
+        except Exception:
+            pass
+        ph = parallel.dp_phase_times(opt) if not collective.startswith("NCCL") else {}
+        mine = torch.tensor([own_total_ms / args.steps, host_ms, sm_now, ph.get("late_wait_grads", 0.0),
+                             ph.get("late_total", 0.0)], device=dev)
+        allr = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(allr, mine)
+        cols = list(zip(*[[round(float(v), 4) for v in t.tolist()] for t in allr]))
+        per_rank = {"device_ms_per_step": cols[0], "host_enqueue_ms_per_step": cols[1], "sm_mhz_after": cols[2],
+                    "late_wait_grads_us": cols[3], "late_total_us": cols[4]}
+        if ph:
+            keys = sorted(ph)
+            t = torch.tensor([ph[k] for k in keys], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            phases = {k: round(float(v), 2) for k, v in zip(keys, t.tolist())}
     stats_vec = model._stats.clone()
 
     # ---------------- e2e: public API with host buffers (H2D of x, D2H of the statistics, every step) ----------------
@@ -537,7 +567,7 @@ def run_ours(args):
             dist.all_reduce(local, op=dist.ReduceOp.SUM)
             rel = abs(bs_chk.elbo - float(local[2].item())) / abs(float(local[2].item()))
         dp_check = {"replicas_identical": bool(identical and parallel.replicas_identical(model)),
-                    "phases_us_max_over_ranks": phases,
+                    "phases_us_max_over_ranks": phases, "per_rank": per_rank,
                     "elbo_vs_nccl_rel": rel, "dp_error_word": parallel.dp_error_word(opt),
                     "overlap": bool(getattr(opt, "dp_overlap", False) and opt._dp is not None)}
     e2e_ms = e2e_s / args.steps * 1e3
@@ -555,7 +585,8 @@ def run_ours(args):
             "data": "synthetic",
             "config": {"workload": desc, "signature": sig, "batch_per_gpu": B, "global_batch": gb, "in_dim": D,
                        "h_dim": H, "parallelism": f"dp{world}", "l2": "flushed between timed steps (256 MiB memset)",
-                       "cuda_graph": bool(model.use_cuda_graph), "optimizer": "Adam(1e-3) + SGD(1e-4) on radii",
+                       "cuda_graph": bool(model.use_cuda_graph),
+                       "optimizer": f"Adam(1e-3) + SGD({curvature_lr:g} = 1e-4 / ranks) on radii",
                        "initial_radius": args.radius,
                        "collective": collective, "numa_bound": bool(numa_bound)},
             "e2e": {"value": gb / (e2e_ms / 1e3), "unit": UNIT, "ms_per_step": e2e_ms,
@@ -572,6 +603,7 @@ def run_ours(args):
                                "api": "the reference's literal call pattern: model.train_step(optimizer, float32 host "
                                       "batch, beta), blocking on the statistics every step (train.py:197-198)"}},
             "gpu_launches": int(launches), "clocks": clocks, "elbo_per_sample": float(bs.elbo) / gb,
+            "host_enqueue_ms_per_step": host_ms,
             "elbo_finite": bool(all(s.elbo == s.elbo and abs(s.elbo) < float("inf") for s in stats_list)),
             "peaks": peaks["source"]}
     if dp_check is not None:
