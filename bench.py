@@ -399,6 +399,7 @@ def run_ours(args):
         model = vae.FusedFeedForwardVAE(H, comps, data.GenericDataset(B, D, recon, binary_inputs=(recon == "bce")),
                                         False, device=dev)  # MNIST-shaped batches are binarised: one exact bf16 plane
     model.use_cuda_graph = not args.no_graph
+    model.adopt_device_inputs = True   # `value`: the resident batches are read in place (one graph per batch tensor)
     # Learnable radii start at R = 10, the value the reference's own schedule gives them in its first training epoch
     # (Trainer._train_epoch: R = 11 - epoch for epoch < 10, train.py:189-194).  The ELBO is a SUM over the batch, so at
     # R = 1 the radius gradient of a 4096 x N batch times the reference's SGD step (1e-4) moves R by O(1) per step: with
@@ -443,7 +444,7 @@ def run_ours(args):
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    for i in range(max(args.warmup, 3)):
+    for i in range(max(args.warmup, n_rot)):   # every resident batch once at least: its graph is captured here
         model.train_step(opt, xs_dev[i % n_rot], 1.0, sync_stats=False)
     barrier()
     n0 = ops.launch_count()
@@ -454,6 +455,11 @@ def run_ours(args):
     t_host = time.perf_counter()
     for i in range(args.steps):
         flush()
+        # the flush takes a different time on every rank and would leave the ranks misaligned when their steps
+        # start — in training they start aligned (the previous step's exchange ends on all ranks together):
+        # re-align them on the device, still outside the timed region
+        if world > 1 and not args.no_rendezvous:
+            parallel.rendezvous(opt)
         starts[i].record()
         model.train_step(opt, xs_dev[i % n_rot], 1.0, sync_stats=False)
         ends[i].record()
@@ -580,11 +586,13 @@ def run_ours(args):
 
     gb = B * world
     line = {"metric": METRIC, "value": gb / (ms / 1e3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": ms, "steps_per_sec": 1e3 / ms, "higher_is_better": True,
+            "warmup": max(args.warmup, n_rot), "ms_per_step": ms, "steps_per_sec": 1e3 / ms, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32 (split-bf16 tensor-core GEMMs, fp32 accumulate)",
             "data": "synthetic",
             "config": {"workload": desc, "signature": sig, "batch_per_gpu": B, "global_batch": gb, "in_dim": D,
-                       "h_dim": H, "parallelism": f"dp{world}", "l2": "flushed between timed steps (256 MiB memset)",
+                       "h_dim": H, "parallelism": f"dp{world}", "l2": "flushed between timed steps (256 MiB memset)" +
+                       ("; ranks re-aligned after the flush by a peer-memory rendezvous kernel, outside the timed region"
+                        if world > 1 and not args.no_rendezvous and not collective.startswith("NCCL") else ""),
                        "cuda_graph": bool(model.use_cuda_graph),
                        "optimizer": f"Adam(1e-3) + SGD({curvature_lr:g} = 1e-4 / ranks) on radii",
                        "initial_radius": args.radius,
@@ -694,6 +702,8 @@ def main():
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly instead of replaying CUDA graphs")
     ap.add_argument("--radius", type=float, default=10.0, help="initial value of the learnable radii")
+    ap.add_argument("--no-rendezvous", action="store_true",
+                    help="N > 1: do not re-align the ranks after the L2 flush that precedes every timed step")
     ap.add_argument("--skip-roofline", action="store_true")
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--float-inputs", action="store_true",

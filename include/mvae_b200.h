@@ -415,7 +415,7 @@ int mvae_opt_step_fused(int64_t n, float* param, const float* grad, float* exp_a
  * zero-initialised: [channel][phase][source rank] slots of 128 bytes) as mapped in THIS process. */
 #define MVAE_DP_MAX_RANKS 8
 #define MVAE_DP_CHANNELS 2
-#define MVAE_DP_FLAG_BYTES (MVAE_DP_CHANNELS * 2 * MVAE_DP_MAX_RANKS * 128)
+#define MVAE_DP_FLAG_BYTES ((MVAE_DP_CHANNELS + 1) * 2 * MVAE_DP_MAX_RANKS * 128)  /* + the rendezvous slots */
 #define MVAE_DP_SYNC_WORDS 528
 #define MVAE_DP_HANDLE_BYTES 64
 typedef struct mvae_dp_comm {
@@ -465,6 +465,10 @@ typedef struct mvae_dp_step_args {
   const mvae_planes* targets;
 } mvae_dp_step_args;
 int mvae_dp_step(const mvae_dp_comm* comm, const mvae_dp_step_args* args, void* stream);
+/* Returns (on the stream) once every rank has launched it: re-aligns the ranks, e.g. after per-rank work of uneven
+ * length that precedes a step (bench.py uses it after its L2 flush, outside the timed region).  Same flags / error
+ * word / time limit as mvae_dp_step. */
+int mvae_dp_rendezvous(const mvae_dp_comm* comm, uint32_t* sync_words, void* stream);
 
 /* Device attributes the host layer needs for grid sizing / reporting. */
 int mvae_device_info(int32_t* sm_count, int32_t* cc_major, int32_t* cc_minor);

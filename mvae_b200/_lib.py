@@ -49,7 +49,7 @@ class GemmArgs(ctypes.Structure):
 
 
 DP_MAX_RANKS, DP_HANDLE_BYTES, DP_CHANNELS, DP_SYNC_WORDS = 8, 64, 2, 528
-DP_FLAG_BYTES = DP_CHANNELS * 2 * DP_MAX_RANKS * 128
+DP_FLAG_BYTES = (DP_CHANNELS + 1) * 2 * DP_MAX_RANKS * 128
 
 
 class DpComm(ctypes.Structure):
@@ -122,6 +122,7 @@ PROTOTYPES = {
     "mvae_dp_ipc_open": (ctypes.c_int, [ctypes.c_char_p, ctypes.POINTER(ctypes.c_void_p)]),
     "mvae_dp_ipc_close": (ctypes.c_int, [_vp]),
     "mvae_dp_step": (ctypes.c_int, [ctypes.POINTER(DpComm), ctypes.POINTER(DpStepArgs), _vp]),
+    "mvae_dp_rendezvous": (ctypes.c_int, [ctypes.POINTER(DpComm), _vp, _vp]),
     "mvae_device_info": (ctypes.c_int, [ctypes.POINTER(_i32), ctypes.POINTER(_i32), ctypes.POINTER(_i32)]),
 }
 

@@ -288,37 +288,96 @@ __global__ void __launch_bounds__(kDpThreads) dp_step_kernel(const __grid_consta
   // ---- all-gather by PULLING: every slice of the range is final in its owner's buffer; read the peers' slices over
   //      NVLink (a load needs no fence — a pushed store would need a system-scope fence that waits for the remote
   //      writes to drain: measured 8 us), keep a local copy, and refresh the split-bf16 planes of the GEMM weights ----
-  for (int64_t i = p.lo4 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < p.hi4; i += stride) {
-    int owner = (int)((i - p.lo4) / per);
-    owner = owner < world ? owner : world - 1;
-    const float4 w = ld_peer4(p.comm.flat[owner] + 4 * i);  // peers' (or my CTAs') fresh values: not through L1
-    if (owner != rank) reinterpret_cast<float4*>(p.comm.flat[rank])[i] = w;
-    const int64_t idx = 4 * i;
-    for (int t = 0; t < p.n_targets; ++t) {
-      const DpPlaneTarget& tg = p.t[t];
-      if (idx < tg.begin || idx >= tg.end) continue;
-      const int64_t rel = idx - tg.begin;
-      const int64_t r = rel / tg.cols;
-      const int c = (int)(rel - r * tg.cols);
-      float v4[4] = {w.x, w.y, w.z, w.w};
-      for (int pl = 0; pl < tg.planes; ++pl) {
-        const __nv_bfloat162 h0 = __floats2bfloat162_rn(v4[0], v4[1]), h1 = __floats2bfloat162_rn(v4[2], v4[3]);
-        const uint32_t u0 = *reinterpret_cast<const uint32_t*>(&h0), u1 = *reinterpret_cast<const uint32_t*>(&h1);
-        *reinterpret_cast<uint2*>(tg.base + pl * tg.plane_stride + r * tg.ld + c) = make_uint2(u0, u1);
-        v4[0] -= __uint_as_float(u0 << 16);
-        v4[1] -= __uint_as_float(u0 & 0xFFFF0000u);
-        v4[2] -= __uint_as_float(u1 << 16);
-        v4[3] -= __uint_as_float(u1 & 0xFFFF0000u);
+  // (four loads in flight per thread: the loop is bound by the latency of a peer load, not by its bandwidth)
+  constexpr int kGatherUnroll = 4;
+  for (int64_t i0 = p.lo4 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < p.hi4; i0 += kGatherUnroll * stride) {
+    float4 wv[kGatherUnroll];
+    int own[kGatherUnroll];
+#pragma unroll
+    for (int u = 0; u < kGatherUnroll; ++u) {
+      const int64_t i = i0 + u * stride;
+      if (i < p.hi4) {
+        int owner = (int)((i - p.lo4) / per);
+        own[u] = owner < world ? owner : world - 1;
+        wv[u] = ld_peer4(p.comm.flat[own[u]] + 4 * i);  // peers' (or my CTAs') fresh values: not through L1
       }
-      break;
+    }
+#pragma unroll
+    for (int u = 0; u < kGatherUnroll; ++u) {
+      const int64_t i = i0 + u * stride;
+      if (i >= p.hi4) break;
+      const float4 w = wv[u];
+      if (own[u] != rank) reinterpret_cast<float4*>(p.comm.flat[rank])[i] = w;
+      const int64_t idx = 4 * i;
+      for (int t = 0; t < p.n_targets; ++t) {
+        const DpPlaneTarget& tg = p.t[t];
+        if (idx < tg.begin || idx >= tg.end) continue;
+        const int64_t rel = idx - tg.begin;
+        const int64_t r = rel / tg.cols;
+        const int c = (int)(rel - r * tg.cols);
+        float v4[4] = {w.x, w.y, w.z, w.w};
+        for (int pl = 0; pl < tg.planes; ++pl) {
+          const __nv_bfloat162 h0 = __floats2bfloat162_rn(v4[0], v4[1]), h1 = __floats2bfloat162_rn(v4[2], v4[3]);
+          const uint32_t u0 = *reinterpret_cast<const uint32_t*>(&h0), u1 = *reinterpret_cast<const uint32_t*>(&h1);
+          *reinterpret_cast<uint2*>(tg.base + pl * tg.plane_stride + r * tg.ld + c) = make_uint2(u0, u1);
+          v4[0] -= __uint_as_float(u0 << 16);
+          v4[1] -= __uint_as_float(u0 & 0xFFFF0000u);
+          v4[2] -= __uint_as_float(u1 << 16);
+          v4[3] -= __uint_as_float(u1 & 0xFFFF0000u);
+        }
+        break;
+      }
     }
   }
   if (stamp) p.sync[p.channel ? 13 : 3] = (uint32_t)global_ns();
 }
 
+// Re-align the ranks: returns when every rank has launched it (flags of "channel" 2; epoch in sync[6]).
+__global__ void dp_rendezvous_kernel(const mvae_dp_comm comm, uint32_t* sync, unsigned long long timeout_ns) {
+  if (sync[kDpErrWord] != 0u) return;
+  const uint32_t e = sync[6] + 1u;
+  if ((int)threadIdx.x < comm.world) {
+    st_release_sys(comm.flags[threadIdx.x] + dp_slot(2, 0, comm.rank), e);
+    const uint32_t* f = comm.flags[comm.rank] + dp_slot(2, 0, threadIdx.x);
+    const unsigned long long t0 = global_ns();
+    while (ld_acquire_sys(f) < e)
+      if (global_ns() - t0 > timeout_ns) {
+        atomicCAS(&sync[kDpErrWord], 0u, 3u);
+        break;
+      }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) sync[6] = e;
+}
+
 }  // namespace mvae
 
 using namespace mvae;
+
+static unsigned long long dp_timeout_ns() {
+  // a peer that has not arrived within this time never will (MVAE_DP_TIMEOUT_S, default 30 s: rank skew of an
+  // evaluation pass or a checkpoint between two steps is legitimate, a dead peer is not)
+  double timeout_s = 30.0;
+  if (const char* env = getenv("MVAE_DP_TIMEOUT_S")) {
+    const double v = atof(env);
+    if (v > 0.0) timeout_s = v;
+  }
+  return (unsigned long long)(timeout_s * 1e9);
+}
+
+extern "C" int mvae_dp_rendezvous(const mvae_dp_comm* comm, uint32_t* sync_words, void* stream) {
+  if (!comm || !sync_words || comm->world < 1 || comm->world > MVAE_DP_MAX_RANKS || comm->rank < 0 ||
+      comm->rank >= comm->world)
+    return MVAE_ERR_INVALID_ARGUMENT;
+  for (int r = 0; r < comm->world; ++r)
+    if (!comm->flags[r]) return MVAE_ERR_INVALID_ARGUMENT;
+  DeviceInfo di;
+  int rc = get_device_info(&di);
+  if (rc != MVAE_OK) return rc;
+  dp_rendezvous_kernel<<<1, 32, 0, as_stream(stream)>>>(*comm, sync_words, dp_timeout_ns());
+  MVAE_LAUNCH_CHECK();
+  return MVAE_OK;
+}
 
 extern "C" int mvae_dp_alloc(size_t bytes, void** dev_ptr) {
   if (!dev_ptr || bytes == 0) return MVAE_ERR_INVALID_ARGUMENT;
@@ -422,14 +481,7 @@ extern "C" int mvae_dp_step(const mvae_dp_comm* comm, const mvae_dp_step_args* a
     p.t[t].plane_stride = pl.planes > 1 ? pl.plane_stride : 0;
     refresh4 = refresh4 > (te - tb) / 4 ? refresh4 : (te - tb) / 4;
   }
-  // a peer that has not arrived within this time never will (MVAE_DP_TIMEOUT_S, default 30 s: rank skew of an
-  // evaluation pass or a checkpoint between two steps is legitimate, a dead peer is not)
-  double timeout_s = 30.0;
-  if (const char* env = getenv("MVAE_DP_TIMEOUT_S")) {
-    const double v = atof(env);
-    if (v > 0.0) timeout_s = v;
-  }
-  p.timeout_ns = (unsigned long long)(timeout_s * 1e9);
+  p.timeout_ns = dp_timeout_ns();
   // The CTAs wait for each other (ticket in phase B), so all of them must be resident at once: at most one CTA per SM.
   // Enough CTAs for one pass over my slice (two float4 per thread) and two passes of the gather over the range.
   const int64_t per4 = (p.hi4 - p.lo4 + comm->world - 1) / comm->world;

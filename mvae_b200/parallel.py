@@ -175,6 +175,19 @@ def attach_p2p(model, optimizer, group=None) -> bool:
     return True
 
 
+def rendezvous(optimizer) -> None:
+    """Enqueue a kernel that returns once every rank has enqueued it (mvae_dp_rendezvous): re-aligns the ranks on the
+    device without a host barrier.  No-op without the peer-memory path."""
+    if getattr(optimizer, "_dp", None) is None:
+        return
+    import ctypes
+
+    from . import _lib as L
+    rc = L.lib().mvae_dp_rendezvous(ctypes.byref(optimizer._dp), optimizer._dp_sync.data_ptr(),
+                                    ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+    L.check(rc, "mvae_dp_rendezvous")
+
+
 def dp_error_word(optimizer) -> int:
     """0 unless a peer failed to arrive at a flag wait of mvae_dp_step within its time limit (sticky: every later step
     is a no-op).  train_step / train_epoch raise on it by themselves — it travels with the step's statistics."""

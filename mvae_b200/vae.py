@@ -266,9 +266,11 @@ class _Workspace:
             self.zp = ops.PlaneBuf(B, Sd, 3, dev, ones_col=True)  # 3 planes: z feeds fc_d0 + relu at fp32 accuracy
             self.gmlp = ops.PlaneBuf(B, P, 3, dev)  # 3 planes: the head weight gradients are read at fp32 accuracy
 
+    adopted = None  # a device-resident input batch used in place (FusedFeedForwardVAE.adopt_device_inputs)
+
     @property
     def x(self) -> Tensor:
-        return self.xbuf[self.slot]
+        return self.adopted if self.adopted is not None else self.xbuf[self.slot]
 
     @property
     def u8(self) -> bool:
@@ -752,6 +754,11 @@ class FusedFeedForwardVAE(nn.Module):
         return False
 
     noise_seed = 0x5EED            # Philox key of the in-kernel N(0, I) draws (set per model from torch's generator)
+    # True: a float32 batch that already lives on the model's device is read IN PLACE by the step's kernels instead of
+    # being copied into the workspace (saves the copy and its launch).  The tensor must stay alive and unchanged until
+    # the step has run; the CUDA graph of the step is keyed by its address (one graph per distinct batch tensor, at most
+    # 32 kept), so this suits a set of resident batches that is cycled through, not a fresh tensor every step.
+    adopt_device_inputs = False
     binarize_seed = 0              # Philox key of the on-device dynamic binarisation
     binarize_invert = False        # ImageDynamicBinarization(invert=...) (Omniglot)
     binarize_eval_dynamic = False  # forward() / log_likelihood() use the fixed 0.5 threshold like the reference's test loader
@@ -760,10 +767,15 @@ class FusedFeedForwardVAE(nn.Module):
         """Copy a batch into input slot `slot`: float batches as they are, uint8 image batches (raw grayscale pixels,
         what the dataset stores) into the slot's uint8 buffer — they are binarised on the device by the forward
         kernels.  Marks which kind the slot's consumer has to read."""
+        ws.adopted = None
         if x.dtype == torch.uint8:
             ws.x8  # allocate on first use
             ws.x8buf[slot].copy_(x.reshape(ws.B, self.in_dim), non_blocking=True)
             ws._u8[slot] = True
+        elif (self.adopt_device_inputs and x.is_cuda and x.dtype == torch.float32 and x.dim() == 2 and
+              x.shape[1] == self.in_dim and x.is_contiguous() and x.device == self.device and x.data_ptr() % 16 == 0):
+            ws.adopted = x   # read in place: no device-to-device copy (the step's graph is keyed by the address)
+            ws._u8[slot] = False
         else:
             ws.xbuf[slot].copy_(x.reshape(ws.B, self.in_dim), non_blocking=True)
             ws._u8[slot] = False
@@ -938,7 +950,8 @@ class FusedFeedForwardVAE(nn.Module):
             if self.check_finite and int(ws.flag.item()) != 0:
                 raise FloatingPointError("non-finite latent sample or KL term (device flag set by mvae_pm_forward)")
             return self._floats_of(h, beta), out
-        return BatchStats(self._stats_report.clone(), beta), out
+        # not synchronised: the device vector itself (valid until the next step overwrites it; clone() to keep it)
+        return BatchStats(self._stats_report, beta), out
 
     def _floats_of(self, h: List[float], beta: float) -> BatchStatsFloat:
         """Host copy of the statistics wire -> BatchStatsFloat; raises if the data-parallel step reported a peer
@@ -1067,10 +1080,11 @@ class FusedFeedForwardVAE(nn.Module):
         (the NCCL data-parallel path) it is split in two and the all-reduce runs between them, eagerly.  Keyed by everything baked into launch
         parameters: batch size, beta, and whether the curvature optimizers step."""
         # ... and every other value a launch bakes into its parameters (a changed learning rate must not replay the old one)
-        key = (ws.B, ws.slot, float(beta), optimizer.curvature_step_enabled(), id(optimizer), bool(draw_eps), ws.u8,
-               self._grad_hook is None, optimizer.hyper_parameters(), self.binarize_seed, self.noise_seed,
-               self.binarize_invert,
-               self.check_finite, self.train_statistics, self.fused_latent, self.latent_gemm)
+        adopted = ws.adopted
+        key = (ws.B, ws.slot, beta, optimizer.curvature_step_enabled(), id(optimizer), draw_eps, ws.u8,
+               self._grad_hook is None, optimizer.lr, optimizer.betas, optimizer.eps, optimizer.curvature_lr,
+               self.binarize_seed, self.noise_seed, self.binarize_invert, self.check_finite, self.train_statistics,
+               self.fused_latent, self.latent_gemm, 0 if adopted is None else adopted.data_ptr())
         entry = self._graphs.get(key)
         # Parameters changed outside the fused optimizer (load_state_dict, broadcast_parameters, an interleaved torch
         # optimizer): the graph's GEMMs read the weight PLANES, so they are rebuilt eagerly before any replay.
@@ -1109,8 +1123,10 @@ class FusedFeedForwardVAE(nn.Module):
                     capture_opt()
             optimizer.step_count = saved  # capture does not execute
             n2 = ops.launch_count()
-            entry = self._graphs[key] = (ga, gb, n1 - n0, n2 - n1)
-        ga, gb, la, lb = entry
+            if len(self._graphs) >= 32:   # bound the captured graphs (each pins its adopted input tensor)
+                self._graphs.pop(next(iter(self._graphs)))
+            entry = self._graphs[key] = (ga, gb, n1 - n0, n2 - n1, adopted)
+        ga, gb, la, lb, _ = entry
         ga.replay()
         if gb is not None:
             if self._grad_hook is not None:

@@ -202,6 +202,32 @@ def test_graph_replay_after_parameters_changed_outside(dev):
         assert normwise(a.cpu().numpy(), b.cpu().numpy()) < 2e-5, k
 
 
+def test_device_resident_batches_are_read_in_place(dev):
+    """adopt_device_inputs (what bench.py's `value` uses): a float32 batch that lives on the device is read in place —
+    same results as the copying path, one graph per batch tensor, and the kernels really see the tensor's CURRENT
+    contents."""
+    sig, B, D, H = "h2,s2,e2", 1024, 784, 400
+    xs, eps = _batches(B, D, 6, seed=13)
+    xs_dev = [x.to(dev) for x in xs[:3]]
+    outs = []
+    for adopt in (False, True):
+        model, opt = _build(sig, B, D, H, dev)
+        model.autotune_gemm = False
+        model.adopt_device_inputs = adopt
+        o = [model.train_step(opt, xs_dev[i % 3], BETA, eps=eps[i].to(dev))[0].elbo for i in range(5)]
+        outs.append((model, o))
+    (m0, o0), (m1, o1) = outs
+    assert len(m0._graphs) == 1 and len(m1._graphs) == 3
+    for a, b in zip(o0, o1):
+        assert abs(a - b) < 2e-6 * abs(a), (o0, o1)
+    for (k, a), (_, b) in zip(m0.state_dict().items(), m1.state_dict().items()):
+        assert normwise(b.cpu().numpy(), a.cpu().numpy()) < 2e-5, k
+    before = m1.train_step(opt, xs_dev[0], BETA, eps=eps[0].to(dev))[0].bce
+    xs_dev[0].copy_(1.0 - xs_dev[0])   # same tensor, new contents: the replayed graph must read them
+    after = m1.train_step(opt, xs_dev[0], BETA, eps=eps[0].to(dev))[0].bce
+    assert abs(after - before) > 0.5 * abs(before)
+
+
 def test_radius_rebind_reaches_the_kernels(dev, oracle):
     """Trainer._train_epoch REBINDS `c._pradius.data = ones_like(...) * (11 - epoch)` in its first ten epochs
     (train.py:189-194).  The kernels read the flat radius vector: the rebind must land there (and the parameter be
