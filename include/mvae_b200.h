@@ -470,6 +470,16 @@ int mvae_dp_step(const mvae_dp_comm* comm, const mvae_dp_step_args* args, void* 
  * word / time limit as mvae_dp_step. */
 int mvae_dp_rendezvous(const mvae_dp_comm* comm, uint32_t* sync_words, void* stream);
 
+/* Thin wrappers over the CUDA runtime (linked statically into the library) for the host side of the pipelined epoch
+ * loop — the batch loop of Trainer._train_epoch (train.py:197-210) with the host->device copy of batch i+1 and the
+ * device->host copy of the statistics overlapped with the kernels: asynchronous copy on a stream (cudaMemcpyDefault),
+ * event record, stream-wait-event.  `stream` / `event` are the caller framework's cudaStream_t / cudaEvent_t handles.
+ * They exist because the same operations through a Python framework cost 10-20 us of host time EACH (stream context
+ * switches), which made the end-to-end step host-bound at 0.2 ms per step. */
+int mvae_rt_memcpy_async(void* dst, const void* src, size_t bytes, void* stream);
+int mvae_rt_event_record(void* event, void* stream);
+int mvae_rt_stream_wait_event(void* stream, void* event);
+
 /* Device attributes the host layer needs for grid sizing / reporting. */
 int mvae_device_info(int32_t* sm_count, int32_t* cc_major, int32_t* cc_minor);
 

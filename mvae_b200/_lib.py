@@ -123,6 +123,9 @@ PROTOTYPES = {
     "mvae_dp_ipc_close": (ctypes.c_int, [_vp]),
     "mvae_dp_step": (ctypes.c_int, [ctypes.POINTER(DpComm), ctypes.POINTER(DpStepArgs), _vp]),
     "mvae_dp_rendezvous": (ctypes.c_int, [ctypes.POINTER(DpComm), _vp, _vp]),
+    "mvae_rt_memcpy_async": (ctypes.c_int, [_vp, _vp, ctypes.c_size_t, _vp]),
+    "mvae_rt_event_record": (ctypes.c_int, [_vp, _vp]),
+    "mvae_rt_stream_wait_event": (ctypes.c_int, [_vp, _vp]),
     "mvae_device_info": (ctypes.c_int, [ctypes.POINTER(_i32), ctypes.POINTER(_i32), ctypes.POINTER(_i32)]),
 }
 

@@ -45,6 +45,26 @@ bool pdl_enabled() {
 
 }  // namespace mvae
 
+// ---- thin CUDA-runtime helpers for the host-side pipeline of train_epoch (no kernels) ----
+extern "C" int mvae_rt_memcpy_async(void* dst, const void* src, size_t bytes, void* stream) {
+  if (!dst || !src) return MVAE_ERR_INVALID_ARGUMENT;
+  if (bytes == 0) return MVAE_OK;
+  MVAE_CUDA_TRY(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, mvae::as_stream(stream)));
+  return MVAE_OK;
+}
+
+extern "C" int mvae_rt_event_record(void* event, void* stream) {
+  if (!event) return MVAE_ERR_INVALID_ARGUMENT;
+  MVAE_CUDA_TRY(cudaEventRecord(reinterpret_cast<cudaEvent_t>(event), mvae::as_stream(stream)));
+  return MVAE_OK;
+}
+
+extern "C" int mvae_rt_stream_wait_event(void* stream, void* event) {
+  if (!event) return MVAE_ERR_INVALID_ARGUMENT;
+  MVAE_CUDA_TRY(cudaStreamWaitEvent(mvae::as_stream(stream), reinterpret_cast<cudaEvent_t>(event), 0));
+  return MVAE_OK;
+}
+
 extern "C" const char* mvae_strerror(int status) {
   switch (status) {
     case MVAE_OK: return "ok";

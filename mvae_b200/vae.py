@@ -18,6 +18,7 @@ Parameters keep the reference's names and shapes (state_dict round-trips, SURVEY
 into one flat fp32 buffer; gradients are views into one flat bucket [net grads | radius grads | ELBO stats] so that
 data-parallel training needs a single SUM all-reduce per step (mvae_b200/parallel.py).
 """
+import ctypes
 import os
 from typing import List, Optional, Tuple
 
@@ -1000,13 +1001,28 @@ class FusedFeedForwardVAE(nn.Module):
             self._copy_stream = torch.cuda.Stream(device=self.device)
             self._slot_ready = [torch.cuda.Event(), torch.cuda.Event()]
             self._slot_free = [torch.cuda.Event(), torch.cuda.Event()]
+            for ev in self._slot_ready + self._slot_free:
+                ev.record(main)   # torch creates the cudaEvent lazily: the raw handles are used below
         copy = self._copy_stream
         ring_n, nst = 64, self._stats_wire.numel()
         if getattr(self, "_stats_ring", None) is None or self._stats_ring.shape[1] != nst:
             self._stats_ring = torch.zeros(ring_n, nst, dtype=torch.float32).pin_memory()
             self._ring_ev = [torch.cuda.Event() for _ in range(ring_n)]
+            for ev in self._ring_ev:
+                ev.record(main)
         ring, ring_ev = self._stats_ring, self._ring_ev
         results: List[BatchStatsFloat] = []
+        # The stream / event / copy calls of the loop go straight to the CUDA runtime (mvae_rt_*): through torch each
+        # of them costs 10-20 us of host time (stream context switches), ~0.2 ms per step in total — more than the
+        # step's kernels take, i.e. the end-to-end loop was host-bound.
+        rt = L.lib()
+        vp = ctypes.c_void_p
+        main_h, copy_h = vp(main.cuda_stream), vp(copy.cuda_stream)
+        ready_h = [vp(e.cuda_event) for e in self._slot_ready]
+        free_h = [vp(e.cuda_event) for e in self._slot_free]
+        ring_h = [vp(e.cuda_event) for e in ring_ev]
+        ring_ptr, ring_row = ring.data_ptr(), nst * 4
+        wire_ptr = self._stats_wire.data_ptr()
 
         def take(item):
             x = item[0] if isinstance(item, (tuple, list)) else item
@@ -1014,12 +1030,22 @@ class FusedFeedForwardVAE(nn.Module):
 
         def prefetch(ws, slot, x, first):
             if not first:
-                copy.wait_event(self._slot_free[slot])  # the step that last read this slot has finished
+                rt.mvae_rt_stream_wait_event(copy_h, free_h[slot])  # the step that last read this slot has finished
             else:
                 copy.wait_stream(main)
-            with torch.cuda.stream(copy):
-                self._stage_x(ws, slot, x)
-                self._slot_ready[slot].record(copy)
+            n = ws.B * self.in_dim
+            if (not x.is_cuda) and x.is_contiguous() and x.numel() == n and x.dtype in (torch.uint8, torch.float32):
+                if x.dtype == torch.uint8:
+                    ws.x8  # allocate on first use
+                    dst, nbytes, ws._u8[slot] = ws.x8buf[slot], n, True
+                else:
+                    dst, nbytes, ws._u8[slot] = ws.xbuf[slot], 4 * n, False
+                ws.adopted = None
+                L.check(rt.mvae_rt_memcpy_async(vp(dst.data_ptr()), vp(x.data_ptr()), nbytes, copy_h), "H2D copy")
+            else:   # device tensors, other dtypes, views: the general path
+                with torch.cuda.stream(copy):
+                    self._stage_x(ws, slot, x)
+            rt.mvae_rt_event_record(ready_h[slot], copy_h)
 
         def drain(i):
             ring_ev[i % ring_n].synchronize()
@@ -1039,7 +1065,7 @@ class FusedFeedForwardVAE(nn.Module):
             B = x.shape[0]
             nxt = next(it, None)
             x_next = take(nxt) if nxt is not None else None
-            main.wait_event(self._slot_ready[slot])
+            rt.mvae_rt_stream_wait_event(main_h, ready_h[slot])
             ws.slot = slot
             if x_next is not None and x_next.shape[0] == B:
                 prefetch(ws, 1 - slot, x_next, first=(i == 0))
@@ -1047,11 +1073,11 @@ class FusedFeedForwardVAE(nn.Module):
             if eps is not None:
                 ws.eps.copy_(eps, non_blocking=True)
             self._step_kernels(optimizer, ws, beta, eps is None)
-            self._slot_free[slot].record(main)
+            rt.mvae_rt_event_record(free_h[slot], main_h)
             if i >= ring_n:
                 drain(i - ring_n)
-            ring[i % ring_n].copy_(self._stats_wire, non_blocking=True)
-            ring_ev[i % ring_n].record(main)
+            rt.mvae_rt_memcpy_async(vp(ring_ptr + (i % ring_n) * ring_row), vp(wire_ptr), ring_row, main_h)
+            rt.mvae_rt_event_record(ring_h[i % ring_n], main_h)
             i += 1
             if x_next is not None and x_next.shape[0] != B:  # ragged last batch: its own workspace, no overlap
                 ws = self._workspace(x_next.shape[0])

@@ -7,6 +7,17 @@ import numpy as np
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 
+def shim_pinned(name_or_sig: str) -> bool:
+    """True for fixtures whose reference run went through oracle/ref_shims/geoopt — a from-memory restatement of
+    geoopt 0.1.0 (the wheel is absent here and on no local index): every fixture with a `p`, `d` or `u` component.
+    Their formulas are pinned by the reference's own property tests; geoopt's guard CONSTANTS
+    (MIN_NORM, the artanh / tanh clamps, lambda_x's clamp_min) are the shim's.  Where those clamps bind, parity is
+    pinned to the shim, not to the real dependency ("parity unpinned")."""
+    body = name_or_sig.split("_", 1)[1] if "_" in name_or_sig else name_or_sig
+    return any(tok in ("p", "d", "u") or (tok[:1] in "pdu" and tok[1:2].isdigit())
+               for tok in body.replace(",", "_").split("_"))
+
+
 def load_golden(name):
     z = np.load(os.path.join(GOLDEN, name + ".npz"), allow_pickle=False)
     d = {k: z[k] for k in z.files}

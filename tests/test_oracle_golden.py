@@ -1,5 +1,9 @@
 """CPU tests: the C oracle against the golden vectors produced by the reference itself
 (tests/golden/generate_golden.py) and the known-answer vectors of SURVEY.md App. C.2."""
+# NOTE on the Poincare / projected-sphere / universal fixtures (helpers.shim_pinned): the reference delegates that
+# arithmetic to geoopt==0.1.0, which is absent here; the fixtures were generated through oracle/ref_shims/geoopt, a
+# restatement from memory.  They pin the oracle to the reference's formulas and call structure; geoopt's guard constants
+# are the shim's ("parity unpinned" where those clamps bind).
 import json
 import os
 
