@@ -342,6 +342,12 @@ int mvae_step_prologue(float* eps, int64_t n_eps, uint64_t seed, const uint64_t*
 /* *counter_dev += inc (the per-model step counter behind the Philox offsets above; one launch per step). */
 int mvae_counter_add(uint64_t* counter_dev, uint64_t inc, void* stream);
 
+/* ring[(*counter_dev) % capacity][0..n) = src[0..n), then ++*counter_dev: the per-step ELBO statistics
+ * (BatchStatsFloat, stats.py:115-127 — the reference reads them with 3 + C .item() calls per step) are parked in a
+ * device-side ring by the step itself and fetched by the epoch loop with ONE device->host copy per `capacity` steps
+ * instead of one per step. */
+int mvae_ring_push(const float* src, int32_t n, float* ring, int32_t capacity, uint64_t* counter_dev, void* stream);
+
 /* ------------------------------------------------------ importance-weighted log-likelihood (evaluation) */
 /* ModelVAE.log_likelihood (vae.py:82-123) draws n samples per input row.  The encoder runs once; per chunk of `ns`
  * samples mvae_iwae_latent does Component.encode's manifold part + rsample_log_probs of EVERY component

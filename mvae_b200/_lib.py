@@ -115,6 +115,7 @@ PROTOTYPES = {
     "mvae_colsum": (ctypes.c_int, [_vp, ctypes.POINTER(Planes), _i64, _i32, _i64, _vp, _vp]),
     "mvae_step_prologue": (ctypes.c_int, [_vp, _i64, ctypes.c_uint64, _vp, _i32, ctypes.POINTER(ctypes.c_void_p),
                                           ctypes.POINTER(_i64), _vp]),
+    "mvae_ring_push": (ctypes.c_int, [_vp, _i32, _vp, _i32, _vp, _vp]),
     "mvae_counter_add": (ctypes.c_int, [_vp, ctypes.c_uint64, _vp]),
     "mvae_dp_alloc": (ctypes.c_int, [ctypes.c_size_t, ctypes.POINTER(ctypes.c_void_p)]),
     "mvae_dp_free": (ctypes.c_int, [_vp]),

@@ -158,6 +158,15 @@ __global__ void __launch_bounds__(256) step_prologue_kernel(const PrologueParams
 
 __global__ void counter_add_kernel(unsigned long long* ctr, unsigned long long inc) { *ctr += inc; }
 
+// ring[(*ctr) % capacity][0..n) = src[0..n); ++*ctr   (one warp)
+__global__ void ring_push_kernel(const float* src, int n, float* ring, int capacity, unsigned long long* ctr) {
+  const unsigned long long c = *ctr;
+  float* dst = ring + (c % (unsigned long long)capacity) * n;
+  for (int i = threadIdx.x; i < n; i += 32) dst[i] = src[i];
+  __syncwarp();
+  if (threadIdx.x == 0) *ctr = c + 1ull;
+}
+
 }  // namespace mvae
 
 using namespace mvae;
@@ -200,6 +209,18 @@ extern "C" int mvae_counter_add(uint64_t* counter_dev, uint64_t inc, void* strea
   if (rc != MVAE_OK) return rc;
   counter_add_kernel<<<1, 1, 0, as_stream(stream)>>>(reinterpret_cast<unsigned long long*>(counter_dev),
                                                      (unsigned long long)inc);
+  MVAE_LAUNCH_CHECK();
+  return MVAE_OK;
+}
+
+extern "C" int mvae_ring_push(const float* src, int32_t n, float* ring, int32_t capacity, uint64_t* counter_dev,
+                              void* stream) {
+  if (!src || !ring || !counter_dev || n < 1 || capacity < 1) return MVAE_ERR_INVALID_ARGUMENT;
+  DeviceInfo di;
+  int rc = get_device_info(&di);
+  if (rc != MVAE_OK) return rc;
+  ring_push_kernel<<<1, 32, 0, as_stream(stream)>>>(src, n, ring, capacity,
+                                                    reinterpret_cast<unsigned long long*>(counter_dev));
   MVAE_LAUNCH_CHECK();
   return MVAE_OK;
 }

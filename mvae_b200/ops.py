@@ -281,6 +281,13 @@ def step_prologue(eps: Optional[torch.Tensor], seed: int, counter_dev: Optional[
     _LAUNCHES[0] += 1
 
 
+def ring_push(src: torch.Tensor, ring: torch.Tensor, counter_dev: torch.Tensor):
+    """ring[counter % capacity] = src; counter += 1 on the device (mvae_ring_push)."""
+    rc = L.lib().mvae_ring_push(_ptr(src), src.numel(), _ptr(ring), ring.shape[0], _ptr(counter_dev), _stream())
+    L.check(rc, "mvae_ring_push")
+    _LAUNCHES[0] += 1
+
+
 def counter_add(counter_dev: torch.Tensor, inc: int = 1):
     rc = L.lib().mvae_counter_add(_ptr(counter_dev), int(inc), _stream())
     L.check(rc, "mvae_counter_add")

@@ -983,6 +983,8 @@ class FusedFeedForwardVAE(nn.Module):
                     ops.clip_grad_norm(self._gradius, self._clip_mask, 1.0)
             optimizer.step()
             self._planes_stale = not getattr(optimizer, "planes_fresh", False)
+            if self._push_stats:
+                self._push_stats_kernel()
 
     @torch.no_grad()
     def train_epoch(self, optimizer, batches, beta: float, eps_batches=None) -> List[BatchStatsFloat]:
@@ -1004,13 +1006,6 @@ class FusedFeedForwardVAE(nn.Module):
             for ev in self._slot_ready + self._slot_free:
                 ev.record(main)   # torch creates the cudaEvent lazily: the raw handles are used below
         copy = self._copy_stream
-        ring_n, nst = 64, self._stats_wire.numel()
-        if getattr(self, "_stats_ring", None) is None or self._stats_ring.shape[1] != nst:
-            self._stats_ring = torch.zeros(ring_n, nst, dtype=torch.float32).pin_memory()
-            self._ring_ev = [torch.cuda.Event() for _ in range(ring_n)]
-            for ev in self._ring_ev:
-                ev.record(main)
-        ring, ring_ev = self._stats_ring, self._ring_ev
         results: List[BatchStatsFloat] = []
         # The stream / event / copy calls of the loop go straight to the CUDA runtime (mvae_rt_*): through torch each
         # of them costs 10-20 us of host time (stream context switches), ~0.2 ms per step in total — more than the
@@ -1020,9 +1015,7 @@ class FusedFeedForwardVAE(nn.Module):
         main_h, copy_h = vp(main.cuda_stream), vp(copy.cuda_stream)
         ready_h = [vp(e.cuda_event) for e in self._slot_ready]
         free_h = [vp(e.cuda_event) for e in self._slot_free]
-        ring_h = [vp(e.cuda_event) for e in ring_ev]
-        ring_ptr, ring_row = ring.data_ptr(), nst * 4
-        wire_ptr = self._stats_wire.data_ptr()
+        cap = self.stats_ring_capacity
 
         def take(item):
             x = item[0] if isinstance(item, (tuple, list)) else item
@@ -1047,9 +1040,18 @@ class FusedFeedForwardVAE(nn.Module):
                     self._stage_x(ws, slot, x)
             rt.mvae_rt_event_record(ready_h[slot], copy_h)
 
-        def drain(i):
-            ring_ev[i % ring_n].synchronize()
-            results.append(self._floats_of(ring[i % ring_n].tolist(), beta))
+        self._ensure_stats_ring()
+        state = {"i": 0}
+
+        def fetch():
+            """Statistics of the steps of this epoch not fetched yet: one device->host copy of the ring."""
+            i = state["i"]
+            if i <= len(results):
+                return
+            rows = self._stats_ring_dev.cpu().tolist()   # synchronises: every enqueued step has finished
+            base = self._ring_count - i                  # value of the device counter when this epoch started
+            for j in range(len(results), i):
+                results.append(self._floats_of(rows[(base + j) % cap], beta))
 
         it = iter(batches)
         eps_it = iter(eps_batches) if eps_batches is not None else None
@@ -1060,38 +1062,56 @@ class FusedFeedForwardVAE(nn.Module):
         ws = self._workspace(x.shape[0])
         slot = ws.slot
         prefetch(ws, slot, x, first=True)
-        i = 0
-        while x is not None:
-            B = x.shape[0]
-            nxt = next(it, None)
-            x_next = take(nxt) if nxt is not None else None
-            rt.mvae_rt_stream_wait_event(main_h, ready_h[slot])
-            ws.slot = slot
-            if x_next is not None and x_next.shape[0] == B:
-                prefetch(ws, 1 - slot, x_next, first=(i == 0))
-            eps = next(eps_it) if eps_it is not None else self._eps_override
-            if eps is not None:
-                ws.eps.copy_(eps, non_blocking=True)
-            self._step_kernels(optimizer, ws, beta, eps is None)
-            rt.mvae_rt_event_record(free_h[slot], main_h)
-            if i >= ring_n:
-                drain(i - ring_n)
-            rt.mvae_rt_memcpy_async(vp(ring_ptr + (i % ring_n) * ring_row), vp(wire_ptr), ring_row, main_h)
-            rt.mvae_rt_event_record(ring_h[i % ring_n], main_h)
-            i += 1
-            if x_next is not None and x_next.shape[0] != B:  # ragged last batch: its own workspace, no overlap
-                ws = self._workspace(x_next.shape[0])
-                slot = ws.slot
-                prefetch(ws, slot, x_next, first=True)
-            else:
-                slot = 1 - slot
-            x = x_next
-        for j in range(max(0, i - ring_n), i):
-            drain(j)
+        self._push_stats = True   # the step's graph ends with mvae_ring_push
+        try:
+            while x is not None:
+                i = state["i"]
+                B = x.shape[0]
+                nxt = next(it, None)
+                x_next = take(nxt) if nxt is not None else None
+                rt.mvae_rt_stream_wait_event(main_h, ready_h[slot])
+                ws.slot = slot
+                if x_next is not None and x_next.shape[0] == B:
+                    prefetch(ws, 1 - slot, x_next, first=(i == 0))
+                eps = next(eps_it) if eps_it is not None else self._eps_override
+                if eps is not None:
+                    ws.eps.copy_(eps, non_blocking=True)
+                self._step_kernels(optimizer, ws, beta, eps is None)
+                rt.mvae_rt_event_record(free_h[slot], main_h)
+                state["i"] = i + 1
+                self._ring_count += 1
+                if state["i"] - len(results) >= cap:   # the ring is about to wrap: fetch it (a bubble once per `cap` steps)
+                    fetch()
+                if x_next is not None and x_next.shape[0] != B:  # ragged last batch: its own workspace, no overlap
+                    ws = self._workspace(x_next.shape[0])
+                    slot = ws.slot
+                    prefetch(ws, slot, x_next, first=True)
+                else:
+                    slot = 1 - slot
+                x = x_next
+            fetch()
+        finally:
+            self._push_stats = False
         self._last_ws = ws
         if self.check_finite and int(ws.flag.item()) != 0:
             raise FloatingPointError("non-finite latent sample or KL term (device flag set by mvae_pm_forward)")
         return results
+
+    # train_epoch: the step parks its statistics in a device-side ring (mvae_ring_push, the last node of its graph); the
+    # loop fetches the ring with one device->host copy per `stats_ring_capacity` steps instead of one per step
+    _push_stats = False
+    stats_ring_capacity = 256
+
+    def _ensure_stats_ring(self) -> None:
+        n = self._stats_wire.numel()
+        ring = getattr(self, "_stats_ring_dev", None)
+        if ring is None or tuple(ring.shape) != (self.stats_ring_capacity, n):
+            self._stats_ring_dev = torch.zeros(self.stats_ring_capacity, n, device=self.device)
+            self._ring_ctr = torch.zeros(1, device=self.device, dtype=torch.int64)
+            self._ring_count = 0   # host mirror of the device counter
+
+    def _push_stats_kernel(self) -> None:
+        ops.ring_push(self._stats_wire, self._stats_ring_dev, self._ring_ctr)
 
     _grad_hook = None
     _early_step = None  # data parallel over peer memory: FusedCurvatureOptimizer.step_early (parallel.attach_p2p)
@@ -1110,7 +1130,7 @@ class FusedFeedForwardVAE(nn.Module):
         key = (ws.B, ws.slot, beta, optimizer.curvature_step_enabled(), id(optimizer), draw_eps, ws.u8,
                self._grad_hook is None, optimizer.lr, optimizer.betas, optimizer.eps, optimizer.curvature_lr,
                self.binarize_seed, self.noise_seed, self.binarize_invert, self.check_finite, self.train_statistics,
-               self.fused_latent, self.latent_gemm, 0 if adopted is None else adopted.data_ptr())
+               self.fused_latent, self.latent_gemm, 0 if adopted is None else adopted.data_ptr(), self._push_stats)
         entry = self._graphs.get(key)
         # Parameters changed outside the fused optimizer (load_state_dict, broadcast_parameters, an interleaved torch
         # optimizer): the graph's GEMMs read the weight PLANES, so they are rebuilt eagerly before any replay.
@@ -1133,6 +1153,8 @@ class FusedFeedForwardVAE(nn.Module):
                 optimizer.step()
                 if not getattr(optimizer, "planes_fresh", False):
                     self.refresh_weight_planes()
+                if self._push_stats:
+                    self._push_stats_kernel()
 
             ga = torch.cuda.CUDAGraph()
             with torch.cuda.graph(ga):
