@@ -11,7 +11,7 @@
 // [B, P] / [B, Sd] / [B, H] intermediates through L2; fused, the per-sample intermediates (ml on the way back, gz, gml)
 // never leave shared memory and the activations h / gdd are read exactly once.
 //
-// A CTA owns R = 16 consecutive rows.  Their rows of h (or gdd and h; fp32, written by the producing GEMM's epilogue
+// A CTA owns R = 16 (backward) or 8 (forward) consecutive rows.  Their rows of h (or gdd and h; fp32, written by the producing GEMM's epilogue
 // for this kernel alone) are contiguous: one bulk asynchronous copy (TMA) lands them in shared memory, where they serve both access
 // patterns — warp-per-row dot products (lanes along the hidden dimension, shuffle reduction) and thread-per-column
 // outer products (rows unrolled in registers).  The manifold arithmetic is pm_math.cuh through dispatch_item, one warp
@@ -28,7 +28,12 @@
 
 namespace mvae {
 
-constexpr int kLatRows = 16;      // rows per CTA (8: twice the weight-gradient reductions, measured slower)
+// rows per CTA.  Backward: 16 (8 doubles the per-CTA weight-gradient reductions: measured slower).  Forward has no
+// reductions: 8 rows halve the serial chain of a CTA (one row per warp in the heads) and double the CTAs in flight.
+#ifndef MVAE_LAT_ROWS_FWD
+#define MVAE_LAT_ROWS_FWD 8
+#endif
+constexpr int kLatRows = MVAE_LAT_BWD ? 16 : MVAE_LAT_ROWS_FWD;
 constexpr int kLatThreads = 256;  // 8 warps
 
 struct LatParams {
