@@ -352,7 +352,7 @@ def step_rooflines(model, opt, x, peaks, flush, C, Sn, Sd, P, H, B):
         "latent_forward": 4 * H + 4 * Sn + 4 * (P + Sd + C) + 2 * 2 * H,       # h, eps -> ml, z, kl, dd (2 planes)
         "latent_backward": 4 * H + 4 * H + 4 * (P + Sn + Sd) + 2 * 2 * H,      # gdd, h, ml, eps, z -> gh (2 planes)
         "pm_forward": 4 * (3 * Sn + Sd + C), "pm_backward": 4 * (5 * Sn + Sd)}
-    rows, gemm_flops, gemm_us = [], 0.0, 0.0
+    rows, gemm_flops, gemm_us, gemm_issued = [], 0.0, 0.0, 0.0
     for name, fn, a, k in calls:
         ms = time_kernel(lambda: fn(*a, **k), 10, flush)
         if name == "gemm":
@@ -360,9 +360,16 @@ def step_rooflines(model, opt, x, peaks, flush, C, Sn, Sd, P, H, B):
             fl = 2.0 * M * N * K
             gemm_flops += fl
             gemm_us += ms * 1e3
+            # bf16 MMAs the kernel issues per algorithmic product: plane pairs (i, j) with i + j < max(planes)
+            pa = k.get("a_planes") or a[0].planes
+            pb = k.get("b_planes") or a[1].planes
+            pa, pb = min(pa, a[0].planes), min(pb, a[1].planes)
+            products = sum(1 for i in range(pa) for j in range(pb) if i + j < max(pa, pb))
+            gemm_issued += fl * products
             rows.append({"kernel": "gemm_tcgen05_kernel", "shape": [M, N, K], "epilogue": int(k.get("epilogue", 0)),
                          "us": ms * 1e3, "tflops": fl / (ms * 1e-3) / 1e12,
-                         "frac": fl / (ms * 1e-3) / 1e12 / peaks["bf16_tflops"]})
+                         "frac": fl / (ms * 1e-3) / 1e12 / peaks["bf16_tflops"], "bf16_mmas_per_product": products,
+                         "issued_frac": fl * products / (ms * 1e-3) / 1e12 / peaks["bf16_tflops"]})
         else:
             by = bytes_of[name] * B
             rows.append({"kernel": name + "_kernel", "us": ms * 1e3, "gbs": by / (ms * 1e-3) / 1e9,
@@ -373,7 +380,10 @@ def step_rooflines(model, opt, x, peaks, flush, C, Sn, Sd, P, H, B):
         tf = gemm_flops / (gemm_us * 1e-6) / 1e12
         out["gemm_total"] = {"launches": sum(1 for r in rows if r["kernel"].startswith("gemm")), "us": gemm_us,
                              "tflops": tf, "peak": peaks["bf16_tflops"], "frac": tf / peaks["bf16_tflops"],
-                             "bound": "tensor", "unit": "TFLOP/s"}
+                             "issued_frac": gemm_issued / (gemm_us * 1e-6) / 1e12 / peaks["bf16_tflops"],
+                             "bound": "tensor", "unit": "TFLOP/s",
+                             "note": "frac: algorithmic fp32 flops; issued_frac: the bf16 MMAs actually issued "
+                                     "(3 per product with 2 + 2 planes, 6 with 3 + 3)"}
     return out
 
 

@@ -226,7 +226,8 @@ class FusedConvolutionalVAE(FusedFeedForwardVAE):
         side.wait_stream(main)
         with torch.cuda.stream(side):
             ops.step_prologue(ws.eps if draw_eps else None, self.noise_seed, self._bin_ctr,
-                              [ws.ml, self._bucket[:self._n_net + self.desc.C] if train else None])
+                              [ws.ml, ws.gz if train else None,
+                               self._bucket[:self._n_net + self.desc.C] if train else None])
         ws.drew_eps = draw_eps
         ws.has_mu_sigma = want_mu_sigma
         ws.fused = False
@@ -289,7 +290,8 @@ class FusedConvolutionalVAE(FusedFeedForwardVAE):
         with torch.cuda.stream(side):
             self._gemm("d0_wgrad", ws.gddf, ws.zp, 2048, Sd + 1, B, a_major=MN, b_major=MN, split_k=0,
                        out_f32=self._gW["d0"], out_col=self._gbias["d0"], col_split=Sd, a_planes=2, b_planes=2)
-        self._gemm("d0_dgrad", ws.gddf, self._Wp["d0"], B, Sd, 2048, b_major=MN, out_f32=ws.gz)
+        # (N = total_z_dim is a single narrow tile and K = 2048 is long: K slices over the SMs, summed into the zeroed gz)
+        self._gemm("d0_dgrad", ws.gddf, self._Wp["d0"], B, Sd, 2048, b_major=MN, out_f32=ws.gz, split_k=0)
         early = early and self._early_step is not None
         if early:   # the decoder's parameters are final: exchange + update them under the rest of the backward pass
             comm = self._comm_stream()

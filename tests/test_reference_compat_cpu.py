@@ -125,3 +125,42 @@ def test_train_step_output_types(ref):
     lr = vae.LazyReparametrized(lambda: calls.append(2) or ["a", "b"])
     assert list(zip(["x", "y"], lr)) == [("x", "a"), ("y", "b")] and lr[1] == "b" and len(lr) == 2
     assert calls.count(2) == 1
+
+
+def test_conv_model_state_dict_equals_the_reference_models(ref):
+    """FusedConvolutionalVAE stores conv filters in GEMM order ([Co, ky, kx, Ci]) behind parameters that keep the
+    reference's names, SHAPES and values (permuted views): same state_dict as ConvolutionalVAE (conv_vae.py:47-55)
+    under the same seed, checkpoints load both ways, gradients are exposed in the reference's layout."""
+    from mt.mvae import utils
+    from mvae_b200 import conv_vae, data
+    sig = "h2,s2,e2"
+    ref_model = rh.build_model(sig, 3072, 8192, False, False, "bce", 0, torch.float32, architecture="conv")
+    want = {k: v.detach().clone() for k, v in ref_model.state_dict().items()}
+    torch.manual_seed(0)
+    fused = conv_vae.FusedConvolutionalVAE(8192, utils.parse_components(sig, False), data.GenericDataset(4, 3072, "bce"),
+                                           False, device="cpu")
+    got = fused.state_dict()
+    assert list(got) == list(want)
+    for k in want:
+        assert tuple(got[k].shape) == tuple(want[k].shape), k
+        assert torch.equal(got[k].float(), want[k].float()), k
+    # the flat buffer holds the filters channel-innermost: rows of the GEMM operand
+    o, n = fused._slices["e1.weight"]
+    master = fused._flat[o:o + n].view(128, 4, 4, 64)
+    assert torch.equal(master, want["e1.weight"].permute(0, 2, 3, 1))
+    assert torch.equal(fused._W["e1"], want["e1.weight"].permute(0, 2, 3, 1).reshape(128, 1024))
+    o, n = fused._slices["d1.weight"]
+    assert torch.equal(fused._flat[o:o + n].view(128, 4, 4, 256), want["d1.weight"].permute(0, 2, 3, 1))
+    # checkpoints: reference -> fused (in place into the permuted views) and back
+    fused.load_state_dict({k: v * 2 for k, v in want.items()})
+    assert torch.equal(fused.e2.weight, want["e2.weight"] * 2) and fused._planes_stale
+    ref_model.load_state_dict({k: v.clone() for k, v in fused.state_dict().items()})
+    assert torch.equal(ref_model.d2.weight, want["d2.weight"] * 2)
+    # gradients live in the bucket in master order and are seen through the same permutation
+    fused._bucket.copy_(torch.arange(fused._bucket.numel(), dtype=torch.float32))
+    o, n = fused._slices["e0.weight"]
+    assert torch.equal(fused.e0.weight.grad, fused._bucket[o:o + n].view(64, 4, 4, 3).permute(0, 3, 1, 2))
+    fused._attach_grads()
+    assert fused.e0.weight.grad.shape == (64, 3, 4, 4) and fused.e0.weight.grad.data_ptr() == fused._bucket[o:].data_ptr()
+    # Trainer.build_optimizer sees reference-shaped parameters
+    assert {tuple(p.shape) for n_, p in fused.named_parameters() if n_.endswith("d3.weight")} == {(64, 3, 4, 4)}
