@@ -395,9 +395,11 @@ int mvae_sgd_step(int64_t n, float* param, const float* grad, float lr, float gr
 /* The whole optimizer step of Trainer.build_optimizer / CurvatureOptimizer (train.py:327-360, utils.py:148-180) in one
  * launch: Adam over the flat bucket of n (multiple of 4) network parameters with the step counter on the device
  * (incremented here), SGD with radius_lr on the C raw radii (radius may be NULL; radius_lr 0 = no curvature step;
- * gradient times radius_mask, NULL = ones), and the split-bf16 planes of up to four weight matrices refreshed from the
+ * gradient times radius_mask, NULL = ones), and the split-bf16 planes of up to eight weight matrices refreshed from the
  * updated values: matrix t occupies [target_begin[t], target_begin[t] + target_rows[t] * targets[t].cols) of the bucket
- * (begin and cols multiples of 4) and is written to targets[t].  done_counter: one zero-initialised device word. */
+ * (begin and cols multiples of 4) and is written to targets[t].  done_counter: one zero-initialised device word; NULL =
+ * the step counter is read but NOT advanced: a step may be several launches over disjoint parts of the parameters
+ * (one that is ready early can run under the rest of the backward pass), the last of which passes the counter. */
 int mvae_opt_step_fused(int64_t n, float* param, const float* grad, float* exp_avg, float* exp_avg_sq, float lr,
                         float beta1, float beta2, float eps, int32_t* step_dev, uint32_t* done_counter, float* radius,
                         const float* gradius, const float* radius_mask, float radius_lr, int32_t C, int32_t n_targets,

@@ -250,10 +250,10 @@ class FusedConvolutionalVAE(FusedFeedForwardVAE):
     def _heads_gemm(self, ws) -> None:
         ops.gemm(ws.hp, self.Whp, ws.B, self.desc.ld_ml, 8192, bias=self.bh, out_f32=ws.ml, split_k=8192 // 64)
 
-    def _backward_kernels(self, ws: _ConvWorkspace, beta: float, early: bool = True):
+    def _backward_kernels(self, ws: _ConvWorkspace, beta: float, early: bool = True, advance: Optional[bool] = None):
         B, P, Sd = ws.B, self.desc.ld_ml, self.desc.ld_z
         MN = L.MN_MAJOR
-        advance = early
+        advance = early if advance is None else advance
         main, side = torch.cuda.current_stream(self.device), self._side_stream()
         side.wait_stream(main)
         with torch.cuda.stream(side):   # weight / bias gradients run beside the chain of input gradients

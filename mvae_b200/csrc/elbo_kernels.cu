@@ -339,7 +339,9 @@ __global__ void __launch_bounds__(256) opt_fused_kernel(const __grid_constant__ 
         }
       }
   }
-  // the last CTA to finish bumps the step counter (every CTA has read it by then)
+  // the last CTA to finish bumps the step counter (every CTA has read it by then); a launch without a done counter
+  // (an early launch over part of the parameters: the rest follows in the launch that ends the step) leaves it alone
+  if (!q.done) return;
   __shared__ bool last;
   __threadfence();
   __syncthreads();
@@ -538,8 +540,7 @@ extern "C" int mvae_opt_step_fused(int64_t n, float* param, const float* grad, f
                                    const float* radius_mask, float radius_lr, int32_t C, int32_t n_targets,
                                    const int64_t* target_begin, const int32_t* target_rows,
                                    const mvae_planes* targets, void* stream) {
-  if (n < 0 || (n & 3) || !step_dev || !done_counter || n_targets < 0 || n_targets > 8 || C < 0)
-    return MVAE_ERR_INVALID_ARGUMENT;
+  if (n < 0 || (n & 3) || !step_dev || n_targets < 0 || n_targets > 8 || C < 0) return MVAE_ERR_INVALID_ARGUMENT;
   if (n > 0 && (!param || !grad || !exp_avg || !exp_avg_sq)) return MVAE_ERR_INVALID_ARGUMENT;
   if (!aligned16(param) || !aligned16(grad) || !aligned16(exp_avg) || !aligned16(exp_avg_sq)) return MVAE_ERR_ALIGNMENT;
   if (radius && radius_lr != 0.f && !gradius) return MVAE_ERR_INVALID_ARGUMENT;

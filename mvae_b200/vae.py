@@ -599,12 +599,12 @@ class FusedFeedForwardVAE(nn.Module):
         if not train:  # training: the reduction runs beside the backward GEMMs (_backward_kernels)
             ops.elbo_reduce(ws.bce, ws.kl, beta, out=self._stats)
 
-    def _backward_kernels(self, ws: _Workspace, beta: float, early: bool = True):
+    def _backward_kernels(self, ws: _Workspace, beta: float, early: bool = True, advance: Optional[bool] = None):
         """`early`: let a data-parallel optimizer exchange + update fc_logits on a third stream as soon as its gradient
         is complete (FusedCurvatureOptimizer.step_early), and advance the step counter behind the Philox draws —
         False for the warm-up pass ahead of a graph capture, which no optimizer step follows and which must leave the
         model's state (counters, exchanged parameters) untouched."""
-        advance = early
+        advance = early if advance is None else advance
         B, D, H, P, Sd, C = ws.B, self.in_dim, self.h_dim, self.desc.ld_ml, self.desc.ld_z, self.desc.C
         MN = L.MN_MAJOR
         # Fork: the ELBO reduction and the weight gradient of fc_logits depend only on the forward pass; they run as a
@@ -967,6 +967,7 @@ class FusedFeedForwardVAE(nn.Module):
     def _step_kernels(self, optimizer, ws: _Workspace, beta: float, draw_eps: bool = False) -> None:
         self._sync_radii()
         fused = isinstance(optimizer, FusedCurvatureOptimizer)
+        self._early_step = optimizer.step_early if fused else None   # the early launch is THIS optimizer's
         if fused and self.use_cuda_graph:
             self._graphed_step(optimizer, ws, beta, draw_eps)
         else:
@@ -974,7 +975,9 @@ class FusedFeedForwardVAE(nn.Module):
                 optimizer.zero_grad()
             self._forward_kernels(ws, beta, train=True, want_mu_sigma=self.train_statistics, logits=None,
                                      draw_eps=draw_eps)
-            self._backward_kernels(ws, beta)
+            # (the early optimizer launch belongs to the fused optimizer; with an all-reduce hook the gradients are not
+            # final before the hook has run)
+            self._backward_kernels(ws, beta, early=fused and self._grad_hook is None, advance=True)
             if self._grad_hook is not None:
                 self._grad_hook(self._bucket)  # data-parallel: one SUM all-reduce over [grads | radius grads | stats]
             if not fused:
@@ -1160,7 +1163,7 @@ class FusedFeedForwardVAE(nn.Module):
             with torch.cuda.graph(ga):
                 self._forward_kernels(ws, beta, train=True, want_mu_sigma=self.train_statistics, logits=None,
                                      draw_eps=draw_eps)
-                self._backward_kernels(ws, beta)
+                self._backward_kernels(ws, beta, early=one_graph, advance=True)
                 if one_graph:
                     capture_opt()
             n1 = ops.launch_count()
@@ -1226,6 +1229,7 @@ class FusedCurvatureOptimizer:
         self.param_groups = [{"params": [p for _, p in model._net_params()], "lr": learning_rate}]
         self._dp = self._dp_tail = self._dp_sync = None  # set by parallel.attach_p2p
         self._early_done = False
+        model._early_step = self.step_early   # used only by steps this optimizer drives (_step_kernels checks)
         self.dp_overlap = os.environ.get("MVAE_DP_OVERLAP", "1") != "0"
         self.dp_early_ctas = int(os.environ.get("MVAE_DP_EARLY_CTAS", "24"))
         self._done = torch.zeros(1, device=model._flat.device, dtype=torch.int32)
@@ -1268,14 +1272,33 @@ class FusedCurvatureOptimizer:
         return [(o, m._n_net), (0, o)] if self.dp_overlap else [(0, m._n_net)]
 
     def step_early(self) -> None:
-        """Data parallel only: exchange + update of fc_logits (half of the parameters), whose gradient is complete as
-        soon as the logits weight-gradient and input-gradient GEMMs are: the model calls this on a side stream so that
-        it runs UNDER the latent backward pass and the fc_e0 weight gradient (mvae_dp_step, channel 0, a few CTAs)."""
-        if self._dp is None or not self.dp_overlap:
+        """Update (under data parallelism: exchange + update) of fc_logits — half of the parameters — whose gradient is
+        complete as soon as the logits weight-gradient and input-gradient GEMMs are: the model calls this on a side
+        stream so that it runs UNDER the latent backward pass and the fc_e0 weight gradient (mvae_dp_step, channel 0,
+        a few CTAs; on one GPU mvae_opt_step_fused over that range, without advancing the step counter)."""
+        if not self.dp_overlap:
             return
         begin, end = self._dp_ranges()[0]
-        self._dp_launch(begin, end, 0, False, max_ctas=self.dp_early_ctas)
+        if self._dp is not None:
+            self._dp_launch(begin, end, 0, False, max_ctas=self.dp_early_ctas)
+        else:
+            self._local_launch(begin, end, last=False)
         self._early_done = True
+
+    def _local_launch(self, begin: int, end: int, last: bool) -> None:
+        """Adam over [begin, end) of the flat buffer + plane refresh of the GEMM weights inside; the launch that ends
+        the step (`last`) also steps the radii and advances the device step counter."""
+        m = self.model
+        targets, late = self._plane_targets()
+        inside = lambda off: begin <= off < end  # noqa: E731
+        ops.opt_step_fused(m._flat[begin:end], m._gnet[begin:end], self.exp_avg[begin:end], self.exp_avg_sq[begin:end],
+                           self.lr, self.betas[0], self.betas[1], self.eps, self.step_dev, self._done if last else None,
+                           m._rflat if last else None, m._gradius, m._radius_mask,
+                           self.curvature_lr if (last and self.curvature_step_enabled()) else 0.0,
+                           [(t[0] - begin, t[1], t[2]) for t in targets if inside(t[0])])
+        for w, buf in late:
+            if inside(w.data_ptr() - m._flat.data_ptr() >> 2):
+                ops.split_planes(w, buf)
 
     def step(self, closure=None) -> None:
         """The Adam step counter lives on the device (mvae_adam_step_dev), so this call can be captured in a CUDA
@@ -1294,14 +1317,11 @@ class FusedCurvatureOptimizer:
             return
         if m._clip_mask is not None:
             ops.clip_grad_norm(m._gradius, m._clip_mask, 1.0)  # vae.py:161-163
-        targets, late = self._plane_targets()
-        # Adam + the radii's SGD step + the refresh of the GEMM weight planes + the step counter: one launch
-        # (fixed radii receive no gradient: radius_mask)
-        ops.opt_step_fused(m._flat, m._gnet, self.exp_avg, self.exp_avg_sq, self.lr, self.betas[0], self.betas[1],
-                           self.eps, self.step_dev, self._done, m._rflat, m._gradius, m._radius_mask,
-                           self.curvature_lr if self.curvature_step_enabled() else 0.0, targets)
-        for w, buf in late:
-            ops.split_planes(w, buf)
+        # Adam + the radii's SGD step + the refresh of the GEMM weight planes + the step counter: one launch over
+        # whatever step_early() has not taken already (fixed radii receive no gradient: radius_mask)
+        end = self._dp_ranges()[-1][1] if self._early_done else m._n_net
+        self._early_done = False
+        self._local_launch(0, end, last=True)
         m._planes_stale = False
         self.planes_fresh = True
 
