@@ -147,12 +147,18 @@ __global__ void __launch_bounds__(kDpThreads) dp_step_kernel(const __grid_consta
   const int64_t per = (p.hi4 - p.lo4 + world - 1) / world;
   const int64_t lo = p.lo4 + rank * per, hi = min(p.hi4, lo + per);
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  const int64_t first = lo + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  // My slice is dealt out in contiguous chunks, one per CTA, so that EVERY SM issues a few of the peer loads: an SM can
+  // keep only so many loads in flight, and with the slice packed into the first CTAs (512 threads x 2 x world loads
+  // each) they went out in several rounds of one NVLink round trip each (measured: the slowest CTA finished 12 us
+  // after phase A at N = 8, the first warp of CTA 0 after 4 us).
+  const int64_t per_cta = ((hi - lo) + gridDim.x - 1) / gridDim.x;
+  const int64_t c_lo = lo + blockIdx.x * per_cta, c_hi = min(hi, c_lo + per_cta);
+  const int64_t first = c_lo + threadIdx.x;
   float4 m0[2], v0[2], p0[2];
 #pragma unroll
   for (int u = 0; u < 2; ++u) {
-    const int64_t i = first + u * stride;
-    if (i < hi) {
+    const int64_t i = first + u * blockDim.x;
+    if (i < c_hi) {
       m0[u] = reinterpret_cast<const float4*>(p.m)[i];
       v0[u] = reinterpret_cast<const float4*>(p.v)[i];
       p0[u] = reinterpret_cast<const float4*>(p.comm.flat[rank])[i];
@@ -182,18 +188,18 @@ __global__ void __launch_bounds__(kDpThreads) dp_step_kernel(const __grid_consta
   // ---- reduce-scatter + Adam on my slice of the range: the new values go into MY parameter buffer only ----
   // Two float4 per thread and iteration: all 2 x world peer loads are in flight before the first is consumed (the
   // loop is latency bound: a peer load is a few microseconds over NVLink).
-  for (int64_t i0 = first; i0 < hi; i0 += 2 * stride) {
-    const int64_t idx[2] = {i0, i0 + stride};
+  for (int64_t i0 = first; i0 < c_hi; i0 += 2 * blockDim.x) {
+    const int64_t idx[2] = {i0, i0 + blockDim.x};
     float4 t[2][MVAE_DP_MAX_RANKS];
 #pragma unroll
     for (int u = 0; u < 2; ++u)
 #pragma unroll
       for (int r = 0; r < MVAE_DP_MAX_RANKS; ++r)
-        if (r < world && idx[u] < hi) t[u][r] = ld_peer4(p.comm.bucket[r] + 4 * idx[u]);
+        if (r < world && idx[u] < c_hi) t[u][r] = ld_peer4(p.comm.bucket[r] + 4 * idx[u]);
 #pragma unroll
     for (int u = 0; u < 2; ++u) {
       const int64_t i = idx[u];
-      if (i >= hi) break;
+      if (i >= c_hi) break;
       float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
       for (int r = 0; r < MVAE_DP_MAX_RANKS; ++r)  // fixed rank order
@@ -490,7 +496,11 @@ extern "C" int mvae_dp_step(const mvae_dp_comm* comm, const mvae_dp_step_args* a
   if (want_gather > want) want = want_gather;
   (void)refresh4;
   int grid = (int)(want < 1 ? 1 : (want > di.sm_count ? di.sm_count : want));
-  if (a->max_ctas > 0 && grid > a->max_ctas) grid = a->max_ctas;
+  if (a->max_ctas > 0) {
+    if (grid > a->max_ctas) grid = a->max_ctas;
+  } else {
+    grid = di.sm_count;  // the launch at the end of the step has the machine to itself: spread the peer loads over all SMs
+  }
   dp_step_kernel<<<grid, kDpThreads, 0, as_stream(stream)>>>(p);
   MVAE_LAUNCH_CHECK();
   return MVAE_OK;
