@@ -413,7 +413,8 @@ int mvae_opt_step_fused(int64_t n, float* param, const float* grad, float* exp_a
  * the optimizer update (Adam on the network parameters, SGD on the radii: train.py:327-360, utils.py:148-180, gradient
  * clip of the "curvature" parameters: vae.py:161-163) for one RANGE of the parameter buffer in ONE kernel over NVLink
  * peer memory: reduce-scatter of the gradients with peer loads, Adam on the rank's slice (its moments are the only
- * optimizer state the rank keeps current), all-gather of the new parameters with peer stores.  A step is one or more
+ * optimizer state the rank keeps current), all-gather of the new parameters with peer loads (no remote stores: a
+ * load completes when its data arrives, a pushed store needs a system-scope fence).  A step is one or more
  * launches over disjoint ranges (a range whose gradient is complete early can be exchanged on a side stream while
  * the backward pass continues; concurrent launches use different channels); exactly one of them owns the tail.
  *

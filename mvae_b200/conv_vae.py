@@ -21,7 +21,7 @@ cfg5: CIFAR, --architecture=conv, --h_dim=8192) on the same kernels as FusedFeed
 Parameters keep the reference's names and SHAPES (`e0.weight` [64, 3, 4, 4], `d1.weight` [128, 256, 4, 4], ...); the
 flat buffer stores conv filters with the channel innermost ([Co, ky, kx, Ci] / [Ci, ky, kx, Co]) — the GEMM's layout —
 and the parameters are permuted views of it (FusedFeedForwardVAE._flatten)."""
-from typing import List, Optional, Tuple
+from typing import Optional, Tuple
 
 import torch
 import torch.nn as nn
