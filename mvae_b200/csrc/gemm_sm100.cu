@@ -64,6 +64,7 @@ struct GemmParams {
   const uint16_t* mask;
   int64_t ld_mask;
   float* rowsum;
+  int tma_store;     // out planes leave through a shared-memory tile and ONE bulk tensor store per plane
 };
 
 // ------------------------------------------------------------------------------------------------ PTX wrappers
@@ -174,6 +175,32 @@ __device__ __forceinline__ void store_planes16(const GemmParams& p, int m, int n
   }
 }
 
+// The same 16 values into the CTA's staging tile (shared memory, [plane][128 rows][block_n] bf16, row-major): the
+// epilogue's plane outputs then leave with one cp.async.bulk.tensor store per plane — full rows, clipped by the
+// tensor map at M and N — instead of 32-byte pieces of 32 different rows per warp instruction.
+__device__ __forceinline__ void stage_planes16(const GemmParams& p, uint8_t* tile, int r, int c, const float (&y)[16]) {
+  float rem[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) rem[j] = y[j];
+  for (int pl = 0; pl < p.op_planes; ++pl) {
+    uint32_t w[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      w[k] = pack_bf16x2(rem[2 * k], rem[2 * k + 1]);
+      rem[2 * k] -= __uint_as_float(w[k] << 16);
+      rem[2 * k + 1] -= __uint_as_float(w[k] & 0xFFFF0000u);
+    }
+    uint4* dst = reinterpret_cast<uint4*>(tile + ((size_t)(pl * kBlockM + r) * p.block_n + c) * 2);
+    dst[0] = make_uint4(w[0], w[1], w[2], w[3]);
+    dst[1] = make_uint4(w[4], w[5], w[6], w[7]);
+  }
+}
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(map), "r"(src),
+               "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+
 __device__ __forceinline__ void store_f32_16(float* out, int64_t ld, int m, int n, int N, const float (&y)[16],
                                              bool vec) {
   float* dst = out + (int64_t)m * ld + n;
@@ -190,7 +217,7 @@ __device__ __forceinline__ void store_f32_16(float* out, int64_t ld, int m, int 
 
 __global__ void __launch_bounds__(kGemmThreads, 2)
     gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-                        const __grid_constant__ GemmParams p) {
+                        const __grid_constant__ CUtensorMap map_out, const __grid_constant__ GemmParams p) {
   extern __shared__ uint8_t smem_raw[];
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -390,6 +417,9 @@ __global__ void __launch_bounds__(kGemmThreads, 2)
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     pdl_launch_dependents();  // main loop done: the next kernel's CTAs may take the SM resources this CTA frees soon
     float row_acc = 0.f;
+    // the operand stages are free once the accumulator is complete (every load consumed, every MMA retired): the first
+    // of them doubles as the staging tile of the plane outputs
+    uint8_t* tile = smem_raw + (base - raw);
     for (int c = c_first; c < p.block_n; c += 32) {
       const int n = n0 + c;
       if (n >= p.N) break;  // warp-uniform
@@ -441,13 +471,15 @@ __global__ void __launch_bounds__(kGemmThreads, 2)
         case MVAE_EPI_BIAS_RELU: {
 #pragma unroll
           for (int j = 0; j < 16; ++j) y[j] = fmaxf(y[j], 0.f);
-          if (p.op_base) store_planes16(p, m, n, y);
+          if (p.tma_store) stage_planes16(p, tile, q * 32 + lane, c, y);
+          else if (p.op_base) store_planes16(p, m, n, y);
           if (p.out_f32) store_f32_16(p.out_f32, p.ld_out, m, n, p.N, y, vec_out);
         } break;
         case MVAE_EPI_RELU_MASK: {
 #pragma unroll
           for (int j = 0; j < 16; ++j) y[j] = ((mk_cur >> j) & 1u) ? y[j] : 0.f;
-          if (p.op_base) store_planes16(p, m, n, y);
+          if (p.tma_store) stage_planes16(p, tile, q * 32 + lane, c, y);
+          else if (p.op_base) store_planes16(p, m, n, y);
           if (p.out_f32) store_f32_16(p.out_f32, p.ld_out, m, n, p.N, y, vec_out);
         } break;
         default: {  // BCE_ROWSUM / NLL_ROWSUM
@@ -475,11 +507,23 @@ __global__ void __launch_bounds__(kGemmThreads, 2)
             }
             if (n + j < p.N) row_acc += loss;
           }
-          if (p.op_base) store_planes16(p, m, n, g);
+          if (p.tma_store) stage_planes16(p, tile, q * 32 + lane, c, g);
+          else if (p.op_base) store_planes16(p, m, n, g);
         } break;
       }
     }
     if (is_loss && row_ok && p.rowsum) atomicAdd(p.rowsum + m, row_acc);
+    if (p.tma_store) {
+      // writes to shared memory -> visible to the async proxy, all 8 epilogue warps done, then one thread stores
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (te == 0) {
+        for (int pl = 0; pl < p.op_planes; ++pl)
+          tma_store_3d(&map_out, base + (uint32_t)(pl * kBlockM * p.block_n * 2), n0, m0, pl);
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // the tile may go away with the CTA
+      }
+    }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   }
   __syncthreads();
@@ -518,6 +562,21 @@ static int encode_planes(CUtensorMap* map, const mvae_planes& pl, int cols_bound
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, pl.base, dims, strides, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? MVAE_OK : MVAE_ERR_CUDA;
+}
+
+// 3-D map over output planes for the epilogue's bulk stores: box {block_n, 128, 1}, no swizzle (the staging tile is
+// plain row-major); the hardware clips the box at the tensor's bounds (rows >= M, columns >= N are not written).
+static int encode_out_planes(CUtensorMap* map, const mvae_planes& pl, int M, int N, int block_n) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return MVAE_ERR_CUDA;
+  cuuint64_t dims[3] = {(cuuint64_t)N, (cuuint64_t)M, (cuuint64_t)pl.planes};
+  cuuint64_t strides[2] = {(cuuint64_t)pl.ld * 2, (cuuint64_t)(pl.planes > 1 ? pl.plane_stride : (int64_t)pl.rows * pl.ld) * 2};
+  cuuint32_t box[3] = {(cuuint32_t)block_n, (cuuint32_t)kBlockM, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, pl.base, dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? MVAE_OK : MVAE_ERR_CUDA;
 }
@@ -659,7 +718,22 @@ extern "C" int mvae_gemm(const mvae_gemm_args* a, void* stream) {
   p.ld_mask = a->ld_mask;
   p.rowsum = a->rowsum;
 
-  CUtensorMap map_a, map_b;
+  CUtensorMap map_a, map_b, map_out;
+  memset(&map_out, 0, sizeof(map_out));
+  {
+    // plane outputs through a staging tile + bulk tensor stores when the tile fits the (then idle) operand stages;
+    // MVAE_GEMM_TMA_STORE=0 keeps the per-thread stores
+    static const bool tma_store_on = [] {
+      const char* e = getenv("MVAE_GEMM_TMA_STORE");
+      return !(e && e[0] == '0');
+    }();
+    const size_t tile_bytes = (size_t)p.op_planes * kBlockM * p.block_n * 2;
+    if (tma_store_on && p.op_planes > 0 && tile_bytes <= (size_t)stages * stage_bytes) {
+      rc = encode_out_planes(&map_out, a->out_planes, a->M, a->N, p.block_n);
+      if (rc != MVAE_OK) return rc;
+      p.tma_store = 1;
+    }
+  }
   // K-major: inner dim = K (logical), box rows = tile rows.  MN-major: inner dim = M or N (logical), box = 64 x 64.
   rc = encode_planes(&map_a, a->a, a_cols, a->a_major == MVAE_K_MAJOR ? kBlockM : kBlockK);
   if (rc != MVAE_OK) return rc;
@@ -677,7 +751,8 @@ extern "C" int mvae_gemm(const mvae_gemm_args* a, void* stream) {
   });
   MVAE_CUDA_TRY(attr_err);
   dim3 grid((a->M + kBlockM - 1) / kBlockM, (a->N + p.block_n - 1) / p.block_n, split);
-  MVAE_CUDA_TRY(launch_pdl(gemm_tcgen05_kernel, grid, dim3(kGemmThreads), smem, as_stream(stream), map_a, map_b, p));
+  MVAE_CUDA_TRY(launch_pdl(gemm_tcgen05_kernel, grid, dim3(kGemmThreads), smem, as_stream(stream), map_a, map_b, map_out,
+                           p));
   MVAE_LAUNCH_CHECK();
   return MVAE_OK;
 }

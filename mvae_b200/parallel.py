@@ -165,7 +165,6 @@ def attach_p2p(model, optimizer, group=None) -> bool:
     model._stats_report = optimizer._dp_tail[C:2 * C + 3]
     model._stats_wire = optimizer._dp_tail[C:]
     model._grad_hook = None
-    model._early_step = optimizer.step_early
     model._dp_region = region
     # dynamic binarisation (uint8 batches): every rank draws its own uniforms
     model.binarize_seed = int(model.binarize_seed) + 0x9E3779B1 * (rank + 1)

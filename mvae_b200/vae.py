@@ -967,7 +967,16 @@ class FusedFeedForwardVAE(nn.Module):
     def _step_kernels(self, optimizer, ws: _Workspace, beta: float, draw_eps: bool = False) -> None:
         self._sync_radii()
         fused = isinstance(optimizer, FusedCurvatureOptimizer)
-        self._early_step = optimizer.step_early if fused else None   # the early launch is THIS optimizer's
+        # the early launch is THIS optimizer's; held only while its step is being enqueued (a model attribute that kept
+        # the bound method would close a model <-> optimizer reference cycle, and cyclic garbage holding CUDA graphs is
+        # collected at arbitrary points — e.g. in the middle of a later graph capture)
+        self._early_step = optimizer.step_early if fused else None
+        try:
+            self._run_step(optimizer, ws, beta, draw_eps, fused)
+        finally:
+            self._early_step = None
+
+    def _run_step(self, optimizer, ws: _Workspace, beta: float, draw_eps: bool, fused: bool) -> None:
         if fused and self.use_cuda_graph:
             self._graphed_step(optimizer, ws, beta, draw_eps)
         else:
@@ -1117,7 +1126,7 @@ class FusedFeedForwardVAE(nn.Module):
         ops.ring_push(self._stats_wire, self._stats_ring_dev, self._ring_ctr)
 
     _grad_hook = None
-    _early_step = None  # data parallel over peer memory: FusedCurvatureOptimizer.step_early (parallel.attach_p2p)
+    _early_step = None  # FusedCurvatureOptimizer.step_early of the optimizer driving the step being enqueued
     use_cuda_graph = False
     latent_gemm = False
     train_statistics = False  # True: train_step keeps q_z's loc / scale (Trainer --train_statistics, train.py:200-206)
@@ -1159,19 +1168,18 @@ class FusedFeedForwardVAE(nn.Module):
                 if self._push_stats:
                     self._push_stats_kernel()
 
-            ga = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(ga):
+            def capture_step():
                 self._forward_kernels(ws, beta, train=True, want_mu_sigma=self.train_statistics, logits=None,
                                      draw_eps=draw_eps)
                 self._backward_kernels(ws, beta, early=one_graph, advance=True)
                 if one_graph:
                     capture_opt()
+
+            ga = self._capture(capture_step)
             n1 = ops.launch_count()
             gb = None
             if not one_graph:
-                gb = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(gb):
-                    capture_opt()
+                gb = self._capture(capture_opt)
             optimizer.step_count = saved  # capture does not execute
             n2 = ops.launch_count()
             if len(self._graphs) >= 32:   # bound the captured graphs (each pins its adopted input tensor)
@@ -1186,6 +1194,27 @@ class FusedFeedForwardVAE(nn.Module):
         optimizer.step_count += 1
         ops.add_launches(la + lb)
         self._planes_stale = False
+
+    @staticmethod
+    def _capture(fn) -> "torch.cuda.CUDAGraph":
+        """Capture fn() into a CUDA graph.  `thread_local` error mode: CUDA calls of OTHER threads (NCCL's watchdog, a
+        monitoring thread) are none of the capture's business.  A capture that still fails — e.g. because the garbage
+        collector released CUDA memory of an old model in the middle of it — is retried once after a full collection;
+        nothing has executed at that point (capture only records)."""
+        import gc
+        for attempt in (0, 1):
+            g = torch.cuda.CUDAGraph()
+            try:
+                with torch.cuda.graph(g, capture_error_mode="thread_local"):
+                    fn()
+                return g
+            except RuntimeError:
+                if attempt:
+                    raise
+                del g
+                gc.collect()
+                torch.cuda.synchronize()
+        raise AssertionError("unreachable")
 
     def _attach_grads(self) -> None:
         """torch optimizers' zero_grad(set_to_none=True) drops .grad; re-attach the bucket views."""
@@ -1229,7 +1258,6 @@ class FusedCurvatureOptimizer:
         self.param_groups = [{"params": [p for _, p in model._net_params()], "lr": learning_rate}]
         self._dp = self._dp_tail = self._dp_sync = None  # set by parallel.attach_p2p
         self._early_done = False
-        model._early_step = self.step_early   # used only by steps this optimizer drives (_step_kernels checks)
         self.dp_overlap = os.environ.get("MVAE_DP_OVERLAP", "1") != "0"
         self.dp_early_ctas = int(os.environ.get("MVAE_DP_EARLY_CTAS", "24"))
         self._done = torch.zeros(1, device=model._flat.device, dtype=torch.int32)
