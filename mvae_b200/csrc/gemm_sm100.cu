@@ -130,6 +130,22 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
       : "r"(taddr));
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+// the same in two halves: the load is in flight while the caller issues independent work (the next chunk's global loads)
+__device__ __forceinline__ void tmem_ld16_issue(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+}
+// (the registers are in/out operands of the wait so that no use of them can be scheduled ahead of it)
+__device__ __forceinline__ void tmem_ld_wait(uint32_t (&r)[16]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                 "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
+               :
+               : "memory");
+}
 
 // UMMA shared-memory descriptor, 128-byte swizzle (cute::UMMA::SmemDescriptor: start>>4 @0, LBO>>4 @16, SBO>>4 @32,
 // version=1 @46, layout SWIZZLE_128B=2 @61).
@@ -427,9 +443,10 @@ __global__ void __launch_bounds__(kGemmThreads, 2)
 #pragma unroll
       for (int j = 0; j < 16; ++j) t[j] = t_nxt[j];
       const uint32_t mk_cur = mk_nxt;
-      if (c + 32 < p.block_n) prefetch(c + 32);
       uint32_t r[16];
-      tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, r);
+      tmem_ld16_issue(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, r);   // in flight under the prefetch below
+      if (c + 32 < p.block_n) prefetch(c + 32);
+      tmem_ld_wait(r);
       if (!row_ok) continue;
       float y[16];
 #pragma unroll
