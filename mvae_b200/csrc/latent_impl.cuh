@@ -333,6 +333,48 @@ __global__ void __launch_bounds__(kLatThreads) latent_backward_kernel(const __gr
         red_add4(p.gWd0 + (int64_t)n * Sd + j, a[0], a[1], a[2], a[3]);
         red_add4(p.gWd0 + (int64_t)(n + 1) * Sd + j, b[0], b[1], b[2], b[3]);
       }
+    } else if (Sd <= 8) {
+      // narrow latent spaces whose width is not a multiple of 4 (h2: 3, p2: 2 coordinates): the 2 Sd gradients of the
+      // column pair (n, n + 1) are contiguous in gWd0 and start on an 8-byte boundary (n is even): Sd two-float
+      // reductions (one four-float reduction for Sd = 2) instead of 2 Sd scalar atomics
+      float c[16];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float a = 0.f, b = 0.f;
+        if (j < Sd) {
+#pragma unroll
+          for (int r = 0; r < R; ++r) {
+            const float zz = sZ[r * Sd + j];
+            a = fmaf(g0[r], zz, a);
+            b = fmaf(g1[r], zz, b);
+          }
+        }
+        c[j] = a;
+        c[8 + j] = b;
+      }
+      float* dst = p.gWd0 + (int64_t)n * Sd;
+      if (Sd == 2) {
+        red_add4(dst, c[0], c[1], c[8], c[9]);
+      } else {
+        // c2[i] = i < Sd ? a[i] : b[i - Sd], reduced in pairs (compile-time indices only: no local memory)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          if (i < Sd) {
+            const int i0 = 2 * i, i1 = 2 * i + 1;
+            float v0 = 0.f, v1 = 0.f;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              if (j < Sd) {
+                if (i0 == j) v0 = c[j];
+                if (i0 == Sd + j) v0 = c[8 + j];
+                if (i1 == j) v1 = c[j];
+                if (i1 == Sd + j) v1 = c[8 + j];
+              }
+            }
+            red_add2(dst + i0, v0, v1);
+          }
+        }
+      }
     } else {
       for (int j = 0; j < Sd; ++j) {
         float a = 0.f, b = 0.f;
