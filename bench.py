@@ -667,18 +667,22 @@ def run_ours(args):
         del ml, eps, z, kl, gz, gml
         # tcgen05 GEMM (tensor bound): encoder layer of the workload, algorithmic flops 2*B*D*H
         if conv:   # the largest forward GEMM of the convolutional stack: e2 as [B*16, 2048] x [512, 2048]^T
-            gm, gn, gk, what = B * 16, 512, 2048, "e2 forward: im2col(a1) . W^T, 3 + 3 planes = 6 bf16 MMAs per product"
+            gm, gn, gk, what, products = (B * 16, 512, 2048,
+                                          "e2 forward: im2col(a1) . W^T, 3 + 3 planes = 6 bf16 MMAs per product", 6)
             ms_g = time_kernel(lambda: ops.gemm(ws.A[2], model._Wp["e2"], gm, gn, gk, epilogue=1,
                                                 bias=model._bias["e2"], out_planes=ws.a[2], tile=(128, 1)), 20, flush)
         else:
-            gm, gn, gk, what = B, H, D, "fc_e0 forward; 3 bf16 MMAs per product (split planes)"
+            products = 3 if model.input_planes == 1 else 6   # x planes (1 for binarised inputs, else 3) x 3 weight planes
+            gm, gn, gk, what = B, H, D, f"fc_e0 forward; {products} bf16 MMAs per product (split planes)"
             ms_g = time_kernel(lambda: ops.gemm(ws.xp, model.We0p, B, H, D, epilogue=1, bias=model.fc_e0.bias.data,
                                                 out_planes=ws.hp), 20, flush)
         tf = 2.0 * gm * gn * gk / (ms_g * 1e-3) / 1e12
         line["roofline_gemm"] = {"kernel": "gemm_tcgen05_kernel", "shape": [gm, gn, gk], "bound": "tensor",
                                  "achieved": tf, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
                                  "frac": tf / peaks["bf16_tflops"], "us_per_launch": ms_g * 1e3,
-                                 "note": "algorithmic fp32 flops; " + what}
+                                 "bf16_mmas_per_product": products,
+                                 "issued_frac": tf * products / peaks["bf16_tflops"],
+                                 "note": "frac: algorithmic fp32 flops; issued_frac: the bf16 MMAs actually issued; " + what}
 
         line["roofline_step"] = step_rooflines(model, opt, xs_dev[0], peaks, flush, C, Sn, Sd, P, H, B)
 
