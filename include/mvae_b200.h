@@ -489,6 +489,13 @@ int mvae_rt_memcpy_async(void* dst, const void* src, size_t bytes, void* stream)
 int mvae_rt_event_record(void* event, void* stream);
 int mvae_rt_stream_wait_event(void* stream, void* event);
 
+/* Diagnostics of the fused latent block (scripts/latent_phases.py; not part of the reference-facing surface).  With a
+ * non-null `stamps` (device memory, 8 words per CTA of the next launches' grids) every CTA of mvae_latent_forward /
+ * mvae_latent_backward records %globaltimer at its phase boundaries; bit 0 of `flags` drops the weight-gradient
+ * reductions of the backward kernel (timing experiments only — the gradients are then wrong).  (NULL, 0) restores the
+ * production behaviour.  Process-wide, not thread-safe. */
+int mvae_debug_latent(unsigned long long* stamps, int32_t flags);
+
 /* Device attributes the host layer needs for grid sizing / reporting. */
 int mvae_device_info(int32_t* sm_count, int32_t* cc_major, int32_t* cc_minor);
 

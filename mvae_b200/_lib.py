@@ -127,6 +127,7 @@ PROTOTYPES = {
     "mvae_rt_memcpy_async": (ctypes.c_int, [_vp, _vp, ctypes.c_size_t, _vp]),
     "mvae_rt_event_record": (ctypes.c_int, [_vp, _vp]),
     "mvae_rt_stream_wait_event": (ctypes.c_int, [_vp, _vp]),
+    "mvae_debug_latent": (ctypes.c_int, [_vp, _i32]),
     "mvae_device_info": (ctypes.c_int, [ctypes.POINTER(_i32), ctypes.POINTER(_i32), ctypes.POINTER(_i32)]),
 }
 

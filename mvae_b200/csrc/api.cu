@@ -33,6 +33,10 @@ int get_device_info(DeviceInfo* out) {
   return MVAE_OK;
 }
 
+// diagnostics of the fused latent block (latent_impl.cuh): read by launch_latent on every launch
+unsigned long long* g_lat_stamps = nullptr;
+int g_lat_debug_flags = 0;
+
 bool pdl_enabled() {
   static const bool on = [] {
     // on by default (round 2: 0.181 -> 0.174 ms on the captured cfg2 step: a kernel's barrier / TMEM set-up runs under
@@ -62,6 +66,12 @@ extern "C" int mvae_rt_event_record(void* event, void* stream) {
 extern "C" int mvae_rt_stream_wait_event(void* stream, void* event) {
   if (!event) return MVAE_ERR_INVALID_ARGUMENT;
   MVAE_CUDA_TRY(cudaStreamWaitEvent(mvae::as_stream(stream), reinterpret_cast<cudaEvent_t>(event), 0));
+  return MVAE_OK;
+}
+
+extern "C" int mvae_debug_latent(unsigned long long* stamps, int32_t flags) {
+  mvae::g_lat_stamps = stamps;
+  mvae::g_lat_debug_flags = flags;
   return MVAE_OK;
 }
 

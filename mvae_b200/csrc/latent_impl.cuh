@@ -72,9 +72,27 @@ struct LatParams {
   float* gbh;
   float* gradius;
   int zero_gml;
+  // diagnostics (mvae_debug_latent; null / 0 in production): per-CTA %globaltimer stamps at the phase boundaries, and
+  // bit 0 of debug_flags drops the global reductions (timing experiments only: the gradients are then wrong)
+  unsigned long long* stamps;
+  int debug_flags;
   // shared-memory layout (bytes from the start of dynamic shared memory), host-computed
-  int off_a, off_b, off_ml, off_eps, off_z, off_kl, off_gz, off_gml, off_bar;
+  int off_a, off_b, off_ml, off_part, off_eps, off_z, off_kl, off_gz, off_gml, off_bar;
 };
+
+// diagnostics: set by mvae_debug_latent (api.cu), copied into LatParams by launch_latent
+extern unsigned long long* g_lat_stamps;
+extern int g_lat_debug_flags;
+constexpr int kLatStampSlots = 8;
+__device__ __forceinline__ void lat_stamp(const LatParams& p, int i, bool sync) {
+  if (p.stamps == nullptr) return;
+  if (sync) __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    p.stamps[(size_t)blockIdx.x * kLatStampSlots + i] = t;
+  }
+}
 
 __device__ __forceinline__ float bf16lo(uint32_t w) { return __uint_as_float(w << 16); }
 __device__ __forceinline__ float bf16hi(uint32_t w) { return __uint_as_float(w & 0xFFFF0000u); }
@@ -101,67 +119,108 @@ __device__ __forceinline__ void red_add4(float* p, float a, float b, float c, fl
   asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
-// out[r][n] = sum_k rowvec[k] * W[n][k] for ONE fp32 row held in shared memory; lanes stride the K = H columns in
-// chunks of 8, W rows are read with 128-bit loads through L1 (every warp of every CTA reads the same few KB).
-template <int NMAX>
-__device__ __forceinline__ void row_dot_WnK(const float* srow, int H, const float* __restrict__ W, int N,
-                                            float (&acc)[NMAX]) {
+// Access pattern of the skinny dot products.  Both kernels were bound by L1 wavefronts, not by arithmetic
+// (scripts/latent_phases.py: 16 of the backward kernel's 31 us sat in gz, 8 of the forward kernel's 17 us in the heads):
+// with a lane owning 8 consecutive hidden units, a warp's load of W touched 8 (W[n][k]) or 32 (W[h][j]) different
+// 128-byte lines per instruction, and every row of the CTA re-read all of W.  Now the lanes of a warp own NEIGHBOURING
+// pieces (one float4 of a W[n][.] row / one W[h][.] row each), and a warp takes NR = 2 rows at once so that every
+// W value it loads is used twice.
+
+// Sum 32 per-lane values across the warp in one go: returns, in lane L, the warp-wide sum of v[OFF + L].  Every round
+// a lane hands one half of what it still carries to its partner and keeps the other: 31 shuffles in 5 dependent
+// rounds (32 separate butterflies: 160 shuffles — and, one per conditional block, 32 x 5 exposed shuffle latencies).
+template <int HALF>
+__device__ __forceinline__ void warp_fold(float (&t)[16], int lane) {
+  const bool up = (lane & HALF) != 0;
+#pragma unroll
+  for (int k = 0; k < HALF; ++k) {
+    const float send = up ? t[k] : t[k + HALF], keep = up ? t[k + HALF] : t[k];
+    t[k] = keep + __shfl_xor_sync(0xffffffffu, send, HALF);
+  }
+}
+template <int OFF, int TOTAL>
+__device__ __forceinline__ float warp_reduce32(const float (&v)[TOTAL]) {
+  static_assert(OFF + 32 <= TOTAL, "slice out of range");
+  const int lane = threadIdx.x & 31;
+  const bool up = (lane & 16) != 0;
+  float t[16];
+#pragma unroll
+  for (int k = 0; k < 16; ++k) {
+    const float send = up ? v[OFF + k] : v[OFF + k + 16], keep = up ? v[OFF + k + 16] : v[OFF + k];
+    t[k] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+  }
+  warp_fold<8>(t, lane);
+  warp_fold<4>(t, lane);
+  warp_fold<2>(t, lane);
+  warp_fold<1>(t, lane);
+  return t[0];
+}
+
+// Per-lane partial sums acc[i * NMAX + n] of <row_i[4f..4f+3], W[n][4f..4f+3]> over the float4 columns f in [f0, f1)
+// (W row-major [N, H]); the caller reduces them over the warp.
+template <int NMAX, int NR>
+__device__ __forceinline__ void rows_dot_WnK(const float* const* srow, int f0, int f1, int H,
+                                             const float* __restrict__ W, int N, float (&acc)[NR * NMAX]) {
   const int lane = threadIdx.x & 31;
 #pragma unroll
-  for (int n = 0; n < NMAX; ++n) acc[n] = 0.f;
-  for (int c = lane; 8 * c < H; c += 32) {
-    float v[8];
-    row_load8(srow + 8 * c, v);
+  for (int i = 0; i < NR * NMAX; ++i) acc[i] = 0.f;
+  for (int f = f0 + lane; f < f1; f += 32) {
+    float4 v[NR];
+#pragma unroll
+    for (int i = 0; i < NR; ++i) v[i] = *reinterpret_cast<const float4*>(srow[i] + 4 * f);
 #pragma unroll
     for (int n = 0; n < NMAX; ++n)
       if (n < N) {
-        const float4 w0 = __ldg(reinterpret_cast<const float4*>(W + (int64_t)n * H + 8 * c));
-        const float4 w1 = __ldg(reinterpret_cast<const float4*>(W + (int64_t)n * H + 8 * c) + 1);
-        float t = acc[n];
-        t = fmaf(v[0], w0.x, t); t = fmaf(v[1], w0.y, t); t = fmaf(v[2], w0.z, t); t = fmaf(v[3], w0.w, t);
-        t = fmaf(v[4], w1.x, t); t = fmaf(v[5], w1.y, t); t = fmaf(v[6], w1.z, t); t = fmaf(v[7], w1.w, t);
-        acc[n] = t;
+        const float4 w = __ldg(reinterpret_cast<const float4*>(W + (int64_t)n * H) + f);
+#pragma unroll
+        for (int i = 0; i < NR; ++i) {
+          float t = acc[i * NMAX + n];
+          t = fmaf(v[i].x, w.x, t); t = fmaf(v[i].y, w.y, t); t = fmaf(v[i].z, w.z, t); t = fmaf(v[i].w, w.w, t);
+          acc[i * NMAX + n] = t;
+        }
       }
   }
-#pragma unroll
-  for (int n = 0; n < NMAX; ++n)
-    if (n < N) acc[n] = warp_sum(acc[n]);
 }
 
-// out[r][j] = sum_h rowvec[h] * W[h][j] (W row-major [H, J], J small): the dgrad of fc_d0 into z
-template <int JMAX>
-__device__ __forceinline__ void row_dot_WKn(const float* srow, int H, const float* __restrict__ W, int J,
-                                            float (&acc)[JMAX]) {
+// Per-lane partial sums acc[i * JMAX + j] of row_i[h] * W[h][j] over h = lane, lane + 32, ...  (W row-major [H, J], J
+// small): the dgrad of fc_d0 into z.  Neighbouring lanes read neighbouring W rows.
+template <int JMAX, int NR>
+__device__ __forceinline__ void rows_dot_WKn(const float* const* srow, int H, const float* __restrict__ W, int J,
+                                             float (&acc)[NR * JMAX]) {
   const int lane = threadIdx.x & 31;
 #pragma unroll
-  for (int j = 0; j < JMAX; ++j) acc[j] = 0.f;
-  const bool vec = (J & 3) == 0;
-  for (int c = lane; 8 * c < H; c += 32) {
-    float v[8];
-    row_load8(srow + 8 * c, v);
+  for (int i = 0; i < NR * JMAX; ++i) acc[i] = 0.f;
+  const bool vec = (J & 3) == 0 && (reinterpret_cast<uintptr_t>(W) & 15) == 0;
+#pragma unroll 2
+  for (int h = lane; h < H; h += 32) {
+    float g[NR];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const float* wr = W + (int64_t)(8 * c + i) * J;
-      if (vec) {
+    for (int i = 0; i < NR; ++i) g[i] = srow[i][h];
+    const float* wr = W + (int64_t)h * J;
+    if (vec) {
 #pragma unroll
-        for (int j = 0; j < JMAX; j += 4)
-          if (j < J) {
-            const float4 w = __ldg(reinterpret_cast<const float4*>(wr + j));
-            acc[j] = fmaf(v[i], w.x, acc[j]);
-            acc[j + 1] = fmaf(v[i], w.y, acc[j + 1]);
-            acc[j + 2] = fmaf(v[i], w.z, acc[j + 2]);
-            acc[j + 3] = fmaf(v[i], w.w, acc[j + 3]);
+      for (int j = 0; j < JMAX; j += 4)
+        if (j < J) {
+          const float4 w = __ldg(reinterpret_cast<const float4*>(wr + j));
+#pragma unroll
+          for (int i = 0; i < NR; ++i) {
+            float* a = acc + i * JMAX + j;
+            a[0] = fmaf(g[i], w.x, a[0]);
+            a[1] = fmaf(g[i], w.y, a[1]);
+            a[2] = fmaf(g[i], w.z, a[2]);
+            a[3] = fmaf(g[i], w.w, a[3]);
           }
-      } else {
+        }
+    } else {
 #pragma unroll
-        for (int j = 0; j < JMAX; ++j)
-          if (j < J) acc[j] = fmaf(v[i], __ldg(wr + j), acc[j]);
-      }
+      for (int j = 0; j < JMAX; ++j)
+        if (j < J) {
+          const float w = __ldg(wr + j);
+#pragma unroll
+          for (int i = 0; i < NR; ++i) acc[i * JMAX + j] = fmaf(g[i], w, acc[i * JMAX + j]);
+        }
     }
   }
-#pragma unroll
-  for (int j = 0; j < JMAX; ++j)
-    if (j < J) acc[j] = warp_sum(acc[j]);
 }
 
 #if !MVAE_LAT_BWD
@@ -186,7 +245,9 @@ __global__ void __launch_bounds__(kLatThreads) latent_forward_kernel(const __gri
     pm_mbar_init(bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
+  lat_stamp(p, 0, false);
   pdl_wait();  // the radii (previous optimizer step) and h (previous GEMM) are read from here on
+  lat_stamp(p, 1, false);
   stage_items(info, p.desc, p.radius);
   if (tid == 0) {
     const uint32_t bytes = (uint32_t)(rows * p.h_ld) * 4u;
@@ -196,18 +257,41 @@ __global__ void __launch_bounds__(kLatThreads) latent_forward_kernel(const __gri
   for (int i = tid; i < rows * Sn; i += blockDim.x) sEPS[i] = __ldg(p.eps + row0 * Sn + i);
   __syncthreads();
   pm_mbar_wait(bar, 0);
+  lat_stamp(p, 2, false);
 
-  // ---- heads: ml[r][p] = <h[r], Wh[p]> + bh[p]; one warp per row ----
-  for (int r = warp; r < rows; r += kLatThreads / 32) {
-    float acc[SMAX];
-    row_dot_WnK<SMAX>(sH + r * p.h_ld, H, p.Wh, P, acc);
-    if (lane == 0) {
+  // ---- heads: ml[r][n] = <h[r], Wh[n]> + bh[n] ----
+  // A warp takes the row pair (pr, pr + R/2) and, with R = 8, one half of the hidden dimension (8 warps = 4 pairs x
+  // 2 halves); the halves meet in shared memory (fixed order: the result does not depend on scheduling).
+  {
+    constexpr int kWarps = kLatThreads / 32, PAIRS = R / 2, KS = kWarps / PAIRS;
+    static_assert(R % 2 == 0 && kWarps % PAIRS == 0 && (KS == 1 || KS == 2), "row pairs x K halves must tile the warps");
+    constexpr int NR = SMAX <= 16 ? 2 : 1;  // wider head blocks: one row at a time (registers)
+    float* sPart = reinterpret_cast<float*>(smem + p.off_part);
+    const int pr = warp % PAIRS, ks = warp / PAIRS;
+    const int nf = H >> 2, f0 = ks * (nf / KS), f1 = ks == KS - 1 ? nf : f0 + nf / KS;
+    float* dst = ks == 0 ? sML : sPart;
 #pragma unroll
-      for (int n = 0; n < SMAX; ++n)
-        if (n < P) sML[r * P + n] = acc[n] + __ldg(p.bh + n);
+    for (int i0 = 0; i0 < 2; i0 += NR) {
+      const float* srow[NR];
+#pragma unroll
+      for (int i = 0; i < NR; ++i) srow[i] = sH + min(pr + (i0 + i) * PAIRS, rows - 1) * p.h_ld;
+      float acc[NR * SMAX];
+      rows_dot_WnK<SMAX, NR>(srow, f0, f1, H, p.Wh, P, acc);
+      // lane L ends up with the warp's sum number L (and 32 + L): one store per lane
+#pragma unroll
+      for (int off = 0; off < NR * SMAX; off += 32) {
+        const float sum = off == 0 ? warp_reduce32<0>(acc) : warp_reduce32<(NR * SMAX > 32 ? 32 : 0)>(acc);
+        const int idx = off + lane, n = idx % SMAX, r = pr + (i0 + idx / SMAX) * PAIRS;
+        if (n < P && r < rows) dst[r * P + n] = sum + (ks == 0 ? __ldg(p.bh + n) : 0.f);
+      }
+    }
+    if (KS > 1) {
+      __syncthreads();
+      for (int i = tid; i < rows * P; i += blockDim.x) sML[i] += sPart[i];
     }
   }
   __syncthreads();
+  lat_stamp(p, 3, false);
 
   // ---- manifold chain: one warp per component, lane = row ----
   bool finite = true;
@@ -226,12 +310,14 @@ __global__ void __launch_bounds__(kLatThreads) latent_forward_kernel(const __gri
     if (bad && lane == 0) atomicOr(p.flag, 1u);
   }
   __syncthreads();
+  lat_stamp(p, 4, false);
   for (int i = tid; i < rows * P; i += blockDim.x) p.ml[row0 * P + i] = sML[i];
   for (int i = tid; i < rows * Sd; i += blockDim.x) p.z[row0 * Sd + i] = sZ[i];
   for (int i = tid; i < rows * C; i += blockDim.x) p.kl[row0 * C + i] = sKL[i];
 
   pdl_launch_dependents();
-  // ---- fc_d0 + relu -> planes: thread per column pair, the 16 rows unrolled in registers ----
+  // ---- fc_d0 + relu -> planes: thread per column pair, the rows unrolled in registers ----
+  const bool vecd = (Sd & 3) == 0 && (reinterpret_cast<uintptr_t>(p.Wd0) & 15) == 0;
   for (int n = 2 * tid; n < H; n += 2 * kLatThreads) {
     float a0[R], a1[R];
     const float b0 = __ldg(p.bd0 + n), b1 = __ldg(p.bd0 + n + 1);
@@ -240,13 +326,30 @@ __global__ void __launch_bounds__(kLatThreads) latent_forward_kernel(const __gri
       a0[r] = b0;
       a1[r] = b1;
     }
-    for (int k = 0; k < Sd; ++k) {
-      const float w0 = __ldg(p.Wd0 + (int64_t)n * Sd + k), w1 = __ldg(p.Wd0 + (int64_t)(n + 1) * Sd + k);
+    if (vecd) {
+      // Sd % 4 == 0: the weights of the column pair as 128-bit loads, z four coordinates at a time (same order of
+      // the fused multiply-adds as the scalar loop)
+      for (int k = 0; k < Sd; k += 4) {
+        const float4 w0 = __ldg(reinterpret_cast<const float4*>(p.Wd0 + (int64_t)n * Sd + k));
+        const float4 w1 = __ldg(reinterpret_cast<const float4*>(p.Wd0 + (int64_t)(n + 1) * Sd + k));
 #pragma unroll
-      for (int r = 0; r < R; ++r) {
-        const float zz = sZ[r * Sd + k];
-        a0[r] = fmaf(zz, w0, a0[r]);
-        a1[r] = fmaf(zz, w1, a1[r]);
+        for (int r = 0; r < R; ++r) {
+          const float4 zz = *reinterpret_cast<const float4*>(sZ + r * Sd + k);
+          a0[r] = fmaf(zz.x, w0.x, a0[r]); a0[r] = fmaf(zz.y, w0.y, a0[r]);
+          a0[r] = fmaf(zz.z, w0.z, a0[r]); a0[r] = fmaf(zz.w, w0.w, a0[r]);
+          a1[r] = fmaf(zz.x, w1.x, a1[r]); a1[r] = fmaf(zz.y, w1.y, a1[r]);
+          a1[r] = fmaf(zz.z, w1.z, a1[r]); a1[r] = fmaf(zz.w, w1.w, a1[r]);
+        }
+      }
+    } else {
+      for (int k = 0; k < Sd; ++k) {
+        const float w0 = __ldg(p.Wd0 + (int64_t)n * Sd + k), w1 = __ldg(p.Wd0 + (int64_t)(n + 1) * Sd + k);
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          const float zz = sZ[r * Sd + k];
+          a0[r] = fmaf(zz, w0, a0[r]);
+          a1[r] = fmaf(zz, w1, a1[r]);
+        }
       }
     }
 #pragma unroll
@@ -254,6 +357,7 @@ __global__ void __launch_bounds__(kLatThreads) latent_forward_kernel(const __gri
       if (r < rows)
         planes_store2(p.dd + (row0 + r) * p.dd_ld + n, p.dd_stride, p.dd_planes, fmaxf(a0[r], 0.f), fmaxf(a1[r], 0.f));
   }
+  lat_stamp(p, 5, true);
 }
 
 #else
@@ -280,7 +384,9 @@ __global__ void __launch_bounds__(kLatThreads) latent_backward_kernel(const __gr
     pm_mbar_init(bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
+  lat_stamp(p, 0, false);
   pdl_wait();
+  lat_stamp(p, 1, false);
   stage_items(info, p.desc, p.radius);
   if (tid == 0) {
     const uint32_t gb = (uint32_t)(rows * p.gdd_ld) * 4u, hb = (uint32_t)(rows * p.h_ld) * 4u;
@@ -296,17 +402,31 @@ __global__ void __launch_bounds__(kLatThreads) latent_backward_kernel(const __gr
   for (int i = tid; i < R * Sd; i += blockDim.x) sZ[i] = i < rows * Sd ? __ldg(p.z_in + row0 * Sd + i) : 0.f;
   __syncthreads();
   pm_mbar_wait(bar, 0);
+  lat_stamp(p, 2, false);
+  const bool nored = (p.debug_flags & 1) != 0;
 
-  // ---- gz[r][j] = sum_h gdd[r][h] Wd0[h][j]; one warp per row ----
-  for (int r = warp; r < rows; r += kLatThreads / 32) {
-    float acc[SMAX];
-    row_dot_WKn<SMAX>(sG + r * p.gdd_ld, H, p.Wd0, Sd, acc);
-    if (lane == 0) {
+  // ---- gz[r][j] = sum_h gdd[r][h] Wd0[h][j]; a warp takes the row pair (warp, warp + R/2) ----
+  {
+    constexpr int kWarps = kLatThreads / 32, PAIRS = R / 2;
+    constexpr int NR = SMAX <= 16 ? 2 : 1;
+    for (int pr = warp; pr < PAIRS; pr += kWarps) {
 #pragma unroll
-      for (int j = 0; j < SMAX; ++j)
-        if (j < Sd) sGZ[r * Sd + j] = acc[j];
+      for (int i0 = 0; i0 < 2; i0 += NR) {
+        const float* srow[NR];
+#pragma unroll
+        for (int i = 0; i < NR; ++i) srow[i] = sG + min(pr + (i0 + i) * PAIRS, rows - 1) * p.gdd_ld;
+        float acc[NR * SMAX];
+        rows_dot_WKn<SMAX, NR>(srow, H, p.Wd0, Sd, acc);
+#pragma unroll
+        for (int off = 0; off < NR * SMAX; off += 32) {
+          const float sum = off == 0 ? warp_reduce32<0>(acc) : warp_reduce32<(NR * SMAX > 32 ? 32 : 0)>(acc);
+          const int idx = off + lane, j = idx % SMAX, r = pr + (i0 + idx / SMAX) * PAIRS;
+          if (j < Sd && r < rows) sGZ[r * Sd + j] = sum;
+        }
+      }
     }
   }
+  lat_stamp(p, 3, true);
   // ---- fc_d0 weight / bias gradient: gWd0[n][j] += sum_r gdd[r][n] z[r][j]; thread per column pair ----
   for (int n = 2 * tid; n < H; n += 2 * kLatThreads) {
     float g0[R], g1[R];
@@ -320,7 +440,7 @@ __global__ void __launch_bounds__(kLatThreads) latent_backward_kernel(const __gr
       s0 += g.x;
       s1 += g.y;
     }
-    if (p.gbd0) red_add2(p.gbd0 + n, s0, s1);
+    if (p.gbd0 && !nored) red_add2(p.gbd0 + n, s0, s1);
     if ((Sd & 3) == 0) {
       for (int j = 0; j < Sd; j += 4) {
         float a[4] = {0.f, 0.f, 0.f, 0.f}, b[4] = {0.f, 0.f, 0.f, 0.f};
@@ -330,8 +450,10 @@ __global__ void __launch_bounds__(kLatThreads) latent_backward_kernel(const __gr
           a[0] = fmaf(g0[r], zz.x, a[0]); a[1] = fmaf(g0[r], zz.y, a[1]); a[2] = fmaf(g0[r], zz.z, a[2]); a[3] = fmaf(g0[r], zz.w, a[3]);
           b[0] = fmaf(g1[r], zz.x, b[0]); b[1] = fmaf(g1[r], zz.y, b[1]); b[2] = fmaf(g1[r], zz.z, b[2]); b[3] = fmaf(g1[r], zz.w, b[3]);
         }
-        red_add4(p.gWd0 + (int64_t)n * Sd + j, a[0], a[1], a[2], a[3]);
-        red_add4(p.gWd0 + (int64_t)(n + 1) * Sd + j, b[0], b[1], b[2], b[3]);
+        if (!nored || a[0] + b[0] == 12345.f) {
+          red_add4(p.gWd0 + (int64_t)n * Sd + j, a[0], a[1], a[2], a[3]);
+          red_add4(p.gWd0 + (int64_t)(n + 1) * Sd + j, b[0], b[1], b[2], b[3]);
+        }
       }
     } else if (Sd <= 8) {
       // narrow latent spaces whose width is not a multiple of 4 (h2: 3, p2: 2 coordinates): the 2 Sd gradients of the
@@ -390,6 +512,7 @@ __global__ void __launch_bounds__(kLatThreads) latent_backward_kernel(const __gr
     }
   }
   __syncthreads();
+  lat_stamp(p, 4, false);
 
   // ---- reverse sweep of the manifold chain: one warp per component, lane = row ----
   for (int ci = warp; ci < C; ci += kLatThreads / 32) {
@@ -404,6 +527,7 @@ __global__ void __launch_bounds__(kLatThreads) latent_backward_kernel(const __gr
     }
   }
   __syncthreads();
+  lat_stamp(p, 5, false);
 
   pdl_launch_dependents();
   // ---- heads: gWh[q][k] += sum_r gml[r][q] h[r][k];  gh[r][k] = (sum_q gml[r][q] Wh[q][k]) 1[h[r][k] > 0] ----
@@ -435,32 +559,60 @@ __global__ void __launch_bounds__(kLatThreads) latent_backward_kernel(const __gr
       y0[r] = 0.f;
       y1[r] = 0.f;
     }
-    for (int q = 0; q < P; ++q) {
-      const float2 w = live ? __ldg(reinterpret_cast<const float2*>(p.Wh + (int64_t)q * H + k)) : make_float2(0.f, 0.f);
-      float a = 0.f, b = 0.f;
+    // four head rows per pass: their Wh loads are issued together (one after the other they were a chain of L2
+    // latencies), and with P % 4 == 0 one 128-bit shared-memory load brings a row's four gml values
+    const bool q4 = (P & 3) == 0;
+    for (int q0 = 0; q0 < P; q0 += 4) {
+      float2 w[4];
+      float a[4], b[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        w[u] = (live && q0 + u < P) ? __ldg(reinterpret_cast<const float2*>(p.Wh + (int64_t)(q0 + u) * H + k))
+                                    : make_float2(0.f, 0.f);
+        a[u] = 0.f;
+        b[u] = 0.f;
+      }
 #pragma unroll
       for (int r = 0; r < R; ++r) {
-        const float g = sGML[r * P + q];
-        y0[r] = fmaf(g, w.x, y0[r]);
-        y1[r] = fmaf(g, w.y, y1[r]);
-        a = fmaf(g, h0[r], a);
-        b = fmaf(g, h1[r], b);
+        float g[4];
+        if (q4) {
+          const float4 gg = *reinterpret_cast<const float4*>(sGML + r * P + q0);
+          g[0] = gg.x; g[1] = gg.y; g[2] = gg.z; g[3] = gg.w;
+        } else {
+#pragma unroll
+          for (int u = 0; u < 4; ++u) g[u] = q0 + u < P ? sGML[r * P + q0 + u] : 0.f;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          y0[r] = fmaf(g[u], w[u].x, y0[r]);
+          y1[r] = fmaf(g[u], w[u].y, y1[r]);
+          a[u] = fmaf(g[u], h0[r], a[u]);
+          b[u] = fmaf(g[u], h1[r], b[u]);
+        }
       }
-      // adjacent lanes own adjacent column pairs: the even lane issues ONE 128-bit reduction for both (the
-      // reductions, not the arithmetic, bound this phase)
-      const float a2 = __shfl_down_sync(0xffffffffu, a, 1), b2 = __shfl_down_sync(0xffffffffu, b, 1);
-      if (pair4) {
-        if ((lane & 1) == 0 && live) red_add4(p.gWh + (int64_t)q * H + k, a, b, a2, b2);
-      } else if (live) {
-        red_add2(p.gWh + (int64_t)q * H + k, a, b);
-      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (q0 + u < P) {
+          // adjacent lanes own adjacent column pairs: the even lane issues ONE 128-bit reduction for both
+          const float a2 = __shfl_down_sync(0xffffffffu, a[u], 1), b2 = __shfl_down_sync(0xffffffffu, b[u], 1);
+          float* dstw = p.gWh + (int64_t)(q0 + u) * H + k;
+          if (nored && a[u] + b2 != 12345.f) {
+            // timing experiment: no reduction (the comparison keeps the arithmetic alive)
+          } else if (pair4) {
+            if ((lane & 1) == 0 && live) red_add4(dstw, a[u], b[u], a2, b2);
+          } else if (live) {
+            red_add2(dstw, a[u], b[u]);
+          }
+        }
     }
+    lat_stamp(p, 6, true);
 #pragma unroll
     for (int r = 0; r < R; ++r)
       if (r < rows && live)
         planes_store2(p.gh + (row0 + r) * p.gh_ld + k, p.gh_stride, p.gh_planes, ((mask >> (2 * r)) & 1u) ? y0[r] : 0.f,
                       ((mask >> (2 * r + 1)) & 1u) ? y1[r] : 0.f);
   }
+  lat_stamp(p, 7, true);
 }
 #endif
 
@@ -489,6 +641,8 @@ static int launch_latent(LatParams& p, void* stream) {
   if (bwd) o += lat_align(R * p.h_ld * 4, 128);
   p.off_ml = o;
   o += lat_align(R * P * 4, 16);
+  p.off_part = o;  // forward: the heads' partial sums of the second half of the hidden dimension
+  if (!bwd) o += lat_align(R * P * 4, 16);
   p.off_eps = o;
   o += lat_align(R * Sn * 4, 16);
   p.off_z = o;
@@ -519,6 +673,8 @@ static int launch_latent(LatParams& p, void* stream) {
   if (smem > 48 * 1024) MVAE_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int64_t grid = (p.B + R - 1) / R;
   if (grid > 0x7fffffff) return MVAE_ERR_UNSUPPORTED;
+  p.stamps = g_lat_stamps;
+  p.debug_flags = g_lat_debug_flags;
   MVAE_CUDA_TRY(launch_pdl(kern, dim3((unsigned)grid), dim3(kLatThreads), smem, as_stream(stream), p));
   MVAE_LAUNCH_CHECK();
   return MVAE_OK;
