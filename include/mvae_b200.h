@@ -266,6 +266,27 @@ int mvae_latent_forward(const mvae_pm_desc* desc, int64_t B, int32_t H, const fl
                         float* ml, float* z, float* kl, const mvae_planes* dd_out, uint32_t* nonfinite_flag,
                         void* stream);
 
+/* The same launch taking the head of the train step with it (what mvae_step_prologue does in a launch of its own):
+ *   draw_eps != 0: eps [B, desc->ld_eps] is DRAWN here — Normal.rsample's noise (wrapped_normal.py:72), Philox4x32-10
+ *                  with seed / offset *counter_dev, element for element the stream of mvae_step_prologue — and written
+ *                  to `eps` for the backward pass, instead of being read;
+ *   zero_ptr / zero_n (n_zero <= 4 spans of floats): zero-filled by this launch — optimizer.zero_grad() (vae.py:151)
+ *                  and the reconstruction row sums; nothing before the latent block of a step accumulates into them.
+ * As a separate launch the prologue was a parallel branch of the step's graph, and this kernel the node that joined it:
+ * a full launch latency behind fc_e0 instead of a programmatic edge (scripts/step_timeline.py: 3.8 us). */
+typedef struct mvae_latent_prologue {
+  int32_t draw_eps;
+  int32_t n_zero;
+  uint64_t seed;
+  const uint64_t* counter_dev;
+  float* zero_ptr[4];
+  int64_t zero_n[4];
+} mvae_latent_prologue;
+int mvae_latent_forward_ex(const mvae_pm_desc* desc, int64_t B, int32_t H, const float* h, int64_t ld_h, const float* Wh,
+                           const float* bh, float* eps, const float* radius, const float* Wd0, const float* bd0,
+                           float* ml, float* z, float* kl, const mvae_planes* dd_out, uint32_t* nonfinite_flag,
+                           const mvae_latent_prologue* prologue, void* stream);
+
 /* backward of the block for d(loss)/d(dd) = gdd (fp32 [B, ld_gdd], already masked by relu'(dd)) and
  * d(loss)/d(kl) = gkl_scalar:
  *   gz = gdd Wd0;  gml = mvae_pm_backward(ml, eps, radius, gz, gkl_scalar);  gh = (gml Wh) * 1[h > 0]  -> planes
@@ -495,6 +516,20 @@ int mvae_rt_stream_wait_event(void* stream, void* event);
  * reductions of the backward kernel (timing experiments only — the gradients are then wrong).  (NULL, 0) restores the
  * production behaviour.  Process-wide, not thread-safe. */
 int mvae_debug_latent(unsigned long long* stamps, int32_t flags);
+/* The same for mvae_gemm: 16 words per CTA (linear CTA index x + gridDim.x (y + gridDim.y z)) — 0 kernel entry, 1
+ * barriers and TMEM set up, 2 predecessor grid complete (griddepcontrol.wait), 3 first operand stage landed, 4 last MMA
+ * issued, 5 accumulator complete, 6 first epilogue warp done, 7 CTA done, 8-10 first epilogue chunk (loaded / loss
+ * math / complete), 11 all epilogue warps done, 12 bulk stores issued (scripts/gemm_phases.py).  `flags` (timing
+ * experiments only, results are then wrong): 1 = no plane staging / stores, 2 = no loss arithmetic, 4 = no prefetch of
+ * the epilogue's global operands. */
+int mvae_debug_gemm(unsigned long long* stamps, int32_t flags);
+/* Timeline mode (scripts/step_timeline.py): with a non-null buffer every following mvae_gemm / mvae_latent_* launch
+ * stamps into its OWN region of the buffer (16 words per CTA, regions in launch order) — launches captured into a CUDA
+ * graph keep their regions, so one replay of a captured train step yields the start / end times of all its stamped
+ * kernels on one clock.  mvae_debug_timeline_log returns the (kind 0 gemm | 1 latent forward | 2 latent backward,
+ * CTAs, M|B, N|H, K) records of the launches since the buffer was set; mvae_debug_timeline(NULL) ends the mode. */
+int mvae_debug_timeline(unsigned long long* buffer);
+int mvae_debug_timeline_log(int32_t* out, int32_t max_entries);
 
 /* Device attributes the host layer needs for grid sizing / reporting. */
 int mvae_device_info(int32_t* sm_count, int32_t* cc_major, int32_t* cc_minor);

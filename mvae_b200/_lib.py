@@ -38,6 +38,11 @@ class Planes(ctypes.Structure):
                 ("cols", ctypes.c_int32), ("ld", ctypes.c_int32), ("planes", ctypes.c_int32)]
 
 
+class LatentPrologue(ctypes.Structure):
+    _fields_ = [("draw_eps", ctypes.c_int32), ("n_zero", ctypes.c_int32), ("seed", ctypes.c_uint64),
+                ("counter_dev", ctypes.c_void_p), ("zero_ptr", ctypes.c_void_p * 4), ("zero_n", ctypes.c_int64 * 4)]
+
+
 class GemmArgs(ctypes.Structure):
     _fields_ = [("a", Planes), ("b", Planes), ("a_major", ctypes.c_int32), ("b_major", ctypes.c_int32),
                 ("M", ctypes.c_int32), ("N", ctypes.c_int32), ("K", ctypes.c_int32), ("epilogue", ctypes.c_int32),
@@ -92,6 +97,9 @@ PROTOTYPES = {
                                          _i64, _vp, _vp, _i32, _vp]),
     "mvae_latent_forward": (ctypes.c_int, [ctypes.POINTER(PmDesc), _i64, _i32, _vp, _i64, _vp, _vp, _vp, _vp,
                                            _vp, _vp, _vp, _vp, _vp, ctypes.POINTER(Planes), _vp, _vp]),
+    "mvae_latent_forward_ex": (ctypes.c_int, [ctypes.POINTER(PmDesc), _i64, _i32, _vp, _i64, _vp, _vp, _vp, _vp,
+                                              _vp, _vp, _vp, _vp, _vp, ctypes.POINTER(Planes), _vp,
+                                              ctypes.POINTER(LatentPrologue), _vp]),
     "mvae_latent_backward": (ctypes.c_int, [ctypes.POINTER(PmDesc), _i64, _i32, _vp, _i64, _vp, _i64, _vp, _vp, _vp,
                                             _vp, _vp, _vp, _f32, ctypes.POINTER(Planes), _vp, _vp, _vp, _vp, _vp, _vp]),
     "mvae_recon_loss": (ctypes.c_int, [_i32, _i64, _i32, _vp, _vp, _vp, _vp, _vp]),
@@ -128,6 +136,9 @@ PROTOTYPES = {
     "mvae_rt_event_record": (ctypes.c_int, [_vp, _vp]),
     "mvae_rt_stream_wait_event": (ctypes.c_int, [_vp, _vp]),
     "mvae_debug_latent": (ctypes.c_int, [_vp, _i32]),
+    "mvae_debug_gemm": (ctypes.c_int, [_vp, _i32]),
+    "mvae_debug_timeline": (ctypes.c_int, [_vp]),
+    "mvae_debug_timeline_log": (ctypes.c_int, [ctypes.POINTER(_i32), _i32]),
     "mvae_device_info": (ctypes.c_int, [ctypes.POINTER(_i32), ctypes.POINTER(_i32), ctypes.POINTER(_i32)]),
 }
 

@@ -36,6 +36,22 @@ int get_device_info(DeviceInfo* out) {
 // diagnostics of the fused latent block (latent_impl.cuh): read by launch_latent on every launch
 unsigned long long* g_lat_stamps = nullptr;
 int g_lat_debug_flags = 0;
+// diagnostics of the tcgen05 GEMM (gemm_sm100.cu)
+unsigned long long* g_gemm_stamps = nullptr;
+int g_gemm_debug_flags = 0;
+// timeline mode (mvae_debug_timeline): every stamped launch gets its OWN 16-word-per-CTA region of one buffer, in launch
+// (= capture) order, so that the launches of a captured step can be laid side by side after a replay
+unsigned long long* g_dbg_cursor = nullptr;
+static int g_dbg_log[256][5];
+static int g_dbg_log_n = 0;
+unsigned long long* debug_timeline_region(int kind, long long ncta, int a, int b, int c) {
+  if (!g_dbg_cursor || g_dbg_log_n >= 256) return nullptr;
+  unsigned long long* r = g_dbg_cursor;
+  g_dbg_cursor += ncta * 16;
+  int* e = g_dbg_log[g_dbg_log_n++];
+  e[0] = kind; e[1] = (int)ncta; e[2] = a; e[3] = b; e[4] = c;
+  return r;
+}
 
 bool pdl_enabled() {
   static const bool on = [] {
@@ -73,6 +89,25 @@ extern "C" int mvae_debug_latent(unsigned long long* stamps, int32_t flags) {
   mvae::g_lat_stamps = stamps;
   mvae::g_lat_debug_flags = flags;
   return MVAE_OK;
+}
+
+extern "C" int mvae_debug_gemm(unsigned long long* stamps, int32_t flags) {
+  mvae::g_gemm_stamps = stamps;
+  mvae::g_gemm_debug_flags = flags;
+  return MVAE_OK;
+}
+
+extern "C" int mvae_debug_timeline(unsigned long long* buffer) {
+  mvae::g_dbg_cursor = buffer;
+  if (buffer) mvae::g_dbg_log_n = 0;
+  return MVAE_OK;
+}
+
+extern "C" int mvae_debug_timeline_log(int32_t* out, int32_t max_entries) {
+  int n = mvae::g_dbg_log_n < max_entries ? mvae::g_dbg_log_n : max_entries;
+  for (int i = 0; i < n; ++i)
+    for (int j = 0; j < 5; ++j) out[i * 5 + j] = mvae::g_dbg_log[i][j];
+  return n;
 }
 
 extern "C" const char* mvae_strerror(int status) {

@@ -65,7 +65,23 @@ struct GemmParams {
   int64_t ld_mask;
   float* rowsum;
   int tma_store;     // out planes leave through a shared-memory tile and ONE bulk tensor store per plane
+  unsigned long long* stamps;  // diagnostics (mvae_debug_gemm): 16 %globaltimer words per CTA, null in production
+  int debug_flags;             // timing experiments: 1 = no plane staging / stores, 2 = no loss math, 4 = no aux prefetch
 };
+
+// diagnostics: set by mvae_debug_gemm (api.cu), copied into GemmParams at launch
+extern unsigned long long* g_gemm_stamps;
+extern int g_gemm_debug_flags;
+__device__ __forceinline__ void gemm_stamp(const GemmParams& p, int i) {
+  if (p.stamps == nullptr) return;
+  // slots 0-7: %globaltimer (comparable across CTAs, ~0.26 us resolution); 8-15: the SM's cycle counter (the first
+  // epilogue thread's own progress; slot 15 = reference taken together with slot 5)
+  unsigned long long t;
+  if (i < 8) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  else t = (unsigned long long)clock64();
+  const size_t cta = ((size_t)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+  p.stamps[cta * 16 + i] = t;
+}
 
 // ------------------------------------------------------------------------------------------------ PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -159,6 +175,12 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes
   return d;
 }
 
+// one-MUFU transcendentals (ex2 / lg2 / rcp .approx.ftz: what __expf / __logf / __fdividef reduce to, without the
+// scaling multiplies the epilogue folds elsewhere)
+__device__ __forceinline__ float exp2f_approx(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float lg2f_approx(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float rcpf_approx(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);
@@ -243,6 +265,7 @@ __global__ void __launch_bounds__(kGemmThreads, 2)
   const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
   if (kb0 >= kb1) return;  // empty split-K slice (uniform over the CTA)
   const int nkb = kb1 - kb0;
+  if (threadIdx.x == 0) gemm_stamp(p, 0);
 
   // ---- shared memory carve-up: [stages x (A planes | B planes)] | barriers | tmem slot ----
   const uint32_t raw = smem_u32(smem_raw);
@@ -279,7 +302,9 @@ __global__ void __launch_bounds__(kGemmThreads, 2)
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot_ptr;
+  if (threadIdx.x == 0) gemm_stamp(p, 1);
   pdl_wait();  // everything above is independent of the previous kernel; operands and epilogue inputs are not
+  if (threadIdx.x == 0) gemm_stamp(p, 2);
 
   if (warp == 0) {
     // ===================================== TMA producer =====================================
@@ -346,6 +371,7 @@ __global__ void __launch_bounds__(kGemmThreads, 2)
         const int k_left = p.K - (kb0 + i) * kBlockK;
         const int nks = k_left >= kBlockK ? kBlockK / kUmmaK : (k_left + kUmmaK - 1) / kUmmaK;
         if (elect_one_sync()) {
+          if (i == 0) gemm_stamp(p, 3);  // first stage landed
           for (int pa = 0; pa < p.a_planes; ++pa)
             for (int pb = 0; pb < p.b_planes; ++pb) {
               if (pa + pb >= pmax) continue;
@@ -359,7 +385,10 @@ __global__ void __launch_bounds__(kGemmThreads, 2)
               }
             }
           umma_commit(empty_bar(s));  // stage reusable once these MMAs retire
-          if (i == nkb - 1) umma_commit(tmem_full_bar);  // accumulator complete
+          if (i == nkb - 1) {
+            umma_commit(tmem_full_bar);  // accumulator complete
+            gemm_stamp(p, 4);            // last MMA issued
+          }
         }
         accumulate = 1;
         __syncwarp();
@@ -388,7 +417,7 @@ __global__ void __launch_bounds__(kGemmThreads, 2)
     uint32_t mk_nxt = 0;
     auto prefetch = [&](int c) {
       const int n = n0 + c;
-      if (!row_ok || n >= p.N) return;
+      if (!row_ok || n >= p.N || (p.debug_flags & 4)) return;
       if (is_loss) {
         const float* xr = p.aux + m_aux * p.ld_aux + n;
         if (vec_aux && n + 16 <= p.N) {
@@ -432,6 +461,8 @@ __global__ void __launch_bounds__(kGemmThreads, 2)
     mbar_wait(tmem_full_bar, 0);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     pdl_launch_dependents();  // main loop done: the next kernel's CTAs may take the SM resources this CTA frees soon
+    if (te == 0) gemm_stamp(p, 5);  // accumulator complete
+    if (te == 0) gemm_stamp(p, 15);
     float row_acc = 0.f;
     // the operand stages are free once the accumulator is complete (every load consumed, every MMA retired): the first
     // of them doubles as the staging tile of the plane outputs
@@ -447,10 +478,12 @@ __global__ void __launch_bounds__(kGemmThreads, 2)
       tmem_ld16_issue(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, r);   // in flight under the prefetch below
       if (c + 32 < p.block_n) prefetch(c + 32);
       tmem_ld_wait(r);
+      if (te == 0 && c == c_first) gemm_stamp(p, 8);   // first accumulator chunk in registers
       if (!row_ok) continue;
       float y[16];
 #pragma unroll
       for (int j = 0; j < 16; ++j) y[j] = __uint_as_float(r[j]) + s_bias[c + j];
+      const bool dbg_nostage = (p.debug_flags & 1) != 0, dbg_nomath = (p.debug_flags & 2) != 0;
       switch (p.epilogue) {
         case MVAE_EPI_STORE: {
           if (p.atomic_out && vec_out && n + 16 <= p.N && !(p.col_split >= n && p.col_split < n + 16)) {
@@ -488,6 +521,7 @@ __global__ void __launch_bounds__(kGemmThreads, 2)
         case MVAE_EPI_BIAS_RELU: {
 #pragma unroll
           for (int j = 0; j < 16; ++j) y[j] = fmaxf(y[j], 0.f);
+          if (dbg_nostage && y[0] != 12345.f) break;
           if (p.tma_store) stage_planes16(p, tile, q * 32 + lane, c, y);
           else if (p.op_base) store_planes16(p, m, n, y);
           if (p.out_f32) store_f32_16(p.out_f32, p.ld_out, m, n, p.N, y, vec_out);
@@ -495,6 +529,7 @@ __global__ void __launch_bounds__(kGemmThreads, 2)
         case MVAE_EPI_RELU_MASK: {
 #pragma unroll
           for (int j = 0; j < 16; ++j) y[j] = ((mk_cur >> j) & 1u) ? y[j] : 0.f;
+          if (dbg_nostage && y[0] != 12345.f) break;
           if (p.tma_store) stage_planes16(p, tile, q * 32 + lane, c, y);
           else if (p.op_base) store_planes16(p, m, n, y);
           if (p.out_f32) store_f32_16(p.out_f32, p.ld_out, m, n, p.N, y, vec_out);
@@ -502,48 +537,85 @@ __global__ void __launch_bounds__(kGemmThreads, 2)
         default: {  // BCE_ROWSUM / NLL_ROWSUM
           if (p.out_f32) store_f32_16(p.out_f32, p.ld_out, m, n, p.N, y, vec_out);
           float g[16];
+          // The epilogue of this GEMM is bound by ALU issue (scripts/gemm_phases.py: ~24 instructions per element at
+          // two issue cycles each), so the arithmetic is written for instruction count:
+          //   loss = (1-t) x - log_sigmoid(x) = max(x, 0) - t x + ln2 lg2(1 + e),  e = exp(-|x|)
+          // is summed as two running sums (the lg2 terms take their ln2 once per chunk), the row-bound test of the
+          // ragged last chunk is hoisted out of the element loop, and sigmoid - t is one select + one FMA behind the
+          // reciprocal.  (log1p(e) as log(1 + e): the rounding of 1 + e costs <= 6e-8 ABSOLUTE per element, i.e. <= 5e-5
+          // on a row sum of order 1e2 and nothing measurable on the ELBO.)
+          const bool full = n + 16 <= p.N;
+          if (dbg_nomath) {
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const float lg = y[j];
-            float loss;
-            if (p.epilogue == MVAE_EPI_BCE_ROWSUM) {
-              // (1-t) x - log_sigmoid(x), log_sigmoid(x) = min(x,0) - log1p(e^-|x|); sigmoid from the same exponential
-              const float ex = __expf(-fabsf(lg));
-              const float u = 1.f + ex;
-              // log1p(ex) as log(1 + ex): the rounding of 1 + ex costs <= 6e-8 ABSOLUTE per element, i.e. <= 5e-5 on a
-              // row sum of order 1e2 and nothing measurable on the ELBO (the compensated form cost a divide, a compare
-              // and a select per element of the 3.2 M-element epilogue)
-              const float l1p = __logf(u);
-              loss = (1.f - t[j]) * lg - (fminf(lg, 0.f) - l1p);
-              const float inv = __fdividef(1.f, u);
-              g[j] = (lg >= 0.f ? inv : ex * inv) - t[j];
-            } else {
-              const float dlt = t[j] - lg;
-              loss = (dlt * dlt) / 2.f + kHalfLn2PiG;
-              g[j] = lg - t[j];
+            for (int j = 0; j < 16; ++j) {
+              g[j] = y[j] - t[j];
+              row_acc += y[j];
             }
-            if (n + j < p.N) row_acc += loss;
+          } else if (p.epilogue == MVAE_EPI_BCE_ROWSUM) {
+            float lin[16], l2[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const float lg = y[j];
+              const float ex = exp2f_approx(fabsf(lg) * -1.4426950408889634f);
+              const float u = 1.f + ex;
+              lin[j] = fmaf(-t[j], lg, fmaxf(lg, 0.f));
+              l2[j] = lg2f_approx(u);
+              g[j] = fmaf(rcpf_approx(u), lg >= 0.f ? 1.f : ex, -t[j]);
+            }
+            float s_lin = 0.f, s_lg2 = 0.f;
+            if (full) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) {
+                s_lin += lin[j];
+                s_lg2 += l2[j];
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 16; ++j)
+                if (n + j < p.N) {
+                  s_lin += lin[j];
+                  s_lg2 += l2[j];
+                }
+            }
+            row_acc += fmaf(s_lg2, 0.6931471805599453f, s_lin);
+          } else {
+            float s_sq = 0.f;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const float dlt = t[j] - y[j];
+              g[j] = -dlt;
+              if (full || n + j < p.N) s_sq = fmaf(dlt, dlt, s_sq);
+            }
+            const int cnt = full ? 16 : p.N - n;
+            row_acc += fmaf(0.5f, s_sq, (float)cnt * kHalfLn2PiG);
           }
+          if (te == 0 && c == c_first) gemm_stamp(p, 9);  // first chunk's loss math done
+          if (dbg_nostage && g[0] != 12345.f) break;
           if (p.tma_store) stage_planes16(p, tile, q * 32 + lane, c, g);
           else if (p.op_base) store_planes16(p, m, n, g);
         } break;
       }
+      if (te == 0 && c == c_first) gemm_stamp(p, 10);  // first chunk complete
     }
     if (is_loss && row_ok && p.rowsum) atomicAdd(p.rowsum + m, row_acc);
+    if (te == 0) gemm_stamp(p, 6);  // this warp's chunks done
     if (p.tma_store) {
       // writes to shared memory -> visible to the async proxy, all 8 epilogue warps done, then one thread stores
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (te == 0) gemm_stamp(p, 11);  // all epilogue warps done
       if (te == 0) {
         for (int pl = 0; pl < p.op_planes; ++pl)
           tma_store_3d(&map_out, base + (uint32_t)(pl * kBlockM * p.block_n * 2), n0, m0, pl);
         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // the tile may go away with the CTA
+        gemm_stamp(p, 12);  // bulk stores have read the tile
       }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   }
   __syncthreads();
+  if (threadIdx.x == 0) gemm_stamp(p, 7);
   if (warp == 1) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols)
@@ -734,6 +806,8 @@ extern "C" int mvae_gemm(const mvae_gemm_args* a, void* stream) {
   p.mask = a->mask;
   p.ld_mask = a->ld_mask;
   p.rowsum = a->rowsum;
+  p.stamps = g_gemm_stamps;
+  p.debug_flags = g_gemm_debug_flags;
 
   CUtensorMap map_a, map_b, map_out;
   memset(&map_out, 0, sizeof(map_out));
@@ -768,6 +842,8 @@ extern "C" int mvae_gemm(const mvae_gemm_args* a, void* stream) {
   });
   MVAE_CUDA_TRY(attr_err);
   dim3 grid((a->M + kBlockM - 1) / kBlockM, (a->N + p.block_n - 1) / p.block_n, split);
+  if (unsigned long long* region = debug_timeline_region(0, (long long)grid.x * grid.y * grid.z, a->M, a->N, a->K))
+    p.stamps = region;
   MVAE_CUDA_TRY(launch_pdl(gemm_tcgen05_kernel, grid, dim3(kGemmThreads), smem, as_stream(stream), map_a, map_b, map_out,
                            p));
   MVAE_LAUNCH_CHECK();

@@ -26,6 +26,10 @@
 #error "define MVAE_LAT_BWD to 0 (forward) or 1 (backward) before including latent_impl.cuh"
 #endif
 
+#if !MVAE_LAT_BWD
+#include <curand_kernel.h>
+#endif
+
 namespace mvae {
 
 // rows per CTA.  Backward: 16 (8 doubles the per-CTA weight-gradient reductions: measured slower).  Forward has no
@@ -72,6 +76,12 @@ struct LatParams {
   float* gbh;
   float* gradius;
   int zero_gml;
+  // forward: the head of the train step taken along (mvae_latent_forward_ex): noise drawn here, zero fills
+  int draw_eps, n_zero;
+  unsigned long long seed;
+  const unsigned long long* counter_dev;
+  float* zptr[4];
+  int64_t zn[4];
   // diagnostics (mvae_debug_latent; null / 0 in production): per-CTA %globaltimer stamps at the phase boundaries, and
   // bit 0 of debug_flags drops the global reductions (timing experiments only: the gradients are then wrong)
   unsigned long long* stamps;
@@ -83,15 +93,38 @@ struct LatParams {
 // diagnostics: set by mvae_debug_latent (api.cu), copied into LatParams by launch_latent
 extern unsigned long long* g_lat_stamps;
 extern int g_lat_debug_flags;
-constexpr int kLatStampSlots = 8;
+constexpr int kLatStampSlots = 16;
 __device__ __forceinline__ void lat_stamp(const LatParams& p, int i, bool sync) {
   if (p.stamps == nullptr) return;
   if (sync) __syncthreads();
   if (threadIdx.x == 0) {
+    // slots 0-7: %globaltimer (comparable across CTAs, ~0.26 us resolution); slots 8-15: the SM's cycle counter
+    // (thread 0's own progress inside a phase; slot 15 = reference taken together with slot 2)
     unsigned long long t;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    if (i < 8) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    else t = (unsigned long long)clock64();
     p.stamps[(size_t)blockIdx.x * kLatStampSlots + i] = t;
   }
+}
+
+#if !MVAE_LAT_BWD
+// one Philox4x32-10 counter block -> four standard normals (Box-Muller), exactly as step_prologue_kernel draws them;
+// not inlined: the generator's state would otherwise sit in the registers of the whole kernel
+__device__ __noinline__ float4 lat_normal4(unsigned long long seed, unsigned long long block, unsigned long long offset) {
+  curandStatePhilox4_32_10_t st;
+  curand_init(seed, block, offset, &st);
+  return curand_normal4(&st);
+}
+#endif
+
+// Pull a weight matrix (a few KB every CTA reads in full) towards the SM while the CTA's activation rows are still in
+// flight.  In a train step the weights were last touched by the previous step's optimizer: read on demand, the first
+// touch of every line is a DRAM round trip inside the dependent chains of the dot products (scripts/step_timeline.py:
+// heads 11.0 us in the captured step against 4.6 us with the weights warm in L2 — without this prefetch).
+__device__ __forceinline__ void lat_prefetch_l1(const float* base, int bytes) {
+  const char* b = reinterpret_cast<const char*>(base);
+  for (int off = threadIdx.x * 128; off < bytes; off += kLatThreads * 128)
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(b + off));
 }
 
 __device__ __forceinline__ float bf16lo(uint32_t w) { return __uint_as_float(w << 16); }
@@ -254,10 +287,47 @@ __global__ void __launch_bounds__(kLatThreads) latent_forward_kernel(const __gri
     pm_mbar_expect_tx(bar, bytes);
     pm_bulk_g2s(pm_smem_u32(sH), p.h + row0 * p.h_ld, bytes, bar);
   }
-  for (int i = tid; i < rows * Sn; i += blockDim.x) sEPS[i] = __ldg(p.eps + row0 * Sn + i);
+  lat_prefetch_l1(p.Wh, P * H * 4);
+  lat_prefetch_l1(p.Wd0, H * Sd * 4);
+  lat_prefetch_l1(p.bh, P * 4);
+  lat_prefetch_l1(p.bd0, H * 4);
+  if (p.draw_eps) {
+    // eps ~ N(0, I) for this CTA's rows: the Philox stream of step_prologue_kernel (input_kernels.cu) element for
+    // element — counter block i serves the flat elements 4i .. 4i+3 of eps [B, Sn]; R * Sn is a multiple of 4, so a
+    // CTA owns whole blocks.  Kept in shared memory for the chain below and written out for the backward pass.
+    const unsigned long long step = p.counter_dev ? *p.counter_dev : 0ull;
+    const int64_t n_eps = p.B * Sn, g0 = row0 * Sn >> 2;
+    const int ng = (rows * Sn + 3) >> 2;
+    float* eps_out = const_cast<float*>(p.eps);
+    for (int i = tid; i < ng; i += blockDim.x) {
+      const float4 v = lat_normal4(p.seed, (unsigned long long)(g0 + i), step * 4ull);
+      const float t[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (4 * (g0 + i) + j < n_eps) {
+          sEPS[4 * i + j] = t[j];
+          eps_out[4 * (g0 + i) + j] = t[j];
+        }
+    }
+  } else {
+    for (int i = tid; i < rows * Sn; i += blockDim.x) sEPS[i] = __ldg(p.eps + row0 * Sn + i);
+  }
+  // zero fills of the step (gradient bucket, reconstruction row sums), spread over the grid
+  for (int s = 0; s < p.n_zero; ++s) {
+    float* q = p.zptr[s];
+    const int64_t n = p.zn[s], gt = (int64_t)blockIdx.x * blockDim.x + tid, nth = (int64_t)gridDim.x * blockDim.x;
+    if ((reinterpret_cast<uintptr_t>(q) & 15) == 0) {
+      const int64_t n4 = n >> 2;
+      for (int64_t i = gt; i < n4; i += nth) reinterpret_cast<float4*>(q)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int64_t i = 4 * n4 + gt; i < n; i += nth) q[i] = 0.f;
+    } else {
+      for (int64_t i = gt; i < n; i += nth) q[i] = 0.f;
+    }
+  }
   __syncthreads();
   pm_mbar_wait(bar, 0);
   lat_stamp(p, 2, false);
+  lat_stamp(p, 15, false);
 
   // ---- heads: ml[r][n] = <h[r], Wh[n]> + bh[n] ----
   // A warp takes the row pair (pr, pr + R/2) and, with R = 8, one half of the hidden dimension (8 warps = 4 pairs x
@@ -277,6 +347,7 @@ __global__ void __launch_bounds__(kLatThreads) latent_forward_kernel(const __gri
       for (int i = 0; i < NR; ++i) srow[i] = sH + min(pr + (i0 + i) * PAIRS, rows - 1) * p.h_ld;
       float acc[NR * SMAX];
       rows_dot_WnK<SMAX, NR>(srow, f0, f1, H, p.Wh, P, acc);
+      lat_stamp(p, 8, false);   // (thread 0's warp) partial dot products done
       // lane L ends up with the warp's sum number L (and 32 + L): one store per lane
 #pragma unroll
       for (int off = 0; off < NR * SMAX; off += 32) {
@@ -285,8 +356,10 @@ __global__ void __launch_bounds__(kLatThreads) latent_forward_kernel(const __gri
         if (n < P && r < rows) dst[r * P + n] = sum + (ks == 0 ? __ldg(p.bh + n) : 0.f);
       }
     }
+    lat_stamp(p, 9, false);     // reduced and stored
     if (KS > 1) {
       __syncthreads();
+      lat_stamp(p, 10, false);  // all warps there
       for (int i = tid; i < rows * P; i += blockDim.x) sML[i] += sPart[i];
     }
   }
@@ -352,6 +425,7 @@ __global__ void __launch_bounds__(kLatThreads) latent_forward_kernel(const __gri
         }
       }
     }
+    if (n == 0) lat_stamp(p, 11, false);  // thread 0: fc_d0 column pair accumulated
 #pragma unroll
     for (int r = 0; r < R; ++r)
       if (r < rows)
@@ -394,6 +468,8 @@ __global__ void __launch_bounds__(kLatThreads) latent_backward_kernel(const __gr
     pm_bulk_g2s(pm_smem_u32(sG), p.gdd + row0 * p.gdd_ld, gb, bar);
     pm_bulk_g2s(pm_smem_u32(sH), p.h + row0 * p.h_ld, hb, bar);
   }
+  lat_prefetch_l1(p.Wd0, H * Sd * 4);
+  lat_prefetch_l1(p.Wh, P * H * 4);
   for (int i = tid; i < R * P; i += blockDim.x) {
     sML[i] = i < rows * P ? __ldg(p.ml_in + row0 * P + i) : 0.f;
     sGML[i] = 0.f;  // rows past the end and columns no component owns contribute nothing below
@@ -403,6 +479,7 @@ __global__ void __launch_bounds__(kLatThreads) latent_backward_kernel(const __gr
   __syncthreads();
   pm_mbar_wait(bar, 0);
   lat_stamp(p, 2, false);
+  lat_stamp(p, 15, false);
   const bool nored = (p.debug_flags & 1) != 0;
 
   // ---- gz[r][j] = sum_h gdd[r][h] Wd0[h][j]; a warp takes the row pair (warp, warp + R/2) ----
@@ -417,6 +494,7 @@ __global__ void __launch_bounds__(kLatThreads) latent_backward_kernel(const __gr
         for (int i = 0; i < NR; ++i) srow[i] = sG + min(pr + (i0 + i) * PAIRS, rows - 1) * p.gdd_ld;
         float acc[NR * SMAX];
         rows_dot_WKn<SMAX, NR>(srow, H, p.Wd0, Sd, acc);
+        lat_stamp(p, 8, false);  // (thread 0's warp) partial dot products done
 #pragma unroll
         for (int off = 0; off < NR * SMAX; off += 32) {
           const float sum = off == 0 ? warp_reduce32<0>(acc) : warp_reduce32<(NR * SMAX > 32 ? 32 : 0)>(acc);
@@ -562,7 +640,9 @@ __global__ void __launch_bounds__(kLatThreads) latent_backward_kernel(const __gr
     // four head rows per pass: their Wh loads are issued together (one after the other they were a chain of L2
     // latencies), and with P % 4 == 0 one 128-bit shared-memory load brings a row's four gml values
     const bool q4 = (P & 3) == 0;
+    lat_stamp(p, 9, false);  // thread 0: h columns in registers
     for (int q0 = 0; q0 < P; q0 += 4) {
+      if (q0 == 4) lat_stamp(p, 10, false);  // thread 0: first pass of four head rows done
       float2 w[4];
       float a[4], b[4];
 #pragma unroll
@@ -675,6 +755,7 @@ static int launch_latent(LatParams& p, void* stream) {
   if (grid > 0x7fffffff) return MVAE_ERR_UNSUPPORTED;
   p.stamps = g_lat_stamps;
   p.debug_flags = g_lat_debug_flags;
+  if (unsigned long long* region = debug_timeline_region(bwd ? 2 : 1, grid, (int)p.B, p.H, 0)) p.stamps = region;
   MVAE_CUDA_TRY(launch_pdl(kern, dim3((unsigned)grid), dim3(kLatThreads), smem, as_stream(stream), p));
   MVAE_LAUNCH_CHECK();
   return MVAE_OK;

@@ -31,6 +31,9 @@ struct DeviceInfo {
 };
 int get_device_info(DeviceInfo* out);  // returns mvae_status
 
+// diagnostics: region of the timeline buffer for the next stamped launch (null when timeline mode is off)
+unsigned long long* debug_timeline_region(int kind, long long ncta, int a, int b, int c);
+
 static inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 
 // ---------------------------------------------------------------------------------------------------------

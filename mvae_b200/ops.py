@@ -456,14 +456,37 @@ def _wide(x):
 
 
 def latent_forward(desc: L.PmDesc, h: torch.Tensor, Wh, bh, eps, radius, Wd0, bd0, ml, z, kl, dd: "PlaneBuf",
-                   flag: Optional[torch.Tensor] = None):
-    """heads + product-manifold forward + fc_d0/relu in one launch (mvae_latent_forward); h: fp32 [B, H]."""
+                   flag: Optional[torch.Tensor] = None, draw: Optional[tuple] = None, zero=()):
+    """heads + product-manifold forward + fc_d0/relu in one launch (mvae_latent_forward); h: fp32 [B, H].
+    draw = (seed, counter_dev): eps is DRAWN by this launch (the Philox stream of step_prologue) and written out;
+    zero: float tensors this launch zero-fills (mvae_latent_forward_ex: the head of a train step taken along)."""
     B, H = ml.shape[0], Wh.shape[1]
     ds = dd.struct()
-    rc = L.lib().mvae_latent_forward(ctypes.byref(desc), B, H, _ptr(h), h.stride(0), _ptr(Wh), _ptr(bh), _ptr(eps),
-                                     _ptr(radius), _ptr(Wd0), _ptr(bd0), _ptr(ml), _ptr(z), _ptr(kl), ctypes.byref(ds),
-                                     _ptr(flag), _stream())
-    L.check(rc, "mvae_latent_forward")
+    zero = [t for t in zero if t is not None and t.numel() > 0]
+    if draw is None and not zero:
+        rc = L.lib().mvae_latent_forward(ctypes.byref(desc), B, H, _ptr(h), h.stride(0), _ptr(Wh), _ptr(bh), _ptr(eps),
+                                         _ptr(radius), _ptr(Wd0), _ptr(bd0), _ptr(ml), _ptr(z), _ptr(kl),
+                                         ctypes.byref(ds), _ptr(flag), _stream())
+        L.check(rc, "mvae_latent_forward")
+    else:
+        if len(zero) > 4:
+            raise L.MvaeError("latent_forward: at most four zero-fill spans")
+        for t in zero:
+            if not (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()):
+                raise L.MvaeError("latent_forward: zero targets must be contiguous float32 CUDA tensors")
+        pro = L.LatentPrologue()
+        pro.draw_eps = 1 if draw is not None else 0
+        if draw is not None:
+            pro.seed = int(draw[0]) & (2**64 - 1)
+            pro.counter_dev = draw[1].data_ptr() if draw[1] is not None else None
+        pro.n_zero = len(zero)
+        for i, t in enumerate(zero):
+            pro.zero_ptr[i] = t.data_ptr()
+            pro.zero_n[i] = t.numel()
+        rc = L.lib().mvae_latent_forward_ex(ctypes.byref(desc), B, H, _ptr(h), h.stride(0), _ptr(Wh), _ptr(bh),
+                                            _ptr(eps), _ptr(radius), _ptr(Wd0), _ptr(bd0), _ptr(ml), _ptr(z), _ptr(kl),
+                                            ctypes.byref(ds), _ptr(flag), ctypes.byref(pro), _stream())
+        L.check(rc, "mvae_latent_forward_ex")
     _LAUNCHES[0] += 1
 
 

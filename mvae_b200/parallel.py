@@ -162,6 +162,7 @@ def attach_p2p(model, optimizer, group=None) -> bool:
     optimizer.exp_avg_sq = torch.zeros_like(model._flat)
     optimizer.step_count = 0
     optimizer.step_dev.zero_()
+    optimizer.step_dev_early.zero_()
     model._stats_report = optimizer._dp_tail[C:2 * C + 3]
     model._stats_wire = optimizer._dp_tail[C:]
     model._grad_hook = None

@@ -546,20 +546,24 @@ class FusedFeedForwardVAE(nn.Module):
         B, D, H, P, Sd = ws.B, self.in_dim, self.h_dim, self.desc.ld_ml, self.desc.ld_z
         if self._planes_stale:
             self.refresh_weight_planes()
-        # Fork: the noise draw and the memsets of the accumulating outputs do not depend on the encoder — they run on a
-        # side stream (a parallel branch of the step's CUDA graph) next to split(x) + fc_e0.
+        fused = self.fused_latent and not want_mu_sigma
+        zero = [ws.bce, ws.ml if self.latent_gemm else None, self._bucket[:self._n_net + self.desc.C] if train else None]
+        # The head of the step — eps ~ N(0, I) (Philox, offset = the model's device step counter), zero fill of the
+        # reconstruction row sums and of the gradient bucket (optimizer.zero_grad(), vae.py:151).  With the fused
+        # latent block that kernel takes it along (mvae_latent_forward_ex): nothing ahead of it accumulates into those
+        # buffers, and as a launch of its own on a side branch it makes the latent kernel the node that JOINS the branch
+        # — a full launch latency behind fc_e0 instead of a programmatic edge (scripts/step_timeline.py: the latent
+        # kernel starts 3.3 us earlier and spends 2.5 us of that on the draw).  MVAE_FOLD_PROLOGUE=0 keeps the branch.
+        fold = fused and self.fold_prologue
         main, side = torch.cuda.current_stream(self.device), self._side_stream()
-        side.wait_stream(main)
-        with torch.cuda.stream(side):
-            # ONE launch: eps ~ N(0, I) (Philox, offset = the model's device step counter) + zero fill of the
-            # reconstruction row sums, of ml (the heads GEMM accumulates its K slices into it) and of the gradient
-            # bucket (optimizer.zero_grad(), vae.py:151)
-            ops.step_prologue(ws.eps if draw_eps else None, self.noise_seed, self._bin_ctr,
-                              [ws.bce, ws.ml if self.latent_gemm else None,
-                               self._bucket[:self._n_net + self.desc.C] if train else None])
+        if not fold:
+            # Fork: a side stream (a parallel branch of the step's CUDA graph) next to split(x) + fc_e0: ONE launch,
+            # + zero fill of ml (the heads GEMM accumulates its K slices into it)
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                ops.step_prologue(ws.eps if draw_eps else None, self.noise_seed, self._bin_ctr, zero)
         ws.drew_eps = draw_eps
         self._input_planes(ws, train)
-        fused = self.fused_latent and not want_mu_sigma
         ws.has_mu_sigma = want_mu_sigma
         if fused:
             self._gemm("e0_fwd32", ws.xp, self.We0p, B, H, D, epilogue=L.EPI_BIAS_RELU, bias=self.fc_e0.bias.data,
@@ -568,12 +572,15 @@ class FusedFeedForwardVAE(nn.Module):
             self._gemm("e0_fwd", ws.xp, self.We0p, B, H, D, epilogue=L.EPI_BIAS_RELU, bias=self.fc_e0.bias.data,
                        out_planes=ws.hp)
         ws.fused = fused
-        main.wait_stream(side)  # join: eps drawn, bce / gradient bucket zeroed
+        if not fold:
+            main.wait_stream(side)  # join: eps drawn, bce / gradient bucket zeroed
         if fused:
             # heads + manifold chain + fc_d0/relu in ONE kernel: ml, z, kl kept for the backward pass / statistics
             ops.latent_forward(self.desc, ws.h32, self.Wh, self.bh, ws.eps, self._rflat, self.fc_d0.weight.data,
                                self.fc_d0.bias.data, ws.ml, ws.z, ws.kl, ws.ddp,
-                               flag=ws.flag if self.check_finite else None)
+                               flag=ws.flag if self.check_finite else None,
+                               draw=(self.noise_seed, self._bin_ctr) if (fold and draw_eps) else None,
+                               zero=zero if fold else ())
         elif self.latent_gemm:
             # wide product: heads and fc_d0 on the tensor cores (3 planes each side: fp32 accuracy ahead of the
             # manifold maps / the relu), the standalone product-manifold kernel between them
@@ -674,16 +681,37 @@ class FusedFeedForwardVAE(nn.Module):
         # fc_e0 (no dgrad into x)
         self._gemm("e0_wgrad", ws.ghp, ws.xp, H, D + 1, B, a_major=MN, b_major=MN, split_k=0, out_f32=self.gWe0,
                  out_col=self.gbe0, col_split=D, b_planes=2)
+        if early and getattr(self._early_step.__self__, "early_is_independent", False) \
+                and self._early_step.__self__._early_done:
+            # The launch that ends the step touches nothing the side branches produce (ELBO statistics, fc_logits'
+            # gradient and update): it follows fc_e0's weight gradient directly, and the branches are joined AFTER it
+            # (_join_pending).  Joined here, the final launch was a three-way join node of the graph — a full launch
+            # latency (~3.5 us, scripts/step_timeline.py) behind the last GEMM instead of a programmatic edge.
+            self._pending_join = (side, comm)
+            return
         main.wait_stream(side)  # join
         if early:
             main.wait_stream(comm)
+
+    def _join_pending(self) -> None:
+        """Join the side branches whose join _backward_kernels left to the end of the step."""
+        pj = getattr(self, "_pending_join", None)
+        if pj is not None:
+            main = torch.cuda.current_stream(self.device)
+            for st in pj:
+                main.wait_stream(st)
+            self._pending_join = None
 
     # ------------------------------------------------------------------------------------------ GEMM tile policy
     # The five big GEMMs of a step are launch- and L2-bound at these shapes and their best tile (BLOCK_N, CTAs per SM,
     # split-K) depends on M, N, K and the operand layouts: each call site times a handful of candidates ONCE per batch
     # size (CUDA events, first eager step) and keeps the fastest.  MVAE_GEMM_AUTOTUNE=0 keeps the automatic policy.
     _GEMM_TILES = [None, (48, 2), (64, 2), (96, 1), (112, 1), (112, 2), (128, 1), (208, 1)]
-    _GEMM_TILES_SPLITK = [None, (64, 2, 0), (64, 2, 4), (64, 2, 6), (80, 1, 0), (96, 1, 0), (112, 1, 0), (128, 1, 0)]
+    # (the split-K GEMMs are the weight gradients, K = batch: their main loops run at the L2 throughput cap —
+    # scripts/gemm_phases.py — and a wider tile re-reads the activations less often: 128 x 208 moves ~30 % fewer bytes
+    # than 128 x 112 for the same product)
+    _GEMM_TILES_SPLITK = [None, (64, 2, 0), (64, 2, 4), (64, 2, 6), (80, 1, 0), (96, 1, 0), (112, 1, 0), (128, 1, 0),
+                          (144, 1, 0), (176, 1, 0), (208, 1, 0), (256, 1, 0)]
     autotune_gemm = os.environ.get("MVAE_GEMM_AUTOTUNE", "1") != "0"
 
     def _gemm(self, site: str, a, b, M: int, N: int, K: int, **kw) -> None:
@@ -715,15 +743,17 @@ class FusedFeedForwardVAE(nn.Module):
             try:
                 for _ in range(2):
                     ops.gemm(a, b, M, N, K, tile=tile, **kw)
-                s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                s.record()
-                for _ in range(8):
-                    ops.gemm(a, b, M, N, K, tile=tile, **kw)
-                e.record()
-                e.synchronize()
+                ms = float("inf")
+                for _ in range(3):   # best of three rounds: one round's noise used to flip between near-equal tiles
+                    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    s.record()
+                    for _ in range(8):
+                        ops.gemm(a, b, M, N, K, tile=tile, **kw)
+                    e.record()
+                    e.synchronize()
+                    ms = min(ms, s.elapsed_time(e))
             except L.MvaeError:
                 continue
-            ms = s.elapsed_time(e)
             if ms < best_ms:
                 best, best_ms = tile, ms
         for t, sv in zip(acc, saved):
@@ -994,6 +1024,7 @@ class FusedFeedForwardVAE(nn.Module):
                 if self._clip_mask is not None:
                     ops.clip_grad_norm(self._gradius, self._clip_mask, 1.0)
             optimizer.step()
+            self._join_pending()
             self._planes_stale = not getattr(optimizer, "planes_fresh", False)
             if self._push_stats:
                 self._push_stats_kernel()
@@ -1128,6 +1159,7 @@ class FusedFeedForwardVAE(nn.Module):
     _grad_hook = None
     _early_step = None  # FusedCurvatureOptimizer.step_early of the optimizer driving the step being enqueued
     use_cuda_graph = False
+    fold_prologue = os.environ.get("MVAE_FOLD_PROLOGUE", "1") != "0"
     latent_gemm = False
     train_statistics = False  # True: train_step keeps q_z's loc / scale (Trainer --train_statistics, train.py:200-206)
 
@@ -1163,6 +1195,7 @@ class FusedFeedForwardVAE(nn.Module):
 
             def capture_opt():
                 optimizer.step()
+                self._join_pending()
                 if not getattr(optimizer, "planes_fresh", False):
                     self.refresh_weight_planes()
                 if self._push_stats:
@@ -1261,6 +1294,12 @@ class FusedCurvatureOptimizer:
         self.dp_overlap = os.environ.get("MVAE_DP_OVERLAP", "1") != "0"
         self.dp_early_ctas = int(os.environ.get("MVAE_DP_EARLY_CTAS", "24"))
         self._done = torch.zeros(1, device=model._flat.device, dtype=torch.int32)
+        # The early launch over fc_logits keeps ITS OWN step counter (advanced by its own last CTA): the launch that ends
+        # the step advances step_dev when it finishes, and the two launches are not ordered against each other (the
+        # model joins the early branch AFTER the final launch: _join_pending) — the early one must not read a counter
+        # the final one may already have bumped.
+        self.step_dev_early = torch.zeros(1, device=model._flat.device, dtype=torch.int32)
+        self._done_early = torch.zeros(1, device=model._flat.device, dtype=torch.int32)
         self.planes_fresh = False  # True after a step that also refreshed the model's weight planes
 
     def zero_grad(self) -> None:
@@ -1313,14 +1352,21 @@ class FusedCurvatureOptimizer:
             self._local_launch(begin, end, last=False)
         self._early_done = True
 
+    @property
+    def early_is_independent(self) -> bool:
+        """True when nothing orders the early launch against the one that ends the step (one GPU: disjoint parameter
+        ranges, separate step counters) — the model may then join the early branch after the final launch."""
+        return self._dp is None
+
     def _local_launch(self, begin: int, end: int, last: bool) -> None:
         """Adam over [begin, end) of the flat buffer + plane refresh of the GEMM weights inside; the launch that ends
-        the step (`last`) also steps the radii and advances the device step counter."""
+        the step (`last`) also steps the radii and advances the device step counter (the early one: its own)."""
         m = self.model
         targets, late = self._plane_targets()
         inside = lambda off: begin <= off < end  # noqa: E731
         ops.opt_step_fused(m._flat[begin:end], m._gnet[begin:end], self.exp_avg[begin:end], self.exp_avg_sq[begin:end],
-                           self.lr, self.betas[0], self.betas[1], self.eps, self.step_dev, self._done if last else None,
+                           self.lr, self.betas[0], self.betas[1], self.eps, self.step_dev if last else self.step_dev_early,
+                           self._done if last else self._done_early,
                            m._rflat if last else None, m._gradius, m._radius_mask,
                            self.curvature_lr if (last and self.curvature_step_enabled()) else 0.0,
                            [(t[0] - begin, t[1], t[2]) for t in targets if inside(t[0])])
@@ -1348,6 +1394,11 @@ class FusedCurvatureOptimizer:
         # Adam + the radii's SGD step + the refresh of the GEMM weight planes + the step counter: one launch over
         # whatever step_early() has not taken already (fixed radii receive no gradient: radius_mask)
         end = self._dp_ranges()[-1][1] if self._early_done else m._n_net
+        if not self._early_done:
+            # no early launch in this step: its counter follows along (an empty launch: the counter bump only)
+            z = m._flat[0:0]
+            ops.opt_step_fused(z, z, z, z, self.lr, self.betas[0], self.betas[1], self.eps, self.step_dev_early,
+                               self._done_early, None, m._gradius, m._radius_mask, 0.0, [])
         self._early_done = False
         self._local_launch(0, end, last=True)
         m._planes_stale = False
@@ -1375,3 +1426,4 @@ class FusedCurvatureOptimizer:
         self.exp_avg_sq.copy_(sd["exp_avg_sq"])
         self.step_count = int(sd["step"])
         self.step_dev.fill_(self.step_count)
+        self.step_dev_early.fill_(self.step_count)

@@ -44,6 +44,12 @@ PH = {"latent_forward": ["pdl_wait", "load h", "heads", "manifold chain", "fc_d0
                           "gh planes store"]}
 
 
+FINE = {"latent_forward": [(8, "heads: partial dot products done (warp 0)"), (9, "heads: reduced + stored (warp 0)"),
+                           (10, "heads: all warps at the combine barrier"), (11, "fc_d0: first column pair accumulated")],
+        "latent_backward": [(8, "gz: partial dot products done (warp 0)"), (9, "heads: h columns in registers"),
+                            (10, "heads: first pass of four head rows done")]}
+
+
 def timed(fn, a, k, rep=20):
     g = torch.cuda.CUDAGraph()
     with torch.cuda.graph(g):
@@ -83,7 +89,7 @@ for name, (fn, a, k) in calls.items():
         lib.mvae_debug_latent(None, 1)
         print(f"   without reductions: back-to-back {timed(fn, a, k):.2f} us, alone {single(fn, a, k):.2f} us")
         lib.mvae_debug_latent(None, 0)
-    st = torch.zeros(grid, 8, dtype=torch.int64, device=dev)
+    st = torch.zeros(grid, 16, dtype=torch.int64, device=dev)
     for flags in ((0, 1) if name == "latent_backward" else (0,)):
         st.zero_()
         torch.cuda.synchronize()
@@ -100,3 +106,7 @@ for name, (fn, a, k) in calls.items():
             d = (t[:, i + 1] - t[:, i]) / 1e3
             print(f"     {ph:22s} median {np.median(d):6.2f}  p90 {np.percentile(d, 90):6.2f}  max {d.max():6.2f} us"
                   f"   (phase ends at median {np.median(t[:, i + 1] - t0) / 1e3:6.2f} us)")
+        for i, what in FINE[name]:   # SM cycle counter, relative to the end of the load phase (slot 15)
+            if (t[:, i] > 0).all():
+                d = (t[:, i] - t[:, 15]) / 1.965e3
+                print(f"     {what:46s} {np.median(d):6.2f} us after the loads landed (p90 {np.percentile(d, 90):6.2f})")

@@ -494,3 +494,46 @@ def test_latent_fused_matches_separate_kernels(dev, oracle, sig, B, H, scalar):
                       (gbh, gml64.sum(0))):
         assert ((got.double() - want).norm() / want.norm()).item() < 1e-4
     assert np.all(np.abs(gR.cpu().numpy() - gR_ref) <= 2e-4 * np.maximum(1.0, np.abs(gml_ref).sum()))
+
+
+@pytest.mark.parametrize("sig,B,H", [("h2,s2,e2", 4096, 400), ("h2", 1003, 64), ("p2,e3", 17, 136)])
+def test_latent_forward_takes_the_step_prologue_along(dev, sig, B, H):
+    """mvae_latent_forward_ex: the noise the kernel draws itself is, bit for bit, what mvae_step_prologue draws for the
+    same seed / device counter (so the fused step and the two-launch step sample the same eps), the spans handed to
+    it are zero afterwards, and every output equals the plain launch fed with that noise."""
+    from mvae_b200 import ops
+    desc = ops.make_desc(sig)
+    P, Sn, Sd, C = desc.ld_ml, desc.ld_eps, desc.ld_z, desc.C
+    g = torch.Generator(device=dev).manual_seed(7 * B + H)
+    h = torch.randn(B, H, device=dev, generator=g).clamp(min=0)
+    Wh = torch.randn(P, H, device=dev, generator=g) / H**0.5
+    bh = torch.randn(P, device=dev, generator=g) * 0.1
+    Wd0 = torch.randn(H, Sd, device=dev, generator=g) / Sd**0.5
+    bd0 = torch.randn(H, device=dev, generator=g) * 0.1
+    R = torch.full((C,), 2.5, device=dev)
+    seed, ctr = 0x5EED1234ABCD, torch.full((1,), 41, device=dev, dtype=torch.int64)
+    eps_ref = torch.full((B, Sn), float("nan"), device=dev)
+    ops.step_prologue(eps_ref, seed, ctr, [])
+    assert torch.isfinite(eps_ref).all()
+
+    def run(eps, **kw):
+        out = [torch.full((B, P), float("nan"), device=dev), torch.full((B, Sd), float("nan"), device=dev),
+               torch.full((B, C), float("nan"), device=dev), ops.PlaneBuf(B, H, 2, dev)]
+        ops.latent_forward(desc, h, Wh, bh, eps, R, Wd0, bd0, out[0], out[1], out[2], out[3], **kw)
+        return out
+
+    plain = run(eps_ref)
+    eps_drawn = torch.full((B, Sn), float("nan"), device=dev)
+    z1 = torch.full((1001,), 3.0, device=dev)
+    z2 = torch.full((B,), -1.0, device=dev)
+    z3 = torch.full((7,), 5.0, device=dev)[1:]   # not 16-byte aligned
+    fused = run(eps_drawn, draw=(seed, ctr), zero=[z1, z2, z3])
+    assert torch.equal(eps_drawn, eps_ref)
+    assert not z1.any() and not z2.any() and not z3.any()
+    for a, b in zip(plain[:3], fused[:3]):
+        assert torch.equal(a, b)
+    assert torch.equal(plain[3].t, fused[3].t)
+    # zero fills alone (noise supplied)
+    z1.fill_(2.0)
+    only_zero = run(eps_ref, zero=[z1])
+    assert not z1.any() and torch.equal(only_zero[1], plain[1])
