@@ -52,7 +52,7 @@ def measured_peaks():
 
 KERNEL_SOURCES = {  # files whose edits invalidate an ncu capture of the kernel
     "pm_forward_kernel": ["pm_kernels_impl.cuh", "pm_item.cuh", "pm_math.cuh", "pm_params.cuh"],
-    "pm_backward_kernel": ["pm_kernels_impl.cuh", "pm_item.cuh", "pm_math.cuh", "pm_params.cuh"],
+    "pm_backward_kernel": ["pm_kernels_impl.cuh", "pm_item.cuh", "pm_math.cuh", "pm_params.cuh", "pm_bwd.cu"],
     "gemm_tcgen05_kernel": ["gemm_sm100.cu"],
 }
 
@@ -247,7 +247,7 @@ def cpu_step_fn(workload, B, seed=0):
         lin = torch.nn.Linear(i_, o)
         params[nm + ".weight"] = lin.weight.detach().numpy().copy()
         params[nm + ".bias"] = lin.bias.detach().numpy().copy()
-    cpu = cpu_baseline.CpuTrainStep(sig, D, H, recon, params)
+    cpu = cpu_baseline.CpuTrainStep(sig, D, H, recon, params, curvature_lr=1e-4 * min(1.0, 4096.0 / B))  # as the GPU arm
     x = synthetic_x(recon, B, D, seed)
     g = torch.Generator().manual_seed(seed)
     n_eps = cpu.desc.ld_eps
@@ -423,7 +423,10 @@ def run_ours(args):
     # radii ran into their clamp within a few hundred steps and the run trained on NaNs.  The curvature step is
     # therefore divided by the number of ranks — the N-rank run then moves the radii like the 1-rank run does.  (Adam's
     # update of the network parameters is invariant to the gradient's scale.)
-    curvature_lr = 1e-4 / world
+    # The same holds for the per-GPU batch: BDP-shaped data at B = 16384 (cfg4a) has a radius gradient of 1.2e5 at
+    # initialisation — one reference-sized step takes R from 10 to -2.3 and the ELBO to NaN (reproduced with the CPU
+    # oracle; rounds 1-2 reported elbo_finite = false there) — so beyond 4096 rows the step shrinks with the batch.
+    curvature_lr = 1e-4 / world * min(1.0, 4096.0 / B)
     opt = vae.FusedCurvatureOptimizer(model, 1e-3, fixed_curvature=fixed, should_do_curvature_step=lambda: True,
                                       curvature_lr=curvature_lr)
     collective = "none"
@@ -604,7 +607,7 @@ def run_ours(args):
                        ("; ranks re-aligned after the flush by a peer-memory rendezvous kernel, outside the timed region"
                         if world > 1 and not args.no_rendezvous and not collective.startswith("NCCL") else ""),
                        "cuda_graph": bool(model.use_cuda_graph),
-                       "optimizer": f"Adam(1e-3) + SGD({curvature_lr:g} = 1e-4 / ranks) on radii",
+                       "optimizer": f"Adam(1e-3) + SGD({curvature_lr:g} = 1e-4 / ranks x min(1, 4096 / batch per GPU)) on radii",
                        "initial_radius": args.radius,
                        "collective": collective, "numa_bound": bool(numa_bound)},
             "e2e": {"value": gb / (e2e_ms / 1e3), "unit": UNIT, "ms_per_step": e2e_ms,
