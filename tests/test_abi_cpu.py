@@ -38,6 +38,13 @@ def test_binding_matches_header(built_lib):
     assert ctypes.sizeof(_lib.PmDesc) == 16 + 32 * _lib.MAX_COMPONENTS
 
 
+def test_integration_notes_name_every_entry_point():
+    """INTEGRATION.md §2 maps every entry point of the header to the reference interface it replaces."""
+    doc = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    missing = [n for n in _declared_symbols() if f"`{n}`" not in doc]
+    assert not missing, missing
+
+
 def test_desc_init_layout_matches_oracle(built_lib, oracle):
     """Host-only entry point: packed descriptor offsets are the oracle's (concat order of vae.py:78)."""
     from mvae_b200 import ops
