@@ -294,8 +294,11 @@ def run_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms, "steps_per_sec": 1e3 / ms, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": desc, "signature": sig, "batch_per_gpu": B, "global_batch": B, "in_dim": D,
-                       "h_dim": H, "note": "CPU arm runs one replica of the per-GPU workload on the host cores"},
+            "config": {"workload": desc, "signature": sig, "batch_per_gpu": B, "global_batch": B * max(args.gpus, 1),
+                       "in_dim": D, "h_dim": H, "parallelism": f"dp{max(args.gpus, 1)}",
+                       "note": "bounded sample: the host cores run full train steps on ONE per-GPU share of the global "
+                               "batch (the CPU arm is compute bound at these batch sizes: its samples/s changes little "
+                               "with the number of shares it is given)"},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample,
                              "omp_num_threads": os.environ.get("OMP_NUM_THREADS")},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
